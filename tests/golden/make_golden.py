@@ -1,0 +1,223 @@
+"""Generate tests/golden/*.npz by running the REAL reference (/root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference is Python-2 source; it is exec'd from where it lies with the
+in-memory textual shims of SURVEY.md App. B (iteritems->items, xrange->range,
+izip->zip, print statements) and stub modules for its absent optional imports.
+Nothing from the reference is written into this repository except the numeric
+outputs stored in the fixtures.  Inputs are regenerated from
+pypore_b200.synth by seed; a sha256 of the input bytes guards generator drift.
+"""
+import hashlib
+import itertools
+import os
+import re
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REFERENCE = "/root/reference"
+
+from oracle import build_oracle  # noqa: E402
+from pypore_b200 import synth  # noqa: E402
+
+
+def _shim(src):
+    src = src.replace("iteritems()", "items()").replace("xrange", "range")
+    src = src.replace("from itertools import tee,izip,chain", "from itertools import tee,chain; izip=zip")
+    src = src.replace("from itertools import chain, izip, tee, combinations",
+                      "from itertools import chain, tee, combinations; izip=zip")
+    src = re.sub(r'^(\s*)print "(.*)"\.format\((.*)\)\s*$', r'\1print("\2".format(\3))', src, flags=re.M)
+    src = re.sub(r'^(\s*)print "(.*)"\s*$', r'\1print("\2")', src, flags=re.M)
+    return src
+
+
+def load_reference():
+    """Returns the reference's PyPore.DataTypes module, loaded per SURVEY App. B."""
+    so = build_oracle.build_ref()
+    itertools.izip = zip
+    pkg = types.ModuleType("PyPore")
+    pkg.__path__ = [os.path.dirname(so)]
+    sys.modules["PyPore"] = pkg
+
+    def exec_into(name, filename, aliases=(), strip=()):
+        with open(os.path.join(REFERENCE, "PyPore", filename)) as f:
+            src = _shim(f.read())
+        for s in strip:
+            src = src.replace(s, "")
+        mod = types.ModuleType(name)
+        mod.__file__ = os.path.join(REFERENCE, "PyPore", filename)
+        sys.modules[name] = mod
+        for a in aliases:
+            sys.modules[a] = mod
+        exec(compile(src, mod.__file__, "exec"), mod.__dict__)
+        return mod
+
+    core = exec_into("core", "core.py", aliases=("PyPore.core",))
+    pkg.core = core
+    import PyPore.cparsers  # noqa: F401  (compiled reference from oracle/_ref)
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm", "MySQLdb", "hmm", "database",
+                 "alignment", "yahmm"):
+        m = types.ModuleType(name)
+        m.__all__ = []
+        sys.modules[name] = m
+    sys.modules["yahmm"].Model = type("Model", (), {})
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].cm = sys.modules["matplotlib.cm"]
+    ra = types.ModuleType("read_abf")
+
+    def read_abf(*a, **k):
+        raise IOError("no .abf data offline")
+    ra.read_abf = read_abf
+    sys.modules["read_abf"] = ra
+    parsers = exec_into("PyPore.parsers", "parsers.py", aliases=("parsers",),
+                        strip=("import pyximport\n",
+                               "pyximport.install( setup_args={'include_dirs':np.get_include()})\n"))
+    pkg.parsers = parsers
+    dt = exec_into("PyPore.DataTypes", "DataTypes.py", aliases=("DataTypes",))
+    pkg.DataTypes = dt
+    return dt, parsers, core
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+SPLIT_SETTINGS = {
+    "default": dict(min_width=100, window_width=10000),
+    "psps10": dict(min_width=100, window_width=10000, prior_segments_per_second=10),
+    "narrow": dict(min_width=50, max_width=2500, window_width=1000, prior_segments_per_second=50),
+}
+
+
+def golden_pipeline(dt, parsers, tier, seed, n_events, fs=1.e5):
+    """File.parse -> Event.parse for several parser settings; records tables in samples."""
+    x32 = synth.make_trace(n_events, seed=seed, tier=tier)
+    out = {"input_sha256": np.array(sha(x32)), "seed": seed, "n_events": n_events, "fs": fs,
+           "tier": np.array(tier), "threshold": 110.0}
+    x64 = x32.astype(np.float64)
+    f = dt.File(current=x64, timestep=1000. / fs)
+    rules = [lambda e: e.duration > 1000, lambda e: e.min > -0.5, lambda e: e.max < 110]
+    f.parse(parser=parsers.lambda_event_parser(threshold=110, rules=rules))
+    second = f.second
+    out["second"] = second
+    out["event_start_s"] = np.array([e.start for e in f.events])
+    out["event_end_s"] = np.array([e.end for e in f.events])
+    out["event_duration_s"] = np.array([e.duration for e in f.events])
+    out["event_n"] = np.array([len(e.current) for e in f.events], np.int64)
+    out["event_min"] = np.array([e.min for e in f.events])
+    out["event_max"] = np.array([e.max for e in f.events])
+    out["event_mean"] = np.array([e.mean for e in f.events])
+    out["event_std"] = np.array([e.std for e in f.events])
+    # default rules reject everything in this regime
+    f2 = dt.File(current=x64, timestep=1000. / fs)
+    f2.parse(parser=parsers.lambda_event_parser(threshold=110))
+    out["n_events_default_rules"] = len(f2.events)
+    for name, kw in SPLIT_SETTINGS.items():
+        ev_id, st, en, mean, std, mn, mx, st_s, en_s = [], [], [], [], [], [], [], [], []
+        p = parsers.SpeedyStatSplit(**kw)
+        for i, e in enumerate(f.events):
+            raw = p.parse(e.current)  # samples, before Event.parse rescales
+            for s in raw:
+                ev_id.append(i); st.append(s.start); en.append(s.end)
+                mean.append(s.mean); std.append(s.std); mn.append(s.min); mx.append(s.max)
+            e.parse(parser=p)  # seconds
+            for s in e.segments:
+                st_s.append(s.start); en_s.append(s.end)
+        out[name + "_event"] = np.array(ev_id, np.int64)
+        out[name + "_start"] = np.array(st, np.int64)
+        out[name + "_end"] = np.array(en, np.int64)
+        out[name + "_mean"] = np.array(mean)
+        out[name + "_std"] = np.array(std)
+        out[name + "_min"] = np.array(mn)
+        out[name + "_max"] = np.array(mx)
+        out[name + "_start_s"] = np.array(st_s)
+        out[name + "_end_s"] = np.array(en_s)
+    return out
+
+
+def golden_filter(dt, parsers, fs, order, cutoff, seed):
+    """Event.filter then SpeedyStatSplit on the first two events of a small trace."""
+    x32 = synth.make_trace(3, seed=seed, tier="A")
+    x64 = x32.astype(np.float64)
+    f = dt.File(current=x64, timestep=1000. / fs)
+    rules = [lambda e: e.duration > 1000, lambda e: e.min > -0.5, lambda e: e.max < 110]
+    f.parse(parser=parsers.lambda_event_parser(threshold=110, rules=rules))
+    out = {"input_sha256": np.array(sha(x32)), "seed": seed, "fs": fs, "order": order, "cutoff": cutoff}
+    from scipy import signal
+    b, a = signal.bessel(order, cutoff / (f.second / 2.), btype='low', analog=0, output='ba')
+    out["b"], out["a"], out["zi"] = b, a, signal.lfilter_zi(b, a)
+    p = parsers.SpeedyStatSplit(min_width=100, window_width=10000, sampling_freq=fs, cutoff_freq=cutoff,
+                                prior_segments_per_second=10)
+    for i, e in enumerate(f.events[:2]):
+        e.filter(order=order, cutoff=cutoff)
+        assert e.filtered and e.current.dtype == np.float64
+        out["event%d_start" % i] = int(round(e.start * f.second))
+        out["event%d_filtered" % i] = e.current.copy()
+        raw = p.parse(e.current)
+        out["event%d_seg_start" % i] = np.array([s.start for s in raw], np.int64)
+        out["event%d_seg_end" % i] = np.array([s.end for s in raw], np.int64)
+        out["event%d_seg_mean" % i] = np.array([s.mean for s in raw])
+        out["event%d_seg_std" % i] = np.array([s.std for s in raw])
+    return out
+
+
+def golden_long(parsers):
+    """One 300k-sample event with forced max_width splits and the window chain (C4 regime, small)."""
+    out = {}
+    for name, kw in {"long_default": dict(min_width=100, max_width=20000, window_width=10000),
+                     "long_psps10": dict(min_width=100, max_width=20000, window_width=10000,
+                                         prior_segments_per_second=10),
+                     "long_highgain": dict(min_width=100, max_width=15000, window_width=4000,
+                                           min_gain_per_sample=2.0)}.items():
+        x32 = synth.make_long_event(300000, seed=100, tier="A")
+        raw = parsers.SpeedyStatSplit(**kw).parse(x32.astype(np.float64))
+        out[name + "_start"] = np.array([s.start for s in raw], np.int64)
+        out[name + "_end"] = np.array([s.end for s in raw], np.int64)
+    out["input_sha256"] = np.array(sha(x32))
+    return out
+
+
+def golden_params(parsers):
+    """min_gain known answers and exception parity."""
+    from PyPore.cparsers import FastStatSplit
+    out = {
+        "min_gain_default": FastStatSplit().min_gain,
+        "min_gain_psps10": FastStatSplit(prior_segments_per_second=10).min_gain,
+        "min_gain_psps10_cut2000": FastStatSplit(prior_segments_per_second=10, cutoff_freq=2000.).min_gain,
+        "min_gain_per_sample_0p5": FastStatSplit(min_gain_per_sample=0.5).min_gain,
+        "min_gain_fpr50_fs250k": FastStatSplit(false_positive_rate=50., sampling_freq=2.5e5,
+                                               prior_segments_per_second=25.).min_gain,
+    }
+    try:
+        FastStatSplit().parse(np.zeros(1000, np.float32))
+        out["float32_error"] = np.array("")
+    except ValueError as e:
+        out["float32_error"] = np.array(str(e))
+    return out
+
+
+def main():
+    dt, parsers, core = load_reference()
+    np.savez_compressed(os.path.join(HERE, "pipeline_tierA.npz"), **golden_pipeline(dt, parsers, "A", 3, 12))
+    np.savez_compressed(os.path.join(HERE, "pipeline_tierB.npz"), **golden_pipeline(dt, parsers, "B", 4, 8))
+    np.savez_compressed(os.path.join(HERE, "filter_o1_100k.npz"), **golden_filter(dt, parsers, 1.e5, 1, 2000., 5))
+    np.savez_compressed(os.path.join(HERE, "filter_o1_250k.npz"), **golden_filter(dt, parsers, 2.5e5, 1, 2000., 6))
+    np.savez_compressed(os.path.join(HERE, "filter_o2_100k.npz"), **golden_filter(dt, parsers, 1.e5, 2, 2000., 5))
+    np.savez_compressed(os.path.join(HERE, "filter_o4_100k.npz"), **golden_filter(dt, parsers, 1.e5, 4, 5000., 5))
+    np.savez_compressed(os.path.join(HERE, "long_event.npz"), **golden_long(parsers))
+    np.savez_compressed(os.path.join(HERE, "params.npz"), **golden_params(parsers))
+    for fn in sorted(os.listdir(HERE)):
+        if fn.endswith(".npz"):
+            print(fn, os.path.getsize(os.path.join(HERE, fn)))
+
+
+if __name__ == "__main__":
+    main()
