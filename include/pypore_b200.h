@@ -1,0 +1,161 @@
+/*
+ * pypore_b200.h -- C ABI of libpypore_b200.so: the B200 (sm_100a) implementation
+ * of PyPore's signal-segmentation hot path.
+ *
+ * The reference (jmschrei/PyPore) has no FFI: its plug-in boundary is the
+ * duck-typed Python protocol `parser.parse(current) -> [Segment]`
+ * (PyPore/parsers.py:57-59) called from File.parse (PyPore/DataTypes.py:589-602),
+ * Event.parse (DataTypes.py:276-289) and Event.filter (DataTypes.py:258-274).
+ * Each entry point below names the reference lines whose arithmetic it
+ * replaces; pypore_b200/ binds them with ctypes (see INTEGRATION.md for the
+ * stub a reference maintainer would add).
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success or
+ * a negative pp_status, with a message available from pp_last_error(); all work
+ * is ordered on the context's CUDA stream; calls that hand data back to the
+ * host synchronise that stream before returning.  A context is bound to one
+ * device and must not be used from two threads at once (the reference is
+ * single-threaded, SURVEY 8b "Threading").
+ *
+ * Index conventions: trace positions and event starts are int64 sample indices
+ * into the trace; segment starts/ends are int64 sample indices RELATIVE to their
+ * event (what FastStatSplit.parse returns, cparsers.pyx:115-116).
+ */
+#ifndef PYPORE_B200_H
+#define PYPORE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pp_ctx pp_ctx;
+
+enum pp_status {
+    PP_OK = 0,
+    PP_ERR_CUDA = -1,      /* a CUDA runtime call failed (message has the cudaError string) */
+    PP_ERR_ARG = -2,       /* invalid argument / call order */
+    PP_ERR_CAPACITY = -3,  /* a caller-supplied output buffer is too small */
+    PP_ERR_STATE = -4,     /* required earlier stage has not run */
+    PP_ERR_FILTER_LEN = -5 /* an event is not longer than filtfilt's padlen (scipy raises ValueError) */
+};
+
+/* Rule mask for pp_select_events: the three default-shaped rules of
+ * lambda_event_parser (parsers.py:133-135). */
+enum pp_rule {
+    PP_RULE_DURATION_GT = 1, /* event.duration > duration_gt  (samples) */
+    PP_RULE_MIN_GT = 2,      /* event.min > min_gt */
+    PP_RULE_MAX_LT = 4,      /* event.max < max_lt */
+    PP_RULE_DURATION_LT = 8  /* event.duration < duration_lt (GUI rule, parsers.py:207) */
+};
+
+/* Prefix-sum strategy for FastStatSplit's cumsums (cparsers.pyx:110-111). */
+enum pp_prefix_mode {
+    PP_PREFIX_AUTO = 0,       /* parallel scan with exactness check, sequential redo of inexact events */
+    PP_PREFIX_SEQUENTIAL = 1, /* strict np.cumsum order, one thread per event */
+    PP_PREFIX_PARALLEL = 2    /* parallel scan only (bit-identical iff all sums are exact) */
+};
+
+/* ---- context ---------------------------------------------------------- */
+int pp_version(void);
+int pp_device_count(void);
+/* stream == NULL: the context creates its own non-blocking stream. */
+int pp_create(int device, void *cuda_stream, pp_ctx **out);
+void pp_destroy(pp_ctx *ctx);
+const char *pp_last_error(pp_ctx *ctx);
+int pp_sync(pp_ctx *ctx);
+/* Number of kernel launches this context has issued since creation. */
+int64_t pp_launch_count(pp_ctx *ctx);
+/* Milliseconds between two internal CUDA events bracketing the named stage of
+ * the LAST pipeline call: 0 threshold, 1 select, 2 filter, 3 prefix, 4 split,
+ * 5 compact, 6 stats.  Valid after pp_sync(). */
+int pp_stage_ms(pp_ctx *ctx, int stage, float *ms);
+
+/* ---- trace residency -------------------------------------------------- */
+/* Copy a host float32 trace to the device (replaces File.current,
+ * DataTypes.py:572-583).  `extra_capacity` samples are reserved after the trace
+ * for pp_trace_append (multi-GPU halo). */
+int pp_trace_upload(pp_ctx *ctx, const float *host, int64_t n, int64_t extra_capacity);
+/* Use device memory the caller owns (no copy; must stay valid; capacity in samples). */
+int pp_trace_adopt(pp_ctx *ctx, const float *dev, int64_t n, int64_t capacity);
+/* Append `n` samples (device or host pointer) after the current trace end: the
+ * continuation of an event that straddles this GPU's chunk boundary. */
+int pp_trace_append(pp_ctx *ctx, const float *src, int64_t n, int src_is_device);
+int64_t pp_trace_len(pp_ctx *ctx);
+const float *pp_trace_device_ptr(pp_ctx *ctx);
+
+/* ---- K1: lambda_event_parser.parse (parsers.py:142-155) -------------- */
+/* Runs of consecutive samples on one side of the threshold, compared as
+ * double(x) < threshold, with per-run min/max (core.py:215-220).
+ * `scan_len` <= trace length restricts the scan to a prefix of the trace
+ * (samples appended as halo are not re-scanned); pass -1 for the whole trace. */
+int pp_threshold_scan(pp_ctx *ctx, double threshold, int64_t scan_len, int64_t *n_runs);
+int pp_runs_download(pp_ctx *ctx, int64_t cap, int64_t *start, int64_t *length, double *mn,
+                     double *mx, uint8_t *below);
+/* _lambda_select for default-shaped rules, evaluated on the device
+ * (parsers.py:133-140).  Runs flagged in `skip_first`/`skip_last` (0/1) are
+ * excluded regardless of the rules (multi-GPU: a run owned by a neighbour). */
+int pp_select_events(pp_ctx *ctx, int rule_mask, int64_t duration_gt, int64_t duration_lt,
+                     double min_gt, double max_lt, int skip_first, int skip_last,
+                     int64_t *n_events, int64_t *n_event_samples);
+/* Events chosen by the host (arbitrary Python rules evaluated on the run table). */
+int pp_set_events(pp_ctx *ctx, const int64_t *start, const int64_t *length, int64_t n_events);
+/* Append one event after the current last event (multi-GPU: the run that starts
+ * in this GPU's chunk and continues into the halo appended with pp_trace_append). */
+int pp_append_event(pp_ctx *ctx, int64_t start, int64_t length);
+int pp_events_download(pp_ctx *ctx, int64_t cap, int64_t *start, int64_t *length);
+
+/* ---- float64 events supplied directly (SpeedyStatSplit.parse(current)) */
+/* `n_events` float64 events packed back to back in `host` (lengths in `length`). */
+int pp_events_upload_f64(pp_ctx *ctx, const double *host, const int64_t *length, int64_t n_events);
+
+/* ---- K5: Event.filter (DataTypes.py:258-274; scipy.signal.filtfilt) -- */
+/* Zero-phase IIR filter of every current event; b, a have `ncoef` entries
+ * (a[0] == 1), zi has ncoef-1 (scipy.signal.lfilter_zi).  Afterwards the events'
+ * current is the float64 filtered signal (later stages read it). */
+int pp_filter_events(pp_ctx *ctx, const double *b, const double *a, const double *zi, int ncoef);
+/* Event samples as float64, packed back to back (filtered if a filter ran). */
+int pp_event_samples_download(pp_ctx *ctx, int64_t cap, double *out);
+
+/* ---- K2+K3: FastStatSplit.parse (cparsers.pyx:103-203) ---------------- */
+/* min_gain is computed by the host exactly as cparsers.pyx:82-101. */
+int pp_statsplit(pp_ctx *ctx, int min_width, int max_width, int window_width, double min_gain,
+                 int prefix_mode, int64_t *n_segments);
+/* ---- K4: Segment.mean/std/min/max (core.py:209-223) ------------------- */
+int pp_segment_stats(pp_ctx *ctx);
+int pp_segments_download(pp_ctx *ctx, int64_t cap, int32_t *event, int64_t *start, int64_t *end,
+                         double *mean, double *std, double *mn, double *mx);
+/* Same statistics for the events themselves (Event is a Segment, DataTypes.py:241). */
+int pp_event_stats_download(pp_ctx *ctx, int64_t cap, double *mean, double *std, double *mn, double *mx);
+/* Device pointers to the compact tables (multi-GPU all-gather reads these):
+ * which = 0 seg_event(int32) 1 seg_start(int64) 2 seg_end(int64) 3 mean 4 std 5 min 6 max (f64)
+ *         7 ev_start(int64) 8 ev_len(int64). */
+const void *pp_table_device_ptr(pp_ctx *ctx, int which);
+/* Work counters of the last pp_statsplit: [0] candidate evaluations,
+ * [1] window scans, [2] events whose prefix sums were redone sequentially,
+ * [3] queue tasks processed. */
+int pp_split_counters(pp_ctx *ctx, int64_t out[4]);
+
+/* ---- whole pipeline, no host synchronisation between stages ----------- */
+typedef struct pp_pipeline_params {
+    double threshold;
+    int rule_mask;
+    int64_t duration_gt, duration_lt;
+    double min_gt, max_lt;
+    int filter_ncoef;          /* 0 = no filter */
+    const double *filter_b, *filter_a, *filter_zi;
+    int min_width, max_width, window_width;
+    double min_gain;
+    int prefix_mode;
+    int with_stats;
+} pp_pipeline_params;
+/* threshold scan -> select -> [filter] -> prefix -> split -> compact -> stats on
+ * the resident trace.  Counts: out[0] runs, out[1] events, out[2] event
+ * samples, out[3] segments. */
+int pp_pipeline(pp_ctx *ctx, const pp_pipeline_params *p, int64_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,321 @@
+"""ctypes binding of libpypore_b200.so (include/pypore_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no B200-class device
+is present, importing works (so CPU-only tooling can introspect the package) but
+the first compute call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpypore_b200.so")
+
+PP_OK = 0
+PP_ERR_CUDA, PP_ERR_ARG, PP_ERR_CAPACITY, PP_ERR_STATE, PP_ERR_FILTER_LEN = -1, -2, -3, -4, -5
+RULE_DURATION_GT, RULE_MIN_GT, RULE_MAX_LT, RULE_DURATION_LT = 1, 2, 4, 8
+PREFIX_AUTO, PREFIX_SEQUENTIAL, PREFIX_PARALLEL = 0, 1, 2
+STAGES = ("threshold", "select", "filter", "prefix", "split", "compact", "stats")
+
+_c = ctypes
+_i64 = _c.c_int64
+_f64p = _c.POINTER(_c.c_double)
+_f32p = _c.POINTER(_c.c_float)
+_i64p = _c.POINTER(_c.c_int64)
+_i32p = _c.POINTER(_c.c_int32)
+_u8p = _c.POINTER(_c.c_uint8)
+
+
+class PipelineParams(_c.Structure):
+    _fields_ = [
+        ("threshold", _c.c_double),
+        ("rule_mask", _c.c_int),
+        ("duration_gt", _i64), ("duration_lt", _i64),
+        ("min_gt", _c.c_double), ("max_lt", _c.c_double),
+        ("filter_ncoef", _c.c_int),
+        ("filter_b", _f64p), ("filter_a", _f64p), ("filter_zi", _f64p),
+        ("min_width", _c.c_int), ("max_width", _c.c_int), ("window_width", _c.c_int),
+        ("min_gain", _c.c_double),
+        ("prefix_mode", _c.c_int),
+        ("with_stats", _c.c_int),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/pypore_b200.h declares
+SIGNATURES = {
+    "pp_version": (_c.c_int, []),
+    "pp_device_count": (_c.c_int, []),
+    "pp_create": (_c.c_int, [_c.c_int, _c.c_void_p, _c.POINTER(_c.c_void_p)]),
+    "pp_destroy": (None, [_c.c_void_p]),
+    "pp_last_error": (_c.c_char_p, [_c.c_void_p]),
+    "pp_sync": (_c.c_int, [_c.c_void_p]),
+    "pp_launch_count": (_i64, [_c.c_void_p]),
+    "pp_stage_ms": (_c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(_c.c_float)]),
+    "pp_trace_upload": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _i64]),
+    "pp_trace_adopt": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _i64]),
+    "pp_trace_append": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _c.c_int]),
+    "pp_trace_len": (_i64, [_c.c_void_p]),
+    "pp_trace_device_ptr": (_c.c_void_p, [_c.c_void_p]),
+    "pp_threshold_scan": (_c.c_int, [_c.c_void_p, _c.c_double, _i64, _i64p]),
+    "pp_runs_download": (_c.c_int, [_c.c_void_p, _i64, _i64p, _i64p, _f64p, _f64p, _u8p]),
+    "pp_select_events": (_c.c_int, [_c.c_void_p, _c.c_int, _i64, _i64, _c.c_double, _c.c_double,
+                                    _c.c_int, _c.c_int, _i64p, _i64p]),
+    "pp_set_events": (_c.c_int, [_c.c_void_p, _i64p, _i64p, _i64]),
+    "pp_append_event": (_c.c_int, [_c.c_void_p, _i64, _i64]),
+    "pp_events_download": (_c.c_int, [_c.c_void_p, _i64, _i64p, _i64p]),
+    "pp_events_upload_f64": (_c.c_int, [_c.c_void_p, _f64p, _i64p, _i64]),
+    "pp_filter_events": (_c.c_int, [_c.c_void_p, _f64p, _f64p, _f64p, _c.c_int]),
+    "pp_event_samples_download": (_c.c_int, [_c.c_void_p, _i64, _f64p]),
+    "pp_statsplit": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _i64p]),
+    "pp_segment_stats": (_c.c_int, [_c.c_void_p]),
+    "pp_segments_download": (_c.c_int, [_c.c_void_p, _i64, _i32p, _i64p, _i64p, _f64p, _f64p, _f64p, _f64p]),
+    "pp_event_stats_download": (_c.c_int, [_c.c_void_p, _i64, _f64p, _f64p, _f64p, _f64p]),
+    "pp_table_device_ptr": (_c.c_void_p, [_c.c_void_p, _c.c_int]),
+    "pp_split_counters": (_c.c_int, [_c.c_void_p, _i64p]),
+    "pp_pipeline": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _i64p]),
+}
+
+_lib = None
+
+
+class PyPoreCudaError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library and attach signatures.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PyPoreCudaError(
+            "libpypore_b200.so is not built (run `python -m pypore_b200.build`); "
+            "pypore_b200 has no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ) if a is not None else None
+
+
+class Context(object):
+    """One pp_ctx: a device, a stream and the resident trace / tables."""
+
+    def __init__(self, device=0, stream=None):
+        self._L = load()
+        h = _c.c_void_p()
+        r = self._L.pp_create(int(device), _c.c_void_p(stream) if stream else None, _c.byref(h))
+        if r != PP_OK or not h:
+            raise PyPoreCudaError(
+                "pp_create(device=%d) failed (code %d): a CUDA device of compute capability 10.x "
+                "(B200) is required; there is no CPU fallback" % (device, r))
+        self._h = h
+        self.device = int(device)
+        self._keep = []  # host arrays that must outlive async copies
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.pp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, r):
+        if r == PP_OK:
+            return
+        msg = self._L.pp_last_error(self._h)
+        msg = msg.decode("utf-8", "replace") if msg else ""
+        if r == PP_ERR_FILTER_LEN:
+            raise ValueError(msg)
+        if r == PP_ERR_ARG:
+            raise ValueError("pypore_b200: " + msg)
+        raise PyPoreCudaError("pypore_b200 error %d: %s" % (r, msg))
+
+    # -- trace ---------------------------------------------------------------
+    def upload_trace(self, x32, extra_capacity=0):
+        x32 = np.ascontiguousarray(x32, dtype=np.float32)
+        self._keep = [x32]
+        self._ck(self._L.pp_trace_upload(self._h, x32.ctypes.data, x32.shape[0], int(extra_capacity)))
+        self.sync()  # pageable host memory: do not return before the copy has consumed it
+        self._keep = []
+        return x32.shape[0]
+
+    def upload_trace_async(self, x32, extra_capacity=0):
+        """For pinned host arrays; caller keeps `x32` alive until sync()."""
+        assert x32.dtype == np.float32 and x32.flags.c_contiguous
+        self._keep = [x32]
+        self._ck(self._L.pp_trace_upload(self._h, x32.ctypes.data, x32.shape[0], int(extra_capacity)))
+
+    def adopt_trace(self, dev_ptr, n, capacity=None):
+        self._ck(self._L.pp_trace_adopt(self._h, _c.c_void_p(int(dev_ptr)), int(n), int(capacity or n)))
+
+    def append_trace(self, src_ptr, n, src_is_device):
+        self._ck(self._L.pp_trace_append(self._h, _c.c_void_p(int(src_ptr)), int(n), int(bool(src_is_device))))
+
+    @property
+    def trace_len(self):
+        return int(self._L.pp_trace_len(self._h))
+
+    @property
+    def trace_ptr(self):
+        return self._L.pp_trace_device_ptr(self._h)
+
+    def sync(self):
+        self._ck(self._L.pp_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._L.pp_launch_count(self._h))
+
+    def stage_ms(self):
+        out = {}
+        ms = _c.c_float()
+        for i, name in enumerate(STAGES):
+            self._ck(self._L.pp_stage_ms(self._h, i, _c.byref(ms)))
+            out[name] = float(ms.value)
+        return out
+
+    # -- K1 ------------------------------------------------------------------
+    def threshold_scan(self, threshold, scan_len=-1):
+        n = _i64()
+        self._ck(self._L.pp_threshold_scan(self._h, float(threshold), int(scan_len), _c.byref(n)))
+        return int(n.value)
+
+    def runs(self, n_runs):
+        start = np.empty(n_runs, np.int64)
+        length = np.empty(n_runs, np.int64)
+        mn = np.empty(n_runs, np.float64)
+        mx = np.empty(n_runs, np.float64)
+        below = np.empty(n_runs, np.uint8)
+        self._ck(self._L.pp_runs_download(self._h, n_runs, _ptr(start, _i64p), _ptr(length, _i64p),
+                                          _ptr(mn, _f64p), _ptr(mx, _f64p), _ptr(below, _u8p)))
+        return start, length, mn, mx, below.astype(bool)
+
+    def select_events(self, rule_mask, duration_gt=0, duration_lt=0, min_gt=0.0, max_lt=0.0,
+                      skip_first=False, skip_last=False):
+        ne, ns = _i64(), _i64()
+        self._ck(self._L.pp_select_events(self._h, int(rule_mask), int(duration_gt), int(duration_lt),
+                                          float(min_gt), float(max_lt), int(skip_first), int(skip_last),
+                                          _c.byref(ne), _c.byref(ns)))
+        return int(ne.value), int(ns.value)
+
+    def set_events(self, start, length):
+        start = np.ascontiguousarray(start, np.int64)
+        length = np.ascontiguousarray(length, np.int64)
+        self._ck(self._L.pp_set_events(self._h, _ptr(start, _i64p), _ptr(length, _i64p), start.shape[0]))
+
+    def append_event(self, start, length):
+        self._ck(self._L.pp_append_event(self._h, int(start), int(length)))
+
+    def events(self, n_events):
+        start = np.empty(n_events, np.int64)
+        length = np.empty(n_events, np.int64)
+        self._ck(self._L.pp_events_download(self._h, n_events, _ptr(start, _i64p), _ptr(length, _i64p)))
+        return start, length
+
+    def upload_events_f64(self, arrays):
+        lens = np.asarray([a.shape[0] for a in arrays], np.int64)
+        flat = np.ascontiguousarray(np.concatenate(arrays) if len(arrays) > 1 else arrays[0], np.float64)
+        self._ck(self._L.pp_events_upload_f64(self._h, _ptr(flat, _f64p), _ptr(lens, _i64p), lens.shape[0]))
+        return lens
+
+    # -- K5 ------------------------------------------------------------------
+    def filter_events(self, b, a, zi):
+        b = np.ascontiguousarray(b, np.float64)
+        a = np.ascontiguousarray(a, np.float64)
+        zi = np.ascontiguousarray(zi, np.float64)
+        self._ck(self._L.pp_filter_events(self._h, _ptr(b, _f64p), _ptr(a, _f64p), _ptr(zi, _f64p), b.shape[0]))
+
+    def event_samples(self, n_samples):
+        out = np.empty(n_samples, np.float64)
+        self._ck(self._L.pp_event_samples_download(self._h, n_samples, _ptr(out, _f64p)))
+        return out
+
+    # -- K2..K4 --------------------------------------------------------------
+    def statsplit(self, min_width, max_width, window_width, min_gain, prefix_mode=PREFIX_AUTO):
+        n = _i64()
+        self._ck(self._L.pp_statsplit(self._h, int(min_width), int(max_width), int(window_width),
+                                      float(min_gain), int(prefix_mode), _c.byref(n)))
+        return int(n.value)
+
+    def segment_stats(self):
+        self._ck(self._L.pp_segment_stats(self._h))
+
+    def segments(self, n_segments, stats=True):
+        ev = np.empty(n_segments, np.int32)
+        start = np.empty(n_segments, np.int64)
+        end = np.empty(n_segments, np.int64)
+        out = {"event": ev, "start": start, "end": end}
+        if stats:
+            for k in ("mean", "std", "min", "max"):
+                out[k] = np.empty(n_segments, np.float64)
+        self._ck(self._L.pp_segments_download(
+            self._h, n_segments, _ptr(ev, _i32p), _ptr(start, _i64p), _ptr(end, _i64p),
+            _ptr(out.get("mean"), _f64p), _ptr(out.get("std"), _f64p), _ptr(out.get("min"), _f64p),
+            _ptr(out.get("max"), _f64p)))
+        return out
+
+    def event_stats(self, n_events):
+        out = {k: np.empty(n_events, np.float64) for k in ("mean", "std", "min", "max")}
+        self._ck(self._L.pp_event_stats_download(self._h, n_events, _ptr(out["mean"], _f64p),
+                                                 _ptr(out["std"], _f64p), _ptr(out["min"], _f64p),
+                                                 _ptr(out["max"], _f64p)))
+        return out
+
+    def table_ptr(self, which):
+        return self._L.pp_table_device_ptr(self._h, int(which))
+
+    def split_counters(self):
+        out = np.zeros(4, np.int64)
+        self._ck(self._L.pp_split_counters(self._h, _ptr(out, _i64p)))
+        return dict(candidates=int(out[0]), scans=int(out[1]), seq_redo=int(out[2]), tasks=int(out[3]))
+
+    def pipeline(self, threshold, rule_mask, duration_gt, duration_lt, min_gt, max_lt, min_width,
+                 max_width, window_width, min_gain, filter_ba=None, prefix_mode=PREFIX_AUTO,
+                 with_stats=True):
+        p = PipelineParams()
+        p.threshold = float(threshold)
+        p.rule_mask = int(rule_mask)
+        p.duration_gt, p.duration_lt = int(duration_gt), int(duration_lt)
+        p.min_gt, p.max_lt = float(min_gt), float(max_lt)
+        keep = []
+        if filter_ba is not None:
+            b, a, zi = [np.ascontiguousarray(v, np.float64) for v in filter_ba]
+            keep = [b, a, zi]
+            p.filter_ncoef = b.shape[0]
+            p.filter_b, p.filter_a, p.filter_zi = _ptr(b, _f64p), _ptr(a, _f64p), _ptr(zi, _f64p)
+        else:
+            p.filter_ncoef = 0
+        p.min_width, p.max_width, p.window_width = int(min_width), int(max_width), int(window_width)
+        p.min_gain = float(min_gain)
+        p.prefix_mode = int(prefix_mode)
+        p.with_stats = int(bool(with_stats))
+        out = np.zeros(4, np.int64)
+        self._ck(self._L.pp_pipeline(self._h, _c.byref(p), _ptr(out, _i64p)))
+        del keep
+        return dict(runs=int(out[0]), events=int(out[1]), event_samples=int(out[2]), segments=int(out[3]))
+
+
+_default = {}
+
+
+def default_context(device=None):
+    """Process-wide context per device (created on first use)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("PYPORE_B200_USE_LOCAL_RANK") else 0
+    ctx = _default.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        _default[device] = ctx
+    return ctx
