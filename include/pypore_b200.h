@@ -82,6 +82,8 @@ int pp_trace_adopt(pp_ctx *ctx, const float *dev, int64_t n, int64_t capacity);
 /* Append `n` samples (device or host pointer) after the current trace end: the
  * continuation of an event that straddles this GPU's chunk boundary. */
 int pp_trace_append(pp_ctx *ctx, const float *src, int64_t n, int src_is_device);
+/* Drop samples appended after position `n` (start of a new multi-GPU step). */
+int pp_trace_truncate(pp_ctx *ctx, int64_t n);
 int64_t pp_trace_len(pp_ctx *ctx);
 const float *pp_trace_device_ptr(pp_ctx *ctx);
 
@@ -93,6 +95,9 @@ const float *pp_trace_device_ptr(pp_ctx *ctx);
 int pp_threshold_scan(pp_ctx *ctx, double threshold, int64_t scan_len, int64_t *n_runs);
 int pp_runs_download(pp_ctx *ctx, int64_t cap, int64_t *start, int64_t *length, double *mn,
                      double *mx, uint8_t *below);
+/* Rows [first, first+count) of the run table (multi-GPU: only the boundary runs travel). */
+int pp_runs_download_range(pp_ctx *ctx, int64_t first, int64_t count, int64_t *start, int64_t *length,
+                           double *mn, double *mx, uint8_t *below);
 /* _lambda_select for default-shaped rules, evaluated on the device
  * (parsers.py:133-140).  Runs flagged in `skip_first`/`skip_last` (0/1) are
  * excluded regardless of the rules (multi-GPU: a run owned by a neighbour). */

@@ -1,0 +1,275 @@
+"""Container drivers: host-side mirror of the hot-path part of PyPore/DataTypes.py.
+
+``File.parse(parser=...)``, ``Event.filter(order, cutoff)`` and
+``Event.parse(parser=...)`` keep the reference's signatures and side effects
+(DataTypes.py:258-289, 589-602).  On top of that, ``File.parse`` accepts
+``segmenter=`` / ``filter_params=`` to run threshold -> [filter] -> split ->
+statistics in one device-resident pass, returning the same objects lazily built
+from the compact tables.  HMM-guided parsing, plotting, MySQL and .abf reading
+are out of scope.
+"""
+import numpy as np
+
+from . import _lib
+from .core import MetaSegment, Segment, ignored
+from .parsers import RuleSet, SpeedyStatSplit, lambda_event_parser, _as_float32_trace
+
+
+class MetaEvent(MetaSegment):
+    """Metadata of an event (DataTypes.py:49-80)."""
+
+    def __init__(self, **kwargs):
+        MetaSegment.__init__(self, **kwargs)
+
+    def delete(self):
+        with ignored(AttributeError):
+            del self.state_parser
+        for segment in self.segments:
+            segment.delete()
+        del self
+
+    @property
+    def n(self):
+        try:
+            return len(self.segments)
+        except Exception:
+            return 0
+
+
+def bessel_coefficients(order, cutoff, second):
+    """(b, a, zi) for Event.filter: scipy.signal.bessel exactly as DataTypes.py:268-270
+    requests it, plus the lfilter_zi steady state filtfilt starts from."""
+    from scipy import signal
+    nyquist = second / 2.
+    b, a = signal.bessel(order, cutoff / nyquist, btype='low', analog=0, output='ba')
+    b = np.atleast_1d(np.asarray(b, np.float64))
+    a = np.atleast_1d(np.asarray(a, np.float64))
+    n = max(len(a), len(b))
+    b = np.r_[b, np.zeros(n - len(b))] / a[0]
+    a = np.r_[a, np.zeros(n - len(a))] / a[0]
+    # lfilter_zi: solve (I - A^T) zi = b[1:] - a[1:] b[0] for the companion matrix A of a
+    comp = np.zeros((n - 1, n - 1))
+    comp[0, :] = -a[1:]
+    for i in range(1, n - 1):
+        comp[i, i - 1] = 1.0
+    zi = np.linalg.solve(np.eye(n - 1) - comp.T, b[1:] - a[1:] * b[0])
+    return b, a, zi
+
+
+class Event(Segment):
+    """An event: a stretch of the file holding useful data (DataTypes.py:241-565)."""
+
+    def __init__(self, current, segments=[], **kwargs):
+        if len(segments) > 0:
+            try:
+                current = np.concatenate([seg.current for seg in segments])
+            except Exception:
+                current = []
+        Segment.__init__(self, current, filtered=False, segments=segments, **kwargs)
+
+    def filter(self, order=1, cutoff=2000.):
+        """Zero-phase Bessel low-pass of ``self.current`` (DataTypes.py:258-274)."""
+        if type(self) != Event:
+            raise TypeError("Cannot filter a metaevent. Must have the current.")
+        b, a, zi = bessel_coefficients(order, cutoff, self.second)
+        cur = np.ascontiguousarray(self.current, dtype=np.float64)
+        padlen = 3 * len(b)
+        if cur.shape[0] <= padlen:
+            raise ValueError("The length of the input vector x must be greater than padlen, which is %d."
+                             % padlen)
+        ctx = _lib.default_context()
+        ctx.upload_events_f64([cur])
+        ctx.filter_events(b, a, zi)
+        self.current = ctx.event_samples(cur.shape[0])
+        self.filtered = True
+        self.filter_order = order
+        self.filter_cutoff = cutoff
+
+    def parse(self, parser=SpeedyStatSplit(prior_segments_per_second=10), hmm=None):
+        """Segment the event with a plug-in state parser (DataTypes.py:276-289,333)."""
+        if hmm:
+            raise NotImplementedError("HMM-guided segmentation needs yahmm and is out of scope")
+        self.segments = parser.parse(self.current)
+        for segment in self.segments:
+            segment.event = self
+            segment.scale(float(self.file.second))
+        self.state_parser = parser
+
+    def delete(self):
+        with ignored(AttributeError):
+            del self.current
+        with ignored(AttributeError):
+            del self.state_parser
+        for segment in self.segments:
+            segment.delete()
+        del self
+
+    def to_meta(self):
+        for prop in ['mean', 'std', 'duration', 'start', 'min', 'max', 'end', 'start']:
+            with ignored(AttributeError, KeyError):
+                self.__dict__[prop] = getattr(self, prop)
+        self.__dict__.pop('_stats', None)
+        with ignored(AttributeError):
+            del self.current
+        for segment in self.segments:
+            segment.to_meta()
+        self.__class__ = type("MetaEvent", (MetaEvent,), self.__dict__)
+
+    @property
+    def n(self):
+        return len(self.segments)
+
+
+class _LazyList(object):
+    """List-like whose items are built on first access (object creation is the
+    dominant host cost at 10^5..10^6 segments)."""
+
+    def __init__(self, n, factory):
+        self._n, self._factory, self._cache = int(n), factory, {}
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        item = self._cache.get(i)
+        if item is None:
+            item = self._cache[i] = self._factory(i)
+        return item
+
+    def __iter__(self):
+        for i in range(self._n):
+            yield self[i]
+
+
+class File(Segment):
+    """A trace and the events detected in it (DataTypes.py:567-602).
+
+    Only the ``current=`` / ``timestep=`` constructor is supported: there is no
+    .abf data offline and the ABF reader is out of scope.
+    """
+
+    def __init__(self, filename=None, current=None, timestep=None, **kwargs):
+        if current is not None and timestep is not None:
+            filename = ""
+        elif filename and current is None and timestep is None:
+            raise NotImplementedError("reading .abf files is out of scope; pass current= and timestep=")
+        else:
+            raise SyntaxError("Must provide current and timestep, or filename "
+                              "corresponding to a valid abf file.")
+        Segment.__init__(self, current=current, filename=filename, second=1000. / timestep,
+                         events=[], sample=None)
+
+    def __getitem__(self, index):
+        return self.events[index]
+
+    @property
+    def n(self):
+        return len(self.events)
+
+    def parse(self, parser=lambda_event_parser(threshold=90), segmenter=None, filter_params=None,
+              context=None):
+        """Detect events with a plug-in event parser (DataTypes.py:589-602).
+
+        With ``segmenter=`` (a ``SpeedyStatSplit``) the whole pipeline runs on the
+        resident trace -- threshold scan, optional ``Event.filter(*filter_params)``,
+        split search, statistics -- and every event comes back with its
+        ``segments`` already parsed, as after ``event.parse(parser=segmenter)``.
+        """
+        if segmenter is None and filter_params is None and not isinstance(parser, lambda_event_parser):
+            # any duck-typed parser, exactly like the reference
+            self.events = [Event(current=seg.current, start=seg.start / self.second,
+                                 end=(seg.start + seg.duration) / self.second,
+                                 duration=seg.duration / self.second, second=self.second, file=self)
+                           for seg in parser.parse(self.current)]
+            self.event_parser = parser
+            return
+        if not isinstance(parser, lambda_event_parser):
+            raise TypeError("the device-resident pipeline needs a pypore_b200 lambda_event_parser")
+        ctx = context or _lib.default_context()
+        host = np.asarray(self.current)
+        ctx.upload_trace(_as_float32_trace(host))
+        self._parse_resident(ctx, host, parser, segmenter, filter_params)
+
+    # ------------------------------------------------------------------
+    def _parse_resident(self, ctx, host, parser, segmenter, filter_params):
+        second = self.second
+        filt = None
+        if filter_params is not None:
+            order, cutoff = filter_params
+            filt = bessel_coefficients(order, cutoff, second)
+        rs = parser._device_rules()
+        tables = None
+        if segmenter is not None:
+            mw, MW, W, gain = segmenter._params()
+        if rs is not None and segmenter is not None:
+            counts = ctx.pipeline(parser.threshold, min_width=mw, max_width=MW, window_width=W, min_gain=gain,
+                                  filter_ba=filt, with_stats=True, **rs.device_args())
+            ev_start, ev_len = ctx.events(counts["events"])
+            tables = ctx.segments(counts["segments"])
+            r_start, _, r_min, r_max, _ = ctx.runs(counts["runs"])
+            idx = np.searchsorted(r_start, ev_start)
+            ev_min, ev_max = r_min[idx], r_max[idx]
+        else:
+            ev_start, ev_len, ev_min, ev_max = parser._detect(ctx, host)
+            if filt is not None and len(ev_start):
+                ctx.filter_events(*filt)
+            if segmenter is not None and len(ev_start):
+                n_seg = ctx.statsplit(mw, MW, W, gain)
+                ctx.segment_stats()
+                tables = ctx.segments(n_seg)
+        filtered = None
+        if filt is not None and len(ev_start):
+            filtered = ctx.event_samples(int(ev_len.sum()))
+        self.event_table = dict(start=ev_start, length=ev_len, min=ev_min, max=ev_max)
+        self.segment_table = tables
+        ev_off = np.concatenate(([0], np.cumsum(ev_len)))
+        seg_bounds = None
+        if tables is not None:
+            seg_bounds = np.searchsorted(tables["event"], np.arange(len(ev_start) + 1))
+
+        def make_event(i):
+            s, n = int(ev_start[i]), int(ev_len[i])
+            if filtered is not None:
+                cur = filtered[ev_off[i]:ev_off[i + 1]]
+            else:
+                cur = np.array(host[s:s + n])
+            ev = Event(current=cur, start=s / second, end=(s + n) / second, duration=n / second,
+                       second=second, file=self)
+            if filtered is not None:
+                ev.filtered = True
+                ev.filter_order, ev.filter_cutoff = filter_params
+            if tables is not None:
+                lo, hi = int(seg_bounds[i]), int(seg_bounds[i + 1])
+
+                def make_segment(k, cur=cur, ev=ev, lo=lo):
+                    k += lo
+                    a, b = int(tables["start"][k]), int(tables["end"][k])
+                    seg = Segment(current=cur[a:b], start=a, duration=(b - a), end=b)
+                    seg._set_stats(tables["mean"][k], tables["std"][k], tables["min"][k], tables["max"][k])
+                    seg.event = ev
+                    seg.scale(float(second))
+                    return seg
+                ev.segments = _LazyList(hi - lo, make_segment)
+                ev.state_parser = segmenter
+            return ev
+
+        self.events = _LazyList(len(ev_start), make_event)
+        self.event_parser = parser
+
+    def delete(self):
+        with ignored(AttributeError):
+            del self.current
+        with ignored(AttributeError):
+            del self.event_parser
+        for event in self.events:
+            event.delete()
+        del self
+
+    def close(self):
+        self.delete()

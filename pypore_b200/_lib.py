@@ -55,10 +55,12 @@ SIGNATURES = {
     "pp_trace_upload": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _i64]),
     "pp_trace_adopt": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _i64]),
     "pp_trace_append": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _c.c_int]),
+    "pp_trace_truncate": (_c.c_int, [_c.c_void_p, _i64]),
     "pp_trace_len": (_i64, [_c.c_void_p]),
     "pp_trace_device_ptr": (_c.c_void_p, [_c.c_void_p]),
     "pp_threshold_scan": (_c.c_int, [_c.c_void_p, _c.c_double, _i64, _i64p]),
     "pp_runs_download": (_c.c_int, [_c.c_void_p, _i64, _i64p, _i64p, _f64p, _f64p, _u8p]),
+    "pp_runs_download_range": (_c.c_int, [_c.c_void_p, _i64, _i64, _i64p, _i64p, _f64p, _f64p, _u8p]),
     "pp_select_events": (_c.c_int, [_c.c_void_p, _c.c_int, _i64, _i64, _c.c_double, _c.c_double,
                                     _c.c_int, _c.c_int, _i64p, _i64p]),
     "pp_set_events": (_c.c_int, [_c.c_void_p, _i64p, _i64p, _i64]),
@@ -163,6 +165,9 @@ class Context(object):
     def append_trace(self, src_ptr, n, src_is_device):
         self._ck(self._L.pp_trace_append(self._h, _c.c_void_p(int(src_ptr)), int(n), int(bool(src_is_device))))
 
+    def truncate_trace(self, n):
+        self._ck(self._L.pp_trace_truncate(self._h, int(n)))
+
     @property
     def trace_len(self):
         return int(self._L.pp_trace_len(self._h))
@@ -200,6 +205,17 @@ class Context(object):
         below = np.empty(n_runs, np.uint8)
         self._ck(self._L.pp_runs_download(self._h, n_runs, _ptr(start, _i64p), _ptr(length, _i64p),
                                           _ptr(mn, _f64p), _ptr(mx, _f64p), _ptr(below, _u8p)))
+        return start, length, mn, mx, below.astype(bool)
+
+    def runs_range(self, first, count):
+        start = np.empty(count, np.int64)
+        length = np.empty(count, np.int64)
+        mn = np.empty(count, np.float64)
+        mx = np.empty(count, np.float64)
+        below = np.empty(count, np.uint8)
+        self._ck(self._L.pp_runs_download_range(self._h, int(first), int(count), _ptr(start, _i64p),
+                                                _ptr(length, _i64p), _ptr(mn, _f64p), _ptr(mx, _f64p),
+                                                _ptr(below, _u8p)))
         return start, length, mn, mx, below.astype(bool)
 
     def select_events(self, rule_mask, duration_gt=0, duration_lt=0, min_gt=0.0, max_lt=0.0,

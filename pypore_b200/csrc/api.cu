@@ -503,6 +503,13 @@ int pp_trace_append(pp_ctx *ctx, const float *src, int64_t n, int src_is_device)
     return PP_OK;
 }
 
+int pp_trace_truncate(pp_ctx *ctx, int64_t n)
+{
+    if (!ctx || n <= 0 || n > ctx->n) return fail(ctx, PP_ERR_ARG, "bad truncate");
+    ctx->n = n;
+    return PP_OK;
+}
+
 int64_t pp_trace_len(pp_ctx *ctx) { return ctx ? ctx->n : 0; }
 const float *pp_trace_device_ptr(pp_ctx *ctx) { return ctx ? ctx->trace : nullptr; }
 
@@ -542,6 +549,25 @@ int pp_runs_download(pp_ctx *ctx, int64_t cap, int64_t *start, int64_t *length, 
     if (mn) CK(cudaMemcpyAsync(mn, ctx->run_min.p, 8 * r, cudaMemcpyDeviceToHost, ctx->stream));
     if (mx) CK(cudaMemcpyAsync(mx, ctx->run_max.p, 8 * r, cudaMemcpyDeviceToHost, ctx->stream));
     if (below) CK(cudaMemcpyAsync(below, ctx->run_below.p, r, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PP_OK;
+}
+
+int pp_runs_download_range(pp_ctx *ctx, int64_t first, int64_t count, int64_t *start, int64_t *length,
+                           double *mn, double *mx, uint8_t *below)
+{
+    if (!ctx) return PP_ERR_ARG;
+    if (ctx->n_runs < 0) return fail(ctx, PP_ERR_STATE, "pp_threshold_scan has not run");
+    if (first < 0 || count < 0 || first + count > ctx->n_runs) return fail(ctx, PP_ERR_ARG, "bad run range");
+    CKR(set_device(ctx));
+    const size_t r = (size_t)count, o = (size_t)first;
+    if (r) {
+        if (start) CK(cudaMemcpyAsync(start, (int64_t *)ctx->run_start.p + o, 8 * r, cudaMemcpyDeviceToHost, ctx->stream));
+        if (length) CK(cudaMemcpyAsync(length, (int64_t *)ctx->run_len.p + o, 8 * r, cudaMemcpyDeviceToHost, ctx->stream));
+        if (mn) CK(cudaMemcpyAsync(mn, (double *)ctx->run_min.p + o, 8 * r, cudaMemcpyDeviceToHost, ctx->stream));
+        if (mx) CK(cudaMemcpyAsync(mx, (double *)ctx->run_max.p + o, 8 * r, cudaMemcpyDeviceToHost, ctx->stream));
+        if (below) CK(cudaMemcpyAsync(below, (unsigned char *)ctx->run_below.p + o, r, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return PP_OK;
 }

@@ -1,0 +1,270 @@
+"""Multi-GPU sharding of the segmentation path.
+
+One process per GPU.  The trace is cut into contiguous chunks, one per rank.
+Every rank threshold-scans its own chunk; a run of samples that crosses a
+chunk boundary is owned by the rank where it STARTS.  Ranks all-gather one tiny
+record about their first and last run, every rank derives the same global plan
+from those records, owners of straddling events receive the continuation
+samples (the halo) from their right neighbour(s) point-to-point, and after the
+(independent) split / statistics stages the compact event and segment tables are
+all-gathered so that every rank ends with the whole result.  Sample data never
+goes through a collective: only halos (a few thousand samples) and tables move.
+
+The planning functions are pure (NumPy in, plain Python out) and the exchange
+helpers work on CPU tensors with the gloo backend as well as on CUDA tensors
+with NCCL, which is how tests/test_dist_cpu.py covers them without a GPU.
+"""
+import numpy as np
+
+INFO_LEN = 12
+(I_N, I_NRUNS, I_FIRST_BELOW, I_FIRST_LEN, I_FIRST_MIN, I_FIRST_MAX,
+ I_LAST_BELOW, I_LAST_START, I_LAST_LEN, I_LAST_MIN, I_LAST_MAX, I_PAD) = range(INFO_LEN)
+
+
+def boundary_info(n_local, n_runs, first_run, last_run):
+    """The record a rank publishes: (start, length, min, max, below) of its first and last run."""
+    info = np.zeros(INFO_LEN, np.float64)
+    info[I_N], info[I_NRUNS] = n_local, n_runs
+    info[I_FIRST_BELOW], info[I_FIRST_LEN] = float(first_run[4]), first_run[1]
+    info[I_FIRST_MIN], info[I_FIRST_MAX] = first_run[2], first_run[3]
+    info[I_LAST_BELOW], info[I_LAST_START], info[I_LAST_LEN] = float(last_run[4]), last_run[0], last_run[1]
+    info[I_LAST_MIN], info[I_LAST_MAX] = last_run[2], last_run[3]
+    return info
+
+
+def rules_accept(rules, duration, mn, mx):
+    """The default-shaped rules of pp_select_events, evaluated on the host for one merged run."""
+    m = rules.get("rule_mask", 0)
+    ok = True
+    if m & 1:
+        ok = ok and duration > rules["duration_gt"]
+    if m & 8:
+        ok = ok and duration < rules["duration_lt"]
+    if m & 2:
+        ok = ok and bool(mn > rules["min_gt"])   # NaN compares false, like the reference's rule
+    if m & 4:
+        ok = ok and bool(mx < rules["max_lt"])
+    return ok
+
+
+def plan_boundaries(infos, rules):
+    """Global plan from the gathered records.  Returns a list (one dict per rank) of
+        skip_first  this rank's first run belongs to a rank on its left
+        skip_last   this rank's last run is decided here on the host (it crosses the right boundary)
+        event       None, or (start_local, total_length) of the straddling event this rank owns and keeps
+        recv        [(src_rank, count)] halo pieces to append after the chunk, in order
+        send        [(dst_rank, count)] prefixes of this chunk to ship to owners on the left
+    """
+    world = len(infos)
+    joins = [bool(infos[r][I_LAST_BELOW] == infos[r + 1][I_FIRST_BELOW]) for r in range(world - 1)]
+    plans = [dict(skip_first=(r > 0 and joins[r - 1]), skip_last=False, event=None, recv=[], send=[])
+             for r in range(world)]
+    for r in range(world - 1):
+        if not joins[r]:
+            continue
+        plans[r]["skip_last"] = True
+        owns = not (infos[r][I_NRUNS] == 1 and plans[r]["skip_first"])
+        if not owns:
+            continue  # the run started further left; that owner accounts for this chunk
+        length = int(infos[r][I_LAST_LEN])
+        mn, mx = infos[r][I_LAST_MIN], infos[r][I_LAST_MAX]
+        pieces = []
+        q = r + 1
+        while True:
+            cnt = int(infos[q][I_FIRST_LEN])
+            pieces.append((q, cnt))
+            length += cnt
+            mn = np.minimum(mn, infos[q][I_FIRST_MIN])  # np.minimum / maximum propagate NaN like np.min / np.max
+            mx = np.maximum(mx, infos[q][I_FIRST_MAX])
+            if infos[q][I_NRUNS] == 1 and q < world - 1 and joins[q]:
+                q += 1
+                continue
+            break
+        if rules_accept(rules, length, mn, mx):
+            plans[r]["event"] = (int(infos[r][I_LAST_START]), length)
+            plans[r]["recv"] = pieces
+            for q, cnt in pieces:
+                plans[q]["send"].append((r, cnt))
+    return plans
+
+
+def exchange_halo(plan, chunk, halo_out, dist, group=None):
+    """Point-to-point halo transfer.  `chunk` is this rank's samples (1-D tensor, CPU or CUDA),
+    `halo_out` a tensor with room for sum(recv counts).  Returns the number of samples received."""
+    ops = []
+    off = 0
+    for src, cnt in plan["recv"]:
+        ops.append(dist.P2POp(dist.irecv, halo_out[off:off + cnt], src, group))
+        off += cnt
+    for dst, cnt in plan["send"]:
+        ops.append(dist.P2POp(dist.isend, chunk[:cnt], dst, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return off
+
+
+def gather_infos(info, dist, device, group=None):
+    import torch
+    world = dist.get_world_size(group)
+    t = torch.from_numpy(info).to(device)
+    out = torch.empty(world * INFO_LEN, dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out.cpu().numpy().reshape(world, INFO_LEN)
+
+
+def gather_tables(int_cols, flt_cols, counts, dist, group=None):
+    """All-gather per-rank tables of different lengths: pad to the longest, gather, strip.
+
+    int_cols: int64 tensor [n_local, ci]; flt_cols: float64 tensor [n_local, cf];
+    counts: list of per-rank row counts (already known to every rank).
+    Returns (int64 [sum(counts), ci], float64 [sum(counts), cf]).
+    """
+    import torch
+    world = len(counts)
+    m = max(max(counts), 1)
+    out = []
+    for cols in (int_cols, flt_cols):
+        pad = torch.zeros((m, cols.shape[1]), dtype=cols.dtype, device=cols.device)
+        pad[:cols.shape[0]] = cols
+        g = torch.empty((world * m, cols.shape[1]), dtype=cols.dtype, device=cols.device)
+        dist.all_gather_into_tensor(g, pad, group=group)
+        g = g.view(world, m, cols.shape[1])
+        out.append(torch.cat([g[r, :counts[r]] for r in range(world)], dim=0))
+    return out[0], out[1]
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic sharded workload (bench / tests): one C2-style piece per rank, cut mid-event
+# ------------------------------------------------------------------------------------------
+def _cut_offset(head, threshold=110.0, depth=2500):
+    first_below = int(np.argmax(head < threshold))
+    return first_below + depth
+
+
+def synthetic_chunk(rank, world, events_per_rank, seed0=1, tier="A"):
+    """Rank `rank`'s chunk of the global trace concat(P_0 .. P_{world-1}), where P_g =
+    synth.make_trace(events_per_rank, seed0 + g) and the ownership boundary between g-1 and g lies
+    2500 samples inside P_g's first event, so an event straddles every boundary."""
+    from . import synth
+    piece = synth.make_trace(events_per_rank, seed=seed0 + rank, tier=tier, tail=(rank == world - 1))
+    lo = _cut_offset(piece[:20000]) if rank > 0 else 0
+    parts = [piece[lo:]]
+    if rank < world - 1:
+        head = synth.make_trace(1, seed=seed0 + rank + 1, tier=tier, tail=False)
+        parts.append(head[:_cut_offset(head)])
+    return np.ascontiguousarray(np.concatenate(parts))
+
+
+def synthetic_global(world, events_per_rank, seed0=1, tier="A"):
+    """The whole trace the chunks of synthetic_chunk partition (tests only)."""
+    from . import synth
+    return np.concatenate([synth.make_trace(events_per_rank, seed=seed0 + g, tier=tier, tail=(g == world - 1))
+                           for g in range(world)])
+
+
+# ------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------
+class _DevArray(object):
+    """Zero-copy torch view of device memory owned by the C library."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def device_view(ptr, n, dtype, device):
+    import torch
+    typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int64: "<i8", torch.int32: "<i4"}[dtype]
+    if n == 0:
+        return torch.empty(0, dtype=dtype, device=device)
+    return torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
+
+
+class ShardedPipeline(object):
+    """threshold -> select -> halo -> split -> stats -> table all-gather on one rank's chunk.
+
+    The context must have been created on torch's current CUDA stream so that NCCL
+    operations and the library's kernels are ordered without extra synchronisation.
+    """
+
+    HALO_CAPACITY = 1 << 20
+
+    def __init__(self, ctx, rank, world, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.dist = dist
+        self.device = torch.device("cuda", ctx.device)
+        self.halo = torch.empty(self.HALO_CAPACITY, dtype=torch.float32, device=self.device)
+        self.n_local = 0
+        self.n_owned = 0
+        self.offsets = None
+        self.tables = None
+
+    def load(self, host_chunk):
+        self.ctx.upload_trace_async(host_chunk, extra_capacity=self.HALO_CAPACITY)
+        self.n_local = int(host_chunk.shape[0])
+
+    def step(self, threshold, rules, mw, MW, W, gain):
+        import torch
+        ctx, dist = self.ctx, self.dist
+        ctx.truncate_trace(self.n_local)
+        n_runs = ctx.threshold_scan(threshold, scan_len=self.n_local)
+        if n_runs == 1:
+            first = last = [a[0] for a in ctx.runs_range(0, 1)]
+        else:
+            f = ctx.runs_range(0, 1)
+            l = ctx.runs_range(n_runs - 1, 1)
+            first, last = [a[0] for a in f], [a[0] for a in l]
+        infos = gather_infos(boundary_info(self.n_local, n_runs, first, last), dist, self.device, self.group)
+        plan = plan_boundaries(infos, rules)[self.rank]
+        lens = infos[:, I_N].astype(np.int64)
+        self.offsets = np.concatenate(([0], np.cumsum(lens)))
+        need = sum(c for _, c in plan["recv"])
+        if need > self.halo.shape[0]:
+            raise RuntimeError("halo of %d samples exceeds HALO_CAPACITY" % need)
+        chunk = device_view(ctx.trace_ptr, self.n_local, torch.float32, self.device)
+        got = exchange_halo(plan, chunk, self.halo, dist, self.group)
+        if got:
+            ctx.append_trace(self.halo.data_ptr(), got, True)
+        ne, ns = ctx.select_events(skip_first=plan["skip_first"], skip_last=plan["skip_last"], **rules)
+        if plan["event"] is not None:
+            ctx.append_event(*plan["event"])
+            ne += 1
+            ns += plan["event"][1]
+        n_seg = ctx.statsplit(mw, MW, W, gain)
+        ctx.segment_stats()
+        self.n_owned = self.n_local
+        self._gather(ne, n_seg)
+        return dict(runs=n_runs, events=ne, event_samples=ns, segments=n_seg)
+
+    def _gather(self, ne, n_seg):
+        import torch
+        ctx, dist, dev = self.ctx, self.dist, self.device
+        cnt = torch.tensor([ne, n_seg], dtype=torch.int64, device=dev)
+        allc = torch.empty(2 * self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, cnt, group=self.group)
+        allc = allc.cpu().numpy().reshape(self.world, 2)
+        ev_counts, seg_counts = [int(v) for v in allc[:, 0]], [int(v) for v in allc[:, 1]]
+        ev_base = int(sum(ev_counts[:self.rank]))
+        # events: global start, length
+        ev_start = device_view(ctx.table_ptr(7), ne, torch.int64, dev) + int(self.offsets[self.rank])
+        ev_len = device_view(ctx.table_ptr(8), ne, torch.int64, dev)
+        ev_int = torch.stack([ev_start, ev_len], dim=1)
+        ev_flt = torch.zeros((ne, 1), dtype=torch.float64, device=dev)
+        g_ev, _ = gather_tables(ev_int, ev_flt, ev_counts, dist, self.group)
+        # segments: global event id, event-relative start / end, statistics
+        seg_ev = device_view(ctx.table_ptr(0), n_seg, torch.int32, dev).to(torch.int64) + ev_base
+        seg_int = torch.stack([seg_ev, device_view(ctx.table_ptr(1), n_seg, torch.int64, dev),
+                               device_view(ctx.table_ptr(2), n_seg, torch.int64, dev)], dim=1)
+        seg_flt = torch.stack([device_view(ctx.table_ptr(k), n_seg, torch.float64, dev) for k in (3, 4, 5, 6)],
+                              dim=1)
+        g_si, g_sf = gather_tables(seg_int, seg_flt, seg_counts, dist, self.group)
+        self.tables = dict(events=g_ev, seg_int=g_si, seg_flt=g_sf)
+
+    def download(self):
+        """Device-to-host read of the gathered tables (what a caller of the public API receives)."""
+        t = self.tables
+        return {k: v.cpu().numpy() for k, v in t.items()}

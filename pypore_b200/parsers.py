@@ -1,0 +1,306 @@
+"""GPU-backed parsers behind the reference's plug-in protocol.
+
+Mirror of PyPore/parsers.py for the hot path: same class names, constructor
+arguments, attributes (so ``to_dict``/``to_json``/``from_json`` round-trip,
+parsers.py:42-55,97-107) and the duck-typed ``parse(current) -> [Segment]``
+contract (parsers.py:57-59).  The arithmetic runs in libpypore_b200.so.
+"""
+import json
+import math
+
+import numpy as np
+
+from . import _lib
+from .core import Segment
+
+
+class parser(object):
+    """Base parser protocol (parsers.py:34-107, GUI hooks omitted)."""
+
+    def __init__(self):
+        pass
+
+    def __repr__(self):
+        return self.to_json()
+
+    def to_dict(self):
+        d = {key: val for key, val in self.__dict__.items() if key != 'param_dict' and not key.startswith('_')
+             if type(val) in (int, float) or ('Qt' not in repr(val)) and 'lambda' not in repr(val)}
+        d['name'] = self.__class__.__name__
+        return d
+
+    def to_json(self, filename=False):
+        d = {k: v for k, v in self.to_dict().items() if not callable(v) and not isinstance(v, RuleSet)}
+        _json = json.dumps(d, indent=4, separators=(',', ' : '))
+        if filename:
+            with open(filename, 'w') as out:
+                out.write(_json)
+        return _json
+
+    def parse(self, current):
+        """Default: the whole current as one segment (parsers.py:57-59)."""
+        return [Segment(current=current, start=0, duration=current.shape[0] / 100000)]
+
+    @classmethod
+    def from_json(cls, _json):
+        if _json.endswith(".json"):
+            with open(_json, 'r') as infile:
+                _json = ''.join(line for line in infile)
+        d = json.loads(_json)
+        name = d['name']
+        del d['name']
+        import pypore_b200.parsers as mod
+        return getattr(mod, name)(**d)
+
+
+class MemoryParse(object):
+    """Rebuild segments from stored split points (parsers.py:110-122)."""
+
+    def __init__(self, starts, ends):
+        self.starts = starts
+        self.ends = ends
+
+    def parse(self, current):
+        return [Segment(current=np.array(current[int(s):int(e)], copy=True), start=s, duration=(e - s))
+                for s, e in zip(self.starts, self.ends)]
+
+
+# --------------------------------------------------------------------------
+# Rules
+# --------------------------------------------------------------------------
+class RuleSet(list):
+    """A list of rule callables that ALSO says what they are, so that
+    ``lambda_event_parser`` can evaluate them on the device instead of calling
+    Python per run.  Iterating it yields ordinary ``rule(event) -> bool``
+    callables, so it is a valid ``rules=`` argument for the reference too."""
+
+    def __init__(self, duration_gt=None, duration_lt=None, min_gt=None, max_lt=None):
+        rules = []
+        self.mask = 0
+        self.duration_gt = self.duration_lt = 0
+        self.min_gt = self.max_lt = 0.0
+        if duration_gt is not None:
+            self.mask |= _lib.RULE_DURATION_GT
+            self.duration_gt = duration_gt
+            rules.append(lambda event, v=duration_gt: event.duration > v)
+        if duration_lt is not None:
+            self.mask |= _lib.RULE_DURATION_LT
+            self.duration_lt = duration_lt
+            rules.append(lambda event, v=duration_lt: event.duration < v)
+        if min_gt is not None:
+            self.mask |= _lib.RULE_MIN_GT
+            self.min_gt = min_gt
+            rules.append(lambda event, v=min_gt: event.min > v)
+        if max_lt is not None:
+            self.mask |= _lib.RULE_MAX_LT
+            self.max_lt = max_lt
+            rules.append(lambda event, v=max_lt: event.max < v)
+        list.__init__(self, rules)
+
+    def device_args(self):
+        """Arguments for pp_select_events.  ``duration > v`` on integer sample counts
+        equals ``duration > floor(v)``; ``duration < v`` equals ``duration < ceil(v)``."""
+        return dict(rule_mask=self.mask,
+                    duration_gt=int(math.floor(self.duration_gt)), duration_lt=int(math.ceil(self.duration_lt)),
+                    min_gt=float(self.min_gt), max_lt=float(self.max_lt))
+
+
+class _RunProxy(object):
+    """What a rule sees of one piece: ``duration``, ``start``,
+    ``min``, ``max``, ``n`` from the device run table; ``current``/``mean``/``std`` lazily."""
+
+    def __init__(self, host_current, start, n, mn, mx):
+        self.start, self.duration, self.n, self.min, self.max = start, n, n, mn, mx
+        self._host = host_current
+        self.copy = True  # the stray attribute of parsers.py:152
+
+    @property
+    def current(self):
+        return self._host[self.start:self.start + self.n]
+
+    @property
+    def mean(self):
+        return Segment(self.current).mean
+
+    @property
+    def std(self):
+        return Segment(self.current).std
+
+
+class lambda_event_parser(parser):
+    """Threshold event detector (parsers.py:124-155).
+
+    Events are maximal runs of samples strictly below ``threshold`` (compared in
+    float64) that satisfy every rule.  ``rules`` may be any list of callables on
+    an event-like object (evaluated on the host against the device run table) or
+    a ``RuleSet`` (evaluated on the device).  ``rules=None`` gives the reference
+    defaults: duration > 100000 samples, min > -0.5, max < threshold.
+    """
+
+    def __init__(self, threshold=90, rules=None):
+        self.threshold = threshold
+        self.rules = rules or [lambda event: event.duration > 100000,
+                               lambda event: event.min > -0.5,
+                               lambda event: event.max < self.threshold]
+        self._default_rules = not rules
+
+    def _device_rules(self):
+        if getattr(self, "_default_rules", False):
+            return RuleSet(duration_gt=100000, min_gt=-0.5, max_lt=self.threshold)
+        if isinstance(self.rules, RuleSet):
+            return self.rules
+        return None
+
+    def _lambda_select(self, events):
+        return [event for event in events if np.all([rule(event) for rule in self.rules])]
+
+    # -- device-side helpers shared with File.parse ---------------------------
+    def _detect(self, ctx, host_current):
+        """Threshold scan + selection on a resident trace.  Returns (start, length,
+        min, max) arrays of the selected events (samples)."""
+        n_runs = ctx.threshold_scan(self.threshold)
+        rs = self._device_rules()
+        if rs is not None:
+            ne, _ = ctx.select_events(**rs.device_args())
+            start, length = ctx.events(ne)
+            r_start, r_len, r_min, r_max, _ = ctx.runs(n_runs)
+            idx = np.searchsorted(r_start, start)
+            return start, length, r_min[idx], r_max[idx]
+        r_start, r_len, r_min, r_max, _ = ctx.runs(n_runs)
+        keep = [i for i in range(n_runs)
+                if np.all([rule(_RunProxy(host_current, int(r_start[i]), int(r_len[i]), r_min[i], r_max[i]))
+                           for rule in self.rules])]
+        keep = np.asarray(keep, dtype=np.int64)
+        ctx.set_events(r_start[keep], r_len[keep])
+        return r_start[keep], r_len[keep], r_min[keep], r_max[keep]
+
+    def parse(self, current):
+        """One Segment per surviving run: ``current`` (a copy), ``start`` (np.int64
+        sample index) and ``duration`` (samples) -- no ``end``, like the reference."""
+        host = np.asarray(current)
+        x32 = _as_float32_trace(host)
+        ctx = _lib.default_context()
+        ctx.upload_trace(x32)
+        start, length, mn, mx = self._detect(ctx, host)
+        out = []
+        for s, n in zip(start, length):
+            seg = Segment(current=np.array(host[int(s):int(s) + int(n)]), copy=True, start=s, duration=int(n))
+            out.append(seg)
+        return out
+
+
+def _as_float32_trace(x):
+    """The device trace is float32.  float64 input is accepted when every sample is
+    float32-representable (then double(x32) == x and all comparisons agree)."""
+    x = np.asarray(x)
+    if x.dtype == np.float32:
+        return np.ascontiguousarray(x)
+    if x.dtype == np.float64:
+        x32 = x.astype(np.float32)
+        if not np.array_equal(x32.astype(np.float64), x, equal_nan=True):
+            raise NotImplementedError(
+                "float64 traces that are not float32-representable are not supported by the "
+                "float32 device trace; pass float32 samples")
+        return x32
+    raise TypeError("trace must be float32 or float64, got %s" % x.dtype)
+
+
+# --------------------------------------------------------------------------
+# Segmenter
+# --------------------------------------------------------------------------
+def statsplit_min_gain(min_width=100, max_width=1000000, window_width=10000, min_gain_per_sample=None,
+                       false_positive_rate=None, prior_segments_per_second=None, sampling_freq=1.e5,
+                       cutoff_freq=None):
+    """FastStatSplit.__init__ (cparsers.pyx:55-101): validation and the gain threshold.
+
+    Returns (min_width, max_width, window_width, min_gain) with the C-int
+    truncation of cparsers.pyx:51.
+    """
+    mw, MW, W = int(min_width), int(max_width), int(window_width)
+    fs = int(sampling_freq)  # stored as a C int; the gain formula uses the Python value
+    del fs
+    if not false_positive_rate:
+        false_positive_rate = sampling_freq
+    if not prior_segments_per_second:
+        prior_segments_per_second = sampling_freq / 2.
+    assert MW >= mw, "Maximum width must be greater than minimum width."
+    assert W >= 2 * mw, "Window width must be greater than twice the minimum width."
+    if cutoff_freq:
+        assert cutoff_freq <= 0.5 * sampling_freq, \
+            "Cutoff freq must be less than half the sampling frequency."
+    if min_gain_per_sample:
+        gain = min_gain_per_sample * W
+    else:
+        k = cutoff_freq / (0.5 * sampling_freq) if cutoff_freq else 1
+        sps = prior_segments_per_second
+        gain = (-math.log(sps / (sampling_freq - sps)) - math.log(false_positive_rate / sampling_freq)) / k
+    return mw, MW, W, gain * 2
+
+
+class SpeedyStatSplit(parser):
+    """Recursive maximum-likelihood changepoint segmenter (parsers.py:505-528,
+    cparsers.pyx:45-203) on the GPU."""
+
+    def __init__(self, min_width=100, max_width=1000000, window_width=10000,
+                 min_gain_per_sample=None, false_positive_rate=None,
+                 prior_segments_per_second=None, sampling_freq=1.e5, cutoff_freq=None):
+        self.min_width = min_width
+        self.max_width = max_width
+        self.min_gain_per_sample = min_gain_per_sample
+        self.window_width = window_width
+        self.prior_segments_per_second = prior_segments_per_second
+        self.false_positive_rate = false_positive_rate
+        self.sampling_freq = sampling_freq
+        self.cutoff_freq = cutoff_freq
+
+    def _params(self):
+        mw, MW, W, gain = statsplit_min_gain(
+            self.min_width, self.max_width, self.window_width, self.min_gain_per_sample,
+            self.false_positive_rate, self.prior_segments_per_second, self.sampling_freq, self.cutoff_freq)
+        if W // 2 == 0:
+            raise ValueError("range() arg 3 must not be zero")  # what the reference's xrange raises
+        return mw, MW, W, gain
+
+    @property
+    def min_gain(self):
+        return self._params()[3]
+
+    def parse(self, current):
+        """Segments of one event: ``current`` views, ``start``/``end``/``duration`` in
+        samples (cparsers.pyx:115-116), statistics precomputed on the device."""
+        return self.parse_many([current])[0]
+
+    def parse_many(self, currents):
+        """Segment many events in one device pass (list of float64 arrays)."""
+        mw, MW, W, gain = self._params()
+        arrays = []
+        for cur in currents:
+            cur = np.asarray(cur)
+            if cur.dtype != np.float64:
+                # FastStatSplit.parse assigns the cumsum to a double[:] memoryview
+                raise ValueError("Buffer dtype mismatch, expected 'double' but got '%s'" %
+                                 {np.dtype(np.float32): 'float'}.get(cur.dtype, str(cur.dtype)))
+            arrays.append(np.ascontiguousarray(cur))
+        out = [None] * len(arrays)
+        live = [i for i, a in enumerate(arrays) if a.shape[0] > 0]
+        for i, a in enumerate(arrays):
+            if a.shape[0] == 0:
+                out[i] = [Segment(current=a[0:0], start=0, duration=0, end=0)]
+        if not live:
+            return out
+        ctx = _lib.default_context()
+        ctx.upload_events_f64([arrays[i] for i in live])
+        n_seg = ctx.statsplit(mw, MW, W, gain)
+        ctx.segment_stats()
+        tab = ctx.segments(n_seg)
+        bounds = np.searchsorted(tab["event"], np.arange(len(live) + 1))
+        for j, i in enumerate(live):
+            a = arrays[i]
+            segs = []
+            for k in range(bounds[j], bounds[j + 1]):
+                s, e = int(tab["start"][k]), int(tab["end"][k])
+                seg = Segment(current=a[s:e], start=s, duration=(e - s), end=e)
+                seg._set_stats(tab["mean"][k], tab["std"][k], tab["min"][k], tab["max"][k])
+                segs.append(seg)
+            out[i] = segs
+        return out

@@ -1,0 +1,150 @@
+"""Multi-GPU host logic on CPU: world_size-2 (and 3) gloo processes exercise the boundary
+planning, the halo exchange and the ragged table all-gather of pypore_b200.dist.  The local
+threshold scan is played by the oracle here (tests may use it); on the GPU box the same
+functions run over NCCL with the CUDA scan (tests/test_gpu_dist.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from pypore_b200 import dist as ppdist
+
+RULES = dict(rule_mask=7, duration_gt=1000, duration_lt=0, min_gt=-0.5, max_lt=110.0)
+PYRULES = [lambda e: e.duration > 1000, lambda e: e.min > -0.5, lambda e: e.max < 110]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def local_events(chunk, rank, world, group=None, device="cpu"):
+    """What ShardedPipeline.step does up to event selection, with the oracle as the scanner."""
+    runs = oracle.threshold_runs(chunk.astype(np.float64), 110.0)
+    n_runs = len(runs[0])
+    info = ppdist.boundary_info(len(chunk), n_runs, [a[0] for a in runs], [a[-1] for a in runs])
+    infos = ppdist.gather_infos(info, dist, device, group)
+    plan = ppdist.plan_boundaries(infos, RULES)[rank]
+    halo = torch.empty(200000, dtype=torch.float32)
+    got = ppdist.exchange_halo(plan, torch.from_numpy(chunk), halo, dist, group)
+    ext = np.concatenate([chunk, halo[:got].numpy()])
+    keep = []
+    for i in range(n_runs):
+        if (i == 0 and plan["skip_first"]) or (i == n_runs - 1 and plan["skip_last"]):
+            continue
+        if ppdist.rules_accept(RULES, runs[1][i], runs[2][i], runs[3][i]):
+            keep.append((int(runs[0][i]), int(runs[1][i])))
+    if plan["event"] is not None:
+        keep.append(plan["event"])
+    offsets = np.concatenate(([0], np.cumsum(infos[:, ppdist.I_N].astype(np.int64))))
+    return keep, ext, offsets, plan
+
+
+def _worker(rank, world, port, epr, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        chunk = ppdist.synthetic_chunk(rank, world, epr, seed0=50)
+        keep, ext, offsets, plan = local_events(chunk, rank, world)
+        glob = ppdist.synthetic_global(world, epr, seed0=50)
+        assert offsets[-1] == len(glob)
+        # every owned event's samples (chunk + halo) equal the global trace there
+        for s, n in keep:
+            assert s + n <= len(ext)
+            assert np.array_equal(ext[s:s + n], glob[offsets[rank] + s:offsets[rank] + s + n])
+        if rank < world - 1:
+            assert plan["event"] is not None and plan["skip_last"]  # cut mid-event by construction
+        if rank > 0:
+            assert plan["skip_first"] and len(plan["send"]) == 1
+        # ragged table all-gather: (global start, length) rows + a float column
+        ints = torch.tensor([[offsets[rank] + s, n] for s, n in keep], dtype=torch.int64).reshape(-1, 2)
+        flts = ints[:, :1].to(torch.float64) * 0.5
+        counts = [None] * world
+        dist.all_gather_object(counts, len(keep))
+        gi, gf = ppdist.gather_tables(ints, flts, counts, dist)
+        ws, wl = oracle.events(glob.astype(np.float64), 110, PYRULES)
+        assert np.array_equal(gi[:, 0].numpy(), ws) and np.array_equal(gi[:, 1].numpy(), wl)
+        assert np.array_equal(gf[:, 0].numpy(), ws * 0.5)
+        # segments of the straddling event, split from chunk+halo, equal the oracle's on the global trace
+        if plan["event"] is not None:
+            s, n = plan["event"]
+            a = oracle.statsplit(ext[s:s + n].astype(np.float64), prior_segments_per_second=10)
+            b = oracle.statsplit(glob[offsets[rank] + s:offsets[rank] + s + n].astype(np.float64),
+                                 prior_segments_per_second=10)
+            assert np.array_equal(a, b)
+        q.put((rank, "ok"))
+    except Exception as e:  # surface the failure to the parent
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_event_detection_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 4, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", "rank %d: %s" % (rank, msg)
+
+
+def _info(n, runs):
+    """runs: list of (below, length, min, max) covering a chunk of n samples."""
+    starts = np.cumsum([0] + [r[1] for r in runs])[:-1]
+    first = (starts[0], runs[0][1], runs[0][2], runs[0][3], runs[0][0])
+    last = (starts[-1], runs[-1][1], runs[-1][2], runs[-1][3], runs[-1][0])
+    return ppdist.boundary_info(n, len(runs), first, last)
+
+
+def test_plan_event_spanning_whole_chunks():
+    # rank0 ends inside an event that covers ALL of rank1 and ends inside rank2
+    infos = [_info(5000, [(False, 3000, 118, 125), (True, 2000, 30, 80)]),
+             _info(4000, [(True, 4000, 25, 85)]),
+             _info(6000, [(True, 1500, 40, 70), (False, 4500, 117, 126)])]
+    plans = ppdist.plan_boundaries(infos, RULES)
+    assert plans[0]["event"] == (3000, 2000 + 4000 + 1500) and plans[0]["recv"] == [(1, 4000), (2, 1500)]
+    assert plans[0]["skip_last"] and not plans[0]["skip_first"]
+    assert plans[1]["skip_first"] and plans[1]["skip_last"] and plans[1]["event"] is None
+    assert plans[1]["send"] == [(0, 4000)] and plans[2]["send"] == [(0, 1500)]
+    assert plans[2]["skip_first"] and not plans[2]["skip_last"]
+
+
+def test_plan_rejected_and_non_straddling_runs():
+    # open channel straddles 0|1 (rejected by max<thr: no halo moves); an edge sits exactly on 1|2
+    infos = [_info(5000, [(True, 3000, 30, 80), (False, 2000, 118, 125)]),
+             _info(4000, [(False, 1000, 117, 124), (True, 3000, 20, 85)]),
+             _info(3000, [(False, 3000, 118, 126)])]
+    plans = ppdist.plan_boundaries(infos, RULES)
+    assert plans[0]["skip_last"] and plans[0]["event"] is None and plans[0]["recv"] == []
+    assert plans[1]["skip_first"] and plans[1]["send"] == [] and not plans[1]["skip_last"]
+    assert not plans[2]["skip_first"]
+    # a straddling event with a sub-zero spike in its continuation is rejected as a whole (min > -0.5)
+    infos = [_info(5000, [(False, 3000, 118, 125), (True, 2000, 30, 80)]),
+             _info(4000, [(True, 900, -20, 85), (False, 3100, 117, 126)])]
+    plans = ppdist.plan_boundaries(infos, RULES)
+    assert plans[0]["event"] is None and plans[0]["skip_last"] and plans[1]["skip_first"]
+    # too short on either side alone, long enough merged (duration > 1000)
+    infos = [_info(5000, [(False, 4400, 118, 125), (True, 600, 30, 80)]),
+             _info(4000, [(True, 600, 35, 85), (False, 3400, 117, 126)])]
+    plans = ppdist.plan_boundaries(infos, RULES)
+    assert plans[0]["event"] == (4400, 1200)
+    # NaN in the continuation poisons min/max like np.min / np.max: rejected
+    infos = [_info(5000, [(False, 3000, 118, 125), (True, 2000, 30, 80)]),
+             _info(4000, [(True, 900, np.nan, np.nan), (False, 3100, 117, 126)])]
+    assert ppdist.plan_boundaries(infos, RULES)[0]["event"] is None

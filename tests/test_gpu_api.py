@@ -1,0 +1,127 @@
+"""The drop-in surface on the GPU: these read like scripts written against PyPore
+(File.parse / Event.filter / Event.parse, Segment attributes) and are checked against the
+fixtures the real reference produced (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import RULES_1000, load_golden
+from pypore_b200 import synth
+from pypore_b200.DataTypes import Event, File
+from pypore_b200.core import MetaSegment, Segment
+from pypore_b200.parsers import MemoryParse, RuleSet, SpeedyStatSplit, lambda_event_parser
+
+pytestmark = pytest.mark.gpu
+
+
+def fixture_file(name="pipeline_tierA.npz"):
+    g = load_golden(name)
+    # float64 like the reference's traces (read_abf.py:210); FastStatSplit rejects float32 events
+    x = synth.make_trace(int(g["n_events"]), seed=int(g["seed"]), tier=str(g["tier"])).astype(np.float64)
+    return g, x, File(current=x, timestep=1000. / float(g["fs"]))
+
+
+def test_reference_style_script_matches_reference_output():
+    g, x, f = fixture_file()
+    assert f.second == float(g["second"])
+    f.parse(parser=lambda_event_parser(threshold=110, rules=RULES_1000))   # arbitrary Python rules (host path)
+    assert len(f.events) == len(g["event_n"]) and f.n == len(f.events)
+    assert np.array_equal([e.start for e in f.events], g["event_start_s"])
+    assert np.array_equal([e.end for e in f.events], g["event_end_s"])
+    assert np.array_equal([e.duration for e in f.events], g["event_duration_s"])
+    p = SpeedyStatSplit(min_width=100, window_width=10000, prior_segments_per_second=10)
+    st, en, mean, std = [], [], [], []
+    for event in f.events:
+        assert isinstance(event, Event) and event.file is f and event.filtered is False
+        event.parse(parser=p)
+        assert event.state_parser is p and event.n == len(event.segments)
+        for seg in event.segments:
+            assert seg.event is event
+            st.append(seg.start); en.append(seg.end); mean.append(seg.mean); std.append(seg.std)
+            assert seg.duration == seg.end - seg.start or abs(seg.duration - (seg.end - seg.start)) < 1e-12
+    assert np.array_equal(st, g["psps10_start_s"]) and np.array_equal(en, g["psps10_end_s"])
+    assert np.allclose(mean, g["psps10_mean"], rtol=1e-9, atol=0) and np.allclose(std, g["psps10_std"], rtol=1e-9, atol=0)
+    # event statistics are properties of the Event itself (it is a Segment)
+    e0 = f.events[0]
+    assert abs(e0.mean - g["event_mean"][0]) <= 1e-9 * abs(g["event_mean"][0])
+    assert e0.min == g["event_min"][0] and e0.max == g["event_max"][0]
+
+
+def test_default_rules_reject_everything_like_the_reference():
+    g, x, f = fixture_file()
+    f.parse(parser=lambda_event_parser(threshold=110))
+    assert len(f.events) == int(g["n_events_default_rules"]) == 0
+
+
+def test_raw_parser_protocol_objects():
+    g, x, f = fixture_file("pipeline_tierB.npz")
+    pieces = lambda_event_parser(threshold=110, rules=RuleSet(duration_gt=1000, min_gt=-0.5, max_lt=110)).parse(x)
+    assert [int(p.duration) for p in pieces] == list(g["event_n"])
+    assert all(isinstance(p.start, np.int64) and not hasattr(p, "end") for p in pieces)
+    assert pieces[0].current.base is None or pieces[0].current.base is not x   # a copy, like parsers.py:152
+    cur = pieces[0].current.astype(np.float64)
+    segs = SpeedyStatSplit(min_width=100, window_width=10000).parse(cur)
+    sel = g["default_event"] == 0
+    assert [s.start for s in segs] == list(g["default_start"][sel]) and [s.end for s in segs] == list(g["default_end"][sel])
+    assert all(s.duration == s.end - s.start and s.n == s.duration for s in segs)
+    assert segs[3].current.base is cur                                     # views, like cparsers.pyx:115
+    assert np.allclose([s.mean for s in segs], g["default_mean"][sel], rtol=1e-9, atol=0)
+    assert np.allclose([s.min for s in segs], g["default_min"][sel], rtol=0, atol=0)
+    d = segs[0].to_dict()
+    assert d["name"] == "Segment" and d["start"] == 0 and set(d) >= {"mean", "std", "min", "max", "end", "duration"}
+    segs[0].to_meta()
+    assert isinstance(segs[0], MetaSegment) and not hasattr(segs[0], "current") and segs[0].mean == d["mean"]
+    # MemoryParse replays stored boundaries (parsers.py:110-122)
+    again = MemoryParse(g["default_start"][sel], g["default_end"][sel]).parse(cur)
+    assert np.allclose([s.mean for s in again], g["default_mean"][sel], rtol=1e-9, atol=0)
+    # an empty event gives the reference's single empty segment
+    empty = SpeedyStatSplit().parse(np.zeros(0))
+    assert len(empty) == 1 and empty[0].start == 0 and empty[0].end == 0
+
+
+def test_user_made_segment_statistics_come_from_the_gpu():
+    rng = np.random.RandomState(1)
+    a = rng.normal(50, 3, 12345)
+    s = Segment(current=a, start=10, duration=12345)
+    assert abs(s.mean - np.mean(a)) < 1e-9 * abs(np.mean(a)) and abs(s.std - np.std(a)) < 1e-9 * np.std(a)
+    assert s.min == a.min() and s.max == a.max() and s.n == 12345
+    s.current = a[:100]                     # new samples invalidate the cached statistics
+    assert abs(s.mean - np.mean(a[:100])) < 1e-9 * abs(np.mean(a[:100]))
+    m = MetaSegment(current=a, start=0, duration=5)
+    assert m.n == 12345 and m.end == 5 and abs(m.std - np.std(a)) < 1e-9 * np.std(a) and not hasattr(m, "current")
+
+
+def test_device_resident_pipeline_equals_event_by_event_calls():
+    g, x, f = fixture_file()
+    seg = SpeedyStatSplit(min_width=50, max_width=2500, window_width=1000, prior_segments_per_second=50)
+    f.parse(parser=lambda_event_parser(threshold=110, rules=RuleSet(duration_gt=1000, min_gt=-0.5, max_lt=110)),
+            segmenter=seg)
+    t = f.segment_table
+    assert np.array_equal(t["event"], g["narrow_event"]) and np.array_equal(t["start"], g["narrow_start"])
+    assert np.array_equal(t["end"], g["narrow_end"])
+    st = [s.start for e in f.events for s in e.segments]
+    en = [s.end for e in f.events for s in e.segments]
+    assert np.array_equal(st, g["narrow_start_s"]) and np.array_equal(en, g["narrow_end_s"])
+    ev = f.events[2]
+    assert ev.state_parser is seg and ev.segments[1].event is ev and ev.n == int((g["narrow_event"] == 2).sum())
+    k = int(np.searchsorted(g["narrow_event"], 2)) + 1
+    assert abs(ev.segments[1].mean - g["narrow_mean"][k]) <= 1e-9 * abs(g["narrow_mean"][k])
+    # host-rule variant of the same pipeline (rules evaluated in Python on the device run table)
+    f2 = File(current=x, timestep=1000. / float(g["fs"]))
+    f2.parse(parser=lambda_event_parser(threshold=110, rules=RULES_1000), segmenter=seg)
+    assert all(np.array_equal(f2.segment_table[k], t[k]) for k in ("event", "start", "end", "mean", "std"))
+
+
+def test_error_behaviour_on_device_paths():
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        SpeedyStatSplit().parse(np.zeros(500, np.float32))
+    with pytest.raises(AssertionError):
+        SpeedyStatSplit(min_width=100, window_width=150).parse(np.zeros(500))
+    f = File(current=np.zeros(10, np.float32), timestep=0.01)
+    with pytest.raises(SyntaxError):
+        File()
+    ev = Event(current=np.zeros(50), start=0, end=1, duration=1, second=1e5, file=f)
+    ev.parse(parser=SpeedyStatSplit())                     # shorter than 2*min_width: one segment
+    assert ev.n == 1 and ev.segments[0].end == 50 / 1e5
+    with pytest.raises(AttributeError):                    # no .file, like DataTypes.py:289
+        Event(current=np.zeros(300), start=0, second=1e5).parse(parser=SpeedyStatSplit())

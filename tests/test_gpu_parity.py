@@ -1,0 +1,253 @@
+"""GPU parity: the CUDA path (through the C ABI, ctypes) against the CPU oracle and
+the reference-generated golden fixtures.
+
+Bars (BASELINE.json north_star): event / segment indices bit-exact; segment
+mean/std/min/max within 1e-9 relative (fp64).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import RULES_1000, load_golden
+from pypore_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+STAT_RTOL = 1e-9
+
+
+def rel_err(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) if len(a) else 0.0
+
+
+def gpu_runs(ctx, x32, thr):
+    ctx.upload_trace(x32)
+    return ctx.runs(ctx.threshold_scan(thr))
+
+
+def check_runs(ctx, x32, thr):
+    got = gpu_runs(ctx, x32, thr)
+    want = oracle.threshold_runs(x32.astype(np.float64), thr)
+    for g, w, name in zip(got, want, ("start", "length", "min", "max", "below")):
+        assert np.array_equal(g, w, equal_nan=True), name
+    return got
+
+
+def gpu_split_f64(ctx, arrays, **kw):
+    gain = oracle.min_gain(**kw)
+    ctx.upload_events_f64(arrays)
+    n = ctx.statsplit(kw.get("min_width", 100), kw.get("max_width", 1000000), kw.get("window_width", 10000), gain)
+    ctx.segment_stats()
+    return ctx.segments(n)
+
+
+def check_split_f64(ctx, arrays, **kw):
+    tab = gpu_split_f64(ctx, arrays, **kw)
+    k = 0
+    for e, a in enumerate(arrays):
+        bp = oracle.statsplit(a, **kw)
+        edges = np.concatenate(([0], bp, [len(a)]))
+        n = len(edges) - 1
+        assert np.all(tab["event"][k:k + n] == e)
+        assert np.array_equal(tab["start"][k:k + n], edges[:-1]), "event %d starts" % e
+        assert np.array_equal(tab["end"][k:k + n], edges[1:]), "event %d ends" % e
+        m, s, mn, mx = oracle.segment_stats(a, edges[:-1], edges[1:])
+        assert rel_err(tab["mean"][k:k + n], m) < STAT_RTOL
+        assert np.max(np.abs(tab["std"][k:k + n] - s)) <= STAT_RTOL * np.max(np.abs(s)) + 1e-300
+        assert np.array_equal(tab["min"][k:k + n], mn) and np.array_equal(tab["max"][k:k + n], mx)
+        k += n
+    assert k == len(tab["start"])
+    return tab
+
+
+# ---------------------------------------------------------------- K1 threshold
+def test_threshold_c1_runs_and_events(ctx):
+    x = synth.make_trace(60, seed=21, tier="A")
+    check_runs(ctx, x, 110.0)
+    ne, ns = ctx.select_events(7, 1000, 0, -0.5, 110.0)
+    s, l = ctx.events(ne)
+    ws, wl = oracle.events(x.astype(np.float64), 110, RULES_1000)
+    assert np.array_equal(s, ws) and np.array_equal(l, wl) and ns == wl.sum()
+    # default rules (duration > 100000) reject everything here
+    assert ctx.select_events(7, 100000, 0, -0.5, 110.0)[0] == 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 31, 32, 33, 4095, 4096, 4097, 8191, 12289, 100003])
+def test_threshold_ragged_lengths(ctx, n):
+    rng = np.random.RandomState(n)
+    x = np.where(rng.uniform(size=n) < 0.5, 50.0, 120.0).astype(np.float32)  # a crossing every ~2 samples
+    x += rng.normal(0, 1, n).astype(np.float32)
+    check_runs(ctx, x, 110.0)
+
+
+def test_threshold_edge_cases(ctx):
+    # starts and ends below; NaN counts as above and poisons that run's min/max; +-inf
+    x = np.array([50, 50, 120, 50, 120, 120, np.nan, 50, 50, np.inf, -np.inf, 50], np.float32)
+    got = check_runs(ctx, x, 110.0)
+    assert np.isnan(got[2][3]) and np.isnan(got[3][3])
+    # no crossing at all, both sides
+    check_runs(ctx, np.full(10000, 120.0, np.float32), 110.0)
+    check_runs(ctx, np.full(10000, 20.0, np.float32), 110.0)
+    # threshold that float32 cannot represent: comparison must be double(x) < thr
+    for thr in (110.1, 0.1, -0.3, 1e-50, 3.5e38 * 10):
+        xs = np.array([np.float32(thr), np.nextafter(np.float32(thr), np.float32(np.inf)),
+                       np.nextafter(np.float32(thr), np.float32(-np.inf)), 0.0, 1e30, -1e30] * 3, np.float32)
+        check_runs(ctx, xs, thr)
+    # one crossing exactly on every tile boundary and many crossings inside one tile (> 64 local runs)
+    x = np.full(4096 * 5 + 17, 120.0, np.float32)
+    x[4096:8192] = 30.0
+    x[8192 + 100:8192 + 100 + 400:2] = 30.0
+    x[-1] = 30.0
+    check_runs(ctx, x, 110.0)
+
+
+def test_threshold_subzero_rule(ctx):
+    x = synth.make_trace(40, seed=5, tier="A")
+    s, l = oracle.events(x.astype(np.float64), 110, RULES_1000)
+    x2, hit = synth.add_subzero_spikes(x, s, l, frac=0.25, seed=3)
+    assert len(hit) > 3
+    check_runs(ctx, x2, 110.0)
+    ne, _ = ctx.select_events(7, 1000, 0, -0.5, 110.0)
+    gs, gl = ctx.events(ne)
+    ws, wl = oracle.events(x2.astype(np.float64), 110, RULES_1000)
+    assert np.array_equal(gs, ws) and np.array_equal(gl, wl) and len(ws) == len(s) - len(hit)
+
+
+# ---------------------------------------------------------------- K2+K3+K4 split
+@pytest.mark.parametrize("kw", [dict(), dict(prior_segments_per_second=10),
+                                dict(min_width=50, max_width=2500, window_width=1000, prior_segments_per_second=50),
+                                dict(min_width=250, window_width=500),          # window == 2*min_width: never scans
+                                dict(min_width=3, max_width=40, window_width=64),
+                                dict(min_gain_per_sample=0.01, window_width=2000)])
+@pytest.mark.parametrize("tier", ["A", "B"])
+def test_split_events_bit_exact(ctx, kw, tier):
+    x = synth.make_trace(24, seed=31, tier=tier).astype(np.float64)
+    s, l = oracle.events(x, 110, RULES_1000)
+    check_split_f64(ctx, [x[a:a + n] for a, n in zip(s, l)], **kw)
+
+
+def test_split_short_and_degenerate_events(ctx):
+    rng = np.random.RandomState(0)
+    arrays = [synth.quantise(rng.normal(50, 1, n)).astype(np.float64)
+              for n in (1, 2, 7, 199, 200, 201, 202, 399, 400, 401, 1000)]
+    arrays.append(np.full(500, 42.0))                       # zero variance: log(0), NaN/inf gains
+    arrays.append(np.r_[np.full(300, 42.0), np.full(300, 43.0)])  # +inf gain at the step
+    check_split_f64(ctx, arrays)
+    check_split_f64(ctx, arrays, prior_segments_per_second=10)
+    check_split_f64(ctx, arrays, min_width=1, max_width=50, window_width=2)
+
+
+def test_split_long_event_spine_and_forced(ctx):
+    """Intervals longer than the shared-memory slab: window chain, queue hand-off, max_width forcing."""
+    g = load_golden("long_event.npz")
+    x = synth.make_long_event(300000, seed=100, tier="A").astype(np.float64)
+    for name, kw in {"long_default": dict(min_width=100, max_width=20000, window_width=10000),
+                     "long_psps10": dict(min_width=100, max_width=20000, window_width=10000,
+                                         prior_segments_per_second=10),
+                     "long_highgain": dict(min_width=100, max_width=15000, window_width=4000,
+                                           min_gain_per_sample=2.0)}.items():
+        tab = check_split_f64(ctx, [x], **kw)
+        assert np.array_equal(tab["start"], g[name + "_start"]) and np.array_equal(tab["end"], g[name + "_end"])
+    # window larger than the slab (global-memory scan path), tier B, two long events + short ones
+    xb = synth.make_long_event(70000, seed=103, tier="B").astype(np.float64)
+    check_split_f64(ctx, [xb, x[:50000], xb[:900]], min_width=100, max_width=1000000, window_width=30000,
+                    prior_segments_per_second=10)
+    check_split_f64(ctx, [xb], min_width=20, max_width=3000, window_width=14000)
+
+
+def test_golden_fixture_tables(ctx):
+    """Reference-generated tables (tests/golden/make_golden.py) straight against the device pipeline."""
+    for name in ("pipeline_tierA.npz", "pipeline_tierB.npz"):
+        g = load_golden(name)
+        x = synth.make_trace(int(g["n_events"]), seed=int(g["seed"]), tier=str(g["tier"]))
+        ctx.upload_trace(x)
+        for key, kw in {"default": dict(min_width=100, window_width=10000),
+                        "psps10": dict(min_width=100, window_width=10000, prior_segments_per_second=10),
+                        "narrow": dict(min_width=50, max_width=2500, window_width=1000,
+                                       prior_segments_per_second=50)}.items():
+            r = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, kw["min_width"], kw.get("max_width", 1000000),
+                             kw["window_width"], oracle.min_gain(**kw))
+            es, el = ctx.events(r["events"])
+            assert np.array_equal(es / float(g["second"]), g["event_start_s"]) and np.array_equal(el, g["event_n"])
+            tab = ctx.segments(r["segments"])
+            assert np.array_equal(tab["event"], g[key + "_event"])
+            assert np.array_equal(tab["start"], g[key + "_start"]) and np.array_equal(tab["end"], g[key + "_end"])
+            assert rel_err(tab["mean"], g[key + "_mean"]) < STAT_RTOL
+            assert rel_err(tab["std"], g[key + "_std"]) < STAT_RTOL
+            assert np.array_equal(tab["min"], g[key + "_min"]) and np.array_equal(tab["max"], g[key + "_max"])
+            st = ctx.event_stats(r["events"])
+            assert rel_err(st["mean"], g["event_mean"]) < STAT_RTOL and rel_err(st["std"], g["event_std"]) < STAT_RTOL
+            assert np.array_equal(st["min"], g["event_min"]) and np.array_equal(st["max"], g["event_max"])
+
+
+def test_pipeline_c1_full_parity_and_work_counters(ctx):
+    """BASELINE config 1 (6 M samples, 500 events), both gain settings, SURVEY known answers."""
+    x = synth.make_trace(500, seed=0, tier="A")
+    x64 = x.astype(np.float64)
+    ctx.upload_trace(x)
+    ws, wl = oracle.events(x64, 110, RULES_1000)
+    for psps, n_seg in ((None, 30643), (10, 2682)):
+        gain = oracle.min_gain(prior_segments_per_second=psps)
+        r = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, gain)
+        assert (r["runs"], r["events"], r["event_samples"], r["segments"]) == (1001, 500, 3998546, n_seg)
+        es, el = ctx.events(r["events"])
+        assert np.array_equal(es, ws) and np.array_equal(el, wl)
+        tab = ctx.segments(r["segments"])
+        oe, ost, oen, ncand = oracle.statsplit_events(x64, ws, wl, gain=gain, threads=8)
+        assert np.array_equal(tab["event"], oe) and np.array_equal(tab["start"], ost) and np.array_equal(tab["end"], oen)
+        assert ctx.split_counters()["candidates"] == ncand  # same candidate evaluations as the reference
+        for e in range(0, 500, 37):
+            sel = oe == e
+            m, s, mn, mx = oracle.segment_stats(x64[ws[e]:ws[e] + wl[e]], ost[sel], oen[sel])
+            assert rel_err(tab["mean"][sel], m) < STAT_RTOL and rel_err(tab["std"][sel], s) < STAT_RTOL
+            assert np.array_equal(tab["min"][sel], mn) and np.array_equal(tab["max"][sel], mx)
+
+
+def test_pipeline_c2_size_properties(ctx):
+    """BASELINE config 2 size (60 M samples, 5k events): size-independent properties + sampled oracle parity."""
+    x = synth.make_trace(5000, seed=1, tier="A")
+    ctx.upload_trace(x)
+    mw = 100
+    r = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, mw, 1000000, 10000, oracle.min_gain())
+    assert r["events"] == 5000
+    es, el = ctx.events(r["events"])
+    tab = ctx.segments(r["segments"])
+    # segments partition every event: sorted, contiguous, first starts at 0, last ends at the event length
+    assert np.all(np.diff(tab["event"]) >= 0)
+    first = np.r_[True, np.diff(tab["event"]) != 0]
+    last = np.r_[np.diff(tab["event"]) != 0, True]
+    assert np.all(tab["start"][first] == 0) and np.array_equal(tab["end"][last], el)
+    assert np.array_equal(tab["start"][~first], tab["end"][:-1][~first[1:]])
+    assert np.all(tab["end"] - tab["start"] >= mw)
+    # checksum of checksums: sum over segments of n*mean equals the sum of all event samples
+    n = (tab["end"] - tab["start"]).astype(np.float64)
+    tot = sum(float(x[s:s + l].astype(np.float64).sum()) for s, l in zip(es[::50], el[::50]))
+    sel = np.isin(tab["event"], np.arange(0, 5000, 50))
+    assert abs(float((n * tab["mean"])[sel].sum()) - tot) <= 1e-9 * abs(tot)
+    assert np.all(tab["min"] <= tab["mean"]) and np.all(tab["mean"] <= tab["max"]) and np.all(tab["std"] >= 0)
+    # idempotence: same tables on a second pass
+    r2 = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, mw, 1000000, 10000, oracle.min_gain())
+    tab2 = ctx.segments(r2["segments"])
+    assert r2 == r and all(np.array_equal(tab[k], tab2[k]) for k in tab)
+    # oracle parity on a sample of events
+    x64 = x.astype(np.float64)
+    for e in range(0, 5000, 250):
+        bp = oracle.statsplit(x64[es[e]:es[e] + el[e]])
+        sel = tab["event"] == e
+        assert np.array_equal(tab["start"][sel][1:], bp)
+
+
+def test_host_selected_events_path(ctx):
+    """Arbitrary Python rules: host picks runs from the device run table, pp_set_events feeds the split."""
+    x = synth.make_trace(30, seed=8, tier="A")
+    x64 = x.astype(np.float64)
+    ctx.upload_trace(x)
+    runs = ctx.runs(ctx.threshold_scan(110.0))
+    keep = np.nonzero(runs[4] & (runs[1] > 7000))[0]  # a rule the device mask cannot express
+    ctx.set_events(runs[0][keep], runs[1][keep])
+    gain = oracle.min_gain(prior_segments_per_second=10)
+    n = ctx.statsplit(100, 1000000, 10000, gain)
+    ctx.segment_stats()
+    tab = ctx.segments(n)
+    oe, ost, oen, _ = oracle.statsplit_events(x64, runs[0][keep], runs[1][keep], gain=gain)
+    assert np.array_equal(tab["event"], oe) and np.array_equal(tab["start"], ost) and np.array_equal(tab["end"], oen)

@@ -1,0 +1,115 @@
+"""Host-side logic that needs no GPU: parameter handling, error parity, the C ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from pypore_b200 import _lib, parsers
+from pypore_b200.DataTypes import bessel_coefficients
+
+
+def test_library_exports_every_declared_symbol():
+    """libpypore_b200.so loads without a GPU and exports exactly what include/pypore_b200.h declares."""
+    header = open(os.path.join(ROOT, "include", "pypore_b200.h")).read()
+    declared = set(re.findall(r"\b(pp_[a-z0-9_]+)\s*\(", header))
+    declared -= {"pp_ctx", "pp_status", "pp_rule", "pp_prefix_mode", "pp_pipeline_params"}
+    assert len(declared) >= 25
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), "missing export " + name
+    assert declared == set(_lib.SIGNATURES), "ctypes binding and header disagree: %s" % (
+        declared ^ set(_lib.SIGNATURES))
+    assert L.pp_version() == 100
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.PyPoreCudaError):
+        _lib.Context(0)
+    with pytest.raises(_lib.PyPoreCudaError):
+        parsers.SpeedyStatSplit().parse(np.zeros(1000))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pypore_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src, f
+
+
+def test_min_gain_mirror_matches_reference_fixture():
+    g = load_golden("params.npz")
+    S = parsers.SpeedyStatSplit
+    assert S().min_gain == float(g["min_gain_default"]) and str(S().min_gain) == "-0.0"
+    assert S(prior_segments_per_second=10).min_gain == float(g["min_gain_psps10"])
+    assert S(prior_segments_per_second=10, cutoff_freq=2000.).min_gain == float(g["min_gain_psps10_cut2000"])
+    assert S(min_gain_per_sample=0.5).min_gain == float(g["min_gain_per_sample_0p5"])
+    assert S(false_positive_rate=50., sampling_freq=2.5e5, prior_segments_per_second=25.).min_gain == \
+        float(g["min_gain_fpr50_fs250k"])
+
+
+def test_statsplit_argument_errors_match_reference():
+    with pytest.raises(AssertionError):
+        parsers.SpeedyStatSplit(min_width=100, max_width=50).parse(np.zeros(1000))
+    with pytest.raises(AssertionError):
+        parsers.SpeedyStatSplit(min_width=100, window_width=150).parse(np.zeros(1000))
+    with pytest.raises(AssertionError):
+        parsers.SpeedyStatSplit(cutoff_freq=60000.).parse(np.zeros(1000))
+    # float32 input: the reference raises ValueError (Buffer dtype mismatch), before any device work
+    with pytest.raises(ValueError, match="Buffer dtype mismatch, expected 'double' but got 'float'"):
+        parsers.SpeedyStatSplit().parse(np.zeros(1000, np.float32))
+
+
+def test_parser_json_round_trip():
+    p = parsers.SpeedyStatSplit(min_width=50, prior_segments_per_second=10, cutoff_freq=2000.)
+    d = p.to_dict()
+    assert d["name"] == "SpeedyStatSplit" and d["min_width"] == 50 and d["cutoff_freq"] == 2000.
+    for key in ("min_width", "max_width", "window_width", "min_gain_per_sample", "false_positive_rate",
+                "prior_segments_per_second", "sampling_freq", "cutoff_freq"):
+        assert key in d
+    q = parsers.parser.from_json(p.to_json())
+    assert isinstance(q, parsers.SpeedyStatSplit) and q.__dict__ == p.__dict__
+    e = parsers.lambda_event_parser(threshold=110)
+    assert e.to_dict() == {"threshold": 110, "name": "lambda_event_parser"}
+    e2 = parsers.parser.from_json(e.to_json())
+    assert isinstance(e2, parsers.lambda_event_parser) and e2.threshold == 110 and len(e2.rules) == 3
+
+
+def test_ruleset_is_plain_callables_too():
+    rs = parsers.RuleSet(duration_gt=1000, min_gt=-0.5, max_lt=110)
+
+    class E(object):
+        duration, min, max = 2000, 10.0, 90.0
+    assert len(rs) == 3 and all(r(E()) for r in rs)
+    E.max = 111.0
+    assert not all(r(E()) for r in rs)
+    a = rs.device_args()
+    assert a["rule_mask"] == 7 and a["duration_gt"] == 1000 and a["min_gt"] == -0.5 and a["max_lt"] == 110.0
+    assert parsers.RuleSet(duration_gt=10.5).device_args()["duration_gt"] == 10
+    assert parsers.RuleSet(duration_lt=10.5).device_args()["duration_lt"] == 11
+
+
+@pytest.mark.parametrize("name", ["filter_o1_100k.npz", "filter_o1_250k.npz", "filter_o2_100k.npz",
+                                  "filter_o4_100k.npz"])
+def test_bessel_coefficients_match_scipy_fixture(name):
+    g = load_golden(name)
+    b, a, zi = bessel_coefficients(int(g["order"]), float(g["cutoff"]), float(g["fs"]))
+    assert np.allclose(b, g["b"], rtol=1e-13) and np.allclose(a, g["a"], rtol=1e-13)
+    assert np.allclose(zi, g["zi"], rtol=1e-10)
+
+
+def test_float64_trace_must_be_float32_representable():
+    x = np.array([1.0, 2.5, 120.03125])
+    assert parsers._as_float32_trace(x).dtype == np.float32
+    with pytest.raises(NotImplementedError):
+        parsers._as_float32_trace(np.array([0.1]))
+    with pytest.raises(TypeError):
+        parsers._as_float32_trace(np.array([1, 2, 3]))
