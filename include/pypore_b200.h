@@ -65,6 +65,11 @@ int pp_create(int device, void *cuda_stream, pp_ctx **out);
 void pp_destroy(pp_ctx *ctx);
 const char *pp_last_error(pp_ctx *ctx);
 int pp_sync(pp_ctx *ctx);
+/* Options: PP_OPT_SCREEN (default 1) -- 1: two-stage split search (bounded-error
+ * screening of every candidate, exact arithmetic for the contenders); 0: exact
+ * arithmetic for every candidate (validation mode, same results, ~6x slower). */
+enum pp_option { PP_OPT_SCREEN = 0 };
+int pp_set_option(pp_ctx *ctx, int option, int64_t value);
 /* Number of kernel launches this context has issued since creation. */
 int64_t pp_launch_count(pp_ctx *ctx);
 /* Milliseconds between two internal CUDA events bracketing the named stage of
@@ -137,10 +142,18 @@ int pp_event_stats_download(pp_ctx *ctx, int64_t cap, double *mean, double *std,
  * which = 0 seg_event(int32) 1 seg_start(int64) 2 seg_end(int64) 3 mean 4 std 5 min 6 max (f64)
  *         7 ev_start(int64) 8 ev_len(int64). */
 const void *pp_table_device_ptr(pp_ctx *ctx, int which);
-/* Work counters of the last pp_statsplit: [0] candidate evaluations,
- * [1] window scans, [2] events whose prefix sums were redone sequentially,
- * [3] queue tasks processed. */
-int pp_split_counters(pp_ctx *ctx, int64_t out[4]);
+/* Work counters of the last pp_statsplit: [0] candidate evaluations (same count
+ * as the reference's inner loop), [1] window scans, [2] events whose prefix sums
+ * were redone sequentially, [3] queue tasks processed, [4] candidates evaluated
+ * with the exact reference arithmetic after screening, [5..7] reserved. */
+int pp_split_counters(pp_ctx *ctx, int64_t out[8]);
+
+/* Validation hook for the screening bound: for window [ps,pe) of event `ev` (prefix sums
+ * from the last pp_statsplit), per candidate i = ps+min_width+j: the screened value, the
+ * reference-arithmetic value fl(low+high) and the validity flag.  Arrays hold
+ * pe-ps-2*min_width+1 entries.  eps receives the bound the kernel applies to this window. */
+int pp_debug_screen(pp_ctx *ctx, int64_t ev, int ps, int pe, int min_width, double *h_screen,
+                    double *h_exact, uint8_t *ok, double *eps);
 
 /* ---- whole pipeline, no host synchronisation between stages ----------- */
 typedef struct pp_pipeline_params {

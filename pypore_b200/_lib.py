@@ -50,6 +50,7 @@ SIGNATURES = {
     "pp_destroy": (None, [_c.c_void_p]),
     "pp_last_error": (_c.c_char_p, [_c.c_void_p]),
     "pp_sync": (_c.c_int, [_c.c_void_p]),
+    "pp_set_option": (_c.c_int, [_c.c_void_p, _c.c_int, _i64]),
     "pp_launch_count": (_i64, [_c.c_void_p]),
     "pp_stage_ms": (_c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(_c.c_float)]),
     "pp_trace_upload": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _i64]),
@@ -75,6 +76,7 @@ SIGNATURES = {
     "pp_event_stats_download": (_c.c_int, [_c.c_void_p, _i64, _f64p, _f64p, _f64p, _f64p]),
     "pp_table_device_ptr": (_c.c_void_p, [_c.c_void_p, _c.c_int]),
     "pp_split_counters": (_c.c_int, [_c.c_void_p, _i64p]),
+    "pp_debug_screen": (_c.c_int, [_c.c_void_p, _i64, _c.c_int, _c.c_int, _c.c_int, _f64p, _f64p, _u8p, _f64p]),
     "pp_pipeline": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _i64p]),
 }
 
@@ -178,6 +180,13 @@ class Context(object):
 
     def sync(self):
         self._ck(self._L.pp_sync(self._h))
+
+    def set_option(self, option, value):
+        self._ck(self._L.pp_set_option(self._h, int(option), int(value)))
+
+    def set_screening(self, on):
+        """Two-stage split search (default on); off = exact arithmetic for every candidate."""
+        self.set_option(0, 1 if on else 0)
 
     @property
     def launch_count(self):
@@ -293,9 +302,18 @@ class Context(object):
         return self._L.pp_table_device_ptr(self._h, int(which))
 
     def split_counters(self):
-        out = np.zeros(4, np.int64)
+        out = np.zeros(8, np.int64)
         self._ck(self._L.pp_split_counters(self._h, _ptr(out, _i64p)))
-        return dict(candidates=int(out[0]), scans=int(out[1]), seq_redo=int(out[2]), tasks=int(out[3]))
+        return dict(candidates=int(out[0]), scans=int(out[1]), seq_redo=int(out[2]), tasks=int(out[3]),
+                    exact=int(out[4]))
+
+    def debug_screen(self, ev, ps, pe, min_width):
+        n = pe - ps - 2 * min_width + 1
+        hs, he, ok = np.empty(n), np.empty(n), np.empty(n, np.uint8)
+        eps = _c.c_double()
+        self._ck(self._L.pp_debug_screen(self._h, int(ev), int(ps), int(pe), int(min_width), _ptr(hs, _f64p),
+                                         _ptr(he, _f64p), _ptr(ok, _u8p), _c.byref(eps)))
+        return hs, he, ok.astype(bool), float(eps.value)
 
     def pipeline(self, threshold, rule_mask, duration_gt, duration_lt, min_gt, max_lt, min_width,
                  max_width, window_width, min_gain, filter_ba=None, prefix_mode=PREFIX_AUTO,

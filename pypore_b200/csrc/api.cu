@@ -57,13 +57,15 @@ struct pp_ctx {
     int64_t flat_cap = 0;  // capacity in samples of flat event space for the current source
 
     // K2/K3
-    DevBuf cc, bits, tasks, ready, block_count, block_off, inexact;
+    DevBuf cc, bits, tasks, ready, block_count, block_off, inexact, Ttab;
+    int T_len = 0;
+    int opt_screen = 1;
     int64_t q_cap = 0;
     DevBuf seg_flat, seg_event, seg_start, seg_end, seg_mean, seg_std, seg_min, seg_max;
     int64_t cap_segs = 0;
     int64_t n_segments = -1;
     bool stats_valid = false;
-    int64_t split_counters[4] = {0, 0, 0, 0};
+    int64_t split_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
     // event stats
     DevBuf evs_mean, evs_std, evs_min, evs_max;
@@ -297,6 +299,14 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
     G.ready = (int *)ctx->ready.p;
     G.q_cap = q_cap;
     G.ctr = ctx->ctr;
+    if (W + 1 > ctx->T_len) {
+        CKR(ensure(ctx, ctx->Ttab, sizeof(double) * (size_t)(W + 1)));
+        k3_fill_T<<<ctx->sm_count, 256, 0, ctx->stream>>>((double *)ctx->Ttab.p, W + 1);
+        LAUNCHED(ctx);
+        ctx->T_len = W + 1;
+    }
+    G.T = (const double *)ctx->Ttab.p;
+    G.screen = ctx->opt_screen;
     K3Params P;
     P.mw = mw; P.MW = MW; P.W = W; P.min_gain = min_gain;
     k3_init_queue<<<ctx->sm_count, 256, 0, ctx->stream>>>(G);
@@ -364,6 +374,7 @@ void absorb_counters(pp_ctx *ctx)
     ctx->split_counters[1] = (int64_t)h->n_scan;
     ctx->split_counters[2] = (int64_t)h->n_seq_redo;
     ctx->split_counters[3] = (int64_t)h->n_tasks;
+    ctx->split_counters[4] = (int64_t)h->n_exact;
 }
 
 }  // namespace
@@ -426,7 +437,7 @@ void pp_destroy(pp_ctx *ctx)
     DevBuf *bufs[] = {&ctx->trace_buf, &ctx->tile_state, &ctx->run_start, &ctx->run_minkey,
                       &ctx->run_maxkey, &ctx->run_len, &ctx->run_min, &ctx->run_max, &ctx->run_below,
                       &ctx->ev_start, &ctx->ev_len, &ctx->ev_off, &ctx->flat64, &ctx->cc, &ctx->bits,
-                      &ctx->tasks, &ctx->ready, &ctx->block_count, &ctx->block_off, &ctx->inexact,
+                      &ctx->tasks, &ctx->ready, &ctx->block_count, &ctx->block_off, &ctx->inexact, &ctx->Ttab,
                       &ctx->seg_flat, &ctx->seg_event, &ctx->seg_start, &ctx->seg_end, &ctx->seg_mean,
                       &ctx->seg_std, &ctx->seg_min, &ctx->seg_max, &ctx->evs_mean, &ctx->evs_std,
                       &ctx->evs_min, &ctx->evs_max, &ctx->filt_tmp, &ctx->filt_carry, &ctx->filt_coef};
@@ -447,6 +458,15 @@ int pp_sync(pp_ctx *ctx)
     CKR(set_device(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
     return PP_OK;
+}
+
+int pp_set_option(pp_ctx *ctx, int option, int64_t value)
+{
+    if (!ctx) return PP_ERR_ARG;
+    switch (option) {
+    case PP_OPT_SCREEN: ctx->opt_screen = value ? 1 : 0; return PP_OK;
+    default: return fail(ctx, PP_ERR_ARG, "unknown option %d", option);
+    }
 }
 
 int64_t pp_launch_count(pp_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -806,10 +826,40 @@ const void *pp_table_device_ptr(pp_ctx *ctx, int which)
     }
 }
 
-int pp_split_counters(pp_ctx *ctx, int64_t out[4])
+int pp_split_counters(pp_ctx *ctx, int64_t out[8])
 {
     if (!ctx || !out) return PP_ERR_ARG;
-    for (int i = 0; i < 4; ++i) out[i] = ctx->split_counters[i];
+    for (int i = 0; i < 8; ++i) out[i] = ctx->split_counters[i];
+    return PP_OK;
+}
+
+int pp_debug_screen(pp_ctx *ctx, int64_t ev, int ps, int pe, int min_width, double *h_screen,
+                    double *h_exact, uint8_t *ok, double *eps)
+{
+    if (!ctx || !h_screen || !h_exact || !ok) return PP_ERR_ARG;
+    if (ctx->n_segments < 0) return fail(ctx, PP_ERR_STATE, "pp_statsplit has not run");
+    const int n = pe - ps - 2 * min_width + 1;
+    if (ev < 0 || ev >= ctx->n_events || ps < 0 || n <= 0 || pe - ps + 1 > ctx->T_len)
+        return fail(ctx, PP_ERR_ARG, "bad debug window");
+    CKR(set_device(ctx));
+    DevBuf a, b, c;
+    CKR(ensure(ctx, a, 8 * (size_t)n));
+    CKR(ensure(ctx, b, 8 * (size_t)n));
+    CKR(ensure(ctx, c, (size_t)n));
+    K3Global G;
+    memset(&G, 0, sizeof G);
+    G.cc = (const double2 *)ctx->cc.p;
+    G.ev_off = (const int64_t *)ctx->ev_off.p;
+    G.T = (const double *)ctx->Ttab.p;
+    k3_debug_screen<<<64, 256, 0, ctx->stream>>>(G, (int)ev, ps, pe, min_width, (double *)a.p, (double *)b.p,
+                                                 (unsigned char *)c.p);
+    LAUNCHED(ctx);
+    CK(cudaMemcpyAsync(h_screen, a.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_exact, b.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ok, c.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    release(a); release(b); release(c);
+    if (eps) *eps = (double)(pe - ps) * K3_EPS_PER_SAMPLE + K3_EPS_CONST;
     return PP_OK;
 }
 

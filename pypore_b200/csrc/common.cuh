@@ -26,6 +26,7 @@ struct PPCounters {
     unsigned long long n_cand;        // candidate evaluations
     unsigned long long n_scan;        // window scans
     unsigned long long n_tasks;       // tasks processed
+    unsigned long long n_exact;       // exact (reference-arithmetic) candidate evaluations
     unsigned long long n_seq_redo;    // events whose prefix sums were redone sequentially
     unsigned long long scan_ticket;   // prefix-scan dynamic tile id
     unsigned int overflow;            // bit0 runs, bit1 queue, bit2 segments, bit3 filter-too-short

@@ -16,24 +16,43 @@
 // Breakpoints are recorded as bits in flat event space; a compaction pass turns
 // the bitmap into the sorted segment table, so no ordering is needed here.
 //
-// Arithmetic contract (bit-exact split decisions): every operation of var_c and
-// of the gain is a separate IEEE fp64 operation in the reference's association
-// (__dsub_rn/__ddiv_rn/__dmul_rn/__dadd_rn are never contracted to FMA), the
-// comparison is a strict '>' against a running maximum seeded with min_gain,
-// and ties go to the lowest index.
+// Two-stage evaluation of a window (bit-exact result, ~6x fewer instructions):
+//   SCREEN  every candidate i gets H~(i) ~= low(i) + high(i) from a division-free
+//           formulation  n1*log(D1) + n2*log(D2) - T[n1] - T[n2],
+//           D = Q*n - S*S = n^2 * V,  T[n] = 2 n ln n  (table), with a table-driven
+//           fp64 log (|err| < 1e-14).  For candidates that pass the validity test
+//           (variance not smaller than 2^-24 of the mean square) the distance to
+//           the reference's own rounded value is rigorously bounded by
+//           eps = n_window * 3e-8 + 1e-6  (derivation in DESIGN.md).
+//   EXACT   only candidates with H~ <= min H~ + 2 eps, and every candidate that
+//           failed the validity test, are evaluated with the reference's exact
+//           arithmetic below; the decision (strict '>' against min_gain, lowest
+//           index on ties, NaN never wins) is taken on exact values only.
+//
+// Exact arithmetic contract: every operation of var_c and of the gain is a
+// separate IEEE fp64 operation in the reference's association
+// (__dsub_rn/__ddiv_rn/__dmul_rn/__dadd_rn are never contracted to FMA).
 #pragma once
 #include "common.cuh"
 
 constexpr int K3_THREADS = 512;
 constexpr int K3_WARPS = K3_THREADS / 32;
-constexpr int K3_CAP = 12288;   // samples of one interval staged in shared memory
-constexpr int K3_LIST = 1024;   // items per level list
+constexpr int K3_CAP = 10240;   // samples of one interval staged in shared memory
+constexpr int K3_LIST = 512;    // items per level list
+constexpr int K3_REQ = 1024;    // exact-evaluation requests per level
 constexpr int K3_BIG = 1024;    // candidates from which a window is scanned CTA-wide
+constexpr int K3_FULL_FLAG = 0x40000000;  // scanlist entry: request list overflowed, scan exactly
+
+constexpr double K3_RATIO_MAX = 16777216.0;  // 2^24: validity bound on mean-square / variance
+constexpr double K3_EPS_PER_SAMPLE = 3e-8;   // > 10.03 * 2^-53 * 2^24 = 1.87e-8
+constexpr double K3_EPS_CONST = 1e-6;
+constexpr double K3_TINY = 1e-280, K3_HUGE = 1e280;
 
 struct PPTask { int ev, s, e, flags; };
 struct K3Item { int s, e, ps; };
 struct K3Params { int mw, MW, W; double min_gain; };
 struct K3Best { double g; int x; };
+struct K3Approx { double b1, b2; int i1, bad; };
 
 struct K3Global {
     const double2 *cc;
@@ -44,17 +63,26 @@ struct K3Global {
     int *ready;
     int64_t q_cap;
     PPCounters *ctr;
+    const double *T;  // T[n] = 2 n ln n for n in [0, W]
+    int screen;       // 0: exact evaluation of every candidate (validation mode)
 };
 
 struct K3Shared {
     K3Item list[2][K3_LIST];
     int scanlist[K3_LIST];
+    unsigned long long best_key[K3_LIST];
+    int best_idx[K3_LIST];
+    int req_k[K3_REQ];
+    int req_i[K3_REQ];
+    double req_g[K3_REQ];
+    double2 logtab[128];
     double red_g[K3_WARPS];
+    double red_b[K3_WARPS];
     int red_x[K3_WARPS];
-    int nA, nB, nbig, nsmall;
+    int nA, nB, nbig, nsmall, nreq;
     PPTask task;
     int have_task;
-    unsigned long long cand, scans;
+    unsigned long long cand, scans, exact;
 };
 
 constexpr size_t K3_SMEM_CC = sizeof(double2) * (K3_CAP + 1);
@@ -75,6 +103,9 @@ struct K3GlobalCC {
     }
 };
 
+// ---------------------------------------------------------------------------
+// exact path
+// ---------------------------------------------------------------------------
 // var_c (cparsers.pyx:31-38); start == 0 subtracts an exact 0.0, bit-identical
 // to the reference's special case.
 __device__ __forceinline__ double k3_var(const double2 hi, const double2 lo, int cnt)
@@ -91,23 +122,34 @@ __device__ __forceinline__ K3Best k3_better(const K3Best a, const K3Best b)
     return a;
 }
 
-// Candidates ps+mw+first, +stride, ... <= pe-mw of window [ps,pe)
+// gain(i) of window [ps,pe) exactly as cparsers.pyx:172-174
+__device__ __forceinline__ double k3_exact_gain(const double2 lo, const double2 mid, const double2 hi,
+                                                int ps, int pe, int i, double tot)
+{
+    const double low = __dmul_rn((double)(i - ps), log(k3_var(mid, lo, i - ps)));
+    const double high = __dmul_rn((double)(pe - i), log(k3_var(hi, mid, pe - i)));
+    return __dsub_rn(tot, __dadd_rn(low, high));
+}
+
+__device__ __forceinline__ double k3_exact_tot(const double2 lo, const double2 hi, int ps, int pe)
+{
+    return __dmul_rn((double)(pe - ps), log(k3_var(hi, lo, pe - ps)));
+}
+
+// Candidates ps+mw+first, +stride, ... <= pe-mw of window [ps,pe), all exact
 // (_best_split_stepwise loop, cparsers.pyx:171-177).
 template <class CC>
 __device__ __forceinline__ K3Best k3_scan_range(const CC &cc, int ps, int pe, int mw,
                                                 double min_gain, int first, int stride)
 {
     const double2 lo = cc.at(ps - 1), hi = cc.at(pe - 1);
-    const double tot = __dmul_rn((double)(pe - ps), log(k3_var(hi, lo, pe - ps)));
+    const double tot = k3_exact_tot(lo, hi, ps, pe);
     K3Best b;
     b.g = min_gain;
     b.x = -1;
     const int last = pe - mw;
     for (int i = ps + mw + first; i <= last; i += stride) {
-        const double2 mid = cc.at(i - 1);
-        const double low = __dmul_rn((double)(i - ps), log(k3_var(mid, lo, i - ps)));
-        const double high = __dmul_rn((double)(pe - i), log(k3_var(hi, mid, pe - i)));
-        const double g = __dsub_rn(tot, __dadd_rn(low, high));
+        const double g = k3_exact_gain(lo, cc.at(i - 1), hi, ps, pe, i, tot);
         if (g > b.g) { b.g = g; b.x = i; }
     }
     return b;
@@ -125,12 +167,10 @@ __device__ __forceinline__ K3Best k3_warp_reduce(K3Best b)
     return b;
 }
 
-template <class CC>
-__device__ __forceinline__ K3Best k3_cta_scan(const CC &cc, int ps, int pe, const K3Params &P,
-                                              K3Shared &S)
+// CTA-wide lexicographic reduction of per-thread exact results (all threads get it)
+__device__ __forceinline__ K3Best k3_cta_reduce(K3Best b, K3Shared &S)
 {
     const int tid = threadIdx.x;
-    K3Best b = k3_scan_range(cc, ps, pe, P.mw, P.min_gain, tid, K3_THREADS);
     b = k3_warp_reduce(b);
     __syncthreads();
     if ((tid & 31) == 0) { S.red_g[tid >> 5] = b.g; S.red_x[tid >> 5] = b.x; }
@@ -148,6 +188,140 @@ __device__ __forceinline__ K3Best k3_cta_scan(const CC &cc, int ps, int pe, cons
     return r;
 }
 
+// ---------------------------------------------------------------------------
+// screening path
+// ---------------------------------------------------------------------------
+// ln(x) for positive, normal, finite x: exponent + 7-bit table + degree-5 series.
+// |error| <= 6e-16 (truncation, |r| <= 2^-8) + a few ulp of the result.
+__device__ __forceinline__ double k3_fastlog(double x, const double2 *tab)
+{
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const int e = (hi >> 20) - 1023;
+    const int k = (hi >> 13) & 127;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double2 t = tab[k];
+    const double r = fma(m, t.x, -1.0);
+    double p = fma(r, 0.2, -0.25);
+    p = fma(r, p, 1.0 / 3.0);
+    p = fma(r, p, -0.5);
+    p = fma(r, p, 1.0);
+    p = p * r;
+    return fma((double)e, 0.6931471805599453094, t.y + p);
+}
+
+// H~(i) and its validity (see file header).  S and Q are the same fp64
+// differences the exact path forms, so both paths start from identical values.
+template <class CC>
+__device__ __forceinline__ bool k3_screen_eval(const CC &cc, const double2 lo, const double2 hi, int ps,
+                                               int pe, int i, const double *__restrict__ T,
+                                               const double2 *tab, double &H)
+{
+    const double2 mid = cc.at(i - 1);
+    const int c1 = i - ps, c2 = pe - i;
+    const double n1 = (double)c1, n2 = (double)c2;
+    const double S1 = __dsub_rn(mid.x, lo.x), Q1 = __dsub_rn(mid.y, lo.y);
+    const double S2 = __dsub_rn(hi.x, mid.x), Q2 = __dsub_rn(hi.y, mid.y);
+    const double P1 = __dmul_rn(Q1, n1), SQ1 = __dmul_rn(S1, S1), D1 = __dsub_rn(P1, SQ1);
+    const double P2 = __dmul_rn(Q2, n2), SQ2 = __dmul_rn(S2, S2), D2 = __dsub_rn(P2, SQ2);
+    const double M1 = fmax(fabs(P1), SQ1), M2 = fmax(fabs(P2), SQ2);
+    bool ok = (c1 > 0) & (c2 > 0);
+    ok = ok & (D1 >= K3_TINY) & (D1 <= K3_HUGE) & (M1 <= K3_RATIO_MAX * D1);
+    ok = ok & (D2 >= K3_TINY) & (D2 <= K3_HUGE) & (M2 <= K3_RATIO_MAX * D2);
+    const double L1 = k3_fastlog(D1, tab), L2 = k3_fastlog(D2, tab);
+    H = fma(n1, L1, n2 * L2) - (__ldg(T + c1) + __ldg(T + c2));
+    return ok & (fabs(H) <= K3_HUGE);
+}
+
+template <class CC>
+__device__ __forceinline__ K3Approx k3_screen_range(const CC &cc, const double2 lo, const double2 hi,
+                                                    int ps, int pe, int mw, int first, int stride,
+                                                    const double *__restrict__ T, const double2 *tab)
+{
+    K3Approx a;
+    a.b1 = a.b2 = __longlong_as_double(0x7ff0000000000000LL);
+    a.i1 = -1;
+    a.bad = 0;
+    const int last = pe - mw;
+    for (int i = ps + mw + first; i <= last; i += stride) {
+        double H;
+        const bool ok = k3_screen_eval(cc, lo, hi, ps, pe, i, T, tab, H);
+        if (!ok) a.bad = 1;
+        else if (H < a.b1) { a.b2 = a.b1; a.b1 = H; a.i1 = i; }
+        else if (H < a.b2) a.b2 = H;
+    }
+    return a;
+}
+
+__device__ __forceinline__ double k3_eps(int n) { return (double)n * K3_EPS_PER_SAMPLE + K3_EPS_CONST; }
+
+// Monotone double -> u64 key (non-NaN); -0.0 is canonicalised to +0.0 first so
+// that equal doubles have equal keys.
+__device__ __forceinline__ unsigned long long k3_okey(double g)
+{
+    const long long b = __double_as_longlong(__dadd_rn(g, 0.0));
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000LL));
+}
+
+// After the window's min H~ is known: which of this thread's candidates need the
+// exact evaluation?  f(i) is called for each.
+template <class CC, class F>
+__device__ __forceinline__ void k3_screen_select(const CC &cc, const double2 lo, const double2 hi, int ps,
+                                                 int pe, int mw, int first, int stride,
+                                                 const double *__restrict__ T, const double2 *tab,
+                                                 const K3Approx &a, double thr, F f)
+{
+    if (a.bad || a.b2 <= thr) {
+        // rare: several of this thread's candidates qualify -> rescan its subset
+        const int last = pe - mw;
+        for (int i = ps + mw + first; i <= last; i += stride) {
+            double H;
+            const bool ok = k3_screen_eval(cc, lo, hi, ps, pe, i, T, tab, H);
+            if (!ok || H <= thr) f(i);
+        }
+    } else if (a.i1 >= 0 && a.b1 <= thr) {
+        f(a.i1);
+    }
+}
+
+// Whole CTA scans one window and returns the exact decision (spine mode).
+template <class CC>
+__device__ __forceinline__ K3Best k3_cta_scan(const CC &cc, int ps, int pe, const K3Params &P,
+                                              const K3Global &G, K3Shared &S)
+{
+    const int tid = threadIdx.x;
+    K3Best b;
+    b.g = P.min_gain;
+    b.x = -1;
+    const double2 lo = cc.at(ps - 1), hi = cc.at(pe - 1);
+    const double tot = k3_exact_tot(lo, hi, ps, pe);
+    if (!G.screen || !(fabs(tot) <= K3_HUGE)) {
+        b = k3_scan_range(cc, ps, pe, P.mw, P.min_gain, tid, K3_THREADS);
+        return k3_cta_reduce(b, S);
+    }
+    const K3Approx a = k3_screen_range(cc, lo, hi, ps, pe, P.mw, tid, K3_THREADS, G.T, S.logtab);
+    double m = a.b1;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmin(m, __shfl_xor_sync(PP_FULL, m, d));
+    __syncthreads();
+    if ((tid & 31) == 0) S.red_b[tid >> 5] = m;
+    __syncthreads();
+    m = S.red_b[0];
+#pragma unroll
+    for (int w = 1; w < K3_WARPS; ++w) m = fmin(m, S.red_b[w]);
+    const double thr = m + 2.0 * k3_eps(pe - ps);
+    unsigned nexact = 0;
+    k3_screen_select(cc, lo, hi, ps, pe, P.mw, tid, K3_THREADS, G.T, S.logtab, a, thr, [&](int i) {
+        const double g = k3_exact_gain(lo, cc.at(i - 1), hi, ps, pe, i, tot);
+        ++nexact;
+        if (g > b.g) { b.g = g; b.x = i; }
+    });
+    if (nexact) atomicAdd(&S.exact, (unsigned long long)nexact);
+    return k3_cta_reduce(b, S);
+}
+
+// ---------------------------------------------------------------------------
+// bookkeeping shared by both modes
+// ---------------------------------------------------------------------------
 __device__ __forceinline__ void k3_emit(const K3Global &G, int64_t off, int x)
 {
     const int64_t f = off + x;
@@ -201,6 +375,12 @@ __device__ __forceinline__ int k3_next_ps(const K3Params &P, int ps, int e)
     return (int)(n < e ? n : e);
 }
 
+__device__ __forceinline__ int k3_window_end(const K3Params &P, const K3Item &it)
+{
+    const long long pe_l = (long long)it.ps + P.W;
+    return (int)(pe_l < it.e ? pe_l : it.e);
+}
+
 // Apply a scan result to an item in local mode (cparsers.pyx:194-203).
 __device__ __forceinline__ void k3_resolve_local(const K3Global &G, K3Shared &S, K3Item *next,
                                                  const K3Params &P, int ev, int64_t off,
@@ -215,6 +395,13 @@ __device__ __forceinline__ void k3_resolve_local(const K3Global &G, K3Shared &S,
     }
 }
 
+__device__ __forceinline__ void k3_request(K3Shared &S, int k, int i)
+{
+    const int r = atomicAdd(&S.nreq, 1);
+    if (r < K3_REQ) { S.req_k[r] = k; S.req_i[r] = i; }
+    else atomicOr(&S.scanlist[k], K3_FULL_FLAG);
+}
+
 __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P)
 {
     extern __shared__ __align__(16) unsigned char k3_smem[];
@@ -222,6 +409,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
     K3Shared &S = *reinterpret_cast<K3Shared *>(k3_smem + K3_SMEM_CC);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mw = P.mw, MW = P.MW, W = P.W;
+
+    if (tid < 128) {
+        // fast-log table: centre of mantissa bucket k, its reciprocal and its logarithm
+        const double c = 1.0 + ((double)tid + 0.5) / 128.0;
+        S.logtab[tid] = make_double2(1.0 / c, log(c));
+    }
 
     for (;;) {
         __syncthreads();
@@ -242,6 +435,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
             S.have_task = ok;
             S.cand = 0;
             S.scans = 0;
+            S.exact = 0;
         }
         __syncthreads();
         if (!S.have_task) break;
@@ -285,13 +479,16 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
                 __syncthreads();
                 K3SmemCC acc;
                 acc.sm = sm_cc; acc.S0 = ps;
-                b = k3_cta_scan(acc, ps, pe, P, S);
+                b = k3_cta_scan(acc, ps, pe, P, G, S);
             } else {
                 K3GlobalCC acc;
                 acc.g = ccg;
-                b = k3_cta_scan(acc, ps, pe, P, S);
+                b = k3_cta_scan(acc, ps, pe, P, G, S);
             }
-            if (tid == 0) { S.cand += (unsigned long long)(pe - ps - 2 * mw + 1); S.scans += 1; }
+            if (tid == 0) {
+                atomicAdd(&S.cand, (unsigned long long)(pe - ps - 2 * mw + 1));
+                atomicAdd(&S.scans, 1ull);
+            }
             if (b.x >= 0) {
                 if (tid == 0) {
                     k3_emit(G, off, b.x);
@@ -325,7 +522,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
                 if (nA == 0) break;
                 K3Item *A = S.list[cur], *Bn = S.list[cur ^ 1];
                 __syncthreads();  // everyone has read nA
-                if (tid == 0) { S.nB = 0; S.nbig = 0; S.nsmall = 0; }
+                if (tid == 0) { S.nB = 0; S.nbig = 0; S.nsmall = 0; S.nreq = 0; }
                 __syncthreads();
                 // step 1: the window-loop bookkeeping of _recursive_split per item
                 for (int t = tid; t < nA; t += K3_THREADS) {
@@ -343,8 +540,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
                         k3_emit(G, off, x);
                         if (k3_worth(P, x, it.e)) k3_push_local(G, S, Bn, ev, x, it.e, x);
                     } else {
-                        const long long pe_l = (long long)it.ps + W;
-                        const int pe = (int)(pe_l < it.e ? pe_l : it.e);
+                        const int pe = k3_window_end(P, it);
                         const int ncand = pe - it.ps - 2 * mw + 1;
                         if (pe - it.ps <= 2 * mw) {
                             k3_push_local(G, S, Bn, ev, it.s, it.e, k3_next_ps(P, it.ps, it.e));
@@ -357,29 +553,117 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
                 }
                 __syncthreads();
                 const int nbig = S.nbig, nsmall = S.nsmall;
-                // step 2: big windows, one at a time, whole CTA
-                for (int bi = 0; bi < nbig; ++bi) {
-                    const K3Item it = A[S.scanlist[bi]];
-                    const long long pe_l = (long long)it.ps + W;
-                    const int pe = (int)(pe_l < it.e ? pe_l : it.e);
-                    const K3Best b = k3_cta_scan(acc, it.ps, pe, P, S);
-                    if (tid == 0) {
-                        atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
-                        atomicAdd(&S.scans, 1ull);
-                        k3_resolve_local(G, S, Bn, P, ev, off, it, b.x);
-                    }
+                // scan slot k: k < nbig are big windows, K3_LIST-1-j (j < nsmall) small ones
+                for (int k = tid; k < K3_LIST; k += K3_THREADS) {
+                    S.best_key[k] = 0ull;
+                    S.best_idx[k] = 0x7fffffff;
                 }
-                // step 3: small windows, one per warp
-                for (int k = warp; k < nsmall; k += K3_WARPS) {
-                    const K3Item it = A[S.scanlist[K3_LIST - 1 - k]];
-                    const long long pe_l = (long long)it.ps + W;
-                    const int pe = (int)(pe_l < it.e ? pe_l : it.e);
-                    K3Best b = k3_scan_range(acc, it.ps, pe, mw, P.min_gain, lane, 32);
-                    b = k3_warp_reduce(b);
-                    if (lane == 0) {
+                if (!G.screen) {
+                    // validation mode: every candidate exactly
+                    for (int bi = 0; bi < nbig; ++bi) {
+                        const K3Item it = A[S.scanlist[bi]];
+                        const int pe = k3_window_end(P, it);
+                        K3Best b = k3_scan_range(acc, it.ps, pe, mw, P.min_gain, tid, K3_THREADS);
+                        b = k3_cta_reduce(b, S);
+                        if (tid == 0) {
+                            atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
+                            atomicAdd(&S.scans, 1ull);
+                            k3_resolve_local(G, S, Bn, P, ev, off, it, b.x);
+                        }
+                    }
+                    for (int k = warp; k < nsmall; k += K3_WARPS) {
+                        const K3Item it = A[S.scanlist[K3_LIST - 1 - k]];
+                        const int pe = k3_window_end(P, it);
+                        K3Best b = k3_scan_range(acc, it.ps, pe, mw, P.min_gain, lane, 32);
+                        b = k3_warp_reduce(b);
+                        if (lane == 0) {
+                            atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
+                            atomicAdd(&S.scans, 1ull);
+                            k3_resolve_local(G, S, Bn, P, ev, off, it, b.x);
+                        }
+                    }
+                } else {
+                    // step 2a: SCREEN big windows, whole CTA each
+                    for (int bi = 0; bi < nbig; ++bi) {
+                        const K3Item it = A[S.scanlist[bi] & ~K3_FULL_FLAG];
+                        const int pe = k3_window_end(P, it);
+                        const double2 lo = acc.at(it.ps - 1), hi = acc.at(pe - 1);
+                        const K3Approx a = k3_screen_range(acc, lo, hi, it.ps, pe, mw, tid, K3_THREADS, G.T,
+                                                           S.logtab);
+                        double m = a.b1;
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) m = fmin(m, __shfl_xor_sync(PP_FULL, m, d));
+                        __syncthreads();
+                        if (lane == 0) S.red_b[warp] = m;
+                        __syncthreads();
+                        m = S.red_b[0];
+#pragma unroll
+                        for (int w = 1; w < K3_WARPS; ++w) m = fmin(m, S.red_b[w]);
+                        const double thr = m + 2.0 * k3_eps(pe - it.ps);
+                        k3_screen_select(acc, lo, hi, it.ps, pe, mw, tid, K3_THREADS, G.T, S.logtab, a, thr,
+                                         [&](int i) { k3_request(S, bi, i); });
+                    }
+                    // step 2b: SCREEN small windows, one warp each
+                    for (int k = warp; k < nsmall; k += K3_WARPS) {
+                        const int slot = K3_LIST - 1 - k;
+                        const K3Item it = A[S.scanlist[slot] & ~K3_FULL_FLAG];
+                        const int pe = k3_window_end(P, it);
+                        const double2 lo = acc.at(it.ps - 1), hi = acc.at(pe - 1);
+                        const K3Approx a = k3_screen_range(acc, lo, hi, it.ps, pe, mw, lane, 32, G.T, S.logtab);
+                        double m = a.b1;
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) m = fmin(m, __shfl_xor_sync(PP_FULL, m, d));
+                        const double thr = m + 2.0 * k3_eps(pe - it.ps);
+                        k3_screen_select(acc, lo, hi, it.ps, pe, mw, lane, 32, G.T, S.logtab, a, thr,
+                                         [&](int i) { k3_request(S, slot, i); });
+                    }
+                    __syncthreads();
+                    // step 3: EXACT evaluation of the requested candidates, one per thread
+                    const int nreq = S.nreq < K3_REQ ? S.nreq : K3_REQ;
+                    for (int r = tid; r < nreq; r += K3_THREADS) {
+                        const int k = S.req_k[r], i = S.req_i[r];
+                        const K3Item it = A[S.scanlist[k] & ~K3_FULL_FLAG];
+                        const int pe = k3_window_end(P, it);
+                        const double2 lo = acc.at(it.ps - 1), hi = acc.at(pe - 1);
+                        const double tot = k3_exact_tot(lo, hi, it.ps, pe);
+                        const double g = k3_exact_gain(lo, acc.at(i - 1), hi, it.ps, pe, i, tot);
+                        S.req_g[r] = g;
+                        if (g > P.min_gain) atomicMax(&S.best_key[k], k3_okey(g));
+                    }
+                    if (tid == 0) atomicAdd(&S.exact, (unsigned long long)nreq);
+                    __syncthreads();
+                    for (int r = tid; r < nreq; r += K3_THREADS) {
+                        const double g = S.req_g[r];
+                        const int k = S.req_k[r];
+                        if (g > P.min_gain && k3_okey(g) == S.best_key[k]) atomicMin(&S.best_idx[k], S.req_i[r]);
+                    }
+                    __syncthreads();
+                    // step 4: resolve every scanned window whose requests all fitted
+                    for (int q = tid; q < nbig + nsmall; q += K3_THREADS) {
+                        const int k = q < nbig ? q : K3_LIST - 1 - (q - nbig);
+                        const int entry = S.scanlist[k];
+                        if (entry & K3_FULL_FLAG) continue;
+                        const K3Item it = A[entry];
+                        const int pe = k3_window_end(P, it);
                         atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
                         atomicAdd(&S.scans, 1ull);
-                        k3_resolve_local(G, S, Bn, P, ev, off, it, b.x);
+                        k3_resolve_local(G, S, Bn, P, ev, off, it, S.best_key[k] ? S.best_idx[k] : -1);
+                    }
+                    // step 5 (rare): windows whose requests overflowed the list -> exact scan, whole CTA
+                    for (int q = 0; q < nbig + nsmall; ++q) {
+                        const int k = q < nbig ? q : K3_LIST - 1 - (q - nbig);
+                        const int entry = S.scanlist[k];
+                        if (!(entry & K3_FULL_FLAG)) continue;
+                        const K3Item it = A[entry & ~K3_FULL_FLAG];
+                        const int pe = k3_window_end(P, it);
+                        K3Best b = k3_scan_range(acc, it.ps, pe, mw, P.min_gain, tid, K3_THREADS);
+                        b = k3_cta_reduce(b, S);
+                        if (tid == 0) {
+                            atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
+                            atomicAdd(&S.scans, 1ull);
+                            atomicAdd(&S.exact, (unsigned long long)(pe - it.ps - 2 * mw + 1));
+                            k3_resolve_local(G, S, Bn, P, ev, off, it, b.x);
+                        }
                     }
                 }
                 __syncthreads();
@@ -392,11 +676,49 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
         if (tid == 0) {
             atomicAdd(&G.ctr->n_cand, S.cand);
             atomicAdd(&G.ctr->n_scan, S.scans);
+            atomicAdd(&G.ctr->n_exact, S.exact);
             atomicAdd(&G.ctr->n_tasks, 1ull);
             __threadfence();
             atomicAdd((unsigned long long *)&G.ctr->q_pending, (unsigned long long)(-1LL));
         }
     }
+}
+
+// Debug / validation: for window [ps,pe) of event `ev`, write per candidate the screened
+// value H~, the reference-arithmetic value fl(low + high) and the validity flag.
+__global__ void __launch_bounds__(256)
+k3_debug_screen(K3Global G, int ev, int ps, int pe, int mw, double *h_screen, double *h_exact,
+                unsigned char *ok_out)
+{
+    __shared__ double2 tab[128];
+    if (threadIdx.x < 128) {
+        const double c = 1.0 + ((double)threadIdx.x + 0.5) / 128.0;
+        tab[threadIdx.x] = make_double2(1.0 / c, log(c));
+    }
+    __syncthreads();
+    K3GlobalCC cc;
+    cc.g = G.cc + G.ev_off[ev];
+    const double2 lo = cc.at(ps - 1), hi = cc.at(pe - 1);
+    const int n = pe - mw - (ps + mw) + 1;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int i = ps + mw + j;
+        double H;
+        const bool ok = k3_screen_eval(cc, lo, hi, ps, pe, i, G.T, tab, H);
+        const double2 mid = cc.at(i - 1);
+        const double low = __dmul_rn((double)(i - ps), log(k3_var(mid, lo, i - ps)));
+        const double high = __dmul_rn((double)(pe - i), log(k3_var(hi, mid, pe - i)));
+        h_screen[j] = H;
+        h_exact[j] = __dadd_rn(low, high);
+        ok_out[j] = ok ? 1 : 0;
+    }
+}
+
+// T[n] = 2 n ln n (n = 0 .. len-1), the part of the screening formula that only
+// depends on the sub-window length.
+__global__ void __launch_bounds__(256) k3_fill_T(double *T, int len)
+{
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < len; n += gridDim.x * blockDim.x)
+        T[n] = n > 0 ? 2.0 * (double)n * log((double)n) : 0.0;
 }
 
 // One initial task per event; event starts are segment starts.
@@ -426,6 +748,7 @@ k3_init_queue(K3Global G)
         G.ctr->n_cand = 0;
         G.ctr->n_scan = 0;
         G.ctr->n_tasks = 0;
+        G.ctr->n_exact = 0;
     }
 }
 

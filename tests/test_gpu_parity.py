@@ -42,7 +42,12 @@ def gpu_split_f64(ctx, arrays, **kw):
 
 
 def check_split_f64(ctx, arrays, **kw):
+    # validation mode (every candidate in exact arithmetic) and the production two-stage search
+    ctx.set_screening(False)
+    ref_tab = gpu_split_f64(ctx, arrays, **kw)
+    ctx.set_screening(True)
     tab = gpu_split_f64(ctx, arrays, **kw)
+    assert all(np.array_equal(ref_tab[k], tab[k]) for k in ("event", "start", "end"))
     k = 0
     for e, a in enumerate(arrays):
         bp = oracle.statsplit(a, **kw)
@@ -132,7 +137,9 @@ def test_split_short_and_degenerate_events(ctx):
               for n in (1, 2, 7, 199, 200, 201, 202, 399, 400, 401, 1000)]
     arrays.append(np.full(500, 42.0))                       # zero variance: log(0), NaN/inf gains
     arrays.append(np.r_[np.full(300, 42.0), np.full(300, 43.0)])  # +inf gain at the step
+    arrays.append(synth.quantise(rng.normal(50, 1, 8000)).astype(np.float64))
     check_split_f64(ctx, arrays)
+    check_split_f64(ctx, arrays, min_width=2, max_width=6, window_width=4)   # > K3_LIST items per level
     check_split_f64(ctx, arrays, prior_segments_per_second=10)
     check_split_f64(ctx, arrays, min_width=1, max_width=50, window_width=2)
 
@@ -235,6 +242,42 @@ def test_pipeline_c2_size_properties(ctx):
         bp = oracle.statsplit(x64[es[e]:es[e] + el[e]])
         sel = tab["event"] == e
         assert np.array_equal(tab["start"][sel][1:], bp)
+
+
+def test_screening_error_bound_holds(ctx):
+    """The screened value of every valid candidate lies within the eps the kernel assumes of the
+    reference-arithmetic value (DESIGN.md derivation), on raw, quantised, filtered-like and low-noise data."""
+    rng = np.random.RandomState(5)
+    cases = {
+        "tierA": synth.make_long_event(40000, seed=7, tier="A").astype(np.float64),
+        "tierB": synth.make_long_event(40000, seed=8, tier="B").astype(np.float64),
+        "smooth": np.convolve(synth.make_long_event(40100, seed=9, tier="B").astype(np.float64),
+                              np.ones(25) / 25, mode="valid")[:40000],          # filtered-like: sigma ~0.2
+        "lownoise": 60.0 + 0.02 * rng.normal(size=40000),                         # mean-square / variance ~ 1e7
+        "offset": 5000.0 + rng.normal(size=40000),                                # ratio 2.5e7 > 2^24: invalid
+        "steps": np.repeat(rng.uniform(20, 90, 40), 1000) + 0.5 * rng.normal(size=40000),
+    }
+    worst = 0.0
+    for name, x in cases.items():
+        ctx.upload_events_f64([x])
+        ctx.statsplit(100, 1000000, 10000, oracle.min_gain())
+        for ps, pe in ((0, 10000), (12345, 22345), (30000, 40000), (100, 700), (20000, 20250)):
+            hs, he, ok, eps = ctx.debug_screen(0, ps, pe, 100)
+            fin = ok & np.isfinite(he)
+            assert np.all(np.isfinite(he[ok])), name                               # valid => exact value finite
+            if fin.any():
+                err = np.max(np.abs(hs[fin] - he[fin]))
+                worst = max(worst, err / eps)
+                assert err <= eps, (name, ps, pe, err, eps)
+        if name == "offset":
+            assert not ok.any()
+        if name in ("tierA", "tierB", "steps"):
+            assert ok.all()
+    assert worst < 0.5      # the bound is conservative
+    # production path on the same awkward data stays bit-exact
+    check_split_f64(ctx, [cases["lownoise"], cases["offset"][:9000], cases["smooth"][:9000]],
+                    prior_segments_per_second=10)
+    check_split_f64(ctx, [cases["lownoise"][:9000], cases["steps"][:9500]])
 
 
 def test_host_selected_events_path(ctx):
