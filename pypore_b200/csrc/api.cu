@@ -247,6 +247,54 @@ int enqueue_select(pp_ctx *ctx, int rule_mask, int64_t duration_gt, int64_t dura
     return PP_OK;
 }
 
+template <int NZ>
+void launch_filter_pass(pp_ctx *ctx, const PPSource &src, int backward)
+{
+    cudaFuncSetAttribute(k5_filter_pass<NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)k5_smem_bytes<NZ>());
+    k5_filter_pass<NZ><<<ctx->sm_count * 4, K5_THREADS, k5_smem_bytes<NZ>(), ctx->stream>>>(
+        src, (const int64_t *)ctx->ev_len.p, ctx->ctr, (const K5Coef *)ctx->filt_coef.p,
+        (double *)ctx->filt_tmp.p, (double *)ctx->flat64.p, backward);
+}
+
+int enqueue_filter(pp_ctx *ctx, const double *b, const double *a, const double *zi, int nc)
+{
+    if (nc < 2 || nc > FILT_MAX_COEF) return fail(ctx, PP_ERR_ARG, "filter order must be 1..%d", FILT_NZ);
+    if (a[0] != 1.0) return fail(ctx, PP_ERR_ARG, "filter coefficients must be normalised (a[0] == 1)");
+    const int64_t ncap = ctx->flat_cap;
+    if (ncap <= 0) return fail(ctx, PP_ERR_STATE, "no events selected");
+    const int P = 3 * nc;
+    int64_t max_events = ncap / (P + 1) + 1;
+    if (ctx->n_events >= 0 && ctx->n_events < max_events) max_events = ctx->n_events;
+    if (ctx->cap_events < max_events) max_events = ctx->cap_events;
+    CKR(ensure(ctx, ctx->filt_tmp, sizeof(double) * (size_t)(ncap + 2 * P * max_events + 64)));
+    CKR(ensure(ctx, ctx->flat64, sizeof(double) * (size_t)ncap));
+    CKR(ensure(ctx, ctx->filt_coef, sizeof(K5Coef)));
+    K5Coef C;
+    k5_prepare(b, a, zi, nc, &C);
+    CK(cudaMemcpyAsync(ctx->filt_coef.p, &C, sizeof C, cudaMemcpyHostToDevice, ctx->stream));
+    for (int backward = 0; backward < 2; ++backward) {
+        PPSource src = make_source(ctx);
+        switch (nc - 1) {
+        case 1: launch_filter_pass<1>(ctx, src, backward); break;
+        case 2: launch_filter_pass<2>(ctx, src, backward); break;
+        case 3: launch_filter_pass<3>(ctx, src, backward); break;
+        case 4: launch_filter_pass<4>(ctx, src, backward); break;
+        case 5: launch_filter_pass<5>(ctx, src, backward); break;
+        case 6: launch_filter_pass<6>(ctx, src, backward); break;
+        case 7: launch_filter_pass<7>(ctx, src, backward); break;
+        default: launch_filter_pass<8>(ctx, src, backward); break;
+        }
+        LAUNCHED(ctx);
+    }
+    ctx->src_kind = 1;  // from here on the events' current is the filtered float64 signal
+    CKR(record_boundary(ctx, ST_FILTER + 1));
+    ctx->stage_ran[ST_FILTER] = true;
+    ctx->n_segments = -1;
+    ctx->stats_valid = false;
+    return PP_OK;
+}
+
 int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefix_mode)
 {
     if (mw < 0 || MW < mw || W < 2 * mw || W / 2 < 1)
@@ -714,9 +762,13 @@ int pp_filter_events(pp_ctx *ctx, const double *b, const double *a, const double
 {
     if (!ctx || !b || !a || ncoef < 2 || ncoef > FILT_MAX_COEF || (ncoef > 1 && !zi))
         return fail(ctx, PP_ERR_ARG, "bad filter coefficients");
-    if (ctx->n_events < 0 && ctx->flat_cap <= 0) return fail(ctx, PP_ERR_STATE, "no event table");
+    if (ctx->n_events < 0) return fail(ctx, PP_ERR_STATE, "no event table");
     CKR(set_device(ctx));
-    return fail(ctx, PP_ERR_STATE, "filter stage not built yet");
+    reset_stages(ctx);
+    CKR(record_boundary(ctx, ST_FILTER));
+    CKR(enqueue_filter(ctx, b, a, zi, ncoef));
+    CKR(fetch_counters(ctx));
+    return check_overflow(ctx);
 }
 
 int pp_event_samples_download(pp_ctx *ctx, int64_t cap, double *out)
@@ -878,7 +930,7 @@ int pp_pipeline(pp_ctx *ctx, const pp_pipeline_params *p, int64_t out[4])
         CKR(record_boundary(ctx, ST_SELECT + 1));
         ctx->stage_ran[ST_SELECT] = true;
         if (p->filter_ncoef > 0)
-            return fail(ctx, PP_ERR_STATE, "filter stage not built yet");
+            CKR(enqueue_filter(ctx, p->filter_b, p->filter_a, p->filter_zi, p->filter_ncoef));
         CKR(enqueue_split(ctx, p->min_width, p->max_width, p->window_width, p->min_gain, p->prefix_mode));
         if (p->with_stats) CKR(enqueue_stats(ctx));
         CKR(fetch_counters(ctx));

@@ -20,7 +20,7 @@
 //   SCREEN  every candidate i gets H~(i) ~= low(i) + high(i) from a division-free
 //           formulation  n1*log(D1) + n2*log(D2) - T[n1] - T[n2],
 //           D = Q*n - S*S = n^2 * V,  T[n] = 2 n ln n  (table), with a table-driven
-//           fp64 log (|err| < 1e-14).  For candidates that pass the validity test
+//           fp64 log (|err| < 1e-11).  For candidates that pass the validity test
 //           (variance not smaller than 2^-24 of the mean square) the distance to
 //           the reference's own rounded value is rigorously bounded by
 //           eps = n_window * 3e-8 + 1e-6  (derivation in DESIGN.md).
@@ -75,7 +75,7 @@ struct K3Shared {
     int req_k[K3_REQ];
     int req_i[K3_REQ];
     double req_g[K3_REQ];
-    double2 logtab[128];
+    double2 logtab[256];
     double red_g[K3_WARPS];
     double red_b[K3_WARPS];
     int red_x[K3_WARPS];
@@ -191,47 +191,53 @@ __device__ __forceinline__ K3Best k3_cta_reduce(K3Best b, K3Shared &S)
 // ---------------------------------------------------------------------------
 // screening path
 // ---------------------------------------------------------------------------
-// ln(x) for positive, normal, finite x: exponent + 7-bit table + degree-5 series.
-// |error| <= 6e-16 (truncation, |r| <= 2^-8) + a few ulp of the result.
+// ln(x) for positive, normal, finite x: exponent + 8-bit table + degree-3 series.
+// |r| <= 2^-9, truncation r^4/4 <= 3.6e-12, rounding a few ulp of the result.
 __device__ __forceinline__ double k3_fastlog(double x, const double2 *tab)
 {
     const int hi = __double2hiint(x), lo = __double2loint(x);
-    const int e = (hi >> 20) - 1023;
-    const int k = (hi >> 13) & 127;
+    const int k = (hi >> 12) & 255;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    // (double)(exponent) without an I2F: 2^52 + 2^31 + (e ^ 2^31) as bits, minus the magic
+    const double ed = __hiloint2double(0x43300000, ((hi >> 20) - 1023) ^ 0x80000000) - 4503601774854144.0;
     const double2 t = tab[k];
     const double r = fma(m, t.x, -1.0);
-    double p = fma(r, 0.2, -0.25);
-    p = fma(r, p, 1.0 / 3.0);
-    p = fma(r, p, -0.5);
+    double p = fma(r, 1.0 / 3.0, -0.5);
     p = fma(r, p, 1.0);
     p = p * r;
-    return fma((double)e, 0.6931471805599453094, t.y + p);
+    return fma(ed, 0.6931471805599453094, t.y + p);
+}
+
+// positive, finite and comfortably normal: 2^-900 <= d < 2^900
+__device__ __forceinline__ bool k3_sane(double d)
+{
+    return (unsigned)(__double2hiint(d) - 0x07b00000) < 0x70800000u;
 }
 
 // H~(i) and its validity (see file header).  S and Q are the same fp64
 // differences the exact path forms, so both paths start from identical values.
+// n1 = i - ps and n2 = pe - i arrive as doubles (exact small integers).
 template <class CC>
 __device__ __forceinline__ bool k3_screen_eval(const CC &cc, const double2 lo, const double2 hi, int ps,
-                                               int pe, int i, const double *__restrict__ T,
-                                               const double2 *tab, double &H)
+                                               int pe, int i, double n1, double n2,
+                                               const double *__restrict__ T, const double2 *tab, double &H)
 {
     const double2 mid = cc.at(i - 1);
-    const int c1 = i - ps, c2 = pe - i;
-    const double n1 = (double)c1, n2 = (double)c2;
+    const double t12 = __ldg(T + (i - ps)) + __ldg(T + (pe - i));
     const double S1 = __dsub_rn(mid.x, lo.x), Q1 = __dsub_rn(mid.y, lo.y);
     const double S2 = __dsub_rn(hi.x, mid.x), Q2 = __dsub_rn(hi.y, mid.y);
     const double P1 = __dmul_rn(Q1, n1), SQ1 = __dmul_rn(S1, S1), D1 = __dsub_rn(P1, SQ1);
     const double P2 = __dmul_rn(Q2, n2), SQ2 = __dmul_rn(S2, S2), D2 = __dsub_rn(P2, SQ2);
-    const double M1 = fmax(fabs(P1), SQ1), M2 = fmax(fabs(P2), SQ2);
-    bool ok = (c1 > 0) & (c2 > 0);
-    ok = ok & (D1 >= K3_TINY) & (D1 <= K3_HUGE) & (M1 <= K3_RATIO_MAX * D1);
-    ok = ok & (D2 >= K3_TINY) & (D2 <= K3_HUGE) & (M2 <= K3_RATIO_MAX * D2);
+    const double R1 = K3_RATIO_MAX * D1, R2 = K3_RATIO_MAX * D2;
+    // max(|P|, SQ) <= R * D, written as two comparisons (false on NaN)
+    bool ok = k3_sane(D1) & k3_sane(D2);
+    ok = ok & (fabs(P1) <= R1) & (SQ1 <= R1) & (fabs(P2) <= R2) & (SQ2 <= R2);
     const double L1 = k3_fastlog(D1, tab), L2 = k3_fastlog(D2, tab);
-    H = fma(n1, L1, n2 * L2) - (__ldg(T + c1) + __ldg(T + c2));
-    return ok & (fabs(H) <= K3_HUGE);
+    H = fma(n1, L1, n2 * L2) - t12;
+    return ok;
 }
 
+// Screen candidates ps+mw+first, +stride, ...  (requires mw >= 1 so that n1, n2 >= 1)
 template <class CC>
 __device__ __forceinline__ K3Approx k3_screen_range(const CC &cc, const double2 lo, const double2 hi,
                                                     int ps, int pe, int mw, int first, int stride,
@@ -242,12 +248,18 @@ __device__ __forceinline__ K3Approx k3_screen_range(const CC &cc, const double2 
     a.i1 = -1;
     a.bad = 0;
     const int last = pe - mw;
+    const double dstride = (double)stride;
+    double n1 = (double)(mw + first), n2 = (double)(pe - ps - mw - first);
     for (int i = ps + mw + first; i <= last; i += stride) {
         double H;
-        const bool ok = k3_screen_eval(cc, lo, hi, ps, pe, i, T, tab, H);
+        const bool ok = k3_screen_eval(cc, lo, hi, ps, pe, i, n1, n2, T, tab, H);
+        n1 += dstride;
+        n2 -= dstride;
         if (!ok) a.bad = 1;
-        else if (H < a.b1) { a.b2 = a.b1; a.b1 = H; a.i1 = i; }
-        else if (H < a.b2) a.b2 = H;
+        else if (H < a.b2) {  // uncommon after the first few candidates
+            if (H < a.b1) { a.b2 = a.b1; a.b1 = H; a.i1 = i; }
+            else a.b2 = H;
+        }
     }
     return a;
 }
@@ -275,7 +287,7 @@ __device__ __forceinline__ void k3_screen_select(const CC &cc, const double2 lo,
         const int last = pe - mw;
         for (int i = ps + mw + first; i <= last; i += stride) {
             double H;
-            const bool ok = k3_screen_eval(cc, lo, hi, ps, pe, i, T, tab, H);
+            const bool ok = k3_screen_eval(cc, lo, hi, ps, pe, i, (double)(i - ps), (double)(pe - i), T, tab, H);
             if (!ok || H <= thr) f(i);
         }
     } else if (a.i1 >= 0 && a.b1 <= thr) {
@@ -294,7 +306,7 @@ __device__ __forceinline__ K3Best k3_cta_scan(const CC &cc, int ps, int pe, cons
     b.x = -1;
     const double2 lo = cc.at(ps - 1), hi = cc.at(pe - 1);
     const double tot = k3_exact_tot(lo, hi, ps, pe);
-    if (!G.screen || !(fabs(tot) <= K3_HUGE)) {
+    if (!G.screen || P.mw < 1 || !(fabs(tot) <= K3_HUGE)) {
         b = k3_scan_range(cc, ps, pe, P.mw, P.min_gain, tid, K3_THREADS);
         return k3_cta_reduce(b, S);
     }
@@ -410,9 +422,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mw = P.mw, MW = P.MW, W = P.W;
 
-    if (tid < 128) {
+    if (tid < 256) {
         // fast-log table: centre of mantissa bucket k, its reciprocal and its logarithm
-        const double c = 1.0 + ((double)tid + 0.5) / 128.0;
+        const double c = 1.0 + ((double)tid + 0.5) / 256.0;
         S.logtab[tid] = make_double2(1.0 / c, log(c));
     }
 
@@ -558,7 +570,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
                     S.best_key[k] = 0ull;
                     S.best_idx[k] = 0x7fffffff;
                 }
-                if (!G.screen) {
+                if (!G.screen || mw < 1) {
                     // validation mode: every candidate exactly
                     for (int bi = 0; bi < nbig; ++bi) {
                         const K3Item it = A[S.scanlist[bi]];
@@ -690,9 +702,9 @@ __global__ void __launch_bounds__(256)
 k3_debug_screen(K3Global G, int ev, int ps, int pe, int mw, double *h_screen, double *h_exact,
                 unsigned char *ok_out)
 {
-    __shared__ double2 tab[128];
-    if (threadIdx.x < 128) {
-        const double c = 1.0 + ((double)threadIdx.x + 0.5) / 128.0;
+    __shared__ double2 tab[256];
+    {
+        const double c = 1.0 + ((double)threadIdx.x + 0.5) / 256.0;
         tab[threadIdx.x] = make_double2(1.0 / c, log(c));
     }
     __syncthreads();
@@ -703,7 +715,7 @@ k3_debug_screen(K3Global G, int ev, int ps, int pe, int mw, double *h_screen, do
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const int i = ps + mw + j;
         double H;
-        const bool ok = k3_screen_eval(cc, lo, hi, ps, pe, i, G.T, tab, H);
+        const bool ok = k3_screen_eval(cc, lo, hi, ps, pe, i, (double)(i - ps), (double)(pe - i), G.T, tab, H);
         const double2 mid = cc.at(i - 1);
         const double low = __dmul_rn((double)(i - ps), log(k3_var(mid, lo, i - ps)));
         const double high = __dmul_rn((double)(pe - i), log(k3_var(hi, mid, pe - i)));

@@ -125,3 +125,30 @@ def test_error_behaviour_on_device_paths():
     assert ev.n == 1 and ev.segments[0].end == 50 / 1e5
     with pytest.raises(AttributeError):                    # no .file, like DataTypes.py:289
         Event(current=np.zeros(300), start=0, second=1e5).parse(parser=SpeedyStatSplit())
+
+
+def test_event_filter_then_parse_like_the_reference():
+    g = load_golden("filter_o1_250k.npz")
+    x = synth.make_trace(3, seed=int(g["seed"]), tier="A").astype(np.float64)
+    f = File(current=x, timestep=1000. / float(g["fs"]))
+    f.parse(parser=lambda_event_parser(threshold=110, rules=RULES_1000))
+    p = SpeedyStatSplit(min_width=100, window_width=10000, sampling_freq=float(g["fs"]), cutoff_freq=2000.,
+                        prior_segments_per_second=10)
+    for i, event in enumerate(f.events[:2]):
+        event.filter(order=1, cutoff=2000.)
+        assert event.filtered and event.filter_order == 1 and event.filter_cutoff == 2000.
+        assert event.current.dtype == np.float64
+        ref = g["event%d_filtered" % i]
+        assert np.max(np.abs(event.current - ref) / np.abs(ref)) < 1e-5
+        event.parse(parser=p)
+        assert [round(s.start * f.second) for s in event.segments] == list(g["event%d_seg_start" % i])
+    with pytest.raises(ValueError, match="padlen"):
+        Event(current=np.zeros(6), start=0, second=1e5, file=f).filter()
+    # whole-file device-resident variant
+    f2 = File(current=x, timestep=1000. / float(g["fs"]))
+    f2.parse(parser=lambda_event_parser(threshold=110, rules=RuleSet(duration_gt=1000, min_gt=-0.5, max_lt=110)),
+             segmenter=p, filter_params=(1, 2000.))
+    ev = f2.events[1]
+    assert ev.filtered and np.max(np.abs(ev.current - g["event1_filtered"]) / np.abs(g["event1_filtered"])) < 1e-5
+    sel = f2.segment_table["event"] == 1
+    assert np.array_equal(f2.segment_table["start"][sel], g["event1_seg_start"])

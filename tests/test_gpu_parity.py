@@ -294,3 +294,93 @@ def test_host_selected_events_path(ctx):
     tab = ctx.segments(n)
     oe, ost, oen, _ = oracle.statsplit_events(x64, runs[0][keep], runs[1][keep], gain=gain)
     assert np.array_equal(tab["event"], oe) and np.array_equal(tab["start"], ost) and np.array_equal(tab["end"], oen)
+
+
+# ---------------------------------------------------------------- K5 filter
+FILTER_RTOL = 1e-5   # BASELINE.json north_star: filtered current within 1e-5 relative
+
+
+@pytest.mark.parametrize("name", ["filter_o1_100k.npz", "filter_o1_250k.npz", "filter_o2_100k.npz",
+                                  "filter_o4_100k.npz"])
+def test_filter_matches_scipy_fixture(ctx, name):
+    """Event.filter arithmetic against what the reference (scipy.signal.filtfilt) produced."""
+    from pypore_b200.DataTypes import bessel_coefficients
+    g = load_golden(name)
+    x = synth.make_trace(3, seed=int(g["seed"]), tier="A").astype(np.float64)
+    start, length = oracle.events(x, 110, RULES_1000)
+    b, a, zi = bessel_coefficients(int(g["order"]), float(g["cutoff"]), float(g["fs"]))
+    evs = [x[start[i]:start[i] + length[i]] for i in range(2)]
+    ctx.upload_events_f64(evs)
+    ctx.filter_events(b, a, zi)
+    y = ctx.event_samples(int(length[:2].sum()))
+    ref = np.concatenate([g["event0_filtered"], g["event1_filtered"]])
+    err = np.max(np.abs(y - ref) / np.abs(ref))
+    assert err < FILTER_RTOL, err
+    assert err < 1e-10          # in practice the scan agrees with scipy to rounding
+    # segmentation of the filtered events (float64 path) equals the reference's on its own filtered signal
+    kw = dict(min_width=100, window_width=10000, sampling_freq=float(g["fs"]), cutoff_freq=float(g["cutoff"]),
+              prior_segments_per_second=10)
+    n = ctx.statsplit(100, 1000000, 10000, oracle.min_gain(**kw))
+    ctx.segment_stats()
+    tab = ctx.segments(n)
+    for i in range(2):
+        sel = tab["event"] == i
+        assert np.array_equal(tab["start"][sel], g["event%d_seg_start" % i])
+        assert np.array_equal(tab["end"][sel], g["event%d_seg_end" % i])
+        assert rel_err(tab["mean"][sel], g["event%d_seg_mean" % i]) < 1e-9
+        assert rel_err(tab["std"][sel], g["event%d_seg_std" % i]) < 1e-7   # std of a 1e-15-perturbed signal
+
+
+def test_filter_edge_lengths_and_orders(ctx):
+    from pypore_b200.DataTypes import bessel_coefficients
+    rng = np.random.RandomState(3)
+    for order, fs in ((1, 1e5), (3, 2.5e5), (8, 1e5)):
+        b, a, zi = bessel_coefficients(order, 2000., fs)
+        pad = 3 * (order + 1)
+        lens = [pad + 1, pad + 2, 100, 4095, 4096 - 2 * pad, 4097, 8192, 20011]
+        evs = [60 + rng.normal(0, 2, n) for n in lens]
+        ctx.upload_events_f64(evs)
+        ctx.filter_events(b, a, zi)
+        y = ctx.event_samples(sum(lens))
+        k = 0
+        for e in evs:
+            ref = oracle.filtfilt(b, a, e)
+            got = y[k:k + len(e)]
+            assert np.max(np.abs(got - ref) / np.abs(ref)) < FILTER_RTOL
+            k += len(e)
+        # not longer than padlen: scipy raises ValueError
+        ctx.upload_events_f64([evs[2], evs[0][:pad]])
+        with pytest.raises(ValueError, match="padlen"):
+            ctx.filter_events(b, a, zi)
+
+
+def test_filtered_pipeline_on_float32_trace(ctx):
+    """BASELINE config 5 shape: threshold -> Event.filter(1, 2000) -> SpeedyStatSplit, device resident."""
+    from pypore_b200.DataTypes import bessel_coefficients
+    fs = 2.5e5
+    x = synth.make_trace(40, seed=1000, tier="A")
+    x64 = x.astype(np.float64)
+    ctx.upload_trace(x)
+    b, a, zi = bessel_coefficients(1, 2000., fs)
+    kw = dict(min_width=100, window_width=10000, sampling_freq=fs, cutoff_freq=2000., prior_segments_per_second=10)
+    r = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, oracle.min_gain(**kw),
+                     filter_ba=(b, a, zi))
+    ws, wl = oracle.events(x64, 110, RULES_1000)
+    es, el = ctx.events(r["events"])
+    assert np.array_equal(es, ws) and np.array_equal(el, wl)
+    y = ctx.event_samples(r["event_samples"])
+    tab = ctx.segments(r["segments"])
+    off = np.concatenate(([0], np.cumsum(wl)))
+    flips = 0
+    for e in range(len(ws)):
+        ref = oracle.filtfilt(b, a, x64[ws[e]:ws[e] + wl[e]])
+        got = y[off[e]:off[e + 1]]
+        assert np.max(np.abs(got - ref) / np.abs(ref)) < FILTER_RTOL
+        sel = tab["event"] == e
+        # bit-exact against the oracle run on the very samples the device segmented
+        assert np.array_equal(tab["start"][sel][1:], oracle.statsplit(got, **kw))
+        m, s, mn, mx = oracle.segment_stats(got, tab["start"][sel], tab["end"][sel])
+        assert rel_err(tab["mean"][sel], m) < STAT_RTOL and rel_err(tab["std"][sel], s) < STAT_RTOL
+        assert np.array_equal(tab["min"][sel], mn) and np.array_equal(tab["max"][sel], mx)
+        flips += not np.array_equal(tab["start"][sel][1:], oracle.statsplit(ref, **kw))
+    assert flips == 0   # and the scipy-filtered signal segments identically on this suite
