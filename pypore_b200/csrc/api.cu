@@ -248,6 +248,14 @@ int enqueue_select(pp_ctx *ctx, int rule_mask, int64_t duration_gt, int64_t dura
 }
 
 template <int NZ>
+void launch_filter_sequential(pp_ctx *ctx, const PPSource &src, int backward)
+{
+    k5_filter_sequential<NZ><<<ctx->sm_count * 8, 64, 0, ctx->stream>>>(
+        src, (const int64_t *)ctx->ev_len.p, ctx->ctr, (const K5Coef *)ctx->filt_coef.p,
+        (double *)ctx->filt_tmp.p, (double *)ctx->flat64.p, backward);
+}
+
+template <int NZ>
 void launch_filter_pass(pp_ctx *ctx, const PPSource &src, int backward)
 {
     cudaFuncSetAttribute(k5_filter_pass<NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -279,11 +287,11 @@ int enqueue_filter(pp_ctx *ctx, const double *b, const double *a, const double *
         case 1: launch_filter_pass<1>(ctx, src, backward); break;
         case 2: launch_filter_pass<2>(ctx, src, backward); break;
         case 3: launch_filter_pass<3>(ctx, src, backward); break;
-        case 4: launch_filter_pass<4>(ctx, src, backward); break;
-        case 5: launch_filter_pass<5>(ctx, src, backward); break;
-        case 6: launch_filter_pass<6>(ctx, src, backward); break;
-        case 7: launch_filter_pass<7>(ctx, src, backward); break;
-        default: launch_filter_pass<8>(ctx, src, backward); break;
+        case 4: launch_filter_sequential<4>(ctx, src, backward); break;
+        case 5: launch_filter_sequential<5>(ctx, src, backward); break;
+        case 6: launch_filter_sequential<6>(ctx, src, backward); break;
+        case 7: launch_filter_sequential<7>(ctx, src, backward); break;
+        default: launch_filter_sequential<8>(ctx, src, backward); break;
         }
         LAUNCHED(ctx);
     }

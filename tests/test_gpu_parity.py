@@ -334,7 +334,7 @@ def test_filter_matches_scipy_fixture(ctx, name):
 def test_filter_edge_lengths_and_orders(ctx):
     from pypore_b200.DataTypes import bessel_coefficients
     rng = np.random.RandomState(3)
-    for order, fs in ((1, 1e5), (3, 2.5e5), (8, 1e5)):
+    for order, fs in ((1, 1e5), (2, 1e5), (3, 2.5e5), (4, 1e5), (6, 1e5), (8, 1e5)):
         b, a, zi = bessel_coefficients(order, 2000., fs)
         pad = 3 * (order + 1)
         lens = [pad + 1, pad + 2, 100, 4095, 4096 - 2 * pad, 4097, 8192, 20011]
@@ -346,7 +346,11 @@ def test_filter_edge_lengths_and_orders(ctx):
         for e in evs:
             ref = oracle.filtfilt(b, a, e)
             got = y[k:k + len(e)]
-            assert np.max(np.abs(got - ref) / np.abs(ref)) < FILTER_RTOL
+            err = np.max(np.abs(got - ref) / np.abs(ref))
+            assert err < FILTER_RTOL, (order, len(e), err)
+            # orders 1-3: parallel scan (rounding differs from the sequential order, measured <= 2e-9);
+            # orders 4-8: scipy's own operation order, bit-identical to the oracle
+            assert err < (1e-8 if order <= 3 else 1e-15), (order, len(e), err)
             k += len(e)
         # not longer than padlen: scipy raises ValueError
         ctx.upload_events_f64([evs[2], evs[0][:pad]])
