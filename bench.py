@@ -286,13 +286,13 @@ def run_ours(args):
     ms, res = timed(step_resident, args.steps)
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
-    stage = ctx.stage_ms()
+    stage = ctx.stage_ms() if shard is None else dict(shard.stage_ms)
     counters = ctx.split_counters()
     # split-kernel duration averaged over a few more steps (CUDA events inside the library, on the launch stream)
     split_ms = []
     for _ in range(min(args.steps, 5)):
         step_resident()
-        split_ms.append(ctx.stage_ms()["split"])
+        split_ms.append(ctx.stage_ms()["split"] if shard is None else shard.stage_ms["split"])
     split_ms = float(np.mean(split_ms))
 
     for _ in range(2):

@@ -202,6 +202,7 @@ class ShardedPipeline(object):
         self.n_owned = 0
         self.offsets = None
         self.tables = None
+        self.stage_ms = {}
 
     def load(self, host_chunk):
         self.ctx.upload_trace_async(host_chunk, extra_capacity=self.HALO_CAPACITY)
@@ -235,6 +236,7 @@ class ShardedPipeline(object):
             ne += 1
             ns += plan["event"][1]
         n_seg = ctx.statsplit(mw, MW, W, gain)
+        self.stage_ms = ctx.stage_ms()   # prefix / split / compact of this step (the next call resets them)
         ctx.segment_stats()
         self.n_owned = self.n_local
         self._gather(ne, n_seg)
