@@ -57,7 +57,8 @@ struct pp_ctx {
     int64_t flat_cap = 0;  // capacity in samples of flat event space for the current source
 
     // K2/K3
-    DevBuf cc, bits, tasks, ready, block_count, block_off, inexact, Ttab;
+    DevBuf cc, bits, tasks, ready, block_count, block_off, inexact, Ttab, ev_tile_off, k2_bits, k2_tiles;
+    int k2_epoch = 0;
     int T_len = 0;
     int opt_screen = 1;
     int64_t q_cap = 0;
@@ -336,10 +337,46 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
     PPSource src = make_source(ctx);
 
     // K2: prefix sums
-    (void)prefix_mode;  // tiled scan with exactness proof is a follow-up; strict order for now
-    k2_prefix_sequential<<<ctx->sm_count * 16, 32, 0, ctx->stream>>>(
-        src, (const int64_t *)ctx->ev_len.p, ctx->ctr, nullptr, (double2 *)ctx->cc.p);
-    LAUNCHED(ctx);
+    if (prefix_mode == PP_PREFIX_SEQUENTIAL) {
+        k2_prefix_sequential<<<ctx->sm_count * 16, 32, 0, ctx->stream>>>(
+            src, (const int64_t *)ctx->ev_len.p, ctx->ctr, nullptr, (double2 *)ctx->cc.p);
+        LAUNCHED(ctx);
+    } else {
+        const int64_t max_tiles = ncap / K2_TILE + ctx->cap_events + 2;
+        CKR(ensure(ctx, ctx->ev_tile_off, sizeof(int64_t) * (ctx->cap_events + 2)));
+        CKR(ensure(ctx, ctx->k2_bits, sizeof(K2EventBits) * (ctx->cap_events + 1)));
+        CKR(ensure(ctx, ctx->inexact, sizeof(unsigned) * (ctx->cap_events + 1)));
+        if (sizeof(K2TileState) * (size_t)max_tiles > ctx->k2_tiles.cap) {
+            CKR(ensure(ctx, ctx->k2_tiles, sizeof(K2TileState) * (size_t)max_tiles));
+            CK(cudaMemsetAsync(ctx->k2_tiles.p, 0, ctx->k2_tiles.cap, ctx->stream));
+            ctx->k2_epoch = 0;
+        }
+        const int epoch = ++ctx->k2_epoch;  // stale tile states of earlier launches are recognised by epoch
+        k2_tile_offsets<<<1, 1024, 0, ctx->stream>>>(ctx->ctr, (const int64_t *)ctx->ev_len.p,
+                                                     (int64_t *)ctx->ev_tile_off.p, (K2EventBits *)ctx->k2_bits.p,
+                                                     (unsigned *)ctx->inexact.p);
+        LAUNCHED(ctx);
+        if (ctx->src_kind == 0)
+            k2_prefix_tiled<float><<<ctx->sm_count * 8, K2_THREADS, 0, ctx->stream>>>(
+                src, ctx->trace, (const int64_t *)ctx->ev_len.p, (const int64_t *)ctx->ev_tile_off.p, ctx->ctr,
+                (K2TileState *)ctx->k2_tiles.p, (K2EventBits *)ctx->k2_bits.p, (double2 *)ctx->cc.p, epoch);
+        else
+            k2_prefix_tiled<double><<<ctx->sm_count * 8, K2_THREADS, 0, ctx->stream>>>(
+                src, (const double *)ctx->flat64.p, (const int64_t *)ctx->ev_len.p,
+                (const int64_t *)ctx->ev_tile_off.p, ctx->ctr, (K2TileState *)ctx->k2_tiles.p,
+                (K2EventBits *)ctx->k2_bits.p, (double2 *)ctx->cc.p, epoch);
+        LAUNCHED(ctx);
+        if (prefix_mode != PP_PREFIX_PARALLEL) {
+            k2_check_exact<<<ctx->sm_count, 256, 0, ctx->stream>>>(ctx->ctr, (const int64_t *)ctx->ev_len.p,
+                                                                  (const K2EventBits *)ctx->k2_bits.p,
+                                                                  (unsigned *)ctx->inexact.p);
+            LAUNCHED(ctx);
+            k2_prefix_sequential<<<ctx->sm_count * 16, 32, 0, ctx->stream>>>(
+                src, (const int64_t *)ctx->ev_len.p, ctx->ctr, (const unsigned *)ctx->inexact.p,
+                (double2 *)ctx->cc.p);
+            LAUNCHED(ctx);
+        }
+    }
     CKR(record_boundary(ctx, ST_PREFIX + 1));
     ctx->stage_ran[ST_PREFIX] = true;
 
@@ -493,7 +530,7 @@ void pp_destroy(pp_ctx *ctx)
     DevBuf *bufs[] = {&ctx->trace_buf, &ctx->tile_state, &ctx->run_start, &ctx->run_minkey,
                       &ctx->run_maxkey, &ctx->run_len, &ctx->run_min, &ctx->run_max, &ctx->run_below,
                       &ctx->ev_start, &ctx->ev_len, &ctx->ev_off, &ctx->flat64, &ctx->cc, &ctx->bits,
-                      &ctx->tasks, &ctx->ready, &ctx->block_count, &ctx->block_off, &ctx->inexact, &ctx->Ttab,
+                      &ctx->tasks, &ctx->ready, &ctx->block_count, &ctx->block_off, &ctx->inexact, &ctx->Ttab, &ctx->ev_tile_off, &ctx->k2_bits, &ctx->k2_tiles,
                       &ctx->seg_flat, &ctx->seg_event, &ctx->seg_start, &ctx->seg_end, &ctx->seg_mean,
                       &ctx->seg_std, &ctx->seg_min, &ctx->seg_max, &ctx->evs_mean, &ctx->evs_std,
                       &ctx->evs_min, &ctx->evs_max, &ctx->filt_tmp, &ctx->filt_carry, &ctx->filt_coef};

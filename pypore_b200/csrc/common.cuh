@@ -29,6 +29,7 @@ struct PPCounters {
     unsigned long long n_exact;       // exact (reference-arithmetic) candidate evaluations
     unsigned long long n_seq_redo;    // events whose prefix sums were redone sequentially
     unsigned long long scan_ticket;   // prefix-scan dynamic tile id
+    unsigned long long n_scan_tiles;  // prefix-scan tiles over all events
     unsigned int overflow;            // bit0 runs, bit1 queue, bit2 segments, bit3 filter-too-short
     unsigned int first_below;         // below-threshold bit of sample 0
 };

@@ -244,6 +244,40 @@ def test_pipeline_c2_size_properties(ctx):
         assert np.array_equal(tab["start"][sel][1:], bp)
 
 
+def test_prefix_modes_agree_and_exactness_proof(ctx):
+    """PP_PREFIX_AUTO = tiled scan + exactness proof + sequential redo of unproven events.  ADC-quantised
+    data is proven exact (no redo); raw float32 data has inexact sums of squares (every event redone);
+    both give the tables of the strict np.cumsum order."""
+    from pypore_b200 import _lib
+    gain = oracle.min_gain(prior_segments_per_second=10)
+    for tier, expect_redo in (("A", 0), ("B", None)):
+        x = synth.make_trace(30, seed=77, tier=tier)
+        ctx.upload_trace(x)
+        ctx.threshold_scan(110.0)
+        ne, _ = ctx.select_events(7, 1000, 0, -0.5, 110.0)
+        tabs = {}
+        for mode in (_lib.PREFIX_SEQUENTIAL, _lib.PREFIX_AUTO):
+            n = ctx.statsplit(100, 1000000, 10000, gain, prefix_mode=mode)
+            ctx.segment_stats()
+            tabs[mode] = ctx.segments(n)
+            if mode == _lib.PREFIX_AUTO:
+                redo = ctx.split_counters()["seq_redo"]
+                assert redo == (ne if expect_redo is None else expect_redo), (tier, redo, ne)
+        a, b = tabs[_lib.PREFIX_SEQUENTIAL], tabs[_lib.PREFIX_AUTO]
+        assert all(np.array_equal(a[k], b[k]) for k in a)
+    # mixed: exact and inexact events in one batch, a long event spanning many tiles, NaN / inf samples
+    rng = np.random.RandomState(2)
+    arrays = [synth.make_long_event(50000, seed=5, tier="A").astype(np.float64),
+              synth.make_long_event(9000, seed=6, tier="B").astype(np.float64),
+              synth.quantise(rng.normal(60, 1, 2049)).astype(np.float64),
+              rng.normal(60, 1, 2047), np.r_[rng.normal(60, 1, 300), np.nan, rng.normal(60, 1, 300)],
+              synth.quantise(rng.normal(60, 1, 1)).astype(np.float64)]
+    ctx.upload_events_f64(arrays)
+    n = ctx.statsplit(100, 1000000, 10000, gain, prefix_mode=_lib.PREFIX_AUTO)
+    assert ctx.split_counters()["seq_redo"] == 3
+    check_split_f64(ctx, arrays[:4] + arrays[5:], prior_segments_per_second=10)
+
+
 def test_screening_error_bound_holds(ctx):
     """The screened value of every valid candidate lies within the eps the kernel assumes of the
     reference-arithmetic value (DESIGN.md derivation), on raw, quantised, filtered-like and low-noise data."""
