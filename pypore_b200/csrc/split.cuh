@@ -39,9 +39,10 @@ constexpr int K3_THREADS = 512;
 constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int K3_CAP = 10240;   // samples of one interval staged in shared memory
 constexpr int K3_LIST = 512;    // items per level list
-constexpr int K3_REQ = 1024;    // exact-evaluation requests per level
-constexpr int K3_BIG = 1024;    // candidates from which a window is scanned CTA-wide
-constexpr int K3_FULL_FLAG = 0x40000000;  // scanlist entry: request list overflowed, scan exactly
+constexpr int K3_REQ = 512;     // exact-evaluation requests per level
+constexpr int K3_CHUNKS = 1024; // 32-candidate chunks per level (<= K3_CAP/32 + K3_LIST)
+constexpr int K3_FULL_FLAG = 0x40000000;  // window entry: screening inconclusive / list overflow, scan exactly
+constexpr int K3_AMB_FLAG = (int)0x80000000;
 
 constexpr double K3_RATIO_MAX = 16777216.0;  // 2^24: validity bound on mean-square / variance
 constexpr double K3_EPS_PER_SAMPLE = 3e-8;   // > 10.03 * 2^-53 * 2^24 = 1.87e-8
@@ -69,9 +70,14 @@ struct K3Global {
 
 struct K3Shared {
     K3Item list[2][K3_LIST];
-    int scanlist[K3_LIST];
-    unsigned long long best_key[K3_LIST];
+    int win_item[K3_LIST];                 // scan window slot -> index into the level list (| K3_FULL_FLAG)
+    int win_chunk0[K3_LIST + 1];           // first chunk of the window (exclusive prefix of chunk counts)
+    unsigned long long win_gmin[K3_LIST];  // ordered key of the window's minimum screened value
+    unsigned long long best_key[K3_LIST];  // ordered key of the best exact gain (0 = none beats min_gain)
     int best_idx[K3_LIST];
+    double chunk_b1[K3_CHUNKS];            // best screened value of the chunk
+    int chunk_i1[K3_CHUNKS];               // its candidate index (| K3_AMB_FLAG: chunk needs the exact scan)
+    unsigned short chunk_slot[K3_CHUNKS];
     int req_k[K3_REQ];
     int req_i[K3_REQ];
     double req_g[K3_REQ];
@@ -79,7 +85,7 @@ struct K3Shared {
     double red_g[K3_WARPS];
     double red_b[K3_WARPS];
     int red_x[K3_WARPS];
-    int nA, nB, nbig, nsmall, nreq;
+    int nA, nB, nwin, nchunk, nreq;
     PPTask task;
     int have_task;
     unsigned long long cand, scans, exact;
@@ -274,6 +280,22 @@ __device__ __forceinline__ unsigned long long k3_okey(double g)
     return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000LL));
 }
 
+__device__ __forceinline__ double k3_okey_inv(unsigned long long k)
+{
+    const long long b = (long long)k;
+    return __longlong_as_double(b < 0 ? (b ^ (long long)0x8000000000000000LL) : ~b);
+}
+
+// warp-wide minimum of a 64-bit key with two 32-bit REDUX operations
+__device__ __forceinline__ unsigned long long k3_warp_min_u64(unsigned long long k)
+{
+    const unsigned hi = (unsigned)(k >> 32);
+    const unsigned mh = __reduce_min_sync(PP_FULL, hi);
+    const unsigned lo = hi == mh ? (unsigned)k : 0xffffffffu;
+    const unsigned ml = __reduce_min_sync(PP_FULL, lo);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
 // After the window's min H~ is known: which of this thread's candidates need the
 // exact evaluation?  f(i) is called for each.
 template <class CC, class F>
@@ -411,7 +433,7 @@ __device__ __forceinline__ void k3_request(K3Shared &S, int k, int i)
 {
     const int r = atomicAdd(&S.nreq, 1);
     if (r < K3_REQ) { S.req_k[r] = k; S.req_i[r] = i; }
-    else atomicOr(&S.scanlist[k], K3_FULL_FLAG);
+    else atomicOr(&S.win_item[k], K3_FULL_FLAG);
 }
 
 __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P)
@@ -534,7 +556,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
                 if (nA == 0) break;
                 K3Item *A = S.list[cur], *Bn = S.list[cur ^ 1];
                 __syncthreads();  // everyone has read nA
-                if (tid == 0) { S.nB = 0; S.nbig = 0; S.nsmall = 0; S.nreq = 0; }
+                if (tid == 0) { S.nB = 0; S.nwin = 0; S.nreq = 0; S.nchunk = 0; }
                 __syncthreads();
                 // step 1: the window-loop bookkeeping of _recursive_split per item
                 for (int t = tid; t < nA; t += K3_THREADS) {
@@ -553,94 +575,156 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
                         if (k3_worth(P, x, it.e)) k3_push_local(G, S, Bn, ev, x, it.e, x);
                     } else {
                         const int pe = k3_window_end(P, it);
-                        const int ncand = pe - it.ps - 2 * mw + 1;
                         if (pe - it.ps <= 2 * mw) {
                             k3_push_local(G, S, Bn, ev, it.s, it.e, k3_next_ps(P, it.ps, it.e));
-                        } else if (ncand >= K3_BIG) {
-                            S.scanlist[atomicAdd(&S.nbig, 1)] = t;
                         } else {
-                            S.scanlist[K3_LIST - 1 - atomicAdd(&S.nsmall, 1)] = t;
+                            const int slot = atomicAdd(&S.nwin, 1);
+                            S.win_item[slot] = t;
+                            S.win_chunk0[slot] = (pe - it.ps - 2 * mw + 1 + 31) >> 5;  // chunk count for now
+                            S.win_gmin[slot] = ~0ull;
+                            S.best_key[slot] = 0ull;
+                            S.best_idx[slot] = 0x7fffffff;
                         }
                     }
                 }
                 __syncthreads();
-                const int nbig = S.nbig, nsmall = S.nsmall;
-                // scan slot k: k < nbig are big windows, K3_LIST-1-j (j < nsmall) small ones
-                for (int k = tid; k < K3_LIST; k += K3_THREADS) {
-                    S.best_key[k] = 0ull;
-                    S.best_idx[k] = 0x7fffffff;
-                }
-                if (!G.screen || mw < 1) {
-                    // validation mode: every candidate exactly
-                    for (int bi = 0; bi < nbig; ++bi) {
-                        const K3Item it = A[S.scanlist[bi]];
-                        const int pe = k3_window_end(P, it);
-                        K3Best b = k3_scan_range(acc, it.ps, pe, mw, P.min_gain, tid, K3_THREADS);
-                        b = k3_cta_reduce(b, S);
-                        if (tid == 0) {
-                            atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
-                            atomicAdd(&S.scans, 1ull);
-                            k3_resolve_local(G, S, Bn, P, ev, off, it, b.x);
+                const int nwin = S.nwin;
+                const bool screen = G.screen && mw >= 1;
+                if (screen) {
+                    // exclusive prefix of the chunk counts (warp 0), in place
+                    if (warp == 0) {
+                        int carry = 0;
+                        for (int b0 = 0; b0 < nwin; b0 += 32) {
+                            const int v = b0 + lane < nwin ? S.win_chunk0[b0 + lane] : 0;
+                            int inc = v;
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                const int t = __shfl_up_sync(PP_FULL, inc, d);
+                                if (lane >= d) inc += t;
+                            }
+                            if (b0 + lane < nwin) S.win_chunk0[b0 + lane] = carry + inc - v;
+                            carry += __shfl_sync(PP_FULL, inc, 31);
                         }
-                    }
-                    for (int k = warp; k < nsmall; k += K3_WARPS) {
-                        const K3Item it = A[S.scanlist[K3_LIST - 1 - k]];
-                        const int pe = k3_window_end(P, it);
-                        K3Best b = k3_scan_range(acc, it.ps, pe, mw, P.min_gain, lane, 32);
-                        b = k3_warp_reduce(b);
-                        if (lane == 0) {
-                            atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
-                            atomicAdd(&S.scans, 1ull);
-                            k3_resolve_local(G, S, Bn, P, ev, off, it, b.x);
-                        }
-                    }
-                } else {
-                    // step 2a: SCREEN big windows, whole CTA each
-                    for (int bi = 0; bi < nbig; ++bi) {
-                        const K3Item it = A[S.scanlist[bi] & ~K3_FULL_FLAG];
-                        const int pe = k3_window_end(P, it);
-                        const double2 lo = acc.at(it.ps - 1), hi = acc.at(pe - 1);
-                        const K3Approx a = k3_screen_range(acc, lo, hi, it.ps, pe, mw, tid, K3_THREADS, G.T,
-                                                           S.logtab);
-                        double m = a.b1;
-#pragma unroll
-                        for (int d = 16; d > 0; d >>= 1) m = fmin(m, __shfl_xor_sync(PP_FULL, m, d));
-                        __syncthreads();
-                        if (lane == 0) S.red_b[warp] = m;
-                        __syncthreads();
-                        m = S.red_b[0];
-#pragma unroll
-                        for (int w = 1; w < K3_WARPS; ++w) m = fmin(m, S.red_b[w]);
-                        const double thr = m + 2.0 * k3_eps(pe - it.ps);
-                        k3_screen_select(acc, lo, hi, it.ps, pe, mw, tid, K3_THREADS, G.T, S.logtab, a, thr,
-                                         [&](int i) { k3_request(S, bi, i); });
-                    }
-                    // step 2b: SCREEN small windows, one warp each
-                    for (int k = warp; k < nsmall; k += K3_WARPS) {
-                        const int slot = K3_LIST - 1 - k;
-                        const K3Item it = A[S.scanlist[slot] & ~K3_FULL_FLAG];
-                        const int pe = k3_window_end(P, it);
-                        const double2 lo = acc.at(it.ps - 1), hi = acc.at(pe - 1);
-                        const K3Approx a = k3_screen_range(acc, lo, hi, it.ps, pe, mw, lane, 32, G.T, S.logtab);
-                        double m = a.b1;
-#pragma unroll
-                        for (int d = 16; d > 0; d >>= 1) m = fmin(m, __shfl_xor_sync(PP_FULL, m, d));
-                        const double thr = m + 2.0 * k3_eps(pe - it.ps);
-                        k3_screen_select(acc, lo, hi, it.ps, pe, mw, lane, 32, G.T, S.logtab, a, thr,
-                                         [&](int i) { k3_request(S, slot, i); });
+                        if (lane == 0) { S.win_chunk0[nwin] = carry; S.nchunk = carry; }
                     }
                     __syncthreads();
-                    // step 3: EXACT evaluation of the requested candidates, one per thread
-                    const int nreq = S.nreq < K3_REQ ? S.nreq : K3_REQ;
-                    for (int r = tid; r < nreq; r += K3_THREADS) {
-                        const int k = S.req_k[r], i = S.req_i[r];
-                        const K3Item it = A[S.scanlist[k] & ~K3_FULL_FLAG];
+                    const int nchunk = S.nchunk;
+                    // step 2: SCREEN -- all windows cut into 32-candidate chunks, spread evenly over the warps
+                    {
+                        const int per = (nchunk + K3_WARPS - 1) / K3_WARPS;
+                        const int c_lo = warp * per;
+                        const int c_hi = c_lo + per < nchunk ? c_lo + per : nchunk;
+                        if (c_lo < c_hi) {
+                            int slot = 0;
+                            {   // largest slot with win_chunk0[slot] <= c_lo
+                                int lo_s = 0, hi_s = nwin;
+                                while (hi_s - lo_s > 1) {
+                                    const int mid = (lo_s + hi_s) >> 1;
+                                    if (S.win_chunk0[mid] <= c_lo) lo_s = mid; else hi_s = mid;
+                                }
+                                slot = lo_s;
+                            }
+                            int next_c0 = S.win_chunk0[slot + 1], w_c0 = 0;
+                            int w_ps = 0, w_pe = 0, w_last = 0;
+                            bool fresh = true;
+                            double2 w_lo = make_double2(0.0, 0.0), w_hi = w_lo;
+                            double w_eps2 = 0.0;
+                            for (int c = c_lo; c < c_hi; ++c) {
+                                if (c >= next_c0) {
+                                    do { ++slot; next_c0 = S.win_chunk0[slot + 1]; } while (c >= next_c0);
+                                    fresh = true;
+                                }
+                                if (fresh) {
+                                    fresh = false;
+                                    const K3Item it = A[S.win_item[slot]];
+                                    w_c0 = S.win_chunk0[slot];
+                                    w_ps = it.ps;
+                                    w_pe = k3_window_end(P, it);
+                                    w_last = w_pe - mw;
+                                    w_lo = acc.at(w_ps - 1);
+                                    w_hi = acc.at(w_pe - 1);
+                                    w_eps2 = 2.0 * k3_eps(w_pe - w_ps);
+                                }
+                                const int i0 = w_ps + mw + (c - w_c0) * 32;
+                                const int i = i0 + lane;
+                                const bool valid = i <= w_last;
+                                const int ic = valid ? i : w_last;  // clamp: evaluate a real candidate, ignore it
+                                double H;
+                                const bool ok = k3_screen_eval(acc, w_lo, w_hi, w_ps, w_pe, ic, (double)(ic - w_ps),
+                                                               (double)(w_pe - ic), G.T, S.logtab, H);
+                                const bool use = valid && ok;
+                                const unsigned bad = __ballot_sync(PP_FULL, valid && !ok);
+                                const unsigned long long k1 = k3_warp_min_u64(use ? k3_okey(H) : ~0ull);
+                                const int l1 = __ffs(__ballot_sync(PP_FULL, use && k3_okey(H) == k1)) - 1;
+                                const double b1 = __shfl_sync(PP_FULL, H, l1 < 0 ? 0 : l1);
+                                // another candidate of this chunk within 2 eps of its best -> exact scan decides
+                                const unsigned close = __ballot_sync(PP_FULL, use && H <= b1 + w_eps2);
+                                if (lane == 0) {
+                                    const bool amb = l1 < 0 || __popc(close) > 1;
+                                    // a candidate that failed the validity test forces the exact scan of its window
+                                    S.chunk_b1[c] = (bad || l1 < 0) ? __longlong_as_double(0xfff0000000000000LL) : b1;
+                                    S.chunk_i1[c] = (i0 + (l1 < 0 ? 0 : l1)) | ((amb || bad) ? K3_AMB_FLAG : 0);
+                                    S.chunk_slot[c] = (unsigned short)slot;
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    // window minimum of the screened values: one warp per window over its chunk records
+                    for (int k = warp; k < nwin; k += K3_WARPS) {
+                        const int c0 = S.win_chunk0[k], c1 = S.win_chunk0[k + 1];
+                        double m = __longlong_as_double(0x7ff0000000000000LL);
+                        bool any_ok = false;
+                        for (int c = c0 + lane; c < c1; c += 32) {
+                            const double v = S.chunk_b1[c];
+                            if (v > __longlong_as_double(0xfff0000000000000LL)) { m = fmin(m, v); any_ok = true; }
+                        }
+                        const unsigned long long km = k3_warp_min_u64(any_ok ? k3_okey(m) : ~0ull);
+                        if (lane == 0) S.win_gmin[k] = km;
+                    }
+                    __syncthreads();
+                    // step 3a: chunks whose best is within 2 eps of the window minimum ask for the exact value
+                    for (int c = tid; c < nchunk; c += K3_THREADS) {
+                        const int slot = S.chunk_slot[c];
+                        const int i1 = S.chunk_i1[c];
+                        const unsigned long long gk = S.win_gmin[slot];
+                        if (gk == ~0ull) { atomicOr(&S.win_item[slot], K3_FULL_FLAG); continue; }
+                        const K3Item it = A[S.win_item[slot] & ~K3_FULL_FLAG];
                         const int pe = k3_window_end(P, it);
-                        const double2 lo = acc.at(it.ps - 1), hi = acc.at(pe - 1);
-                        const double tot = k3_exact_tot(lo, hi, it.ps, pe);
-                        const double g = k3_exact_gain(lo, acc.at(i - 1), hi, it.ps, pe, i, tot);
-                        S.req_g[r] = g;
-                        if (g > P.min_gain) atomicMax(&S.best_key[k], k3_okey(g));
+                        const double thr = k3_okey_inv(gk) + 2.0 * k3_eps(pe - it.ps);
+                        if (i1 & K3_AMB_FLAG) {
+                            // only matters if this chunk can reach the window minimum at all
+                            if (!(S.chunk_b1[c] > thr)) atomicOr(&S.win_item[slot], K3_FULL_FLAG);
+                        } else if (S.chunk_b1[c] <= thr) {
+                            k3_request(S, slot, i1);
+                        }
+                    }
+                    __syncthreads();
+                    // step 3b: EXACT evaluation of the requests; 3 lanes per request (tot / low / high)
+                    const int nreq = S.nreq < K3_REQ ? S.nreq : K3_REQ;
+                    for (int r0 = 0; r0 < nreq; r0 += 10 * K3_WARPS) {
+                        const int part = lane % 3;
+                        const int r = r0 + warp * 10 + lane / 3;
+                        const bool act = lane < 30 && r < nreq;
+                        double v = 0.0;
+                        int k = 0, i = 0, w_ps = 0, w_pe = 0;
+                        if (act) {
+                            k = S.req_k[r];
+                            i = S.req_i[r];
+                            const K3Item it = A[S.win_item[k] & ~K3_FULL_FLAG];
+                            w_ps = it.ps;
+                            w_pe = k3_window_end(P, it);
+                            const double2 lo = acc.at(w_ps - 1), hi = acc.at(w_pe - 1), mid = acc.at(i - 1);
+                            if (part == 0) v = k3_exact_tot(lo, hi, w_ps, w_pe);
+                            else if (part == 1) v = __dmul_rn((double)(i - w_ps), log(k3_var(mid, lo, i - w_ps)));
+                            else v = __dmul_rn((double)(w_pe - i), log(k3_var(hi, mid, w_pe - i)));
+                        }
+                        const double low = __shfl_down_sync(PP_FULL, v, 1), high = __shfl_down_sync(PP_FULL, v, 2);
+                        if (act && part == 0) {
+                            const double g = __dsub_rn(v, __dadd_rn(low, high));   // cparsers.pyx:174
+                            S.req_g[r] = g;
+                            if (g > P.min_gain) atomicMax(&S.best_key[k], k3_okey(g));
+                        }
                     }
                     if (tid == 0) atomicAdd(&S.exact, (unsigned long long)nreq);
                     __syncthreads();
@@ -650,10 +734,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
                         if (g > P.min_gain && k3_okey(g) == S.best_key[k]) atomicMin(&S.best_idx[k], S.req_i[r]);
                     }
                     __syncthreads();
-                    // step 4: resolve every scanned window whose requests all fitted
-                    for (int q = tid; q < nbig + nsmall; q += K3_THREADS) {
-                        const int k = q < nbig ? q : K3_LIST - 1 - (q - nbig);
-                        const int entry = S.scanlist[k];
+                    // step 4: resolve every window whose screening was conclusive
+                    for (int k = tid; k < nwin; k += K3_THREADS) {
+                        const int entry = S.win_item[k];
                         if (entry & K3_FULL_FLAG) continue;
                         const K3Item it = A[entry];
                         const int pe = k3_window_end(P, it);
@@ -661,21 +744,20 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
                         atomicAdd(&S.scans, 1ull);
                         k3_resolve_local(G, S, Bn, P, ev, off, it, S.best_key[k] ? S.best_idx[k] : -1);
                     }
-                    // step 5 (rare): windows whose requests overflowed the list -> exact scan, whole CTA
-                    for (int q = 0; q < nbig + nsmall; ++q) {
-                        const int k = q < nbig ? q : K3_LIST - 1 - (q - nbig);
-                        const int entry = S.scanlist[k];
-                        if (!(entry & K3_FULL_FLAG)) continue;
-                        const K3Item it = A[entry & ~K3_FULL_FLAG];
-                        const int pe = k3_window_end(P, it);
-                        K3Best b = k3_scan_range(acc, it.ps, pe, mw, P.min_gain, tid, K3_THREADS);
-                        b = k3_cta_reduce(b, S);
-                        if (tid == 0) {
-                            atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
-                            atomicAdd(&S.scans, 1ull);
-                            atomicAdd(&S.exact, (unsigned long long)(pe - it.ps - 2 * mw + 1));
-                            k3_resolve_local(G, S, Bn, P, ev, off, it, b.x);
-                        }
+                }
+                // step 5: windows left for the exact scan (validation mode: all of them), whole CTA each
+                for (int k = 0; k < nwin; ++k) {
+                    const int entry = S.win_item[k];
+                    if (screen && !(entry & K3_FULL_FLAG)) continue;
+                    const K3Item it = A[entry & ~K3_FULL_FLAG];
+                    const int pe = k3_window_end(P, it);
+                    K3Best b = k3_scan_range(acc, it.ps, pe, mw, P.min_gain, tid, K3_THREADS);
+                    b = k3_cta_reduce(b, S);
+                    if (tid == 0) {
+                        atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
+                        atomicAdd(&S.scans, 1ull);
+                        if (screen) atomicAdd(&S.exact, (unsigned long long)(pe - it.ps - 2 * mw + 1));
+                        k3_resolve_local(G, S, Bn, P, ev, off, it, b.x);
                     }
                 }
                 __syncthreads();
