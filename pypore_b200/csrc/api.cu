@@ -404,7 +404,7 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
     P.mw = mw; P.MW = MW; P.W = W; P.min_gain = min_gain;
     k3_init_queue<<<ctx->sm_count, 256, 0, ctx->stream>>>(G);
     LAUNCHED(ctx);
-    k3_split<<<ctx->sm_count, K3_THREADS, K3_SMEM_BYTES, ctx->stream>>>(G, P);
+    k3_split<<<ctx->sm_count * K3_CTAS_PER_SM, K3_THREADS, K3_SMEM_BYTES, ctx->stream>>>(G, P);
     LAUNCHED(ctx);
     CKR(record_boundary(ctx, ST_SPLIT + 1));
     ctx->stage_ran[ST_SPLIT] = true;

@@ -35,9 +35,10 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int K3_THREADS = 512;
+constexpr int K3_THREADS = 256;
+constexpr int K3_CTAS_PER_SM = 3;
 constexpr int K3_WARPS = K3_THREADS / 32;
-constexpr int K3_CAP = 10240;   // samples of one interval staged in shared memory
+constexpr int K3_CAP = 10240;   // longest interval resolved level by level inside one CTA
 constexpr int K3_LIST = 512;    // items per level list
 constexpr int K3_REQ = 512;     // exact-evaluation requests per level
 constexpr int K3_CHUNKS = 1024; // 32-candidate chunks per level (<= K3_CAP/32 + K3_LIST)
@@ -91,8 +92,7 @@ struct K3Shared {
     unsigned long long cand, scans, exact;
 };
 
-constexpr size_t K3_SMEM_CC = sizeof(double2) * (K3_CAP + 1);
-constexpr size_t K3_SMEM_BYTES = K3_SMEM_CC + sizeof(K3Shared);
+constexpr size_t K3_SMEM_BYTES = sizeof(K3Shared);
 
 // prefix-sum accessors: at(p) = {c[p], c2[p]} with c[-1] = c2[-1] = 0
 struct K3SmemCC {
@@ -105,7 +105,7 @@ struct K3GlobalCC {
     __device__ __forceinline__ double2 at(int p) const
     {
         if (p < 0) return make_double2(0.0, 0.0);
-        return __ldcg(g + p);
+        return __ldg(g + p);
     }
 };
 
@@ -436,11 +436,10 @@ __device__ __forceinline__ void k3_request(K3Shared &S, int k, int i)
     else atomicOr(&S.win_item[k], K3_FULL_FLAG);
 }
 
-__global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P)
+__global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global G, K3Params P)
 {
     extern __shared__ __align__(16) unsigned char k3_smem[];
-    double2 *sm_cc = reinterpret_cast<double2 *>(k3_smem);
-    K3Shared &S = *reinterpret_cast<K3Shared *>(k3_smem + K3_SMEM_CC);
+    K3Shared &S = *reinterpret_cast<K3Shared *>(k3_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mw = P.mw, MW = P.MW, W = P.W;
 
@@ -503,22 +502,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
             const long long pe_l = (long long)ps + W;
             const int pe = (int)(pe_l < e ? pe_l : e);
             if (pe - ps <= 2 * mw) { ps = k3_next_ps(P, ps, e); continue; }
-            K3Best b;
-            if (pe - ps <= K3_CAP) {
-                __syncthreads();
-                for (int k = tid; k <= pe - ps; k += K3_THREADS) {
-                    const int p = ps - 1 + k;
-                    sm_cc[k] = p < 0 ? make_double2(0.0, 0.0) : __ldcg(ccg + p);
-                }
-                __syncthreads();
-                K3SmemCC acc;
-                acc.sm = sm_cc; acc.S0 = ps;
-                b = k3_cta_scan(acc, ps, pe, P, G, S);
-            } else {
-                K3GlobalCC acc;
-                acc.g = ccg;
-                b = k3_cta_scan(acc, ps, pe, P, G, S);
-            }
+            K3GlobalCC gacc;
+            gacc.g = ccg;
+            const K3Best b = k3_cta_scan(gacc, ps, pe, P, G, S);
             if (tid == 0) {
                 atomicAdd(&S.cand, (unsigned long long)(pe - ps - 2 * mw + 1));
                 atomicAdd(&S.scans, 1ull);
@@ -537,18 +523,14 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_split(K3Global G, K3Params P
         // ---- local mode: whole subtree from one staged slab --------------------
         if (!done) {
             __syncthreads();
-            for (int k = tid; k <= e - s; k += K3_THREADS) {
-                const int p = s - 1 + k;
-                sm_cc[k] = p < 0 ? make_double2(0.0, 0.0) : __ldcg(ccg + p);
-            }
             if (tid == 0) {
                 K3Item it;
                 it.s = s; it.e = e; it.ps = ps;
                 S.list[0][0] = it;
                 S.nA = 1;
             }
-            K3SmemCC acc;
-            acc.sm = sm_cc; acc.S0 = s;
+            K3GlobalCC acc;
+            acc.g = ccg;
             int cur = 0;
             __syncthreads();
             for (;;) {
