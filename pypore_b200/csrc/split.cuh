@@ -35,13 +35,13 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int K3_THREADS = 256;
-constexpr int K3_CTAS_PER_SM = 3;
+constexpr int K3_THREADS = 128;
+constexpr int K3_CTAS_PER_SM = 6;
 constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int K3_CAP = 10240;   // longest interval resolved level by level inside one CTA
-constexpr int K3_LIST = 512;    // items per level list
-constexpr int K3_REQ = 512;     // exact-evaluation requests per level
-constexpr int K3_CHUNKS = 1024; // 32-candidate chunks per level (<= K3_CAP/32 + K3_LIST)
+constexpr int K3_LIST = 256;    // items per level list
+constexpr int K3_REQ = 256;     // exact-evaluation requests per level
+constexpr int K3_CHUNKS = 640;  // 32-candidate chunks per level (<= K3_CAP/32 + K3_LIST)
 constexpr int K3_FULL_FLAG = 0x40000000;  // window entry: screening inconclusive / list overflow, scan exactly
 constexpr int K3_AMB_FLAG = (int)0x80000000;
 
@@ -443,10 +443,10 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mw = P.mw, MW = P.MW, W = P.W;
 
-    if (tid < 256) {
+    for (int k = tid; k < 256; k += K3_THREADS) {
         // fast-log table: centre of mantissa bucket k, its reciprocal and its logarithm
-        const double c = 1.0 + ((double)tid + 0.5) / 256.0;
-        S.logtab[tid] = make_double2(1.0 / c, log(c));
+        const double c = 1.0 + ((double)k + 0.5) / 256.0;
+        S.logtab[k] = make_double2(1.0 / c, log(c));
     }
 
     for (;;) {
