@@ -67,7 +67,7 @@ const char *pp_last_error(pp_ctx *ctx);
 int pp_sync(pp_ctx *ctx);
 /* Options: PP_OPT_SCREEN (default 1) -- 1: two-stage split search (bounded-error
  * screening of every candidate, exact arithmetic for the contenders); 0: exact
- * arithmetic for every candidate (validation mode, same results, ~6x slower). */
+ * arithmetic for every candidate (validation mode, same results, many times slower). */
 enum pp_option { PP_OPT_SCREEN = 0 };
 int pp_set_option(pp_ctx *ctx, int option, int64_t value);
 /* Number of kernel launches this context has issued since creation. */
@@ -154,6 +154,12 @@ int pp_split_counters(pp_ctx *ctx, int64_t out[8]);
  * pe-ps-2*min_width+1 entries.  eps receives the bound the kernel applies to this window. */
 int pp_debug_screen(pp_ctx *ctx, int64_t ev, int ps, int pe, int min_width, double *h_screen,
                     double *h_exact, uint8_t *ok, double *eps);
+
+/* Validation hook for the hardware term of the screening bound: the largest absolute error,
+ * over all 2^23 float32 mantissas in [1, 2), of the 23-bit fixed-point log2 the screening
+ * builds from MUFU.LG2 (lg2.approx.f32) and one float32 addition.  The bound in
+ * split.cuh assumes <= 2^-22 + 2^-24. */
+int pp_debug_lg2_error(pp_ctx *ctx, double *max_err);
 
 /* ---- whole pipeline, no host synchronisation between stages ----------- */
 typedef struct pp_pipeline_params {

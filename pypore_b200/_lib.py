@@ -77,6 +77,7 @@ SIGNATURES = {
     "pp_table_device_ptr": (_c.c_void_p, [_c.c_void_p, _c.c_int]),
     "pp_split_counters": (_c.c_int, [_c.c_void_p, _i64p]),
     "pp_debug_screen": (_c.c_int, [_c.c_void_p, _i64, _c.c_int, _c.c_int, _c.c_int, _f64p, _f64p, _u8p, _f64p]),
+    "pp_debug_lg2_error": (_c.c_int, [_c.c_void_p, _f64p]),
     "pp_pipeline": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _i64p]),
 }
 
@@ -314,6 +315,11 @@ class Context(object):
         self._ck(self._L.pp_debug_screen(self._h, int(ev), int(ps), int(pe), int(min_width), _ptr(hs, _f64p),
                                          _ptr(he, _f64p), _ptr(ok, _u8p), _c.byref(eps)))
         return hs, he, ok.astype(bool), float(eps.value)
+
+    def debug_lg2_error(self):
+        v = _c.c_double()
+        self._ck(self._L.pp_debug_lg2_error(self._h, _c.byref(v)))
+        return float(v.value)
 
     def pipeline(self, threshold, rule_mask, duration_gt, duration_lt, min_gt, max_lt, min_width,
                  max_width, window_width, min_gain, filter_ba=None, prefix_mode=PREFIX_AUTO,

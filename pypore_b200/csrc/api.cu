@@ -394,11 +394,11 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
     G.ctr = ctx->ctr;
     if (W + 1 > ctx->T_len) {
         CKR(ensure(ctx, ctx->Ttab, sizeof(double) * (size_t)(W + 1)));
-        k3_fill_T<<<ctx->sm_count, 256, 0, ctx->stream>>>((double *)ctx->Ttab.p, W + 1);
+        k3_fill_RN<<<ctx->sm_count, 256, 0, ctx->stream>>>((double *)ctx->Ttab.p, W + 1);
         LAUNCHED(ctx);
         ctx->T_len = W + 1;
     }
-    G.T = (const double *)ctx->Ttab.p;
+    G.RN = (const double *)ctx->Ttab.p;
     G.screen = ctx->opt_screen;
     K3Params P;
     P.mw = mw; P.MW = MW; P.W = W; P.min_gain = min_gain;
@@ -947,7 +947,7 @@ int pp_debug_screen(pp_ctx *ctx, int64_t ev, int ps, int pe, int min_width, doub
     memset(&G, 0, sizeof G);
     G.cc = (const double2 *)ctx->cc.p;
     G.ev_off = (const int64_t *)ctx->ev_off.p;
-    G.T = (const double *)ctx->Ttab.p;
+    G.RN = (const double *)ctx->Ttab.p;
     k3_debug_screen<<<64, 256, 0, ctx->stream>>>(G, (int)ev, ps, pe, min_width, (double *)a.p, (double *)b.p,
                                                  (unsigned char *)c.p);
     LAUNCHED(ctx);
@@ -957,6 +957,21 @@ int pp_debug_screen(pp_ctx *ctx, int64_t ev, int ps, int pe, int min_width, doub
     CK(cudaStreamSynchronize(ctx->stream));
     release(a); release(b); release(c);
     if (eps) *eps = (double)(pe - ps) * K3_EPS_PER_SAMPLE + K3_EPS_CONST;
+    return PP_OK;
+}
+
+int pp_debug_lg2_error(pp_ctx *ctx, double *max_err)
+{
+    if (!ctx || !max_err) return PP_ERR_ARG;
+    CKR(set_device(ctx));
+    DevBuf a;
+    CKR(ensure(ctx, a, 256));
+    CK(cudaMemsetAsync(a.p, 0, 8, ctx->stream));
+    k3_debug_lg2_error<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>((unsigned long long *)a.p);
+    LAUNCHED(ctx);
+    CK(cudaMemcpyAsync(max_err, a.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    release(a);
     return PP_OK;
 }
 

@@ -9,25 +9,28 @@
 //     sequential dependency of App. A.3), scanning each window CTA-wide, pushing
 //     the left child to the global queue for another CTA and continuing with
 //     the right child itself; and
-//   * once the interval fits in shared memory (<= K3_CAP samples), stages its
-//     slab of {c, c2} once and resolves the whole subtree locally, level by
-//     level, with big windows scanned by the whole CTA and small windows one
-//     per warp.
+//   * once the interval is short enough (<= K3_CAP samples) resolves the whole
+//     subtree locally, level by level: all windows of a level are cut into
+//     32-candidate chunks that are spread evenly over the CTA's warps.
 // Breakpoints are recorded as bits in flat event space; a compaction pass turns
 // the bitmap into the sorted segment table, so no ordering is needed here.
 //
-// Two-stage evaluation of a window (bit-exact result, ~6x fewer instructions):
-//   SCREEN  every candidate i gets H~(i) ~= low(i) + high(i) from a division-free
-//           formulation  n1*log(D1) + n2*log(D2) - T[n1] - T[n2],
-//           D = Q*n - S*S = n^2 * V,  T[n] = 2 n ln n  (table), with a table-driven
-//           fp64 log (|err| < 1e-11).  For candidates that pass the validity test
-//           (variance not smaller than 2^-24 of the mean square) the distance to
-//           the reference's own rounded value is rigorously bounded by
-//           eps = n_window * 3e-8 + 1e-6  (derivation in DESIGN.md).
-//   EXACT   only candidates with H~ <= min H~ + 2 eps, and every candidate that
-//           failed the validity test, are evaluated with the reference's exact
-//           arithmetic below; the decision (strict '>' against min_gain, lowest
-//           index on ties, NaN never wins) is taken on exact values only.
+// Two-stage evaluation of a window (bit-exact result, ~7x fewer instructions):
+//   SCREEN  every candidate i gets an integer key
+//               key(i) = n1 * L(V1) + n2 * L(V2),   L(V) = log2(V) in 2^-23 units (+ a per-window constant)
+//           from a division-free variance V = Q r - (S r)^2 (r = 1/n from a table)
+//           and the hardware lg2 of V's top 24 mantissa bits (MUFU.LG2), accumulated
+//           exactly in 64-bit integers.  For candidates that pass the validity test
+//           (V positive, normal, within 2^+-127 of the window's variance, and not
+//           smaller than 2^-24 of the mean square) the distance between
+//           key * ln2 / 2^23 and the reference's own fl(low + high) is rigorously
+//           bounded by eps = n_window * 3.6e-7 + 1e-6  (derivation in DESIGN.md; the
+//           MUFU error term is measured exhaustively by pp_debug_lg2_error).
+//   EXACT   only candidates with key <= min key + 2 eps, and every window holding a
+//           candidate that failed the validity test, are evaluated with the
+//           reference's exact arithmetic below; the decision (strict '>' against
+//           min_gain, lowest index on ties, NaN never wins) is taken on exact values
+//           only.
 //
 // Exact arithmetic contract: every operation of var_c and of the gain is a
 // separate IEEE fp64 operation in the reference's association
@@ -41,20 +44,24 @@ constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int K3_CAP = 10240;   // longest interval resolved level by level inside one CTA
 constexpr int K3_LIST = 256;    // items per level list
 constexpr int K3_REQ = 256;     // exact-evaluation requests per level
-constexpr int K3_CHUNKS = 640;  // 32-candidate chunks per level (<= K3_CAP/32 + K3_LIST)
+constexpr int K3_PIECES = K3_LIST + K3_WARPS;  // (warp, window) screening records per level
 constexpr int K3_FULL_FLAG = 0x40000000;  // window entry: screening inconclusive / list overflow, scan exactly
-constexpr int K3_AMB_FLAG = (int)0x80000000;
+constexpr int K3_BAD_FLAG = 0x40000000;    // piece record: a candidate failed the validity test
+constexpr int K3_RESCAN_FLAG = (int)0x80000000;  // piece record: several candidates within 2 eps of the minimum
+constexpr int K3_MAX_SCREEN_W = 1 << 24;   // keys stay below 2^56
 
-constexpr double K3_RATIO_MAX = 16777216.0;  // 2^24: validity bound on mean-square / variance
-constexpr double K3_EPS_PER_SAMPLE = 3e-8;   // > 10.03 * 2^-53 * 2^24 = 1.87e-8
+constexpr int K3_RATIO_BITS = 24;            // validity: (S/n)^2 < 2^24 * V
+constexpr double K3_EPS_PER_SAMPLE = 3.6e-7; // nats; > (2^-23/ln2 + 2^-22 + 2^-24) * ln2 + 14.01 * 2^-53 * 2^24
 constexpr double K3_EPS_CONST = 1e-6;
-constexpr double K3_TINY = 1e-280, K3_HUGE = 1e280;
+constexpr double K3_KEY_PER_NAT = 12102203.161561485;  // 2^23 / ln 2
+constexpr double K3_HUGE = 1e280;
+constexpr unsigned long long K3_NOKEY = ~0ull;
 
 struct PPTask { int ev, s, e, flags; };
 struct K3Item { int s, e, ps; };
 struct K3Params { int mw, MW, W; double min_gain; };
 struct K3Best { double g; int x; };
-struct K3Approx { double b1, b2; int i1, bad; };
+struct K3Scr { unsigned long long k1, k2; int i1, bad; };  // per-lane screening state: two smallest keys
 
 struct K3Global {
     const double2 *cc;
@@ -65,28 +72,28 @@ struct K3Global {
     int *ready;
     int64_t q_cap;
     PPCounters *ctr;
-    const double *T;  // T[n] = 2 n ln n for n in [0, W]
-    int screen;       // 0: exact evaluation of every candidate (validation mode)
+    const double *RN;  // RN[n] = 1/n for n in [1, W], RN[0] = 0
+    int screen;        // 0: exact evaluation of every candidate (validation mode)
 };
 
 struct K3Shared {
     K3Item list[2][K3_LIST];
     int win_item[K3_LIST];                 // scan window slot -> index into the level list (| K3_FULL_FLAG)
     int win_chunk0[K3_LIST + 1];           // first chunk of the window (exclusive prefix of chunk counts)
-    unsigned long long win_gmin[K3_LIST];  // ordered key of the window's minimum screened value
+    int win_ebase[K3_LIST];                // biased exponent of the window's variance - 127
+    unsigned long long win_thr[K3_LIST];   // min key + 2 eps
     unsigned long long best_key[K3_LIST];  // ordered key of the best exact gain (0 = none beats min_gain)
     int best_idx[K3_LIST];
-    double chunk_b1[K3_CHUNKS];            // best screened value of the chunk
-    int chunk_i1[K3_CHUNKS];               // its candidate index (| K3_AMB_FLAG: chunk needs the exact scan)
-    unsigned short chunk_slot[K3_CHUNKS];
+    unsigned long long pc_k1[K3_PIECES];   // smallest key of the piece
+    unsigned long long pc_k2[K3_PIECES];   // second smallest (== k1 on a tie)
+    int pc_i1[K3_PIECES];                  // candidate index of k1 | K3_BAD_FLAG | K3_RESCAN_FLAG
     int req_k[K3_REQ];
     int req_i[K3_REQ];
     double req_g[K3_REQ];
-    double2 logtab[256];
     double red_g[K3_WARPS];
-    double red_b[K3_WARPS];
+    unsigned long long red_k[K3_WARPS];
     int red_x[K3_WARPS];
-    int nA, nB, nwin, nchunk, nreq;
+    int nA, nB, nwin, nchunk, nreq, nrescan;
     PPTask task;
     int have_task;
     unsigned long long cand, scans, exact;
@@ -94,12 +101,7 @@ struct K3Shared {
 
 constexpr size_t K3_SMEM_BYTES = sizeof(K3Shared);
 
-// prefix-sum accessors: at(p) = {c[p], c2[p]} with c[-1] = c2[-1] = 0
-struct K3SmemCC {
-    const double2 *sm;
-    int S0;  // sm[k] holds position S0 - 1 + k
-    __device__ __forceinline__ double2 at(int p) const { return sm[p - S0 + 1]; }
-};
+// prefix-sum accessor: at(p) = {c[p], c2[p]} with c[-1] = c2[-1] = 0
 struct K3GlobalCC {
     const double2 *g;  // event base
     __device__ __forceinline__ double2 at(int p) const
@@ -197,80 +199,84 @@ __device__ __forceinline__ K3Best k3_cta_reduce(K3Best b, K3Shared &S)
 // ---------------------------------------------------------------------------
 // screening path
 // ---------------------------------------------------------------------------
-// ln(x) for positive, normal, finite x: exponent + 8-bit table + degree-3 series.
-// |r| <= 2^-9, truncation r^4/4 <= 3.6e-12, rounding a few ulp of the result.
-__device__ __forceinline__ double k3_fastlog(double x, const double2 *tab)
+// Window-level screening constants.  ebase = (biased exponent of the window's own
+// variance) - 127; a candidate side is valid when its variance lies within 2^+-127
+// of that, so that x = exponent - ebase fits [0, 254] and L(V) fits 32 bits.
+// Returns false (-> exact scan of the window) when the window variance is not a
+// comfortably normal positive number.
+__device__ __forceinline__ bool k3_window_ebase(double vtot, int &ebase)
 {
-    const int hi = __double2hiint(x), lo = __double2loint(x);
-    const int k = (hi >> 12) & 255;
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    // (double)(exponent) without an I2F: 2^52 + 2^31 + (e ^ 2^31) as bits, minus the magic
-    const double ed = __hiloint2double(0x43300000, ((hi >> 20) - 1023) ^ 0x80000000) - 4503601774854144.0;
-    const double2 t = tab[k];
-    const double r = fma(m, t.x, -1.0);
-    double p = fma(r, 1.0 / 3.0, -0.5);
-    p = fma(r, p, 1.0);
-    p = p * r;
-    return fma(ed, 0.6931471805599453094, t.y + p);
+    const int e = __double2hiint(vtot) >> 20;  // sign folded in: negative -> e < 0
+    ebase = e - 127;
+    return e >= 128 && e <= 1919;
 }
 
-// positive, finite and comfortably normal: 2^-900 <= d < 2^900
-__device__ __forceinline__ bool k3_sane(double d)
+// One side of a candidate: key += n * L(V), V = Q r - (S r)^2 with r = fl(1/n).
+//   L(V) = (exponent - ebase) * 2^23 + bits(1.0f + lg2(1.mantissa[51:29]))
+//        = 2^23 * (log2 V - ebase + 1150) up to the screening error.
+// S and Q are the same fp64 differences the exact path forms.
+__device__ __forceinline__ bool k3_side(double S, double Q, double r, unsigned n, int ebase,
+                                        unsigned long long &key)
 {
-    return (unsigned)(__double2hiint(d) - 0x07b00000) < 0x70800000u;
+    const double m = __dmul_rn(S, r);
+    const double m2 = __dmul_rn(m, m);
+    const double V = fma(Q, r, -m2);
+    const int vh = __double2hiint(V);
+    const unsigned mant = (__funnelshift_l((unsigned)__double2loint(V), (unsigned)vh, 3) & 0x007fffffu) | 0x3f800000u;
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(__uint_as_float(mant)));
+    const unsigned tb = __float_as_uint(__fadd_rn(lg, 1.0f));
+    const unsigned x = (unsigned)((vh >> 20) - ebase);
+    const unsigned LV = x * 0x00800000u + tb;
+    key += (unsigned long long)n * LV;
+    // V positive/normal/in range, and (S/n)^2 < 2^24 V (hence Q/n < (2^24 + 1) V)
+    return (x <= 254u) & ((__double2hiint(m2) - vh) < (K3_RATIO_BITS << 20));
 }
 
-// H~(i) and its validity (see file header).  S and Q are the same fp64
-// differences the exact path forms, so both paths start from identical values.
-// n1 = i - ps and n2 = pe - i arrive as doubles (exact small integers).
 template <class CC>
-__device__ __forceinline__ bool k3_screen_eval(const CC &cc, const double2 lo, const double2 hi, int ps,
-                                               int pe, int i, double n1, double n2,
-                                               const double *__restrict__ T, const double2 *tab, double &H)
+__device__ __forceinline__ bool k3_screen_key(const CC &cc, const double2 lo, const double2 hi, int ps, int pe,
+                                              int i, const double *__restrict__ RN, int ebase,
+                                              unsigned long long &key)
 {
     const double2 mid = cc.at(i - 1);
-    const double t12 = __ldg(T + (i - ps)) + __ldg(T + (pe - i));
-    const double S1 = __dsub_rn(mid.x, lo.x), Q1 = __dsub_rn(mid.y, lo.y);
-    const double S2 = __dsub_rn(hi.x, mid.x), Q2 = __dsub_rn(hi.y, mid.y);
-    const double P1 = __dmul_rn(Q1, n1), SQ1 = __dmul_rn(S1, S1), D1 = __dsub_rn(P1, SQ1);
-    const double P2 = __dmul_rn(Q2, n2), SQ2 = __dmul_rn(S2, S2), D2 = __dsub_rn(P2, SQ2);
-    const double R1 = K3_RATIO_MAX * D1, R2 = K3_RATIO_MAX * D2;
-    // max(|P|, SQ) <= R * D, written as two comparisons (false on NaN)
-    bool ok = k3_sane(D1) & k3_sane(D2);
-    ok = ok & (fabs(P1) <= R1) & (SQ1 <= R1) & (fabs(P2) <= R2) & (SQ2 <= R2);
-    const double L1 = k3_fastlog(D1, tab), L2 = k3_fastlog(D2, tab);
-    H = fma(n1, L1, n2 * L2) - t12;
-    return ok;
+    const unsigned n1 = (unsigned)(i - ps), n2 = (unsigned)(pe - i);
+    const double r1 = __ldg(RN + n1), r2 = __ldg(RN + n2);
+    key = 0ull;
+    const bool ok1 = k3_side(__dsub_rn(mid.x, lo.x), __dsub_rn(mid.y, lo.y), r1, n1, ebase, key);
+    const bool ok2 = k3_side(__dsub_rn(hi.x, mid.x), __dsub_rn(hi.y, mid.y), r2, n2, ebase, key);
+    return ok1 & ok2;
 }
 
-// Screen candidates ps+mw+first, +stride, ...  (requires mw >= 1 so that n1, n2 >= 1)
-template <class CC>
-__device__ __forceinline__ K3Approx k3_screen_range(const CC &cc, const double2 lo, const double2 hi,
-                                                    int ps, int pe, int mw, int first, int stride,
-                                                    const double *__restrict__ T, const double2 *tab)
+__device__ __forceinline__ void k3_scr_init(K3Scr &a)
 {
-    K3Approx a;
-    a.b1 = a.b2 = __longlong_as_double(0x7ff0000000000000LL);
+    a.k1 = a.k2 = K3_NOKEY;
     a.i1 = -1;
     a.bad = 0;
-    const int last = pe - mw;
-    const double dstride = (double)stride;
-    double n1 = (double)(mw + first), n2 = (double)(pe - ps - mw - first);
-    for (int i = ps + mw + first; i <= last; i += stride) {
-        double H;
-        const bool ok = k3_screen_eval(cc, lo, hi, ps, pe, i, n1, n2, T, tab, H);
-        n1 += dstride;
-        n2 -= dstride;
-        if (!ok) a.bad = 1;
-        else if (H < a.b2) {  // uncommon after the first few candidates
-            if (H < a.b1) { a.b2 = a.b1; a.b1 = H; a.i1 = i; }
-            else a.b2 = H;
-        }
-    }
-    return a;
 }
 
-__device__ __forceinline__ double k3_eps(int n) { return (double)n * K3_EPS_PER_SAMPLE + K3_EPS_CONST; }
+// Screen candidates i, i+stride, ... <= i_last (requires mw >= 1 so that n1, n2 >= 1).
+template <class CC>
+__device__ __forceinline__ void k3_screen_lane(const CC &cc, const double2 lo, const double2 hi, int ps, int pe,
+                                               int ebase, const double *__restrict__ RN, int i, int i_last,
+                                               int stride, K3Scr &a)
+{
+#pragma unroll 2
+    for (; i <= i_last; i += stride) {
+        unsigned long long key;
+        const bool ok = k3_screen_key(cc, lo, hi, ps, pe, i, RN, ebase, key);
+        if (!ok) a.bad = 1;
+        else if (key < a.k2) {  // uncommon after the first few candidates
+            if (key < a.k1) { a.k2 = a.k1; a.k1 = key; a.i1 = i; }
+            else a.k2 = key;
+        }
+    }
+}
+
+// 2 eps of a window of n samples, in key units (rounded up)
+__device__ __forceinline__ unsigned long long k3_eps2_key(int n)
+{
+    return (unsigned long long)(2.0 * ((double)n * K3_EPS_PER_SAMPLE + K3_EPS_CONST) * K3_KEY_PER_NAT) + 2ull;
+}
 
 // Monotone double -> u64 key (non-NaN); -0.0 is canonicalised to +0.0 first so
 // that equal doubles have equal keys.
@@ -278,12 +284,6 @@ __device__ __forceinline__ unsigned long long k3_okey(double g)
 {
     const long long b = __double_as_longlong(__dadd_rn(g, 0.0));
     return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000LL));
-}
-
-__device__ __forceinline__ double k3_okey_inv(unsigned long long k)
-{
-    const long long b = (long long)k;
-    return __longlong_as_double(b < 0 ? (b ^ (long long)0x8000000000000000LL) : ~b);
 }
 
 // warp-wide minimum of a 64-bit key with two 32-bit REDUX operations
@@ -296,25 +296,17 @@ __device__ __forceinline__ unsigned long long k3_warp_min_u64(unsigned long long
     return ((unsigned long long)mh << 32) | ml;
 }
 
-// After the window's min H~ is known: which of this thread's candidates need the
-// exact evaluation?  f(i) is called for each.
-template <class CC, class F>
-__device__ __forceinline__ void k3_screen_select(const CC &cc, const double2 lo, const double2 hi, int ps,
-                                                 int pe, int mw, int first, int stride,
-                                                 const double *__restrict__ T, const double2 *tab,
-                                                 const K3Approx &a, double thr, F f)
+// Warp-level summary of the lanes' screening states: smallest key, its candidate,
+// and the second smallest key of the whole warp (== the smallest on a tie).
+__device__ __forceinline__ void k3_warp_summary(const K3Scr &a, unsigned long long &K1, unsigned long long &K2,
+                                                int &I1, bool &bad)
 {
-    if (a.bad || a.b2 <= thr) {
-        // rare: several of this thread's candidates qualify -> rescan its subset
-        const int last = pe - mw;
-        for (int i = ps + mw + first; i <= last; i += stride) {
-            double H;
-            const bool ok = k3_screen_eval(cc, lo, hi, ps, pe, i, (double)(i - ps), (double)(pe - i), T, tab, H);
-            if (!ok || H <= thr) f(i);
-        }
-    } else if (a.i1 >= 0 && a.b1 <= thr) {
-        f(a.i1);
-    }
+    const int lane = threadIdx.x & 31;
+    K1 = k3_warp_min_u64(a.k1);
+    const int winner = __ffs(__ballot_sync(PP_FULL, a.k1 == K1)) - 1;
+    K2 = k3_warp_min_u64(lane == winner ? a.k2 : a.k1);
+    I1 = __shfl_sync(PP_FULL, a.i1, winner);
+    bad = __any_sync(PP_FULL, a.bad != 0);
 }
 
 // Whole CTA scans one window and returns the exact decision (spine mode).
@@ -328,27 +320,45 @@ __device__ __forceinline__ K3Best k3_cta_scan(const CC &cc, int ps, int pe, cons
     b.x = -1;
     const double2 lo = cc.at(ps - 1), hi = cc.at(pe - 1);
     const double tot = k3_exact_tot(lo, hi, ps, pe);
-    if (!G.screen || P.mw < 1 || !(fabs(tot) <= K3_HUGE)) {
+    int ebase = 0;
+    bool screen = G.screen && P.mw >= 1 && pe - ps <= K3_MAX_SCREEN_W && fabs(tot) <= K3_HUGE;
+    screen = screen && k3_window_ebase(k3_var(hi, lo, pe - ps), ebase);
+    K3Scr a;
+    k3_scr_init(a);
+    if (screen) {
+        k3_screen_lane(cc, lo, hi, ps, pe, ebase, G.RN, ps + P.mw + tid, pe - P.mw, K3_THREADS, a);
+        // a candidate that failed the validity test sends the whole window to the exact scan
+        if (__syncthreads_or(a.bad)) screen = false;
+    }
+    if (!screen) {
         b = k3_scan_range(cc, ps, pe, P.mw, P.min_gain, tid, K3_THREADS);
         return k3_cta_reduce(b, S);
     }
-    const K3Approx a = k3_screen_range(cc, lo, hi, ps, pe, P.mw, tid, K3_THREADS, G.T, S.logtab);
-    double m = a.b1;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) m = fmin(m, __shfl_xor_sync(PP_FULL, m, d));
+    unsigned long long m = k3_warp_min_u64(a.k1);
+    if ((tid & 31) == 0) S.red_k[tid >> 5] = m;
     __syncthreads();
-    if ((tid & 31) == 0) S.red_b[tid >> 5] = m;
-    __syncthreads();
-    m = S.red_b[0];
+    m = S.red_k[0];
 #pragma unroll
-    for (int w = 1; w < K3_WARPS; ++w) m = fmin(m, S.red_b[w]);
-    const double thr = m + 2.0 * k3_eps(pe - ps);
+    for (int w = 1; w < K3_WARPS; ++w) m = S.red_k[w] < m ? S.red_k[w] : m;
+    const unsigned long long thr = m + k3_eps2_key(pe - ps);
     unsigned nexact = 0;
-    k3_screen_select(cc, lo, hi, ps, pe, P.mw, tid, K3_THREADS, G.T, S.logtab, a, thr, [&](int i) {
-        const double g = k3_exact_gain(lo, cc.at(i - 1), hi, ps, pe, i, tot);
+    if (a.k2 <= thr) {
+        // rare: several of this thread's candidates qualify -> rescan its subset
+        const int last = pe - P.mw;
+        for (int i = ps + P.mw + tid; i <= last; i += K3_THREADS) {
+            unsigned long long key;
+            k3_screen_key(cc, lo, hi, ps, pe, i, G.RN, ebase, key);
+            if (key <= thr) {
+                const double g = k3_exact_gain(lo, cc.at(i - 1), hi, ps, pe, i, tot);
+                ++nexact;
+                if (g > b.g) { b.g = g; b.x = i; }
+            }
+        }
+    } else if (a.k1 <= thr) {
+        const double g = k3_exact_gain(lo, cc.at(a.i1 - 1), hi, ps, pe, a.i1, tot);
         ++nexact;
-        if (g > b.g) { b.g = g; b.x = i; }
-    });
+        if (g > b.g) { b.g = g; b.x = a.i1; }
+    }
     if (nexact) atomicAdd(&S.exact, (unsigned long long)nexact);
     return k3_cta_reduce(b, S);
 }
@@ -436,18 +446,38 @@ __device__ __forceinline__ void k3_request(K3Shared &S, int k, int i)
     else atomicOr(&S.win_item[k], K3_FULL_FLAG);
 }
 
+// The (warp, window) pieces of a level: the level's chunks [0, nchunk) are dealt to
+// the warps in equal contiguous shares; f(slot, first_chunk_in_window, end_chunk_in_window)
+// is called for every window a warp's share touches.  Piece id = slot + warp.
+template <class F>
+__device__ __forceinline__ void k3_for_pieces(const K3Shared &S, int warp, int nwin, int nchunk, F f)
+{
+    const int per = (nchunk + K3_WARPS - 1) / K3_WARPS;
+    const int c_lo = warp * per;
+    const int c_hi = c_lo + per < nchunk ? c_lo + per : nchunk;
+    if (c_lo >= c_hi) return;
+    int lo_s = 0, hi_s = nwin;  // largest slot with win_chunk0[slot] <= c_lo
+    while (hi_s - lo_s > 1) {
+        const int mid = (lo_s + hi_s) >> 1;
+        if (S.win_chunk0[mid] <= c_lo) lo_s = mid; else hi_s = mid;
+    }
+    int slot = lo_s;
+    int c = c_lo;
+    while (c < c_hi) {
+        while (S.win_chunk0[slot + 1] <= c) ++slot;
+        const int w_c0 = S.win_chunk0[slot], w_c1 = S.win_chunk0[slot + 1];
+        const int cb = w_c1 < c_hi ? w_c1 : c_hi;
+        f(slot, c - w_c0, cb - w_c0);
+        c = cb;
+    }
+}
+
 __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global G, K3Params P)
 {
     extern __shared__ __align__(16) unsigned char k3_smem[];
     K3Shared &S = *reinterpret_cast<K3Shared *>(k3_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mw = P.mw, MW = P.MW, W = P.W;
-
-    for (int k = tid; k < 256; k += K3_THREADS) {
-        // fast-log table: centre of mantissa bucket k, its reciprocal and its logarithm
-        const double c = 1.0 + ((double)k + 0.5) / 256.0;
-        S.logtab[k] = make_double2(1.0 / c, log(c));
-    }
 
     for (;;) {
         __syncthreads();
@@ -476,9 +506,10 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
         int s = S.task.s;
         const int e = S.task.e;
         const int64_t off = G.ev_off[ev];
-        const double2 *ccg = G.cc + off;
+        K3GlobalCC acc;
+        acc.g = G.cc + off;
 
-        // ---- spine mode: interval too long for shared memory -------------------
+        // ---- spine mode: interval too long to resolve locally ------------------
         int ps = s;
         bool done = false;
         while ((long long)e - s > K3_CAP) {
@@ -502,9 +533,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
             const long long pe_l = (long long)ps + W;
             const int pe = (int)(pe_l < e ? pe_l : e);
             if (pe - ps <= 2 * mw) { ps = k3_next_ps(P, ps, e); continue; }
-            K3GlobalCC gacc;
-            gacc.g = ccg;
-            const K3Best b = k3_cta_scan(gacc, ps, pe, P, G, S);
+            const K3Best b = k3_cta_scan(acc, ps, pe, P, G, S);
             if (tid == 0) {
                 atomicAdd(&S.cand, (unsigned long long)(pe - ps - 2 * mw + 1));
                 atomicAdd(&S.scans, 1ull);
@@ -520,7 +549,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
             }
         }
 
-        // ---- local mode: whole subtree from one staged slab --------------------
+        // ---- local mode: whole subtree, level by level --------------------------
         if (!done) {
             __syncthreads();
             if (tid == 0) {
@@ -529,16 +558,15 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                 S.list[0][0] = it;
                 S.nA = 1;
             }
-            K3GlobalCC acc;
-            acc.g = ccg;
             int cur = 0;
+            const bool screen = G.screen && mw >= 1 && W <= K3_MAX_SCREEN_W;
             __syncthreads();
             for (;;) {
                 const int nA = S.nA;
                 if (nA == 0) break;
                 K3Item *A = S.list[cur], *Bn = S.list[cur ^ 1];
                 __syncthreads();  // everyone has read nA
-                if (tid == 0) { S.nB = 0; S.nwin = 0; S.nreq = 0; S.nchunk = 0; }
+                if (tid == 0) { S.nB = 0; S.nwin = 0; S.nreq = 0; S.nchunk = 0; S.nrescan = 0; }
                 __syncthreads();
                 // step 1: the window-loop bookkeeping of _recursive_split per item
                 for (int t = tid; t < nA; t += K3_THREADS) {
@@ -561,9 +589,15 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                             k3_push_local(G, S, Bn, ev, it.s, it.e, k3_next_ps(P, it.ps, it.e));
                         } else {
                             const int slot = atomicAdd(&S.nwin, 1);
-                            S.win_item[slot] = t;
-                            S.win_chunk0[slot] = (pe - it.ps - 2 * mw + 1 + 31) >> 5;  // chunk count for now
-                            S.win_gmin[slot] = ~0ull;
+                            int ebase = 0;
+                            bool ok = screen;
+                            if (ok) {
+                                const double2 lo = acc.at(it.ps - 1), hi = acc.at(pe - 1);
+                                ok = k3_window_ebase(k3_var(hi, lo, pe - it.ps), ebase);
+                            }
+                            S.win_item[slot] = ok ? t : (t | K3_FULL_FLAG);
+                            S.win_ebase[slot] = ebase;
+                            S.win_chunk0[slot] = ok ? (pe - it.ps - 2 * mw + 1 + 31) >> 5 : 0;  // chunk count for now
                             S.best_key[slot] = 0ull;
                             S.best_idx[slot] = 0x7fffffff;
                         }
@@ -571,9 +605,8 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                 }
                 __syncthreads();
                 const int nwin = S.nwin;
-                const bool screen = G.screen && mw >= 1;
                 if (screen) {
-                    // exclusive prefix of the chunk counts (warp 0), in place
+                    // exclusive prefix of the chunk counts (warp 0), in place; other warps clear the piece records
                     if (warp == 0) {
                         int carry = 0;
                         for (int b0 = 0; b0 < nwin; b0 += 32) {
@@ -588,100 +621,86 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                             carry += __shfl_sync(PP_FULL, inc, 31);
                         }
                         if (lane == 0) { S.win_chunk0[nwin] = carry; S.nchunk = carry; }
+                    } else {
+                        for (int p = tid - 32; p < nwin + K3_WARPS; p += K3_THREADS - 32) {
+                            S.pc_k1[p] = K3_NOKEY;
+                            S.pc_k2[p] = K3_NOKEY;
+                            S.pc_i1[p] = 0;
+                        }
                     }
                     __syncthreads();
                     const int nchunk = S.nchunk;
-                    // step 2: SCREEN -- all windows cut into 32-candidate chunks, spread evenly over the warps
-                    {
-                        const int per = (nchunk + K3_WARPS - 1) / K3_WARPS;
-                        const int c_lo = warp * per;
-                        const int c_hi = c_lo + per < nchunk ? c_lo + per : nchunk;
-                        if (c_lo < c_hi) {
-                            int slot = 0;
-                            {   // largest slot with win_chunk0[slot] <= c_lo
-                                int lo_s = 0, hi_s = nwin;
-                                while (hi_s - lo_s > 1) {
-                                    const int mid = (lo_s + hi_s) >> 1;
-                                    if (S.win_chunk0[mid] <= c_lo) lo_s = mid; else hi_s = mid;
-                                }
-                                slot = lo_s;
-                            }
-                            int next_c0 = S.win_chunk0[slot + 1], w_c0 = 0;
-                            int w_ps = 0, w_pe = 0, w_last = 0;
-                            bool fresh = true;
-                            double2 w_lo = make_double2(0.0, 0.0), w_hi = w_lo;
-                            double w_eps2 = 0.0;
-                            for (int c = c_lo; c < c_hi; ++c) {
-                                if (c >= next_c0) {
-                                    do { ++slot; next_c0 = S.win_chunk0[slot + 1]; } while (c >= next_c0);
-                                    fresh = true;
-                                }
-                                if (fresh) {
-                                    fresh = false;
-                                    const K3Item it = A[S.win_item[slot]];
-                                    w_c0 = S.win_chunk0[slot];
-                                    w_ps = it.ps;
-                                    w_pe = k3_window_end(P, it);
-                                    w_last = w_pe - mw;
-                                    w_lo = acc.at(w_ps - 1);
-                                    w_hi = acc.at(w_pe - 1);
-                                    w_eps2 = 2.0 * k3_eps(w_pe - w_ps);
-                                }
-                                const int i0 = w_ps + mw + (c - w_c0) * 32;
-                                const int i = i0 + lane;
-                                const bool valid = i <= w_last;
-                                const int ic = valid ? i : w_last;  // clamp: evaluate a real candidate, ignore it
-                                double H;
-                                const bool ok = k3_screen_eval(acc, w_lo, w_hi, w_ps, w_pe, ic, (double)(ic - w_ps),
-                                                               (double)(w_pe - ic), G.T, S.logtab, H);
-                                const bool use = valid && ok;
-                                const unsigned bad = __ballot_sync(PP_FULL, valid && !ok);
-                                const unsigned long long k1 = k3_warp_min_u64(use ? k3_okey(H) : ~0ull);
-                                const int l1 = __ffs(__ballot_sync(PP_FULL, use && k3_okey(H) == k1)) - 1;
-                                const double b1 = __shfl_sync(PP_FULL, H, l1 < 0 ? 0 : l1);
-                                // another candidate of this chunk within 2 eps of its best -> exact scan decides
-                                const unsigned close = __ballot_sync(PP_FULL, use && H <= b1 + w_eps2);
-                                if (lane == 0) {
-                                    const bool amb = l1 < 0 || __popc(close) > 1;
-                                    // a candidate that failed the validity test forces the exact scan of its window
-                                    S.chunk_b1[c] = (bad || l1 < 0) ? __longlong_as_double(0xfff0000000000000LL) : b1;
-                                    S.chunk_i1[c] = (i0 + (l1 < 0 ? 0 : l1)) | ((amb || bad) ? K3_AMB_FLAG : 0);
-                                    S.chunk_slot[c] = (unsigned short)slot;
-                                }
-                            }
+                    const int per = (nchunk + K3_WARPS - 1) / K3_WARPS;
+                    // step 2: SCREEN -- every lane keeps the two smallest keys of its candidates of a piece
+                    k3_for_pieces(S, warp, nwin, nchunk, [&](int slot, int ca, int cb) {
+                        const K3Item it = A[S.win_item[slot]];
+                        const int w_pe = k3_window_end(P, it);
+                        const int w_last = w_pe - mw;
+                        const int i_end = it.ps + mw + cb * 32 - 1;
+                        const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
+                        K3Scr a;
+                        k3_scr_init(a);
+                        k3_screen_lane(acc, w_lo, w_hi, it.ps, w_pe, S.win_ebase[slot], G.RN,
+                                       it.ps + mw + ca * 32 + lane, i_end < w_last ? i_end : w_last, 32, a);
+                        unsigned long long K1, K2;
+                        int I1;
+                        bool bad;
+                        k3_warp_summary(a, K1, K2, I1, bad);
+                        if (lane == 0) {
+                            S.pc_k1[slot + warp] = K1;
+                            S.pc_k2[slot + warp] = K2;
+                            S.pc_i1[slot + warp] = ((I1 - it.ps) & 0x3fffffff) | (bad ? K3_BAD_FLAG : 0);
                         }
-                    }
+                    });
                     __syncthreads();
-                    // window minimum of the screened values: one warp per window over its chunk records
-                    for (int k = warp; k < nwin; k += K3_WARPS) {
+                    // step 3a: window minimum over its pieces; pieces within 2 eps of it ask for exact values
+                    for (int k = tid; k < nwin; k += K3_THREADS) {
                         const int c0 = S.win_chunk0[k], c1 = S.win_chunk0[k + 1];
-                        double m = __longlong_as_double(0x7ff0000000000000LL);
-                        bool any_ok = false;
-                        for (int c = c0 + lane; c < c1; c += 32) {
-                            const double v = S.chunk_b1[c];
-                            if (v > __longlong_as_double(0xfff0000000000000LL)) { m = fmin(m, v); any_ok = true; }
+                        if (c1 == c0) continue;  // already marked for the exact scan
+                        const int w_first = c0 / per, w_last = (c1 - 1) / per;
+                        unsigned long long gmin = K3_NOKEY;
+                        bool bad = false;
+                        for (int w = w_first; w <= w_last; ++w) {
+                            const unsigned long long k1 = S.pc_k1[k + w];
+                            gmin = k1 < gmin ? k1 : gmin;
+                            bad = bad || (S.pc_i1[k + w] & K3_BAD_FLAG);
                         }
-                        const unsigned long long km = k3_warp_min_u64(any_ok ? k3_okey(m) : ~0ull);
-                        if (lane == 0) S.win_gmin[k] = km;
-                    }
-                    __syncthreads();
-                    // step 3a: chunks whose best is within 2 eps of the window minimum ask for the exact value
-                    for (int c = tid; c < nchunk; c += K3_THREADS) {
-                        const int slot = S.chunk_slot[c];
-                        const int i1 = S.chunk_i1[c];
-                        const unsigned long long gk = S.win_gmin[slot];
-                        if (gk == ~0ull) { atomicOr(&S.win_item[slot], K3_FULL_FLAG); continue; }
-                        const K3Item it = A[S.win_item[slot] & ~K3_FULL_FLAG];
-                        const int pe = k3_window_end(P, it);
-                        const double thr = k3_okey_inv(gk) + 2.0 * k3_eps(pe - it.ps);
-                        if (i1 & K3_AMB_FLAG) {
-                            // only matters if this chunk can reach the window minimum at all
-                            if (!(S.chunk_b1[c] > thr)) atomicOr(&S.win_item[slot], K3_FULL_FLAG);
-                        } else if (S.chunk_b1[c] <= thr) {
-                            k3_request(S, slot, i1);
+                        if (bad || gmin == K3_NOKEY) { S.win_item[k] |= K3_FULL_FLAG; continue; }
+                        const K3Item it = A[S.win_item[k]];
+                        const unsigned long long thr = gmin + k3_eps2_key(k3_window_end(P, it) - it.ps);
+                        S.win_thr[k] = thr;
+                        for (int w = w_first; w <= w_last; ++w) {
+                            if (S.pc_k2[k + w] <= thr) {
+                                S.pc_i1[k + w] |= K3_RESCAN_FLAG;
+                                atomicAdd(&S.nrescan, 1);
+                            } else if (S.pc_k1[k + w] <= thr) {
+                                k3_request(S, k, it.ps + (S.pc_i1[k + w] & 0x3fffffff));
+                            }
                         }
                     }
                     __syncthreads();
+                    // step 3a': pieces with several contenders are screened again, every contender is requested
+                    if (S.nrescan) {
+                        k3_for_pieces(S, warp, nwin, nchunk, [&](int slot, int ca, int cb) {
+                            if (!(S.pc_i1[slot + warp] & K3_RESCAN_FLAG)) return;
+                            const int entry = S.win_item[slot];
+                            if (entry & K3_FULL_FLAG) return;  // request list overflowed: exact scan decides
+                            const K3Item it = A[entry & ~K3_FULL_FLAG];
+                            const int w_pe = k3_window_end(P, it);
+                            const int w_last = w_pe - mw;
+                            int i_end = it.ps + mw + cb * 32 - 1;
+                            i_end = i_end < w_last ? i_end : w_last;
+                            const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
+                            const unsigned long long thr = S.win_thr[slot];
+                            const int ebase = S.win_ebase[slot];
+                            for (int i = it.ps + mw + ca * 32 + lane; i <= i_end; i += 32) {
+                                unsigned long long key;
+                                k3_screen_key(acc, w_lo, w_hi, it.ps, w_pe, i, G.RN, ebase, key);
+                                if (key <= thr) k3_request(S, slot, i);
+                            }
+                        });
+                        __syncthreads();
+                    }
                     // step 3b: EXACT evaluation of the requests; 3 lanes per request (tot / low / high)
                     const int nreq = S.nreq < K3_REQ ? S.nreq : K3_REQ;
                     for (int r0 = 0; r0 < nreq; r0 += 10 * K3_WARPS) {
@@ -761,40 +780,55 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
 }
 
 // Debug / validation: for window [ps,pe) of event `ev`, write per candidate the screened
-// value H~, the reference-arithmetic value fl(low + high) and the validity flag.
+// value (key converted to nats), the reference-arithmetic value fl(low + high) and the
+// validity flag.
 __global__ void __launch_bounds__(256)
 k3_debug_screen(K3Global G, int ev, int ps, int pe, int mw, double *h_screen, double *h_exact,
                 unsigned char *ok_out)
 {
-    __shared__ double2 tab[256];
-    {
-        const double c = 1.0 + ((double)threadIdx.x + 0.5) / 256.0;
-        tab[threadIdx.x] = make_double2(1.0 / c, log(c));
-    }
-    __syncthreads();
     K3GlobalCC cc;
     cc.g = G.cc + G.ev_off[ev];
     const double2 lo = cc.at(ps - 1), hi = cc.at(pe - 1);
+    int ebase = 0;
+    const bool wok = k3_window_ebase(k3_var(hi, lo, pe - ps), ebase);
     const int n = pe - mw - (ps + mw) + 1;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const int i = ps + mw + j;
-        double H;
-        const bool ok = k3_screen_eval(cc, lo, hi, ps, pe, i, (double)(i - ps), (double)(pe - i), G.T, tab, H);
+        unsigned long long key = 0;
+        const bool ok = wok && k3_screen_key(cc, lo, hi, ps, pe, i, G.RN, ebase, key);
         const double2 mid = cc.at(i - 1);
         const double low = __dmul_rn((double)(i - ps), log(k3_var(mid, lo, i - ps)));
         const double high = __dmul_rn((double)(pe - i), log(k3_var(hi, mid, pe - i)));
-        h_screen[j] = H;
+        // key = 2^23 * sum n (log2 V - ebase + 1150)
+        h_screen[j] = 0.6931471805599453094 * ((double)key / 8388608.0 + (double)(pe - ps) * (double)(ebase - 1150));
         h_exact[j] = __dadd_rn(low, high);
         ok_out[j] = ok ? 1 : 0;
     }
 }
 
-// T[n] = 2 n ln n (n = 0 .. len-1), the part of the screening formula that only
-// depends on the sub-window length.
-__global__ void __launch_bounds__(256) k3_fill_T(double *T, int len)
+// Exhaustive measurement of the hardware term of the screening bound: over all 2^23
+// float32 mantissas m in [1, 2), the largest | fixed23(1 + lg2.approx(m)) - 1 - log2(m) |
+// (MUFU.LG2 error plus the rounding of the +1.0f), returned as an ordered-u64 maximum.
+__global__ void __launch_bounds__(256) k3_debug_lg2_error(unsigned long long *max_bits)
+{
+    double worst = 0.0;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < (1u << 23); k += gridDim.x * blockDim.x) {
+        const float m = __uint_as_float(0x3f800000u | k);
+        float lg;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(m));
+        const unsigned tb = __float_as_uint(__fadd_rn(lg, 1.0f));
+        const double fixed = (double)(tb - 0x3f800000u) / 8388608.0;
+        const double err = fabs(fixed - log2((double)m));
+        worst = err > worst ? err : worst;
+    }
+    atomicMax(max_bits, (unsigned long long)__double_as_longlong(worst));  // non-negative doubles order as integers
+}
+
+// RN[n] = 1/n (n = 1 .. len-1), correctly rounded; RN[0] = 0.
+__global__ void __launch_bounds__(256) k3_fill_RN(double *RN, int len)
 {
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < len; n += gridDim.x * blockDim.x)
-        T[n] = n > 0 ? 2.0 * (double)n * log((double)n) : 0.0;
+        RN[n] = n > 0 ? __ddiv_rn(1.0, (double)n) : 0.0;
 }
 
 // One initial task per event; event starts are segment starts.

@@ -422,3 +422,10 @@ def test_filtered_pipeline_on_float32_trace(ctx):
         assert np.array_equal(tab["min"][sel], mn) and np.array_equal(tab["max"][sel], mx)
         flips += not np.array_equal(tab["start"][sel][1:], oracle.statsplit(ref, **kw))
     assert flips == 0   # and the scipy-filtered signal segments identically on this suite
+
+
+def test_hardware_lg2_error_within_screening_bound(ctx):
+    """Exhaustive over all 2^23 mantissas: the 23-bit fixed-point log2 built from MUFU.LG2 plus one float32
+    addition stays within the 2^-22 + 2^-24 the screening bound (split.cuh K3_EPS_PER_SAMPLE) assumes."""
+    err = ctx.debug_lg2_error()
+    assert 0.0 < err <= 2.0 ** -22 + 2.0 ** -24, err
