@@ -58,7 +58,6 @@ struct pp_ctx {
 
     // K2/K3
     DevBuf cc, bits, tasks, ready, block_count, block_off, inexact, Ttab, ev_tile_off, k2_bits, k2_tiles;
-    int k2_epoch = 0;
     int T_len = 0;
     int opt_screen = 1;
     int64_t q_cap = 0;
@@ -346,31 +345,38 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
         CKR(ensure(ctx, ctx->ev_tile_off, sizeof(int64_t) * (ctx->cap_events + 2)));
         CKR(ensure(ctx, ctx->k2_bits, sizeof(K2EventBits) * (ctx->cap_events + 1)));
         CKR(ensure(ctx, ctx->inexact, sizeof(unsigned) * (ctx->cap_events + 1)));
-        if (sizeof(K2TileState) * (size_t)max_tiles > ctx->k2_tiles.cap) {
-            CKR(ensure(ctx, ctx->k2_tiles, sizeof(K2TileState) * (size_t)max_tiles));
-            CK(cudaMemsetAsync(ctx->k2_tiles.p, 0, ctx->k2_tiles.cap, ctx->stream));
-            ctx->k2_epoch = 0;
-        }
-        const int epoch = ++ctx->k2_epoch;  // stale tile states of earlier launches are recognised by epoch
+        CKR(ensure(ctx, ctx->k2_tiles, sizeof(K2TileState) * (size_t)max_tiles));
         k2_tile_offsets<<<1, 1024, 0, ctx->stream>>>(ctx->ctr, (const int64_t *)ctx->ev_len.p,
                                                      (int64_t *)ctx->ev_tile_off.p, (K2EventBits *)ctx->k2_bits.p,
                                                      (unsigned *)ctx->inexact.p);
         LAUNCHED(ctx);
+        const int grid = ctx->sm_count * 8;
         if (ctx->src_kind == 0)
-            k2_prefix_tiled<float><<<ctx->sm_count * 8, K2_THREADS, 0, ctx->stream>>>(
+            k2_tile_reduce<float><<<grid, K2_THREADS, 0, ctx->stream>>>(
                 src, ctx->trace, (const int64_t *)ctx->ev_len.p, (const int64_t *)ctx->ev_tile_off.p, ctx->ctr,
-                (K2TileState *)ctx->k2_tiles.p, (K2EventBits *)ctx->k2_bits.p, (double2 *)ctx->cc.p, epoch);
+                (K2TileState *)ctx->k2_tiles.p, (K2EventBits *)ctx->k2_bits.p);
         else
-            k2_prefix_tiled<double><<<ctx->sm_count * 8, K2_THREADS, 0, ctx->stream>>>(
+            k2_tile_reduce<double><<<grid, K2_THREADS, 0, ctx->stream>>>(
                 src, (const double *)ctx->flat64.p, (const int64_t *)ctx->ev_len.p,
                 (const int64_t *)ctx->ev_tile_off.p, ctx->ctr, (K2TileState *)ctx->k2_tiles.p,
-                (K2EventBits *)ctx->k2_bits.p, (double2 *)ctx->cc.p, epoch);
+                (K2EventBits *)ctx->k2_bits.p);
+        LAUNCHED(ctx);
+        k2_event_carries<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(
+            ctx->ctr, (const int64_t *)ctx->ev_len.p, (const int64_t *)ctx->ev_tile_off.p,
+            (K2TileState *)ctx->k2_tiles.p, (const K2EventBits *)ctx->k2_bits.p, (unsigned *)ctx->inexact.p,
+            prefix_mode != PP_PREFIX_PARALLEL);
+        LAUNCHED(ctx);
+        if (ctx->src_kind == 0)
+            k2_tile_scan<float><<<grid, K2_THREADS, 0, ctx->stream>>>(
+                src, ctx->trace, (const int64_t *)ctx->ev_len.p, (const int64_t *)ctx->ev_tile_off.p, ctx->ctr,
+                (const K2TileState *)ctx->k2_tiles.p, (double2 *)ctx->cc.p);
+        else
+            k2_tile_scan<double><<<grid, K2_THREADS, 0, ctx->stream>>>(
+                src, (const double *)ctx->flat64.p, (const int64_t *)ctx->ev_len.p,
+                (const int64_t *)ctx->ev_tile_off.p, ctx->ctr, (const K2TileState *)ctx->k2_tiles.p,
+                (double2 *)ctx->cc.p);
         LAUNCHED(ctx);
         if (prefix_mode != PP_PREFIX_PARALLEL) {
-            k2_check_exact<<<ctx->sm_count, 256, 0, ctx->stream>>>(ctx->ctr, (const int64_t *)ctx->ev_len.p,
-                                                                  (const K2EventBits *)ctx->k2_bits.p,
-                                                                  (unsigned *)ctx->inexact.p);
-            LAUNCHED(ctx);
             k2_prefix_sequential<<<ctx->sm_count * 16, 32, 0, ctx->stream>>>(
                 src, (const int64_t *)ctx->ev_len.p, ctx->ctr, (const unsigned *)ctx->inexact.p,
                 (double2 *)ctx->cc.p);
@@ -435,11 +441,18 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
 
 int enqueue_stats(pp_ctx *ctx)
 {
-    PPSource src = make_source(ctx);
-    k4_segment_stats<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
-        src, ctx->ctr, 0, (const int64_t *)ctx->seg_flat.p, (const int *)ctx->seg_event.p, ctx->cap_segs,
-        (double *)ctx->seg_mean.p, (double *)ctx->seg_std.p, (double *)ctx->seg_min.p,
-        (double *)ctx->seg_max.p);
+    if (ctx->src_kind == 0)
+        k4_segment_stats<float><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+            ctx->trace, (const int64_t *)ctx->ev_start.p, (const int64_t *)ctx->ev_off.p, ctx->ctr, 0,
+            (const int64_t *)ctx->seg_flat.p, (const int *)ctx->seg_event.p, ctx->cap_segs,
+            (double *)ctx->seg_mean.p, (double *)ctx->seg_std.p, (double *)ctx->seg_min.p,
+            (double *)ctx->seg_max.p);
+    else
+        k4_segment_stats<double><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+            (const double *)ctx->flat64.p, (const int64_t *)ctx->ev_off.p, (const int64_t *)ctx->ev_off.p,
+            ctx->ctr, 0, (const int64_t *)ctx->seg_flat.p, (const int *)ctx->seg_event.p, ctx->cap_segs,
+            (double *)ctx->seg_mean.p, (double *)ctx->seg_std.p, (double *)ctx->seg_min.p,
+            (double *)ctx->seg_max.p);
     LAUNCHED(ctx);
     CKR(record_boundary(ctx, ST_STATS + 1));
     ctx->stage_ran[ST_STATS] = true;
@@ -893,10 +906,16 @@ int pp_event_stats_download(pp_ctx *ctx, int64_t cap, double *mean, double *std,
     CKR(ensure(ctx, ctx->evs_std, 8 * e));
     CKR(ensure(ctx, ctx->evs_min, 8 * e));
     CKR(ensure(ctx, ctx->evs_max, 8 * e));
-    PPSource src = make_source(ctx);
-    k4_segment_stats<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
-        src, ctx->ctr, 1, (const int64_t *)ctx->ev_off.p, nullptr, (int64_t)e, (double *)ctx->evs_mean.p,
-        (double *)ctx->evs_std.p, (double *)ctx->evs_min.p, (double *)ctx->evs_max.p);
+    if (ctx->src_kind == 0)
+        k4_segment_stats<float><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+            ctx->trace, (const int64_t *)ctx->ev_start.p, (const int64_t *)ctx->ev_off.p, ctx->ctr, 1,
+            (const int64_t *)ctx->ev_off.p, nullptr, (int64_t)e, (double *)ctx->evs_mean.p,
+            (double *)ctx->evs_std.p, (double *)ctx->evs_min.p, (double *)ctx->evs_max.p);
+    else
+        k4_segment_stats<double><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+            (const double *)ctx->flat64.p, (const int64_t *)ctx->ev_off.p, (const int64_t *)ctx->ev_off.p,
+            ctx->ctr, 1, (const int64_t *)ctx->ev_off.p, nullptr, (int64_t)e, (double *)ctx->evs_mean.p,
+            (double *)ctx->evs_std.p, (double *)ctx->evs_min.p, (double *)ctx->evs_max.p);
     LAUNCHED(ctx);
     if (mean) CK(cudaMemcpyAsync(mean, ctx->evs_mean.p, 8 * e, cudaMemcpyDeviceToHost, ctx->stream));
     if (std) CK(cudaMemcpyAsync(std, ctx->evs_std.p, 8 * e, cudaMemcpyDeviceToHost, ctx->stream));

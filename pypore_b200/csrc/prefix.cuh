@@ -59,11 +59,15 @@ k2_prefix_sequential(PPSource src, const int64_t *__restrict__ ev_len, PPCounter
 
 
 // ---------------------------------------------------------------------------
-// Tiled scan with exactness proof.
+// Tiled scan with exactness proof (reduce-then-scan, no inter-CTA dependencies).
 //
 // Tiles never straddle events: event e owns tiles [ev_tile_off[e], ev_tile_off[e+1]) of
-// K2_TILE samples each, so the look-back of a tile only walks over earlier tiles of its own
-// event and no segmented operator is needed.
+// K2_TILE samples each.  Three stream-ordered kernels:
+//   k2_tile_reduce    per tile: sum of x and of x*x, and the exponent statistics below
+//   k2_event_carries  per event: exclusive prefix of its tiles' sums, exactness verdict
+//   k2_tile_scan      per tile: scan with the known carry, 16 B written per sample
+// The samples are read twice (4 B each time, the second time mostly from L2); in exchange no
+// CTA ever waits for another one.
 //
 // Exactness proof (order independent).  Let q = 2^elow be the coarsest power of two that
 // divides every summand of an event (elow = min over samples of the position of the lowest
@@ -72,8 +76,10 @@ k2_prefix_sequential(PPSource src, const int64_t *__restrict__ ev_len, PPCounter
 //         ceil(log2 n) + emax + 1 - elow <= 53
 // every such sum is exactly representable, so every partial sum of ANY summation order --
 // this scan's and np.cumsum's sequential one -- is computed without rounding and the two
-// agree bit for bit.  The test is evaluated separately for x and for fl(x*x).  Events that
-// fail it (or contain inf/NaN) are redone by k2_prefix_sequential.
+// agree bit for bit.  The test is evaluated separately for x and for fl(x*x).  For float32
+// samples x*x is exact in fp64 (24 x 24 mantissa bits), its lowest set bit is exactly twice
+// that of x and its magnitude exponent is at most 2 emax + 1, so only x is analysed.
+// Events that fail the test (or contain inf/NaN) are redone by k2_prefix_sequential.
 // ---------------------------------------------------------------------------
 constexpr int K2_THREADS = 256;
 constexpr int K2_ITEMS = 8;
@@ -81,10 +87,8 @@ constexpr int K2_TILE = K2_THREADS * K2_ITEMS;  // 2048 samples
 constexpr int K2_PAD = K2_ITEMS + 1;
 
 struct K2TileState {
-    double agg_c, agg_c2;  // sum over this tile
-    double inc_c, inc_c2;  // sum over this and all earlier tiles of the event
-    int status;            // (epoch << 2) | 1 aggregate published, | 2 inclusive published; other epochs = invalid
-    int pad[3];
+    double agg_c, agg_c2;      // sum over this tile
+    double carry_c, carry_c2;  // sum over all earlier tiles of the event
 };
 
 struct K2EventBits {  // per event: quantum / magnitude exponents of x and of x*x
@@ -112,6 +116,51 @@ __device__ __forceinline__ void k2_exponents(double v, int &elow, int &emax)
     elow = E - 1023 - 52 + (__ffsll((long long)m) - 1);
     emax = E - 1023;
 }
+
+// same for a float32 sample, 32-bit arithmetic only
+__device__ __forceinline__ void k2_exponents(float v, int &elow, int &emax)
+{
+    const unsigned b = __float_as_uint(v);
+    const int E = (int)((b >> 23) & 0xff);
+    unsigned m = b & 0x007fffffu;
+    if (E == 0xff) { elow = -K2_BAD_EXP; emax = K2_BAD_EXP; return; }
+    if (E == 0) {
+        if (m == 0) { elow = K2_ELOW_INIT; emax = K2_EMAX_INIT; return; }
+        elow = -149 + (__ffs((int)m) - 1);
+        emax = -127;
+        return;
+    }
+    m |= 0x00800000u;
+    elow = E - 127 - 23 + (__ffs((int)m) - 1);
+    emax = E - 127;
+}
+
+struct K2Exp {
+    int el1, em1, el2, em2;
+    __device__ __forceinline__ void init() { el1 = el2 = K2_ELOW_INIT; em1 = em2 = K2_EMAX_INIT; }
+    __device__ __forceinline__ void add(float x)
+    {
+        int a, b;
+        k2_exponents(x, a, b);
+        el1 = min(el1, a); em1 = max(em1, b);
+    }
+    __device__ __forceinline__ void add(double x)
+    {
+        int a, b;
+        k2_exponents(x, a, b);
+        el1 = min(el1, a); em1 = max(em1, b);
+        k2_exponents(__dmul_rn(x, x), a, b);
+        el2 = min(el2, a); em2 = max(em2, b);
+    }
+    __device__ __forceinline__ void warp_reduce()
+    {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            el1 = min(el1, __shfl_xor_sync(PP_FULL, el1, d)); em1 = max(em1, __shfl_xor_sync(PP_FULL, em1, d));
+            el2 = min(el2, __shfl_xor_sync(PP_FULL, el2, d)); em2 = max(em2, __shfl_xor_sync(PP_FULL, em2, d));
+        }
+    }
+};
 
 // exclusive prefix of tiles per event (one CTA; the event table is small)
 __global__ void __launch_bounds__(1024)
@@ -153,65 +202,166 @@ k2_tile_offsets(PPCounters *ctr, const int64_t *__restrict__ ev_len, int64_t *__
     if (tid == 0) {
         ev_tile_off[n_events] = s_carry;
         ctr->n_scan_tiles = (unsigned long long)s_carry;
-        ctr->scan_ticket = 0;
         ctr->n_seq_redo = 0;
     }
 }
 
+// Which event owns `tile`, and where the tile's samples are.
+struct K2Tile {
+    int64_t ev, base, off;
+    int cnt;
+};
+__device__ __forceinline__ K2Tile k2_locate(const PPSource &src, const int64_t *__restrict__ ev_len,
+                                            const int64_t *__restrict__ ev_tile_off, int64_t n_events, int64_t tile)
+{
+    K2Tile t;
+    t.ev = pp_upper_index(ev_tile_off, n_events, tile);
+    t.base = (tile - ev_tile_off[t.ev]) * K2_TILE;  // sample offset inside the event
+    const int64_t rest = ev_len[t.ev] - t.base;
+    t.cnt = (int)(rest < K2_TILE ? rest : K2_TILE);
+    t.off = src.ev_off[t.ev];
+    return t;
+}
+
+// Pass 1: per-tile sums and exponent statistics.  Any summation order will do (see above).
 template <typename T>
 __global__ void __launch_bounds__(K2_THREADS)
-k2_prefix_tiled(PPSource src, const T *__restrict__ samples /* trace (kind 0) or flat (kind 1) */,
-                const int64_t *__restrict__ ev_len, const int64_t *__restrict__ ev_tile_off, PPCounters *ctr,
-                K2TileState *__restrict__ tiles, K2EventBits *__restrict__ bits, double2 *__restrict__ cc,
-                int epoch)
+k2_tile_reduce(PPSource src, const T *__restrict__ samples /* trace (kind 0) or flat (kind 1) */,
+               const int64_t *__restrict__ ev_len, const int64_t *__restrict__ ev_tile_off, const PPCounters *ctr,
+               K2TileState *__restrict__ tiles, K2EventBits *__restrict__ bits)
+{
+    __shared__ double wc[K2_THREADS / 32], wc2[K2_THREADS / 32];
+    __shared__ int wex[4][K2_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n_events = (int64_t)ctr->n_events;
+    const int64_t n_tiles = (int64_t)ctr->n_scan_tiles;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const K2Tile t = k2_locate(src, ev_len, ev_tile_off, n_events, tile);
+        const T *in = samples + (src.kind == 0 ? src.ev_start[t.ev] : t.off) + t.base;
+        T xv[K2_ITEMS];
+#pragma unroll
+        for (int i = 0; i < K2_ITEMS; ++i) {
+            const int q = i * K2_THREADS + tid;
+            xv[i] = q < t.cnt ? __ldg(in + q) : (T)0;
+        }
+        double c = 0.0, c2 = 0.0;
+        K2Exp ex;
+        ex.init();
+#pragma unroll
+        for (int i = 0; i < K2_ITEMS; ++i) {
+            const double x = (double)xv[i];
+            ex.add(xv[i]);
+            c = __dadd_rn(c, x);
+            c2 = __dadd_rn(c2, __dmul_rn(x, x));
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            c = __dadd_rn(c, __shfl_xor_sync(PP_FULL, c, d));
+            c2 = __dadd_rn(c2, __shfl_xor_sync(PP_FULL, c2, d));
+        }
+        ex.warp_reduce();
+        __syncthreads();  // previous iteration's readers are done
+        if (lane == 0) {
+            wc[warp] = c; wc2[warp] = c2;
+            wex[0][warp] = ex.el1; wex[1][warp] = ex.em1; wex[2][warp] = ex.el2; wex[3][warp] = ex.em2;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0, tot2 = 0.0;
+            int a1 = K2_ELOW_INIT, b1 = K2_EMAX_INIT, a2 = K2_ELOW_INIT, b2 = K2_EMAX_INIT;
+#pragma unroll
+            for (int w = 0; w < K2_THREADS / 32; ++w) {
+                tot = __dadd_rn(tot, wc[w]); tot2 = __dadd_rn(tot2, wc2[w]);
+                a1 = min(a1, wex[0][w]); b1 = max(b1, wex[1][w]); a2 = min(a2, wex[2][w]); b2 = max(b2, wex[3][w]);
+            }
+            tiles[tile].agg_c = tot;
+            tiles[tile].agg_c2 = tot2;
+            if (sizeof(T) == 4 && b1 != K2_EMAX_INIT) {  // float32: x*x is exact, its exponents follow from x's
+                a2 = a1 > -K2_BAD_EXP ? 2 * a1 : -K2_BAD_EXP;
+                b2 = b1 < K2_BAD_EXP ? 2 * b1 + 1 : K2_BAD_EXP;
+            }
+            atomicMin(&bits[t.ev].elow1, a1); atomicMax(&bits[t.ev].emax1, b1);
+            atomicMin(&bits[t.ev].elow2, a2); atomicMax(&bits[t.ev].emax2, b2);
+        }
+    }
+}
+
+// Pass 2: one warp per event -- exclusive prefix of the event's tile sums, and the exactness verdict.
+__global__ void __launch_bounds__(256)
+k2_event_carries(const PPCounters *ctr, const int64_t *__restrict__ ev_len, const int64_t *__restrict__ ev_tile_off,
+                 K2TileState *__restrict__ tiles, const K2EventBits *__restrict__ bits, unsigned *__restrict__ inexact,
+                 int check)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t n_events = (int64_t)ctr->n_events;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n_events; e += warps) {
+        const int64_t t0 = ev_tile_off[e], t1 = ev_tile_off[e + 1];
+        double carry_c = 0.0, carry_c2 = 0.0;
+        for (int64_t b = t0; b < t1; b += 32) {
+            const int64_t t = b + lane;
+            const double v = t < t1 ? tiles[t].agg_c : 0.0, v2 = t < t1 ? tiles[t].agg_c2 : 0.0;
+            double ic = v, ic2 = v2;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double u1 = __shfl_up_sync(PP_FULL, ic, d), u2 = __shfl_up_sync(PP_FULL, ic2, d);
+                if (lane >= d) { ic = __dadd_rn(u1, ic); ic2 = __dadd_rn(u2, ic2); }
+            }
+            if (t < t1) {
+                tiles[t].carry_c = __dadd_rn(carry_c, __dsub_rn(ic, v));
+                tiles[t].carry_c2 = __dadd_rn(carry_c2, __dsub_rn(ic2, v2));
+            }
+            carry_c = __dadd_rn(carry_c, __shfl_sync(PP_FULL, ic, 31));
+            carry_c2 = __dadd_rn(carry_c2, __shfl_sync(PP_FULL, ic2, 31));
+        }
+        if (check && lane == 0) {
+            const long long n = ev_len[e];
+            int lg = 0;
+            while ((1LL << lg) < n) ++lg;
+            const K2EventBits b = bits[e];
+            bool ok = true;
+            if (b.emax1 != K2_EMAX_INIT) ok = ok && ((long long)lg + b.emax1 + 1 - b.elow1 <= 53);
+            if (b.emax2 != K2_EMAX_INIT) ok = ok && ((long long)lg + b.emax2 + 1 - b.elow2 <= 53);
+            inexact[e] = ok ? 0u : 1u;
+        }
+    }
+}
+
+// Pass 3: per-tile scan with the carry of the earlier tiles.
+template <typename T>
+__global__ void __launch_bounds__(K2_THREADS, 4)
+k2_tile_scan(PPSource src, const T *__restrict__ samples, const int64_t *__restrict__ ev_len,
+             const int64_t *__restrict__ ev_tile_off, const PPCounters *ctr,
+             const K2TileState *__restrict__ tiles, double2 *__restrict__ cc)
 {
     // input staging (T) and output staging (double2) share the same shared memory
     __shared__ __align__(16) unsigned char raw[sizeof(double2) * K2_THREADS * K2_PAD];
     __shared__ double wc[K2_THREADS / 32], wc2[K2_THREADS / 32];
-    __shared__ int wel1[K2_THREADS / 32], wem1[K2_THREADS / 32], wel2[K2_THREADS / 32], wem2[K2_THREADS / 32];
-    __shared__ long long s_tile;
-    __shared__ double s_carry_c, s_carry_c2;
     T *sin = reinterpret_cast<T *>(raw);
     double2 *sout = reinterpret_cast<double2 *>(raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n_events = (int64_t)ctr->n_events;
     const int64_t n_tiles = (int64_t)ctr->n_scan_tiles;
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_tile = (long long)atomicAdd(&ctr->scan_ticket, 1ull);
-        __syncthreads();
-        const int64_t tile = s_tile;
-        if (tile >= n_tiles) return;
-        const int64_t ev = pp_upper_index(ev_tile_off, n_events, tile);
-        const int64_t first_tile = ev_tile_off[ev];
-        const int64_t base = (tile - first_tile) * K2_TILE;       // sample offset inside the event
-        const int64_t len = ev_len[ev];
-        const int cnt = (int)((len - base) < K2_TILE ? (len - base) : K2_TILE);
-        const int64_t off = src.ev_off[ev];
-        const T *in = samples + (src.kind == 0 ? src.ev_start[ev] : off) + base;
-
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const K2Tile t = k2_locate(src, ev_len, ev_tile_off, n_events, tile);
+        const T *in = samples + (src.kind == 0 ? src.ev_start[t.ev] : t.off) + t.base;
+        const double carry_c = tiles[tile].carry_c, carry_c2 = tiles[tile].carry_c2;
+        __syncthreads();  // the previous tile's output staging has been drained
         // coalesced load -> padded shared memory (conflict-free blocked reads)
 #pragma unroll
         for (int i = 0; i < K2_ITEMS; ++i) {
             const int q = i * K2_THREADS + tid;
-            sin[(q / K2_ITEMS) * K2_PAD + (q % K2_ITEMS)] = q < cnt ? __ldg(in + q) : (T)0;
+            sin[(q / K2_ITEMS) * K2_PAD + (q % K2_ITEMS)] = q < t.cnt ? __ldg(in + q) : (T)0;
         }
         __syncthreads();
         double pc[K2_ITEMS], pc2[K2_ITEMS];
         double c = 0.0, c2 = 0.0;
-        int el1 = K2_ELOW_INIT, em1 = K2_EMAX_INIT, el2 = K2_ELOW_INIT, em2 = K2_EMAX_INIT;
 #pragma unroll
         for (int k = 0; k < K2_ITEMS; ++k) {
             const double x = (double)sin[tid * K2_PAD + k];
-            const double x2 = __dmul_rn(x, x);
-            int a, b;
-            k2_exponents(x, a, b);
-            el1 = min(el1, a); em1 = max(em1, b);
-            k2_exponents(x2, a, b);
-            el2 = min(el2, a); em2 = max(em2, b);
             c = __dadd_rn(c, x);
-            c2 = __dadd_rn(c2, x2);
+            c2 = __dadd_rn(c2, __dmul_rn(x, x));
             pc[k] = c; pc2[k] = c2;
         }
         // warp scan of thread totals
@@ -221,87 +371,22 @@ k2_prefix_tiled(PPSource src, const T *__restrict__ samples /* trace (kind 0) or
             const double t1 = __shfl_up_sync(PP_FULL, ic, d), t2 = __shfl_up_sync(PP_FULL, ic2, d);
             if (lane >= d) { ic = __dadd_rn(t1, ic); ic2 = __dadd_rn(t2, ic2); }
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            el1 = min(el1, __shfl_xor_sync(PP_FULL, el1, d)); em1 = max(em1, __shfl_xor_sync(PP_FULL, em1, d));
-            el2 = min(el2, __shfl_xor_sync(PP_FULL, el2, d)); em2 = max(em2, __shfl_xor_sync(PP_FULL, em2, d));
-        }
         if (lane == 31) { wc[warp] = ic; wc2[warp] = ic2; }
-        if (lane == 0) { wel1[warp] = el1; wem1[warp] = em1; wel2[warp] = el2; wem2[warp] = em2; }
         __syncthreads();  // also: every thread has consumed its inputs from `raw`
-        double wpre = 0.0, wpre2 = 0.0;
+        double wpre = carry_c, wpre2 = carry_c2;
         for (int w = 0; w < warp; ++w) { wpre = __dadd_rn(wpre, wc[w]); wpre2 = __dadd_rn(wpre2, wc2[w]); }
-        if (tid == 0) {
-            double tot = 0.0, tot2 = 0.0;
-            int a1 = K2_ELOW_INIT, b1 = K2_EMAX_INIT, a2 = K2_ELOW_INIT, b2 = K2_EMAX_INIT;
-            for (int w = 0; w < K2_THREADS / 32; ++w) {
-                tot = __dadd_rn(tot, wc[w]); tot2 = __dadd_rn(tot2, wc2[w]);
-                a1 = min(a1, wel1[w]); b1 = max(b1, wem1[w]); a2 = min(a2, wel2[w]); b2 = max(b2, wem2[w]);
-            }
-            atomicMin(&bits[ev].elow1, a1); atomicMax(&bits[ev].emax1, b1);
-            atomicMin(&bits[ev].elow2, a2); atomicMax(&bits[ev].emax2, b2);
-            // decoupled look-back over the earlier tiles of this event
-            K2TileState *me = tiles + tile;
-            double carry_c = 0.0, carry_c2 = 0.0;
-            if (tile == first_tile) {
-                me->inc_c = tot; me->inc_c2 = tot2;
-                __threadfence();
-                atomicExch(&me->status, (epoch << 2) | 2);
-            } else {
-                me->agg_c = tot; me->agg_c2 = tot2;
-                __threadfence();
-                atomicExch(&me->status, (epoch << 2) | 1);
-                for (int64_t j = tile - 1;; --j) {
-                    K2TileState *p = tiles + j;
-                    int st;
-                    while (((st = *((volatile int *)&p->status)) >> 2) != epoch) __nanosleep(64);
-                    __threadfence();
-                    if ((st & 3) == 2) {
-                        carry_c = __dadd_rn(*((volatile double *)&p->inc_c), carry_c);
-                        carry_c2 = __dadd_rn(*((volatile double *)&p->inc_c2), carry_c2);
-                        break;
-                    }
-                    carry_c = __dadd_rn(*((volatile double *)&p->agg_c), carry_c);
-                    carry_c2 = __dadd_rn(*((volatile double *)&p->agg_c2), carry_c2);
-                }
-                me->inc_c = __dadd_rn(carry_c, tot); me->inc_c2 = __dadd_rn(carry_c2, tot2);
-                __threadfence();
-                atomicExch(&me->status, (epoch << 2) | 2);
-            }
-            s_carry_c = carry_c; s_carry_c2 = carry_c2;
-        }
-        __syncthreads();
         // exclusive prefix of this thread = carry + earlier warps + earlier lanes
-        const double ec = __dadd_rn(__dadd_rn(s_carry_c, wpre), __dsub_rn(ic, c));
-        const double ec2 = __dadd_rn(__dadd_rn(s_carry_c2, wpre2), __dsub_rn(ic2, c2));
+        const double ec = __dadd_rn(wpre, __dsub_rn(ic, c));
+        const double ec2 = __dadd_rn(wpre2, __dsub_rn(ic2, c2));
 #pragma unroll
         for (int k = 0; k < K2_ITEMS; ++k)
             sout[tid * K2_PAD + k] = make_double2(__dadd_rn(ec, pc[k]), __dadd_rn(ec2, pc2[k]));
         __syncthreads();
-        double2 *dst = cc + off + base;
+        double2 *dst = cc + t.off + t.base;
 #pragma unroll
         for (int i = 0; i < K2_ITEMS; ++i) {
             const int q = i * K2_THREADS + tid;
-            if (q < cnt) dst[q] = sout[(q / K2_ITEMS) * K2_PAD + (q % K2_ITEMS)];
+            if (q < t.cnt) dst[q] = sout[(q / K2_ITEMS) * K2_PAD + (q % K2_ITEMS)];
         }
-    }
-}
-
-// Evaluate the exactness condition per event; flag the events that need the sequential redo.
-__global__ void __launch_bounds__(256)
-k2_check_exact(PPCounters *ctr, const int64_t *__restrict__ ev_len, const K2EventBits *__restrict__ bits,
-               unsigned *__restrict__ inexact)
-{
-    const int64_t n_events = (int64_t)ctr->n_events;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_events;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        const long long n = ev_len[e];
-        int lg = 0;
-        while ((1LL << lg) < n) ++lg;
-        const K2EventBits b = bits[e];
-        bool ok = true;
-        if (b.emax1 != K2_EMAX_INIT) ok = ok && ((long long)lg + b.emax1 + 1 - b.elow1 <= 53);
-        if (b.emax2 != K2_EMAX_INIT) ok = ok && ((long long)lg + b.emax2 + 1 - b.elow2 <= 53);
-        inexact[e] = ok ? 0u : 1u;
     }
 }
