@@ -242,11 +242,11 @@ def run_ours(args):
 
     def step_e2e():
         if shard is None:
-            ctx.upload_trace_async(xp)
+            # public host-memory entry point: chunked H2D copy overlapped with the stages, then table download
             r = ctx.pipeline(THRESHOLD, min_width=mw, max_width=MW, window_width=W, min_gain=gain,
-                             with_stats=True, **rules)
+                             with_stats=True, host_trace=xp, **rules)
             ctx.events(r["events"])
-            ctx.segments(r["segments"])
+            ctx.segments(r["segments"], pinned=True)
             return r
         shard.load(xp)
         r = shard.step(THRESHOLD, rules, mw, MW, W, gain)

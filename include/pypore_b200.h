@@ -65,6 +65,10 @@ int pp_create(int device, void *cuda_stream, pp_ctx **out);
 void pp_destroy(pp_ctx *ctx);
 const char *pp_last_error(pp_ctx *ctx);
 int pp_sync(pp_ctx *ctx);
+/* Page-locked host memory (cudaMallocHost) for traces handed to pp_pipeline_host /
+ * pp_trace_upload and for table downloads: copies to and from it run at full PCIe rate. */
+int pp_host_alloc(pp_ctx *ctx, int64_t bytes, void **out);
+void pp_host_free(pp_ctx *ctx, void *p);
 /* Options: PP_OPT_SCREEN (default 1) -- 1: two-stage split search (bounded-error
  * screening of every candidate, exact arithmetic for the contenders); 0: exact
  * arithmetic for every candidate (validation mode, same results, many times slower). */
@@ -178,6 +182,14 @@ typedef struct pp_pipeline_params {
  * the resident trace.  Counts: out[0] runs, out[1] events, out[2] event
  * samples, out[3] segments. */
 int pp_pipeline(pp_ctx *ctx, const pp_pipeline_params *p, int64_t out[4]);
+/* The same pipeline for a trace in HOST memory (File(current=...).parse(...) end to end): the
+ * trace is copied in chunks of `chunk_samples` (<= 0: 16 Mi samples; use pinned memory for an
+ * asynchronous copy) on a second stream while the threshold scan, event selection, prefix sums and
+ * split search already run on the events completed by the chunks that have arrived; compaction and
+ * statistics follow the last chunk.  Results are identical to pp_trace_upload + pp_pipeline.
+ * With a filter, or a trace of at most one chunk, it is exactly that sequence. */
+int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_samples,
+                     const pp_pipeline_params *p, int64_t out[4]);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpypore_b200.so")
+LIB_PATH = os.environ.get("PYPORE_B200_LIB") or os.path.join(HERE, "libpypore_b200.so")  # override: development variants only
 
 PP_OK = 0
 PP_ERR_CUDA, PP_ERR_ARG, PP_ERR_CAPACITY, PP_ERR_STATE, PP_ERR_FILTER_LEN = -1, -2, -3, -4, -5
@@ -78,6 +78,9 @@ SIGNATURES = {
     "pp_split_counters": (_c.c_int, [_c.c_void_p, _i64p]),
     "pp_debug_screen": (_c.c_int, [_c.c_void_p, _i64, _c.c_int, _c.c_int, _c.c_int, _f64p, _f64p, _u8p, _f64p]),
     "pp_debug_lg2_error": (_c.c_int, [_c.c_void_p, _f64p]),
+    "pp_host_alloc": (_c.c_int, [_c.c_void_p, _i64, _c.POINTER(_c.c_void_p)]),
+    "pp_host_free": (None, [_c.c_void_p, _c.c_void_p]),
+    "pp_pipeline_host": (_c.c_int, [_c.c_void_p, _f32p, _i64, _i64, _c.POINTER(PipelineParams), _i64p]),
     "pp_pipeline": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _i64p]),
 }
 
@@ -127,8 +130,43 @@ class Context(object):
 
     def close(self):
         if getattr(self, "_h", None):
+            if getattr(self, "_arena", None):
+                self._L.pp_host_free(self._h, self._arena[0])
+                self._arena = None
             self._L.pp_destroy(self._h)
             self._h = None
+
+    def pinned_empty(self, n, dtype):
+        """A new page-locked numpy array (freed with the context); for traces given to
+        pipeline(host_trace=...) so that the chunked copy really is asynchronous."""
+        dtype = np.dtype(dtype)
+        p = _c.c_void_p()
+        nbytes = max(int(n) * dtype.itemsize, 1)
+        self._ck(self._L.pp_host_alloc(self._h, nbytes, _c.byref(p)))
+        self._pinned_keep = getattr(self, "_pinned_keep", [])
+        self._pinned_keep.append(p.value)
+        buf = (_c.c_char * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def _arena_views(self, spec):
+        """Views (name -> array) laid out back to back in the context's grow-only pinned arena.
+        Valid until the next pinned download on this context."""
+        total = sum(((n * np.dtype(dt).itemsize + 63) // 64) * 64 for _, n, dt in spec) + 64
+        arena = getattr(self, "_arena", None)
+        if arena is None or arena[1] < total:
+            if arena is not None:
+                self._L.pp_host_free(self._h, arena[0])
+            p = _c.c_void_p()
+            cap = int(total * 1.25)
+            self._ck(self._L.pp_host_alloc(self._h, cap, _c.byref(p)))
+            self._arena = arena = (p.value, cap)
+        out, off = {}, 0
+        for name, n, dt in spec:
+            nbytes = n * np.dtype(dt).itemsize
+            buf = (_c.c_char * max(nbytes, 1)).from_address(arena[0] + off)
+            out[name] = np.frombuffer(buf, dtype=dt, count=n)
+            off += ((nbytes + 63) // 64) * 64
+        return out
 
     def __del__(self):
         try:
@@ -278,14 +316,23 @@ class Context(object):
     def segment_stats(self):
         self._ck(self._L.pp_segment_stats(self._h))
 
-    def segments(self, n_segments, stats=True):
-        ev = np.empty(n_segments, np.int32)
-        start = np.empty(n_segments, np.int64)
-        end = np.empty(n_segments, np.int64)
-        out = {"event": ev, "start": start, "end": end}
-        if stats:
-            for k in ("mean", "std", "min", "max"):
-                out[k] = np.empty(n_segments, np.float64)
+    def segments(self, n_segments, stats=True, pinned=False):
+        """Segment table as numpy arrays.  pinned=True returns views of the context's page-locked
+        arena (full-rate D2H copy, no extra host copy); they are overwritten by the next pinned download."""
+        if pinned:
+            spec = [("event", n_segments, np.int32), ("start", n_segments, np.int64), ("end", n_segments, np.int64)]
+            if stats:
+                spec += [(k, n_segments, np.float64) for k in ("mean", "std", "min", "max")]
+            out = self._arena_views(spec)
+            ev, start, end = out["event"], out["start"], out["end"]
+        else:
+            ev = np.empty(n_segments, np.int32)
+            start = np.empty(n_segments, np.int64)
+            end = np.empty(n_segments, np.int64)
+            out = {"event": ev, "start": start, "end": end}
+            if stats:
+                for k in ("mean", "std", "min", "max"):
+                    out[k] = np.empty(n_segments, np.float64)
         self._ck(self._L.pp_segments_download(
             self._h, n_segments, _ptr(ev, _i32p), _ptr(start, _i64p), _ptr(end, _i64p),
             _ptr(out.get("mean"), _f64p), _ptr(out.get("std"), _f64p), _ptr(out.get("min"), _f64p),
@@ -323,7 +370,9 @@ class Context(object):
 
     def pipeline(self, threshold, rule_mask, duration_gt, duration_lt, min_gt, max_lt, min_width,
                  max_width, window_width, min_gain, filter_ba=None, prefix_mode=PREFIX_AUTO,
-                 with_stats=True):
+                 with_stats=True, host_trace=None, chunk_samples=0):
+        """Whole pipeline on the resident trace, or -- with `host_trace` (float32, ideally pinned) --
+        streamed from host memory in chunks that overlap the copy with the computation."""
         p = PipelineParams()
         p.threshold = float(threshold)
         p.rule_mask = int(rule_mask)
@@ -342,7 +391,12 @@ class Context(object):
         p.prefix_mode = int(prefix_mode)
         p.with_stats = int(bool(with_stats))
         out = np.zeros(4, np.int64)
-        self._ck(self._L.pp_pipeline(self._h, _c.byref(p), _ptr(out, _i64p)))
+        if host_trace is None:
+            self._ck(self._L.pp_pipeline(self._h, _c.byref(p), _ptr(out, _i64p)))
+        else:
+            x = np.ascontiguousarray(host_trace, np.float32)
+            self._ck(self._L.pp_pipeline_host(self._h, _ptr(x, _f32p), x.shape[0], int(chunk_samples),
+                                              _c.byref(p), _ptr(out, _i64p)))
         del keep
         return dict(runs=int(out[0]), events=int(out[1]), event_samples=int(out[2]), segments=int(out[3]))
 

@@ -41,11 +41,13 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, defines=(), out=None):
+    """`defines` / `out` build an experimental variant next to the product library (development only;
+    select it with PYPORE_B200_LIB)."""
+    if out is None and not force and up_to_date():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
+          [os.path.join(CSRC, f) for f in SOURCES] + ["-o", out or LIB]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
@@ -53,4 +55,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs,
+                out=outs[0] if outs else None))

@@ -73,6 +73,11 @@ struct pp_ctx {
     // filter scratch
     DevBuf filt_tmp, filt_carry, filt_coef;
 
+    // streamed pipeline (pp_pipeline_host): copies run on their own stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev = nullptr, compute_ev = nullptr;
+    int64_t n_words = 0, n_blocks = 0;
+
     cudaEvent_t ev[ST_COUNT + 1] = {0};
     bool stage_ran[ST_COUNT] = {false};
     bool rec[ST_COUNT + 1] = {false};  // boundary i recorded in the current call sequence
@@ -197,10 +202,9 @@ int ensure_event_buffers(pp_ctx *ctx, int64_t cap_events)
 
 // ---- stage enqueue helpers (no host synchronisation) ----------------------
 
-int enqueue_threshold(pp_ctx *ctx, double threshold, int64_t scan_len)
+// Buffers and zeroed state for a threshold scan of the first scan_len samples.
+int begin_threshold(pp_ctx *ctx, int64_t scan_len)
 {
-    if (!ctx->trace || ctx->n <= 0) return fail(ctx, PP_ERR_STATE, "no trace resident");
-    if (scan_len < 0 || scan_len > ctx->n) scan_len = ctx->n;
     ctx->scan_len = scan_len;
     int64_t want = scan_len / 64 + 4096;
     if (want < ctx->cap_runs) want = ctx->cap_runs;
@@ -208,31 +212,46 @@ int enqueue_threshold(pp_ctx *ctx, double threshold, int64_t scan_len)
     CKR(ensure_event_buffers(ctx, ctx->cap_runs));
     const int64_t ntiles = (scan_len + K1_TILE - 1) / K1_TILE;
     CKR(ensure(ctx, ctx->tile_state, sizeof(unsigned long long) * ntiles));
-    // smallest float32 >= threshold: double(x) < thr  <=>  x < thr_up for every float32 x
-    float thr_f = (float)threshold;
-    if ((double)thr_f < threshold) thr_f = nextafterf(thr_f, INFINITY);
     CK(cudaMemsetAsync(ctx->ctr, 0, sizeof(PPCounters), ctx->stream));
     CK(cudaMemsetAsync(ctx->tile_state.p, 0, sizeof(unsigned long long) * ntiles, ctx->stream));
     CK(cudaMemsetAsync(ctx->run_minkey.p, 0xff, sizeof(unsigned) * ctx->cap_runs, ctx->stream));
     CK(cudaMemsetAsync(ctx->run_maxkey.p, 0, sizeof(unsigned) * ctx->cap_runs, ctx->stream));
-    k1_threshold_scan<<<(unsigned)ntiles, K1_THREADS, 0, ctx->stream>>>(
-        ctx->trace, scan_len, thr_f, (unsigned long long *)ctx->tile_state.p, ctx->ctr,
-        (int64_t *)ctx->run_start.p, (unsigned *)ctx->run_minkey.p, (unsigned *)ctx->run_maxkey.p,
-        ctx->cap_runs);
-    LAUNCHED(ctx);
-    k1_finalize_runs<<<ctx->sm_count, 256, 0, ctx->stream>>>(
-        scan_len, ctx->ctr, (const int64_t *)ctx->run_start.p, (const unsigned *)ctx->run_minkey.p,
-        (const unsigned *)ctx->run_maxkey.p, ctx->cap_runs, (int64_t *)ctx->run_len.p,
-        (double *)ctx->run_min.p, (double *)ctx->run_max.p, (unsigned char *)ctx->run_below.p);
-    LAUNCHED(ctx);
     ctx->n_runs = -1;
     ctx->n_events = ctx->n_event_samples = ctx->n_segments = -1;
     ctx->stats_valid = false;
     return PP_OK;
 }
 
+// Scan the next `ntiles` tiles (the tile counter continues across calls) of the trace prefix
+// [0, upto) and decode the run table found so far.
+int enqueue_threshold_tiles(pp_ctx *ctx, double threshold, int64_t upto, int64_t ntiles)
+{
+    // smallest float32 >= threshold: double(x) < thr  <=>  x < thr_up for every float32 x
+    float thr_f = (float)threshold;
+    if ((double)thr_f < threshold) thr_f = nextafterf(thr_f, INFINITY);
+    k1_threshold_scan<<<(unsigned)ntiles, K1_THREADS, 0, ctx->stream>>>(
+        ctx->trace, upto, thr_f, (unsigned long long *)ctx->tile_state.p, ctx->ctr,
+        (int64_t *)ctx->run_start.p, (unsigned *)ctx->run_minkey.p, (unsigned *)ctx->run_maxkey.p,
+        ctx->cap_runs);
+    LAUNCHED(ctx);
+    k1_finalize_runs<<<ctx->sm_count, 256, 0, ctx->stream>>>(
+        upto, ctx->ctr, (const int64_t *)ctx->run_start.p, (const unsigned *)ctx->run_minkey.p,
+        (const unsigned *)ctx->run_maxkey.p, ctx->cap_runs, (int64_t *)ctx->run_len.p,
+        (double *)ctx->run_min.p, (double *)ctx->run_max.p, (unsigned char *)ctx->run_below.p);
+    LAUNCHED(ctx);
+    return PP_OK;
+}
+
+int enqueue_threshold(pp_ctx *ctx, double threshold, int64_t scan_len)
+{
+    if (!ctx->trace || ctx->n <= 0) return fail(ctx, PP_ERR_STATE, "no trace resident");
+    if (scan_len < 0 || scan_len > ctx->n) scan_len = ctx->n;
+    CKR(begin_threshold(ctx, scan_len));
+    return enqueue_threshold_tiles(ctx, threshold, scan_len, (scan_len + K1_TILE - 1) / K1_TILE);
+}
+
 int enqueue_select(pp_ctx *ctx, int rule_mask, int64_t duration_gt, int64_t duration_lt,
-                   double min_gt, double max_lt, int skip_first, int skip_last)
+                   double min_gt, double max_lt, int skip_first, int skip_last, int incremental = 0)
 {
     ctx->src_kind = 0;
     ctx->flat_cap = ctx->n;
@@ -240,7 +259,7 @@ int enqueue_select(pp_ctx *ctx, int rule_mask, int64_t duration_gt, int64_t dura
         ctx->ctr, (const int64_t *)ctx->run_start.p, (const int64_t *)ctx->run_len.p,
         (const double *)ctx->run_min.p, (const double *)ctx->run_max.p, ctx->cap_runs, rule_mask,
         duration_gt, duration_lt, min_gt, max_lt, skip_first, skip_last, (int64_t *)ctx->ev_start.p,
-        (int64_t *)ctx->ev_len.p, (int64_t *)ctx->ev_off.p, ctx->cap_events);
+        (int64_t *)ctx->ev_len.p, (int64_t *)ctx->ev_off.p, ctx->cap_events, incremental);
     LAUNCHED(ctx);
     ctx->n_events = ctx->n_event_samples = ctx->n_segments = -1;
     ctx->stats_valid = false;
@@ -303,7 +322,8 @@ int enqueue_filter(pp_ctx *ctx, const double *b, const double *a, const double *
     return PP_OK;
 }
 
-int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefix_mode)
+// Argument checks and buffers for K2/K3/compaction, sized by upper bounds (no host sync later).
+int prepare_split(pp_ctx *ctx, int mw, int MW, int W)
 {
     if (mw < 0 || MW < mw || W < 2 * mw || W / 2 < 1)
         return fail(ctx, PP_ERR_ARG, "invalid split parameters (min_width=%d max_width=%d window_width=%d)",
@@ -333,9 +353,23 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
         ctx->cap_segs = cap_segs;
     }
     ctx->q_cap = q_cap;
-    PPSource src = make_source(ctx);
+    ctx->n_words = n_words;
+    ctx->n_blocks = n_blocks;
+    if (W + 1 > ctx->T_len) {
+        CKR(ensure(ctx, ctx->Ttab, sizeof(double) * (size_t)(W + 1)));
+        k3_fill_RN<<<ctx->sm_count, 256, 0, ctx->stream>>>((double *)ctx->Ttab.p, W + 1);
+        LAUNCHED(ctx);
+        ctx->T_len = W + 1;
+    }
+    CK(cudaMemsetAsync(ctx->bits.p, 0, sizeof(unsigned) * n_words, ctx->stream));
+    return PP_OK;
+}
 
-    // K2: prefix sums
+// K2 over the events [ev_begin, n_events) (device-side range)
+int enqueue_prefix(pp_ctx *ctx, int prefix_mode)
+{
+    const int64_t ncap = ctx->flat_cap;
+    PPSource src = make_source(ctx);
     if (prefix_mode == PP_PREFIX_SEQUENTIAL) {
         k2_prefix_sequential<<<ctx->sm_count * 16, 32, 0, ctx->stream>>>(
             src, (const int64_t *)ctx->ev_len.p, ctx->ctr, nullptr, (double2 *)ctx->cc.p);
@@ -383,11 +417,13 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
             LAUNCHED(ctx);
         }
     }
-    CKR(record_boundary(ctx, ST_PREFIX + 1));
-    ctx->stage_ran[ST_PREFIX] = true;
+    return PP_OK;
+}
 
-    // K3: split search
-    CK(cudaMemsetAsync(ctx->bits.p, 0, sizeof(unsigned) * n_words, ctx->stream));
+// K3 over the events [ev_begin, n_events)
+int enqueue_search(pp_ctx *ctx, int mw, int MW, int W, double min_gain)
+{
+    const int64_t q_cap = ctx->q_cap;
     CK(cudaMemsetAsync(ctx->ready.p, 0, sizeof(int) * q_cap, ctx->stream));
     K3Global G;
     G.cc = (const double2 *)ctx->cc.p;
@@ -412,10 +448,13 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
     LAUNCHED(ctx);
     k3_split<<<ctx->sm_count * K3_CTAS_PER_SM, K3_THREADS, K3_SMEM_BYTES, ctx->stream>>>(G, P);
     LAUNCHED(ctx);
-    CKR(record_boundary(ctx, ST_SPLIT + 1));
-    ctx->stage_ran[ST_SPLIT] = true;
+    return PP_OK;
+}
 
-    // bitmap -> segment table
+// bitmap -> segment table (all events)
+int enqueue_compact(pp_ctx *ctx)
+{
+    const int64_t n_words = ctx->n_words, n_blocks = ctx->n_blocks;
     k3c_count<<<(unsigned)n_blocks, CP_THREADS, 0, ctx->stream>>>((const unsigned *)ctx->bits.p, n_words,
                                                                  (unsigned *)ctx->block_count.p);
     LAUNCHED(ctx);
@@ -432,6 +471,19 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
                                                      (const int64_t *)ctx->ev_off.p,
                                                      (int64_t *)ctx->seg_end.p, ctx->cap_segs);
     LAUNCHED(ctx);
+    return PP_OK;
+}
+
+int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefix_mode)
+{
+    CKR(prepare_split(ctx, mw, MW, W));
+    CKR(enqueue_prefix(ctx, prefix_mode));
+    CKR(record_boundary(ctx, ST_PREFIX + 1));
+    ctx->stage_ran[ST_PREFIX] = true;
+    CKR(enqueue_search(ctx, mw, MW, W, min_gain));
+    CKR(record_boundary(ctx, ST_SPLIT + 1));
+    ctx->stage_ran[ST_SPLIT] = true;
+    CKR(enqueue_compact(ctx));
     CKR(record_boundary(ctx, ST_COMPACT + 1));
     ctx->stage_ran[ST_COMPACT] = true;
     ctx->n_segments = -1;
@@ -552,11 +604,28 @@ void pp_destroy(pp_ctx *ctx)
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     for (int i = 0; i <= ST_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->copy_ev) cudaEventDestroy(ctx->copy_ev);
+    if (ctx->compute_ev) cudaEventDestroy(ctx->compute_ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 const char *pp_last_error(pp_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+int pp_host_alloc(pp_ctx *ctx, int64_t bytes, void **out)
+{
+    if (!ctx || !out || bytes <= 0) return fail(ctx, PP_ERR_ARG, "bad host allocation");
+    CKR(set_device(ctx));
+    CK(cudaMallocHost(out, (size_t)bytes));
+    return PP_OK;
+}
+
+void pp_host_free(pp_ctx *ctx, void *p)
+{
+    if (ctx) cudaSetDevice(ctx->device);
+    if (p) cudaFreeHost(p);
+}
 
 int pp_sync(pp_ctx *ctx)
 {
@@ -1031,6 +1100,71 @@ int pp_pipeline(pp_ctx *ctx, const pp_pipeline_params *p, int64_t out[4])
         return PP_OK;
     }
     return fail(ctx, PP_ERR_CAPACITY, "run table overflow");
+}
+
+// Same pipeline fed from host memory: the trace is copied in chunks on a second stream and every
+// stage up to the split search runs on the events completed so far while the next chunk is in flight.
+int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_samples,
+                     const pp_pipeline_params *p, int64_t out[4])
+{
+    if (!ctx || !p || !host || n <= 0) return fail(ctx, PP_ERR_ARG, "bad trace");
+    CKR(set_device(ctx));
+    if (chunk_samples <= 0) chunk_samples = (int64_t)16 << 20;
+    chunk_samples = (chunk_samples + K1_TILE - 1) / K1_TILE * K1_TILE;
+    if (p->filter_ncoef > 0 || n <= chunk_samples) {
+        // filtering needs every event before the split; a short trace gains nothing from chunking
+        CKR(pp_trace_upload(ctx, host, n, 0));
+        return pp_pipeline(ctx, p, out);
+    }
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->compute_ev, cudaEventDisableTiming));
+    }
+    CKR(ensure(ctx, ctx->trace_buf, sizeof(float) * (size_t)n));
+    ctx->trace = (const float *)ctx->trace_buf.p;
+    ctx->n = n;
+    ctx->trace_cap = (int64_t)(ctx->trace_buf.cap / sizeof(float));
+    ctx->adopted = false;
+    ctx->src_kind = 0;
+    ctx->flat_cap = n;
+    reset_stages(ctx);
+    CKR(begin_threshold(ctx, n));
+    CKR(prepare_split(ctx, p->min_width, p->max_width, p->window_width));
+    // the copies must not overtake earlier work that still reads the trace buffer
+    CK(cudaEventRecord(ctx->compute_ev, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_ev, 0));
+    for (int64_t a = 0; a < n; a += chunk_samples) {
+        const int64_t b = a + chunk_samples < n ? a + chunk_samples : n;
+        CK(cudaMemcpyAsync((void *)(ctx->trace + a), host + a, sizeof(float) * (size_t)(b - a),
+                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->copy_ev, ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev, 0));
+        CKR(enqueue_threshold_tiles(ctx, p->threshold, b, (b - a + K1_TILE - 1) / K1_TILE));
+        CKR(enqueue_select(ctx, p->rule_mask, p->duration_gt, p->duration_lt, p->min_gt, p->max_lt, 0, 0,
+                           b == n ? 2 : 1));
+        CKR(enqueue_prefix(ctx, p->prefix_mode));
+        CKR(enqueue_search(ctx, p->min_width, p->max_width, p->window_width, p->min_gain));
+    }
+    CKR(enqueue_compact(ctx));
+    if (p->with_stats) CKR(enqueue_stats(ctx));
+    CKR(fetch_counters(ctx));
+    const int64_t runs = (int64_t)ctx->h_ctr->n_runs;
+    if (runs > ctx->cap_runs) {  // rare: noisy trace with many crossings; the trace is resident now, redo it whole
+        CKR(ensure_run_buffers(ctx, runs + 16));
+        return pp_pipeline(ctx, p, out);
+    }
+    absorb_counters(ctx);
+    ctx->n_runs = runs;
+    CKR(check_overflow(ctx));
+    ctx->n_segments = (int64_t)ctx->h_ctr->n_segments;
+    if (out) {
+        out[0] = runs;
+        out[1] = ctx->n_events;
+        out[2] = ctx->n_event_samples;
+        out[3] = ctx->n_segments;
+    }
+    return PP_OK;
 }
 
 }  // extern "C"

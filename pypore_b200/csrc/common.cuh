@@ -28,8 +28,12 @@ struct PPCounters {
     unsigned long long n_tasks;       // tasks processed
     unsigned long long n_exact;       // exact (reference-arithmetic) candidate evaluations
     unsigned long long n_seq_redo;    // events whose prefix sums were redone sequentially
-    unsigned long long scan_ticket;   // prefix-scan dynamic tile id
     unsigned long long n_scan_tiles;  // prefix-scan tiles over all events
+    // incremental (streamed) pipeline: the stages after the threshold scan work on the events
+    // [ev_begin, n_events) and the prefix-scan tiles [tile_begin, n_scan_tiles) added by the last select
+    unsigned long long sel_next_run;  // first run the next incremental select looks at
+    unsigned long long ev_begin;
+    unsigned long long tile_begin;
     unsigned int overflow;            // bit0 runs, bit1 queue, bit2 segments, bit3 filter-too-short
     unsigned int first_below;         // below-threshold bit of sample 0
 };

@@ -27,7 +27,7 @@ k2_prefix_sequential(PPSource src, const int64_t *__restrict__ ev_len, PPCounter
                      double2 *__restrict__ cc)
 {
     const int64_t n_events = (int64_t)ctr->n_events;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_events;
+    for (int64_t e = (int64_t)ctr->ev_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_events;
          e += (int64_t)gridDim.x * blockDim.x) {
         if (inexact) {
             if (inexact[e] == 0u) continue;
@@ -171,9 +171,11 @@ k2_tile_offsets(PPCounters *ctr, const int64_t *__restrict__ ev_len, int64_t *__
     __shared__ long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n_events = (int64_t)ctr->n_events;
-    if (tid == 0) s_carry = 0;
+    const int64_t ev_begin = (int64_t)ctr->ev_begin;
+    const long long tiles_before = ev_begin > 0 ? (long long)ctr->n_scan_tiles : 0;
+    if (tid == 0) s_carry = tiles_before;
     __syncthreads();
-    for (int64_t c0 = 0; c0 < n_events; c0 += 1024) {
+    for (int64_t c0 = ev_begin; c0 < n_events; c0 += 1024) {
         const int64_t e = c0 + tid;
         long long v = e < n_events ? (ev_len[e] + K2_TILE - 1) / K2_TILE : 0;
         long long inc = v;
@@ -202,7 +204,8 @@ k2_tile_offsets(PPCounters *ctr, const int64_t *__restrict__ ev_len, int64_t *__
     if (tid == 0) {
         ev_tile_off[n_events] = s_carry;
         ctr->n_scan_tiles = (unsigned long long)s_carry;
-        ctr->n_seq_redo = 0;
+        ctr->tile_begin = (unsigned long long)tiles_before;
+        if (ev_begin == 0) ctr->n_seq_redo = 0;
     }
 }
 
@@ -235,7 +238,7 @@ k2_tile_reduce(PPSource src, const T *__restrict__ samples /* trace (kind 0) or 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n_events = (int64_t)ctr->n_events;
     const int64_t n_tiles = (int64_t)ctr->n_scan_tiles;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = (int64_t)ctr->tile_begin + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const K2Tile t = k2_locate(src, ev_len, ev_tile_off, n_events, tile);
         const T *in = samples + (src.kind == 0 ? src.ev_start[t.ev] : t.off) + t.base;
         T xv[K2_ITEMS];
@@ -295,7 +298,8 @@ k2_event_carries(const PPCounters *ctr, const int64_t *__restrict__ ev_len, cons
     const int lane = threadIdx.x & 31;
     const int64_t n_events = (int64_t)ctr->n_events;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n_events; e += warps) {
+    for (int64_t e = (int64_t)ctr->ev_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < n_events;
+         e += warps) {
         const int64_t t0 = ev_tile_off[e], t1 = ev_tile_off[e + 1];
         double carry_c = 0.0, carry_c2 = 0.0;
         for (int64_t b = t0; b < t1; b += 32) {
@@ -343,7 +347,7 @@ k2_tile_scan(PPSource src, const T *__restrict__ samples, const int64_t *__restr
     const int64_t n_events = (int64_t)ctr->n_events;
     const int64_t n_tiles = (int64_t)ctr->n_scan_tiles;
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = (int64_t)ctr->tile_begin + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const K2Tile t = k2_locate(src, ev_len, ev_tile_off, n_events, tile);
         const T *in = samples + (src.kind == 0 ? src.ev_start[t.ev] : t.off) + t.base;
         const double carry_c = tiles[tile].carry_c, carry_c2 = tiles[tile].carry_c2;

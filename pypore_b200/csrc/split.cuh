@@ -38,8 +38,14 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int K3_THREADS = 128;
-constexpr int K3_CTAS_PER_SM = 6;
+#ifndef K3_CFG_THREADS  // development knobs: -DK3_CFG_THREADS=.. -DK3_CFG_CTAS=..
+#define K3_CFG_THREADS 128
+#endif
+#ifndef K3_CFG_CTAS
+#define K3_CFG_CTAS 6
+#endif
+constexpr int K3_THREADS = K3_CFG_THREADS;
+constexpr int K3_CTAS_PER_SM = K3_CFG_CTAS;
 constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int K3_CAP = 10240;   // longest interval resolved level by level inside one CTA
 constexpr int K3_LIST = 256;    // items per level list
@@ -233,18 +239,23 @@ __device__ __forceinline__ bool k3_side(double S, double Q, double r, unsigned n
     return (x <= 254u) & ((__double2hiint(m2) - vh) < (K3_RATIO_BITS << 20));
 }
 
-template <class CC>
-__device__ __forceinline__ bool k3_screen_key(const CC &cc, const double2 lo, const double2 hi, int ps, int pe,
-                                              int i, const double *__restrict__ RN, int ebase,
+__device__ __forceinline__ bool k3_screen_key(const double2 mid, const double r1, const double r2, const double2 lo,
+                                              const double2 hi, unsigned n1, unsigned n2, int ebase,
                                               unsigned long long &key)
 {
-    const double2 mid = cc.at(i - 1);
-    const unsigned n1 = (unsigned)(i - ps), n2 = (unsigned)(pe - i);
-    const double r1 = __ldg(RN + n1), r2 = __ldg(RN + n2);
     key = 0ull;
     const bool ok1 = k3_side(__dsub_rn(mid.x, lo.x), __dsub_rn(mid.y, lo.y), r1, n1, ebase, key);
     const bool ok2 = k3_side(__dsub_rn(hi.x, mid.x), __dsub_rn(hi.y, mid.y), r2, n2, ebase, key);
     return ok1 & ok2;
+}
+
+// same, loading its operands (candidate i of window [ps,pe), i >= 1)
+__device__ __forceinline__ bool k3_screen_key_at(const double2 *__restrict__ ccg, const double2 lo, const double2 hi,
+                                                 int ps, int pe, int i, const double *__restrict__ RN, int ebase,
+                                                 unsigned long long &key)
+{
+    return k3_screen_key(__ldg(ccg + (i - 1)), __ldg(RN + (i - ps)), __ldg(RN + (pe - i)), lo, hi,
+                         (unsigned)(i - ps), (unsigned)(pe - i), ebase, key);
 }
 
 __device__ __forceinline__ void k3_scr_init(K3Scr &a)
@@ -254,21 +265,40 @@ __device__ __forceinline__ void k3_scr_init(K3Scr &a)
     a.bad = 0;
 }
 
-// Screen candidates i, i+stride, ... <= i_last (requires mw >= 1 so that n1, n2 >= 1).
-template <class CC>
-__device__ __forceinline__ void k3_screen_lane(const CC &cc, const double2 lo, const double2 hi, int ps, int pe,
-                                               int ebase, const double *__restrict__ RN, int i, int i_last,
-                                               int stride, K3Scr &a)
+// Screen candidates i, i+stride, ... <= i_last of window [ps,pe) (requires mw >= 1 so that
+// n1, n2 >= 1 and i >= 1).  Plain pointer increments; the operands of the next candidate are
+// requested before the current one is evaluated.
+__device__ __forceinline__ void k3_screen_lane(const double2 *__restrict__ ccg, const double2 lo, const double2 hi,
+                                               int ps, int pe, int ebase, const double *__restrict__ RN, int i,
+                                               int i_last, int stride, K3Scr &a)
 {
-#pragma unroll 2
-    for (; i <= i_last; i += stride) {
+    if (i > i_last) return;
+    const double2 *pm = ccg + (i - 1);
+    const double *p1 = RN + (i - ps), *p2 = RN + (pe - i);
+    unsigned n1 = (unsigned)(i - ps), n2 = (unsigned)(pe - i);
+    double2 mid = __ldg(pm);
+    double r1 = __ldg(p1), r2 = __ldg(p2);
+    for (;;) {
+        const bool more = i + stride <= i_last;
+        double2 mid_n = mid;
+        double r1_n = r1, r2_n = r2;
+        if (more) {
+            mid_n = __ldg(pm + stride);
+            r1_n = __ldg(p1 + stride);
+            r2_n = __ldg(p2 - stride);
+        }
         unsigned long long key;
-        const bool ok = k3_screen_key(cc, lo, hi, ps, pe, i, RN, ebase, key);
+        const bool ok = k3_screen_key(mid, r1, r2, lo, hi, n1, n2, ebase, key);
         if (!ok) a.bad = 1;
-        else if (key < a.k2) {  // uncommon after the first few candidates
+        else if (key < a.k2) {
             if (key < a.k1) { a.k2 = a.k1; a.k1 = key; a.i1 = i; }
             else a.k2 = key;
         }
+        if (!more) break;
+        mid = mid_n; r1 = r1_n; r2 = r2_n;
+        pm += stride; p1 += stride; p2 -= stride;
+        n1 += (unsigned)stride; n2 -= (unsigned)stride;
+        i += stride;
     }
 }
 
@@ -326,7 +356,7 @@ __device__ __forceinline__ K3Best k3_cta_scan(const CC &cc, int ps, int pe, cons
     K3Scr a;
     k3_scr_init(a);
     if (screen) {
-        k3_screen_lane(cc, lo, hi, ps, pe, ebase, G.RN, ps + P.mw + tid, pe - P.mw, K3_THREADS, a);
+        k3_screen_lane(cc.g, lo, hi, ps, pe, ebase, G.RN, ps + P.mw + tid, pe - P.mw, K3_THREADS, a);
         // a candidate that failed the validity test sends the whole window to the exact scan
         if (__syncthreads_or(a.bad)) screen = false;
     }
@@ -347,7 +377,7 @@ __device__ __forceinline__ K3Best k3_cta_scan(const CC &cc, int ps, int pe, cons
         const int last = pe - P.mw;
         for (int i = ps + P.mw + tid; i <= last; i += K3_THREADS) {
             unsigned long long key;
-            k3_screen_key(cc, lo, hi, ps, pe, i, G.RN, ebase, key);
+            k3_screen_key_at(cc.g, lo, hi, ps, pe, i, G.RN, ebase, key);
             if (key <= thr) {
                 const double g = k3_exact_gain(lo, cc.at(i - 1), hi, ps, pe, i, tot);
                 ++nexact;
@@ -640,7 +670,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                         const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
                         K3Scr a;
                         k3_scr_init(a);
-                        k3_screen_lane(acc, w_lo, w_hi, it.ps, w_pe, S.win_ebase[slot], G.RN,
+                        k3_screen_lane(acc.g, w_lo, w_hi, it.ps, w_pe, S.win_ebase[slot], G.RN,
                                        it.ps + mw + ca * 32 + lane, i_end < w_last ? i_end : w_last, 32, a);
                         unsigned long long K1, K2;
                         int I1;
@@ -695,7 +725,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                             const int ebase = S.win_ebase[slot];
                             for (int i = it.ps + mw + ca * 32 + lane; i <= i_end; i += 32) {
                                 unsigned long long key;
-                                k3_screen_key(acc, w_lo, w_hi, it.ps, w_pe, i, G.RN, ebase, key);
+                                k3_screen_key_at(acc.g, w_lo, w_hi, it.ps, w_pe, i, G.RN, ebase, key);
                                 if (key <= thr) k3_request(S, slot, i);
                             }
                         });
@@ -795,7 +825,7 @@ k3_debug_screen(K3Global G, int ev, int ps, int pe, int mw, double *h_screen, do
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const int i = ps + mw + j;
         unsigned long long key = 0;
-        const bool ok = wok && k3_screen_key(cc, lo, hi, ps, pe, i, G.RN, ebase, key);
+        const bool ok = wok && k3_screen_key_at(cc.g, lo, hi, ps, pe, i, G.RN, ebase, key);
         const double2 mid = cc.at(i - 1);
         const double low = __dmul_rn((double)(i - ps), log(k3_var(mid, lo, i - ps)));
         const double high = __dmul_rn((double)(pe - i), log(k3_var(hi, mid, pe - i)));
@@ -831,34 +861,39 @@ __global__ void __launch_bounds__(256) k3_fill_RN(double *RN, int len)
         RN[n] = n > 0 ? __ddiv_rn(1.0, (double)n) : 0.0;
 }
 
-// One initial task per event; event starts are segment starts.
+// One initial task per event of [ev_begin, n_events); event starts are segment starts.
 __global__ void __launch_bounds__(256)
 k3_init_queue(K3Global G)
 {
     const int64_t n_events = (int64_t)G.ctr->n_events;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_events;
+    const int64_t ev_begin = (int64_t)G.ctr->ev_begin;
+    for (int64_t e = ev_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_events;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t off = G.ev_off[e];
         const int64_t len = G.ev_len[e];
+        const int64_t slot = e - ev_begin;
         atomicOr(&G.bits[off >> 5], 1u << (unsigned)(off & 31));
-        if (e < G.q_cap && len < 0x7fffffffLL) {
+        if (slot < G.q_cap && len < 0x7fffffffLL) {
             PPTask t;
             t.ev = (int)e; t.s = 0; t.e = (int)len; t.flags = 0;
-            G.tasks[e] = t;
-            G.ready[e] = 1;
+            G.tasks[slot] = t;
+            G.ready[slot] = 1;
         } else {
             atomicOr(&G.ctr->overflow, (unsigned)PP_OVF_QUEUE);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const int64_t q = n_events < G.q_cap ? n_events : G.q_cap;
+        const int64_t cnt = n_events - ev_begin;
+        const int64_t q = cnt < G.q_cap ? cnt : G.q_cap;
         G.ctr->q_head = 0;
         G.ctr->q_tail = (unsigned long long)q;
         G.ctr->q_pending = (long long)q;
-        G.ctr->n_cand = 0;
-        G.ctr->n_scan = 0;
-        G.ctr->n_tasks = 0;
-        G.ctr->n_exact = 0;
+        if (ev_begin == 0) {
+            G.ctr->n_cand = 0;
+            G.ctr->n_scan = 0;
+            G.ctr->n_tasks = 0;
+            G.ctr->n_exact = 0;
+        }
     }
 }
 

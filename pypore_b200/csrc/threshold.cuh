@@ -279,7 +279,9 @@ k1_select_events(PPCounters *ctr, const int64_t *__restrict__ run_start,
                  const double *__restrict__ run_max, int64_t cap_runs, int rule_mask,
                  int64_t duration_gt, int64_t duration_lt, double min_gt, double max_lt,
                  int skip_first, int skip_last, int64_t *__restrict__ ev_start,
-                 int64_t *__restrict__ ev_len, int64_t *__restrict__ ev_off, int64_t cap_events)
+                 int64_t *__restrict__ ev_len, int64_t *__restrict__ ev_off, int64_t cap_events,
+                 int incremental /* 0: whole run table; 1: append the runs completed since the last call,
+                                    the still open last run excluded; 2: same, last call (open run included) */)
 {
     __shared__ unsigned wcnt[SEL_THREADS / 32];
     __shared__ long long wlen[SEL_THREADS / 32];
@@ -288,9 +290,19 @@ k1_select_events(PPCounters *ctr, const int64_t *__restrict__ run_start,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int64_t n_runs = (int64_t)ctr->n_runs;
     if (n_runs > cap_runs) n_runs = cap_runs;
-    if (tid == 0) { s_cnt_carry = 0; s_len_carry = 0; }
+    int64_t r_begin = 0;
+    const unsigned long long ev_before = incremental ? ctr->n_events : 0ull;
+    if (incremental) {
+        r_begin = (int64_t)ctr->sel_next_run;
+        if (incremental == 1 && n_runs > 0) n_runs -= 1;
+        if (n_runs < r_begin) n_runs = r_begin;
+    }
+    if (tid == 0) {
+        s_cnt_carry = ev_before;
+        s_len_carry = incremental ? (long long)ctr->n_event_samples : 0;
+    }
     __syncthreads();
-    for (int64_t c0 = 0; c0 < n_runs; c0 += SEL_THREADS) {
+    for (int64_t c0 = r_begin; c0 < n_runs; c0 += SEL_THREADS) {
         const int64_t r = c0 + tid;
         bool keep = false;
         long long len = 0;
@@ -338,6 +350,8 @@ k1_select_events(PPCounters *ctr, const int64_t *__restrict__ run_start,
         if ((int64_t)ne > cap_events) { ne = cap_events; atomicOr(&ctr->overflow, PP_OVF_RUNS); }
         ctr->n_events = ne;
         ctr->n_event_samples = (unsigned long long)s_len_carry;
+        ctr->sel_next_run = (unsigned long long)n_runs;
+        ctr->ev_begin = ev_before < ne ? ev_before : ne;
         ev_off[ne] = s_len_carry;
     }
 }
@@ -375,5 +389,6 @@ k1_event_offsets(PPCounters *ctr, const int64_t *__restrict__ ev_len, int64_t n_
         ev_off[n_events] = s_carry;
         ctr->n_events = (unsigned long long)n_events;
         ctr->n_event_samples = (unsigned long long)s_carry;
+        ctr->ev_begin = 0;
     }
 }

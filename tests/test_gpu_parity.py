@@ -429,3 +429,57 @@ def test_hardware_lg2_error_within_screening_bound(ctx):
     addition stays within the 2^-22 + 2^-24 the screening bound (split.cuh K3_EPS_PER_SAMPLE) assumes."""
     err = ctx.debug_lg2_error()
     assert 0.0 < err <= 2.0 ** -22 + 2.0 ** -24, err
+
+
+@pytest.mark.parametrize("chunk", [4096, 65536, 1 << 20])
+def test_streamed_host_pipeline_equals_resident(ctx, chunk):
+    """pp_pipeline_host (chunked copy overlapped with scan / select / prefix / split per chunk) returns exactly
+    the tables of upload + pp_pipeline, for chunk sizes that cut events, gaps and K1 tiles in every way;
+    the trace starts and ends below the threshold so that the open first/last runs are events too."""
+    body = synth.make_trace(60, seed=21, tier="A")
+    lead = synth.quantise(np.random.RandomState(3).normal(50, 1, 5000)).astype(np.float32)
+    x = np.concatenate([lead, body, lead[:3000]])
+    x64 = x.astype(np.float64)
+    for psps in (None, 10):
+        gain = oracle.min_gain(prior_segments_per_second=psps)
+        ctx.upload_trace(x)
+        r0 = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, gain)
+        ev0, tab0, c0 = ctx.events(r0["events"]), ctx.segments(r0["segments"]), ctx.split_counters()
+        r1 = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, gain, host_trace=x,
+                          chunk_samples=chunk)
+        ev1, tab1, c1 = ctx.events(r1["events"]), ctx.segments(r1["segments"]), ctx.split_counters()
+        assert r1 == r0 and r0["events"] == 62
+        assert np.array_equal(ev0[0], ev1[0]) and np.array_equal(ev0[1], ev1[1])
+        assert all(np.array_equal(tab0[k], tab1[k]) for k in tab0)
+        assert c1["candidates"] == c0["candidates"] and c1["scans"] == c0["scans"]
+        ws, wl = oracle.events(x64, 110, RULES_1000)
+        assert np.array_equal(ev1[0], ws) and np.array_equal(ev1[1], wl)
+        oe, ost, oen, _ = oracle.statsplit_events(x64, ws, wl, gain=gain)
+        assert np.array_equal(tab1["event"], oe) and np.array_equal(tab1["start"], ost) and np.array_equal(tab1["end"], oen)
+
+
+def test_streamed_host_pipeline_no_events_and_single_chunk(ctx):
+    rng = np.random.RandomState(4)
+    x = synth.quantise(rng.normal(120, 1.5, 300000)).astype(np.float32)   # never below the threshold
+    r = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, oracle.min_gain(), host_trace=x,
+                     chunk_samples=8192)
+    assert (r["runs"], r["events"], r["segments"]) == (1, 0, 0)
+    x = synth.make_trace(5, seed=2, tier="A")                               # shorter than one chunk
+    r = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, oracle.min_gain(), host_trace=x)
+    ctx.upload_trace(x)
+    assert r == ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, oracle.min_gain())
+
+
+def test_pinned_downloads_and_pinned_trace(ctx):
+    """Page-locked host buffers: a pinned trace through the streamed pipeline and the pinned segment table
+    equal the pageable path."""
+    x = synth.make_trace(20, seed=5, tier="A")
+    xp = ctx.pinned_empty(len(x), np.float32)
+    xp[:] = x
+    gain = oracle.min_gain(prior_segments_per_second=10)
+    r = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, gain, host_trace=xp, chunk_samples=65536)
+    a = ctx.segments(r["segments"])
+    b = ctx.segments(r["segments"], pinned=True)
+    assert set(a) == set(b) and all(np.array_equal(a[k], b[k]) for k in a)
+    c = ctx.segments(r["segments"], stats=False, pinned=True)
+    assert set(c) == {"event", "start", "end"} and np.array_equal(c["end"], a["end"])
