@@ -193,11 +193,10 @@ class File(Segment):
             raise TypeError("the device-resident pipeline needs a pypore_b200 lambda_event_parser")
         ctx = context or _lib.default_context()
         host = np.asarray(self.current)
-        ctx.upload_trace(_as_float32_trace(host))
-        self._parse_resident(ctx, host, parser, segmenter, filter_params)
+        self._parse_resident(ctx, host, _as_float32_trace(host), parser, segmenter, filter_params)
 
     # ------------------------------------------------------------------
-    def _parse_resident(self, ctx, host, parser, segmenter, filter_params):
+    def _parse_resident(self, ctx, host, x32, parser, segmenter, filter_params):
         second = self.second
         filt = None
         if filter_params is not None:
@@ -208,14 +207,16 @@ class File(Segment):
         if segmenter is not None:
             mw, MW, W, gain = segmenter._params()
         if rs is not None and segmenter is not None:
+            # one call from host memory: the copy is chunked and overlapped with the stages (pp_pipeline_host)
             counts = ctx.pipeline(parser.threshold, min_width=mw, max_width=MW, window_width=W, min_gain=gain,
-                                  filter_ba=filt, with_stats=True, **rs.device_args())
+                                  filter_ba=filt, with_stats=True, host_trace=x32, **rs.device_args())
             ev_start, ev_len = ctx.events(counts["events"])
             tables = ctx.segments(counts["segments"])
             r_start, _, r_min, r_max, _ = ctx.runs(counts["runs"])
             idx = np.searchsorted(r_start, ev_start)
             ev_min, ev_max = r_min[idx], r_max[idx]
         else:
+            ctx.upload_trace(x32)
             ev_start, ev_len, ev_min, ev_max = parser._detect(ctx, host)
             if filt is not None and len(ev_start):
                 ctx.filter_events(*filt)

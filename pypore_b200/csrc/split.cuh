@@ -51,6 +51,22 @@ constexpr int K3_CAP = 10240;   // longest interval resolved level by level insi
 constexpr int K3_LIST = 256;    // items per level list
 constexpr int K3_REQ = 256;     // exact-evaluation requests per level
 constexpr int K3_PIECES = K3_LIST + K3_WARPS;  // (warp, window) screening records per level
+// Measured on B200 at BASELINE configs[1] (profiles/r01f_k3_variants.txt): taking 2 events per CTA
+// or handing intervals to idle CTAs both LOSE time (the search is bound by L2 -> SM traffic of the
+// prefix sums, and both widen a CTA's working set), so the defaults keep one event per CTA.
+#ifndef K3_CFG_BATCH
+#define K3_CFG_BATCH 1
+#endif
+#ifndef K3_CFG_DONATE
+#define K3_CFG_DONATE 0
+#endif
+#ifndef K3_CFG_LDCS
+#define K3_CFG_LDCS 0
+#endif
+constexpr int K3_BATCH = K3_CFG_BATCH;  // events a CTA resolves together (amortises the per-level latencies)
+constexpr int K3_DONATE_MIN = 8; // fresh intervals of at least this many min_widths may go to idle CTAs
+constexpr int K3_NO_EBASE = 0x7fffffff;
+constexpr unsigned long long K3_NO_TICKET = ~0ull;
 constexpr int K3_FULL_FLAG = 0x40000000;  // window entry: screening inconclusive / list overflow, scan exactly
 constexpr int K3_BAD_FLAG = 0x40000000;    // piece record: a candidate failed the validity test
 constexpr int K3_RESCAN_FLAG = (int)0x80000000;  // piece record: several candidates within 2 eps of the minimum
@@ -64,7 +80,7 @@ constexpr double K3_HUGE = 1e280;
 constexpr unsigned long long K3_NOKEY = ~0ull;
 
 struct PPTask { int ev, s, e, flags; };
-struct K3Item { int s, e, ps; };
+struct K3Item { int s, e, ps, b; };  // interval, next window start, batch slot of its event
 struct K3Params { int mw, MW, W; double min_gain; };
 struct K3Best { double g; int x; };
 struct K3Scr { unsigned long long k1, k2; int i1, bad; };  // per-lane screening state: two smallest keys
@@ -86,7 +102,6 @@ struct K3Shared {
     K3Item list[2][K3_LIST];
     int win_item[K3_LIST];                 // scan window slot -> index into the level list (| K3_FULL_FLAG)
     int win_chunk0[K3_LIST + 1];           // first chunk of the window (exclusive prefix of chunk counts)
-    int win_ebase[K3_LIST];                // biased exponent of the window's variance - 127
     unsigned long long win_thr[K3_LIST];   // min key + 2 eps
     unsigned long long best_key[K3_LIST];  // ordered key of the best exact gain (0 = none beats min_gain)
     int best_idx[K3_LIST];
@@ -100,8 +115,14 @@ struct K3Shared {
     unsigned long long red_k[K3_WARPS];
     int red_x[K3_WARPS];
     int nA, nB, nwin, nchunk, nreq, nrescan;
-    PPTask task;
-    int have_task;
+    int nb;                                // tasks of the current batch
+    int batch;                             // tasks a CTA takes at once (1 .. K3_BATCH)
+    int donate;                            // fresh intervals this level may hand to idle CTAs
+    int b_ev[K3_BATCH];                    // per batch slot: event, flat offset, screening exponent base
+    long long b_off[K3_BATCH];
+    int b_ebase[K3_BATCH];                 // biased exponent of the event's variance - 127, or K3_NO_EBASE
+    PPTask b_task[K3_BATCH];
+    unsigned long long carry;              // claimed global ticket that was not served yet
     unsigned long long cand, scans, exact;
 };
 
@@ -276,14 +297,19 @@ __device__ __forceinline__ void k3_screen_lane(const double2 *__restrict__ ccg, 
     const double2 *pm = ccg + (i - 1);
     const double *p1 = RN + (i - ps), *p2 = RN + (pe - i);
     unsigned n1 = (unsigned)(i - ps), n2 = (unsigned)(pe - i);
-    double2 mid = __ldg(pm);
+#if K3_CFG_LDCS
+#define K3_LD_MID(p) __ldcs(p)
+#else
+#define K3_LD_MID(p) __ldg(p)
+#endif
+    double2 mid = K3_LD_MID(pm);
     double r1 = __ldg(p1), r2 = __ldg(p2);
     for (;;) {
         const bool more = i + stride <= i_last;
         double2 mid_n = mid;
         double r1_n = r1, r2_n = r2;
         if (more) {
-            mid_n = __ldg(pm + stride);
+            mid_n = K3_LD_MID(pm + stride);
             r1_n = __ldg(p1 + stride);
             r2_n = __ldg(p2 - stride);
         }
@@ -424,16 +450,21 @@ __device__ void k3_push_global(const K3Global &G, int ev, int s, int e)
     atomicExch(&G.ready[slot], 1);
 }
 
-__device__ __forceinline__ void k3_push_local(const K3Global &G, K3Shared &S, K3Item *next, int ev,
-                                              int s, int e, int ps)
+__device__ __forceinline__ void k3_push_local(const K3Global &G, K3Shared &S, K3Item *next, const K3Params &P,
+                                              int b, int s, int e, int ps)
 {
+    // idle CTAs are waiting: a fresh, big enough interval goes to the global queue instead
+    if (ps == s && S.donate > 0 && e - s >= K3_DONATE_MIN * P.mw && atomicSub(&S.donate, 1) > 0) {
+        k3_push_global(G, S.b_ev[b], s, e);
+        return;
+    }
     const int idx = atomicAdd(&S.nB, 1);
     if (idx < K3_LIST) {
         K3Item it;
-        it.s = s; it.e = e; it.ps = ps;
+        it.s = s; it.e = e; it.ps = ps; it.b = b;
         next[idx] = it;
     } else {
-        k3_push_global(G, ev, s, e);  // restart at ps = s elsewhere: redundant scans, same result
+        k3_push_global(G, S.b_ev[b], s, e);  // restart at ps = s elsewhere: redundant scans, same result
     }
 }
 
@@ -457,15 +488,14 @@ __device__ __forceinline__ int k3_window_end(const K3Params &P, const K3Item &it
 
 // Apply a scan result to an item in local mode (cparsers.pyx:194-203).
 __device__ __forceinline__ void k3_resolve_local(const K3Global &G, K3Shared &S, K3Item *next,
-                                                 const K3Params &P, int ev, int64_t off,
-                                                 const K3Item it, int x)
+                                                 const K3Params &P, const K3Item it, int x)
 {
     if (x >= 0) {
-        k3_emit(G, off, x);
-        if (k3_worth(P, it.s, x)) k3_push_local(G, S, next, ev, it.s, x, it.s);
-        if (k3_worth(P, x, it.e)) k3_push_local(G, S, next, ev, x, it.e, x);
+        k3_emit(G, (int64_t)S.b_off[it.b], x);
+        if (k3_worth(P, it.s, x)) k3_push_local(G, S, next, P, it.b, it.s, x, it.s);
+        if (k3_worth(P, x, it.e)) k3_push_local(G, S, next, P, it.b, x, it.e, x);
     } else {
-        k3_push_local(G, S, next, ev, it.s, it.e, k3_next_ps(P, it.ps, it.e));
+        k3_push_local(G, S, next, P, it.b, it.s, it.e, k3_next_ps(P, it.ps, it.e));
     }
 }
 
@@ -508,88 +538,123 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
     K3Shared &S = *reinterpret_cast<K3Shared *>(k3_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mw = P.mw, MW = P.MW, W = P.W;
+    const bool screen = G.screen && mw >= 1 && W <= K3_MAX_SCREEN_W;
+
+    if (tid == 0) {
+        S.carry = K3_NO_TICKET;
+        // few events per CTA: take them one at a time so that every CTA gets some
+        const long long cnt = (long long)G.ctr->n_events - (long long)G.ctr->ev_begin;
+        const long long per = cnt / (2LL * gridDim.x);
+        S.batch = per < 1 ? 1 : (per > K3_BATCH ? K3_BATCH : (int)per);
+    }
 
     for (;;) {
         __syncthreads();
+        // ---- take up to S.batch tasks; wait only while holding none ------------------------
         if (tid == 0) {
-            const unsigned long long h = atomicAdd(&G.ctr->q_head, 1ull);
-            int ok = 0;
-            for (;;) {
-                if ((int64_t)h < G.q_cap && *((volatile int *)&G.ready[h]) != 0) {
-                    __threadfence();
-                    const int4 t = __ldcg(reinterpret_cast<const int4 *>(&G.tasks[h]));
-                    S.task.ev = t.x; S.task.s = t.y; S.task.e = t.z; S.task.flags = t.w;
-                    ok = 1;
-                    break;
+            int nb = 0;
+            while (nb < S.batch) {
+                unsigned long long h = S.carry;
+                if (h == K3_NO_TICKET) {
+                    if (nb > 0 && *((volatile unsigned long long *)&G.ctr->q_head) >=
+                                      *((volatile unsigned long long *)&G.ctr->q_tail))
+                        break;  // nothing is waiting right now
+                    h = atomicAdd(&G.ctr->q_head, 1ull);
                 }
-                if (*((volatile long long *)&G.ctr->q_pending) <= 0) break;
-                __nanosleep(256);
+                bool ok = false;
+                for (;;) {
+                    if ((int64_t)h < G.q_cap && *((volatile int *)&G.ready[h]) != 0) { ok = true; break; }
+                    if (nb > 0) break;
+                    if (*((volatile long long *)&G.ctr->q_pending) <= 0) break;
+                    __nanosleep(256);
+                }
+                if (!ok) { S.carry = nb > 0 ? h : K3_NO_TICKET; break; }
+                S.carry = K3_NO_TICKET;
+                __threadfence();
+                const int4 t = __ldcg(reinterpret_cast<const int4 *>(&G.tasks[h]));
+                PPTask tk;
+                tk.ev = t.x; tk.s = t.y; tk.e = t.z; tk.flags = t.w;
+                S.b_task[nb] = tk;
+                S.b_ev[nb] = t.x;
+                S.b_off[nb] = (long long)G.ev_off[t.x];
+                ++nb;
             }
-            S.have_task = ok;
+            S.nb = nb;
             S.cand = 0;
             S.scans = 0;
             S.exact = 0;
+            S.nA = 0;
         }
         __syncthreads();
-        if (!S.have_task) break;
-        const int ev = S.task.ev;
-        int s = S.task.s;
-        const int e = S.task.e;
-        const int64_t off = G.ev_off[ev];
-        K3GlobalCC acc;
-        acc.g = G.cc + off;
+        const int nb = S.nb;
+        if (nb == 0) break;
+        // screening exponent base of every task: the variance of its whole interval (any value
+        // within 2^+-127 of the candidates' variances will do; the validity test checks each one)
+        if (tid < nb) {
+            const PPTask tk = S.b_task[tid];
+            K3GlobalCC a;
+            a.g = G.cc + S.b_off[tid];
+            int ebase = 0;
+            const bool ok = screen && k3_window_ebase(k3_var(a.at(tk.e - 1), a.at(tk.s - 1), tk.e - tk.s), ebase);
+            S.b_ebase[tid] = ok ? ebase : K3_NO_EBASE;
+        }
 
-        // ---- spine mode: interval too long to resolve locally ------------------
-        int ps = s;
-        bool done = false;
-        while ((long long)e - s > K3_CAP) {
-            const long long lim = (long long)e - 2LL * mw;
-            if (ps >= lim) {
-                if (e - s <= MW) { done = true; break; }
-                const int x = k3_forced(P, s, e);
-                if (tid == 0) {
-                    k3_emit(G, off, x);
-                    if (k3_worth(P, s, x)) k3_push_global(G, ev, s, x);
+        // ---- spine mode: intervals too long to resolve locally, one task after the other ---
+        for (int bt = 0; bt < nb; ++bt) {
+            const int ev = S.b_ev[bt];
+            const int64_t off = (int64_t)S.b_off[bt];
+            int s = S.b_task[bt].s;
+            const int e = S.b_task[bt].e;
+            K3GlobalCC acc;
+            acc.g = G.cc + off;
+            int ps = s;
+            bool done = false;
+            while ((long long)e - s > K3_CAP) {
+                const long long lim = (long long)e - 2LL * mw;
+                if (ps >= lim) {
+                    if (e - s <= MW) { done = true; break; }
+                    const int x = k3_forced(P, s, e);
+                    if (tid == 0) {
+                        k3_emit(G, off, x);
+                        if (k3_worth(P, s, x)) k3_push_global(G, ev, s, x);
+                    }
+                    s = x; ps = s;
+                    continue;
                 }
-                s = x; ps = s;
-                continue;
-            }
-            if (ps > (long long)s + MW) {
-                const int x = k3_forced(P, s, e);
-                if (tid == 0) k3_emit(G, off, x);
-                s = x; ps = s;  // the left part is not revisited (cparsers.pyx:189-191)
-                continue;
-            }
-            const long long pe_l = (long long)ps + W;
-            const int pe = (int)(pe_l < e ? pe_l : e);
-            if (pe - ps <= 2 * mw) { ps = k3_next_ps(P, ps, e); continue; }
-            const K3Best b = k3_cta_scan(acc, ps, pe, P, G, S);
-            if (tid == 0) {
-                atomicAdd(&S.cand, (unsigned long long)(pe - ps - 2 * mw + 1));
-                atomicAdd(&S.scans, 1ull);
-            }
-            if (b.x >= 0) {
-                if (tid == 0) {
-                    k3_emit(G, off, b.x);
-                    if (k3_worth(P, s, b.x)) k3_push_global(G, ev, s, b.x);
+                if (ps > (long long)s + MW) {
+                    const int x = k3_forced(P, s, e);
+                    if (tid == 0) k3_emit(G, off, x);
+                    s = x; ps = s;  // the left part is not revisited (cparsers.pyx:189-191)
+                    continue;
                 }
-                s = b.x; ps = s;
-            } else {
-                ps = k3_next_ps(P, ps, e);
+                const long long pe_l = (long long)ps + W;
+                const int pe = (int)(pe_l < e ? pe_l : e);
+                if (pe - ps <= 2 * mw) { ps = k3_next_ps(P, ps, e); continue; }
+                const K3Best b = k3_cta_scan(acc, ps, pe, P, G, S);
+                if (tid == 0) {
+                    atomicAdd(&S.cand, (unsigned long long)(pe - ps - 2 * mw + 1));
+                    atomicAdd(&S.scans, 1ull);
+                }
+                if (b.x >= 0) {
+                    if (tid == 0) {
+                        k3_emit(G, off, b.x);
+                        if (k3_worth(P, s, b.x)) k3_push_global(G, ev, s, b.x);
+                    }
+                    s = b.x; ps = s;
+                } else {
+                    ps = k3_next_ps(P, ps, e);
+                }
+            }
+            if (!done && tid == 0) {
+                K3Item it;
+                it.s = s; it.e = e; it.ps = ps; it.b = bt;
+                S.list[0][S.nA++] = it;
             }
         }
 
-        // ---- local mode: whole subtree, level by level --------------------------
-        if (!done) {
-            __syncthreads();
-            if (tid == 0) {
-                K3Item it;
-                it.s = s; it.e = e; it.ps = ps;
-                S.list[0][0] = it;
-                S.nA = 1;
-            }
+        // ---- local mode: the subtrees of all tasks of the batch, level by level ---------------
+        {
             int cur = 0;
-            const bool screen = G.screen && mw >= 1 && W <= K3_MAX_SCREEN_W;
             __syncthreads();
             for (;;) {
                 const int nA = S.nA;
@@ -597,36 +662,37 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                 K3Item *A = S.list[cur], *Bn = S.list[cur ^ 1];
                 __syncthreads();  // everyone has read nA
                 if (tid == 0) { S.nB = 0; S.nwin = 0; S.nreq = 0; S.nchunk = 0; S.nrescan = 0; }
+                if (tid == K3_THREADS - 1) {
+                    // CTAs waiting for work (claimed tickets without a task)
+                    const long long d = (long long)*((volatile unsigned long long *)&G.ctr->q_head) -
+                                        (long long)*((volatile unsigned long long *)&G.ctr->q_tail);
+                    S.donate = (K3_CFG_DONATE && d > 0) ? (int)(d > 16 ? 16 : d) : 0;
+                }
                 __syncthreads();
                 // step 1: the window-loop bookkeeping of _recursive_split per item
                 for (int t = tid; t < nA; t += K3_THREADS) {
                     const K3Item it = A[t];
+                    const int64_t off = (int64_t)S.b_off[it.b];
                     const long long lim = (long long)it.e - 2LL * mw;
                     if (it.ps >= lim) {
                         if (it.e - it.s > MW) {
                             const int x = k3_forced(P, it.s, it.e);
                             k3_emit(G, off, x);
-                            if (k3_worth(P, it.s, x)) k3_push_local(G, S, Bn, ev, it.s, x, it.s);
-                            if (k3_worth(P, x, it.e)) k3_push_local(G, S, Bn, ev, x, it.e, x);
+                            if (k3_worth(P, it.s, x)) k3_push_local(G, S, Bn, P, it.b, it.s, x, it.s);
+                            if (k3_worth(P, x, it.e)) k3_push_local(G, S, Bn, P, it.b, x, it.e, x);
                         }
                     } else if (it.ps > (long long)it.s + MW) {
                         const int x = k3_forced(P, it.s, it.e);
                         k3_emit(G, off, x);
-                        if (k3_worth(P, x, it.e)) k3_push_local(G, S, Bn, ev, x, it.e, x);
+                        if (k3_worth(P, x, it.e)) k3_push_local(G, S, Bn, P, it.b, x, it.e, x);
                     } else {
                         const int pe = k3_window_end(P, it);
                         if (pe - it.ps <= 2 * mw) {
-                            k3_push_local(G, S, Bn, ev, it.s, it.e, k3_next_ps(P, it.ps, it.e));
+                            k3_push_local(G, S, Bn, P, it.b, it.s, it.e, k3_next_ps(P, it.ps, it.e));
                         } else {
                             const int slot = atomicAdd(&S.nwin, 1);
-                            int ebase = 0;
-                            bool ok = screen;
-                            if (ok) {
-                                const double2 lo = acc.at(it.ps - 1), hi = acc.at(pe - 1);
-                                ok = k3_window_ebase(k3_var(hi, lo, pe - it.ps), ebase);
-                            }
+                            const bool ok = screen && S.b_ebase[it.b] != K3_NO_EBASE;
                             S.win_item[slot] = ok ? t : (t | K3_FULL_FLAG);
-                            S.win_ebase[slot] = ebase;
                             S.win_chunk0[slot] = ok ? (pe - it.ps - 2 * mw + 1 + 31) >> 5 : 0;  // chunk count for now
                             S.best_key[slot] = 0ull;
                             S.best_idx[slot] = 0x7fffffff;
@@ -664,13 +730,16 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                     // step 2: SCREEN -- every lane keeps the two smallest keys of its candidates of a piece
                     k3_for_pieces(S, warp, nwin, nchunk, [&](int slot, int ca, int cb) {
                         const K3Item it = A[S.win_item[slot]];
+                        const double2 *ccg = G.cc + S.b_off[it.b];
+                        K3GlobalCC acc;
+                        acc.g = ccg;
                         const int w_pe = k3_window_end(P, it);
                         const int w_last = w_pe - mw;
                         const int i_end = it.ps + mw + cb * 32 - 1;
                         const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
                         K3Scr a;
                         k3_scr_init(a);
-                        k3_screen_lane(acc.g, w_lo, w_hi, it.ps, w_pe, S.win_ebase[slot], G.RN,
+                        k3_screen_lane(ccg, w_lo, w_hi, it.ps, w_pe, S.b_ebase[it.b], G.RN,
                                        it.ps + mw + ca * 32 + lane, i_end < w_last ? i_end : w_last, 32, a);
                         unsigned long long K1, K2;
                         int I1;
@@ -716,16 +785,19 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                             const int entry = S.win_item[slot];
                             if (entry & K3_FULL_FLAG) return;  // request list overflowed: exact scan decides
                             const K3Item it = A[entry & ~K3_FULL_FLAG];
+                            const double2 *ccg = G.cc + S.b_off[it.b];
+                            K3GlobalCC acc;
+                            acc.g = ccg;
                             const int w_pe = k3_window_end(P, it);
                             const int w_last = w_pe - mw;
                             int i_end = it.ps + mw + cb * 32 - 1;
                             i_end = i_end < w_last ? i_end : w_last;
                             const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
                             const unsigned long long thr = S.win_thr[slot];
-                            const int ebase = S.win_ebase[slot];
+                            const int ebase = S.b_ebase[it.b];
                             for (int i = it.ps + mw + ca * 32 + lane; i <= i_end; i += 32) {
                                 unsigned long long key;
-                                k3_screen_key_at(acc.g, w_lo, w_hi, it.ps, w_pe, i, G.RN, ebase, key);
+                                k3_screen_key_at(ccg, w_lo, w_hi, it.ps, w_pe, i, G.RN, ebase, key);
                                 if (key <= thr) k3_request(S, slot, i);
                             }
                         });
@@ -743,6 +815,8 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                             k = S.req_k[r];
                             i = S.req_i[r];
                             const K3Item it = A[S.win_item[k] & ~K3_FULL_FLAG];
+                            K3GlobalCC acc;
+                            acc.g = G.cc + S.b_off[it.b];
                             w_ps = it.ps;
                             w_pe = k3_window_end(P, it);
                             const double2 lo = acc.at(w_ps - 1), hi = acc.at(w_pe - 1), mid = acc.at(i - 1);
@@ -773,7 +847,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                         const int pe = k3_window_end(P, it);
                         atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
                         atomicAdd(&S.scans, 1ull);
-                        k3_resolve_local(G, S, Bn, P, ev, off, it, S.best_key[k] ? S.best_idx[k] : -1);
+                        k3_resolve_local(G, S, Bn, P, it, S.best_key[k] ? S.best_idx[k] : -1);
                     }
                 }
                 // step 5: windows left for the exact scan (validation mode: all of them), whole CTA each
@@ -781,6 +855,8 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                     const int entry = S.win_item[k];
                     if (screen && !(entry & K3_FULL_FLAG)) continue;
                     const K3Item it = A[entry & ~K3_FULL_FLAG];
+                    K3GlobalCC acc;
+                    acc.g = G.cc + S.b_off[it.b];
                     const int pe = k3_window_end(P, it);
                     K3Best b = k3_scan_range(acc, it.ps, pe, mw, P.min_gain, tid, K3_THREADS);
                     b = k3_cta_reduce(b, S);
@@ -788,7 +864,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                         atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
                         atomicAdd(&S.scans, 1ull);
                         if (screen) atomicAdd(&S.exact, (unsigned long long)(pe - it.ps - 2 * mw + 1));
-                        k3_resolve_local(G, S, Bn, P, ev, off, it, b.x);
+                        k3_resolve_local(G, S, Bn, P, it, b.x);
                     }
                 }
                 __syncthreads();
@@ -802,9 +878,9 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
             atomicAdd(&G.ctr->n_cand, S.cand);
             atomicAdd(&G.ctr->n_scan, S.scans);
             atomicAdd(&G.ctr->n_exact, S.exact);
-            atomicAdd(&G.ctr->n_tasks, 1ull);
+            atomicAdd(&G.ctr->n_tasks, (unsigned long long)nb);
             __threadfence();
-            atomicAdd((unsigned long long *)&G.ctr->q_pending, (unsigned long long)(-1LL));
+            atomicAdd((unsigned long long *)&G.ctr->q_pending, (unsigned long long)(-(long long)nb));
         }
     }
 }

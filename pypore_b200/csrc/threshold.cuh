@@ -12,7 +12,10 @@
 #include "common.cuh"
 
 constexpr int K1_THREADS = 256;
-constexpr int K1_ROWS = 4;
+#ifndef K1_CFG_ROWS  // development knob
+#define K1_CFG_ROWS 4
+#endif
+constexpr int K1_ROWS = K1_CFG_ROWS;  // <= 8 (one thread per mask word)
 constexpr int K1_TILE = K1_THREADS * 4 * K1_ROWS;  // 4096 samples
 constexpr int K1_WORDS = K1_TILE / 32;             // 128 mask words
 constexpr int K1_LOCAL_RUNS = 64;
