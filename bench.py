@@ -216,8 +216,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mw, MW, W, gain = statsplit_min_gain(**SPLIT)
-    stream = torch.cuda.current_stream()
-    ctx = _lib.Context(local, stream=stream.cuda_stream)
+    ctx = _lib.Context(local)
+    # every kernel, copy-stream join and collective of a step is ordered on the context's stream:
+    # the timing events are recorded there
+    stream = torch.cuda.ExternalStream(ctx.stream_handle, device=torch.device("cuda", local))
 
     # ---- synthetic input ---------------------------------------------------------------
     epg = args.events_per_gpu

@@ -65,6 +65,8 @@ int pp_create(int device, void *cuda_stream, pp_ctx **out);
 void pp_destroy(pp_ctx *ctx);
 const char *pp_last_error(pp_ctx *ctx);
 int pp_sync(pp_ctx *ctx);
+/* The CUDA stream (cudaStream_t) all of the context's work is ordered on. */
+void *pp_stream(pp_ctx *ctx);
 /* Page-locked host memory (cudaMallocHost) for traces handed to pp_pipeline_host /
  * pp_trace_upload and for table downloads: copies to and from it run at full PCIe rate. */
 int pp_host_alloc(pp_ctx *ctx, int64_t bytes, void **out);
@@ -190,6 +192,25 @@ int pp_pipeline(pp_ctx *ctx, const pp_pipeline_params *p, int64_t out[4]);
  * With a filter, or a trace of at most one chunk, it is exactly that sequence. */
 int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_samples,
                      const pp_pipeline_params *p, int64_t out[4]);
+
+/* ---- multi-GPU: one context per rank, contiguous trace chunks -------------
+ * The exchange itself (NCCL all-gathers of the records / tables, point-to-point halos) is
+ * driven by pypore_b200/dist.py; these calls keep every stage on the device between them.
+ * pp_shard_scan: threshold scan of the chunk's first scan_len samples; writes the 12-double
+ *   boundary record [n_local, n_runs, first run: below,len,min,max, last run: below,start,len,
+ *   min,max, run-table-overflow flag] to DEVICE memory, no host synchronisation.
+ * pp_shard_finish: select (first / last run optionally owned by a neighbour), optional
+ *   straddling event appended, prefix + split + compaction + statistics; writes the 8-word result
+ *   record [runs, events, event samples, segments, overflow flags, candidates, scans, exact
+ *   evaluations] to DEVICE memory, no host synchronisation.
+ * pp_shard_commit: hands the (all-gathered, host-read) result record back so that downloads work.
+ * pp_pack_tables: event rows {global start, length} and segment rows {global event id, start,
+ *   end, mean, std, min, max} as 8-byte words in one device buffer (2 E + 7 S words). */
+int pp_shard_scan(pp_ctx *ctx, double threshold, int64_t scan_len, double *dev_record);
+int pp_shard_finish(pp_ctx *ctx, const pp_pipeline_params *p, int skip_first, int skip_last, int has_event,
+                    int64_t ev_start, int64_t ev_len, int64_t *dev_record);
+int pp_shard_commit(pp_ctx *ctx, const int64_t rec[8]);
+int pp_pack_tables(pp_ctx *ctx, int64_t sample_offset, int64_t event_base, int64_t *dev_out, int64_t cap_words);
 
 #ifdef __cplusplus
 }

@@ -78,8 +78,14 @@ SIGNATURES = {
     "pp_split_counters": (_c.c_int, [_c.c_void_p, _i64p]),
     "pp_debug_screen": (_c.c_int, [_c.c_void_p, _i64, _c.c_int, _c.c_int, _c.c_int, _f64p, _f64p, _u8p, _f64p]),
     "pp_debug_lg2_error": (_c.c_int, [_c.c_void_p, _f64p]),
+    "pp_stream": (_c.c_void_p, [_c.c_void_p]),
     "pp_host_alloc": (_c.c_int, [_c.c_void_p, _i64, _c.POINTER(_c.c_void_p)]),
     "pp_host_free": (None, [_c.c_void_p, _c.c_void_p]),
+    "pp_shard_scan": (_c.c_int, [_c.c_void_p, _c.c_double, _i64, _c.c_void_p]),
+    "pp_shard_finish": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _c.c_int, _c.c_int, _c.c_int, _i64, _i64,
+                                   _c.c_void_p]),
+    "pp_shard_commit": (_c.c_int, [_c.c_void_p, _i64p]),
+    "pp_pack_tables": (_c.c_int, [_c.c_void_p, _i64, _i64, _c.c_void_p, _i64]),
     "pp_pipeline_host": (_c.c_int, [_c.c_void_p, _f32p, _i64, _i64, _c.POINTER(PipelineParams), _i64p]),
     "pp_pipeline": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _i64p]),
 }
@@ -219,6 +225,11 @@ class Context(object):
 
     def sync(self):
         self._ck(self._L.pp_sync(self._h))
+
+    @property
+    def stream_handle(self):
+        """cudaStream_t of the context as an integer (for torch.cuda.ExternalStream)."""
+        return int(self._L.pp_stream(self._h) or 0)
 
     def set_option(self, option, value):
         self._ck(self._L.pp_set_option(self._h, int(option), int(value)))
@@ -373,6 +384,21 @@ class Context(object):
                  with_stats=True, host_trace=None, chunk_samples=0):
         """Whole pipeline on the resident trace, or -- with `host_trace` (float32, ideally pinned) --
         streamed from host memory in chunks that overlap the copy with the computation."""
+        p, keep = self._params(threshold, rule_mask, duration_gt, duration_lt, min_gt, max_lt, min_width,
+                               max_width, window_width, min_gain, filter_ba, prefix_mode, with_stats)
+        out = np.zeros(4, np.int64)
+        if host_trace is None:
+            self._ck(self._L.pp_pipeline(self._h, _c.byref(p), _ptr(out, _i64p)))
+        else:
+            x = np.ascontiguousarray(host_trace, np.float32)
+            self._ck(self._L.pp_pipeline_host(self._h, _ptr(x, _f32p), x.shape[0], int(chunk_samples),
+                                              _c.byref(p), _ptr(out, _i64p)))
+        del keep
+        return dict(runs=int(out[0]), events=int(out[1]), event_samples=int(out[2]), segments=int(out[3]))
+
+    @staticmethod
+    def _params(threshold, rule_mask, duration_gt, duration_lt, min_gt, max_lt, min_width, max_width,
+                window_width, min_gain, filter_ba=None, prefix_mode=PREFIX_AUTO, with_stats=True):
         p = PipelineParams()
         p.threshold = float(threshold)
         p.rule_mask = int(rule_mask)
@@ -390,15 +416,28 @@ class Context(object):
         p.min_gain = float(min_gain)
         p.prefix_mode = int(prefix_mode)
         p.with_stats = int(bool(with_stats))
-        out = np.zeros(4, np.int64)
-        if host_trace is None:
-            self._ck(self._L.pp_pipeline(self._h, _c.byref(p), _ptr(out, _i64p)))
-        else:
-            x = np.ascontiguousarray(host_trace, np.float32)
-            self._ck(self._L.pp_pipeline_host(self._h, _ptr(x, _f32p), x.shape[0], int(chunk_samples),
-                                              _c.byref(p), _ptr(out, _i64p)))
-        del keep
-        return dict(runs=int(out[0]), events=int(out[1]), event_samples=int(out[2]), segments=int(out[3]))
+        return p, keep
+
+    # -- multi-GPU (driven by pypore_b200.dist) ----------------------------------
+    def shard_scan(self, threshold, scan_len, dev_record_ptr):
+        self._ck(self._L.pp_shard_scan(self._h, float(threshold), int(scan_len), _c.c_void_p(int(dev_record_ptr))))
+
+    def shard_finish(self, threshold, rules, min_width, max_width, window_width, min_gain, skip_first, skip_last,
+                     event, dev_record_ptr):
+        p, keep = self._params(threshold, min_width=min_width, max_width=max_width, window_width=window_width,
+                               min_gain=min_gain, **rules)
+        has = event is not None
+        self._ck(self._L.pp_shard_finish(self._h, _c.byref(p), int(bool(skip_first)), int(bool(skip_last)),
+                                         int(has), int(event[0]) if has else 0, int(event[1]) if has else 0,
+                                         _c.c_void_p(int(dev_record_ptr))))
+
+    def shard_commit(self, rec):
+        rec = np.ascontiguousarray(rec, np.int64)
+        self._ck(self._L.pp_shard_commit(self._h, _ptr(rec, _i64p)))
+
+    def pack_tables(self, sample_offset, event_base, dev_out_ptr, cap_words):
+        self._ck(self._L.pp_pack_tables(self._h, int(sample_offset), int(event_base),
+                                        _c.c_void_p(int(dev_out_ptr)), int(cap_words)))
 
 
 _default = {}

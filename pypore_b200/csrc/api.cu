@@ -613,6 +613,8 @@ void pp_destroy(pp_ctx *ctx)
 
 const char *pp_last_error(pp_ctx *ctx) { return ctx ? ctx->err : "null context"; }
 
+void *pp_stream(pp_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
 int pp_host_alloc(pp_ctx *ctx, int64_t bytes, void **out)
 {
     if (!ctx || !out || bytes <= 0) return fail(ctx, PP_ERR_ARG, "bad host allocation");
@@ -1100,6 +1102,81 @@ int pp_pipeline(pp_ctx *ctx, const pp_pipeline_params *p, int64_t out[4])
         return PP_OK;
     }
     return fail(ctx, PP_ERR_CAPACITY, "run table overflow");
+}
+
+// ---- multi-GPU (one context per rank; pypore_b200/dist.py drives the exchange) ------------
+int pp_shard_scan(pp_ctx *ctx, double threshold, int64_t scan_len, double *dev_record)
+{
+    if (!ctx || !dev_record) return PP_ERR_ARG;
+    CKR(set_device(ctx));
+    reset_stages(ctx);
+    CKR(record_boundary(ctx, 0));
+    CKR(enqueue_threshold(ctx, threshold, scan_len));
+    CKR(record_boundary(ctx, ST_THRESHOLD + 1));
+    ctx->stage_ran[ST_THRESHOLD] = true;
+    k1_boundary_record<<<1, 32, 0, ctx->stream>>>(
+        ctx->scan_len, ctx->ctr, (const int64_t *)ctx->run_start.p, (const int64_t *)ctx->run_len.p,
+        (const double *)ctx->run_min.p, (const double *)ctx->run_max.p, (const unsigned char *)ctx->run_below.p,
+        ctx->cap_runs, dev_record);
+    LAUNCHED(ctx);
+    return PP_OK;
+}
+
+int pp_shard_finish(pp_ctx *ctx, const pp_pipeline_params *p, int skip_first, int skip_last, int has_event,
+                    int64_t ev_start, int64_t ev_len, int64_t *dev_record)
+{
+    if (!ctx || !p || !dev_record) return PP_ERR_ARG;
+    if (p->filter_ncoef > 0) return fail(ctx, PP_ERR_ARG, "the sharded path does not filter");
+    CKR(set_device(ctx));
+    CKR(enqueue_select(ctx, p->rule_mask, p->duration_gt, p->duration_lt, p->min_gt, p->max_lt, skip_first,
+                       skip_last));
+    if (has_event) {
+        if (ev_start < 0 || ev_len <= 0 || ev_start + ev_len > ctx->n)
+            return fail(ctx, PP_ERR_ARG, "bad appended event");
+        k_append_event<<<1, 1, 0, ctx->stream>>>(ctx->ctr, (int64_t *)ctx->ev_start.p, (int64_t *)ctx->ev_len.p,
+                                                 (int64_t *)ctx->ev_off.p, ev_start, ev_len);
+        LAUNCHED(ctx);
+    }
+    CKR(record_boundary(ctx, ST_SELECT + 1));
+    ctx->stage_ran[ST_SELECT] = true;
+    CKR(enqueue_split(ctx, p->min_width, p->max_width, p->window_width, p->min_gain, p->prefix_mode));
+    if (p->with_stats) CKR(enqueue_stats(ctx));
+    k_result_record<<<1, 32, 0, ctx->stream>>>(ctx->ctr, (long long *)dev_record);
+    LAUNCHED(ctx);
+    return PP_OK;
+}
+
+int pp_shard_commit(pp_ctx *ctx, const int64_t rec[8])
+{
+    if (!ctx || !rec) return PP_ERR_ARG;
+    ctx->n_runs = rec[0];
+    ctx->n_events = rec[1];
+    ctx->n_event_samples = rec[2];
+    ctx->n_segments = rec[3];
+    ctx->split_counters[0] = rec[5];
+    ctx->split_counters[1] = rec[6];
+    ctx->split_counters[4] = rec[7];
+    const unsigned o = (unsigned)rec[4];
+    if (rec[0] > ctx->cap_runs) return fail(ctx, PP_ERR_CAPACITY, "run table overflow");
+    if (o & PP_OVF_QUEUE) return fail(ctx, PP_ERR_CAPACITY, "split work queue overflow");
+    if (o & PP_OVF_SEGS) return fail(ctx, PP_ERR_CAPACITY, "segment table overflow");
+    return PP_OK;
+}
+
+int pp_pack_tables(pp_ctx *ctx, int64_t sample_offset, int64_t event_base, int64_t *dev_out, int64_t cap_words)
+{
+    if (!ctx || !dev_out) return PP_ERR_ARG;
+    if (ctx->n_events < 0 || ctx->n_segments < 0 || !ctx->stats_valid)
+        return fail(ctx, PP_ERR_STATE, "tables are not complete");
+    if (2 * ctx->n_events + 7 * ctx->n_segments > cap_words) return fail(ctx, PP_ERR_CAPACITY, "pack buffer too small");
+    CKR(set_device(ctx));
+    k_pack_tables<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(
+        ctx->n_events, ctx->n_segments, sample_offset, event_base, (const int64_t *)ctx->ev_start.p,
+        (const int64_t *)ctx->ev_len.p, (const int *)ctx->seg_event.p, (const int64_t *)ctx->seg_start.p,
+        (const int64_t *)ctx->seg_end.p, (const double *)ctx->seg_mean.p, (const double *)ctx->seg_std.p,
+        (const double *)ctx->seg_min.p, (const double *)ctx->seg_max.p, (long long *)dev_out);
+    LAUNCHED(ctx);
+    return PP_OK;
 }
 
 // Same pipeline fed from host memory: the trace is copied in chunks on a second stream and every

@@ -395,3 +395,73 @@ k1_event_offsets(PPCounters *ctr, const int64_t *__restrict__ ev_len, int64_t n_
         ctr->ev_begin = 0;
     }
 }
+
+// Multi-GPU: the record a rank publishes about its chunk (pypore_b200/dist.py boundary_info):
+// [n_local, n_runs, first_below, first_len, first_min, first_max,
+//  last_below, last_start, last_len, last_min, last_max, run-table-overflow flag]
+__global__ void k1_boundary_record(int64_t n_local, const PPCounters *ctr, const int64_t *__restrict__ run_start,
+                                   const int64_t *__restrict__ run_len, const double *__restrict__ run_min,
+                                   const double *__restrict__ run_max, const unsigned char *__restrict__ run_below,
+                                   int64_t cap_runs, double *__restrict__ rec)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int64_t n_runs = (int64_t)ctr->n_runs;
+    const bool ovf = n_runs > cap_runs || n_runs <= 0;
+    const int64_t last = ovf ? 0 : n_runs - 1;
+    rec[0] = (double)n_local;
+    rec[1] = (double)n_runs;
+    rec[2] = (double)run_below[0];
+    rec[3] = (double)run_len[0];
+    rec[4] = run_min[0];
+    rec[5] = run_max[0];
+    rec[6] = (double)run_below[last];
+    rec[7] = (double)run_start[last];
+    rec[8] = (double)run_len[last];
+    rec[9] = run_min[last];
+    rec[10] = run_max[last];
+    rec[11] = ovf ? 1.0 : 0.0;
+}
+
+// Multi-GPU: [n_runs, n_events, n_event_samples, n_segments, overflow flags, candidates, scans, exact]
+__global__ void k_result_record(const PPCounters *ctr, long long *__restrict__ rec)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    rec[0] = (long long)ctr->n_runs;
+    rec[1] = (long long)ctr->n_events;
+    rec[2] = (long long)ctr->n_event_samples;
+    rec[3] = (long long)ctr->n_segments;
+    rec[4] = (long long)ctr->overflow;
+    rec[5] = (long long)ctr->n_cand;
+    rec[6] = (long long)ctr->n_scan;
+    rec[7] = (long long)ctr->n_exact;
+}
+
+// Multi-GPU: event and segment tables packed into 8-byte words for ONE all-gather:
+// n_events rows {global start, length}, then n_segments rows
+// {global event id, start, end, mean, std, min, max} (doubles as their bit patterns).
+__global__ void __launch_bounds__(256)
+k_pack_tables(int64_t n_events, int64_t n_segments, int64_t sample_offset, int64_t event_base,
+              const int64_t *__restrict__ ev_start, const int64_t *__restrict__ ev_len,
+              const int *__restrict__ seg_event, const int64_t *__restrict__ seg_start,
+              const int64_t *__restrict__ seg_end, const double *__restrict__ mean,
+              const double *__restrict__ sd, const double *__restrict__ mn, const double *__restrict__ mx,
+              long long *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t e = t0; e < n_events; e += stride) {
+        out[2 * e] = ev_start[e] + sample_offset;
+        out[2 * e + 1] = ev_len[e];
+    }
+    long long *seg = out + 2 * n_events;
+    for (int64_t k = t0; k < n_segments; k += stride) {
+        long long *row = seg + 7 * k;
+        row[0] = (long long)seg_event[k] + event_base;
+        row[1] = seg_start[k];
+        row[2] = seg_end[k];
+        row[3] = __double_as_longlong(mean[k]);
+        row[4] = __double_as_longlong(sd[k]);
+        row[5] = __double_as_longlong(mn[k]);
+        row[6] = __double_as_longlong(mx[k]);
+    }
+}

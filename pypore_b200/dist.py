@@ -134,6 +134,25 @@ def gather_tables(int_cols, flt_cols, counts, dist, group=None):
     return out[0], out[1]
 
 
+def gather_packed(words, counts, dist, group=None):
+    """All-gather the packed tables (pp_pack_tables layout: 2 words per event, then 7 per segment) with ONE
+    collective.  `words`: int64 tensor holding this rank's 2 E + 7 S words (it may be longer); `counts`: per-rank
+    (events, segments), known to every rank.  Returns dict(events int64 [sum E, 2], seg_int int64 [sum S, 3],
+    seg_flt float64 [sum S, 4])."""
+    import torch
+    world = len(counts)
+    sizes = [2 * e + 7 * s for e, s in counts]
+    m = max(max(sizes), 1)
+    if words.shape[0] < m:
+        words = torch.cat([words, torch.zeros(m - words.shape[0], dtype=words.dtype, device=words.device)])
+    g = torch.empty(world * m, dtype=torch.int64, device=words.device)
+    dist.all_gather_into_tensor(g, words[:m].contiguous(), group=group)
+    g = g.view(world, m)
+    ev = torch.cat([g[r, :2 * counts[r][0]].view(-1, 2) for r in range(world)], dim=0)
+    seg = torch.cat([g[r, 2 * counts[r][0]:sizes[r]].view(-1, 7) for r in range(world)], dim=0)
+    return dict(events=ev, seg_int=seg[:, :3].contiguous(), seg_flt=seg[:, 3:].contiguous().view(torch.float64))
+
+
 # ------------------------------------------------------------------------------------------
 # synthetic sharded workload (bench / tests): one C2-style piece per rank, cut mid-event
 # ------------------------------------------------------------------------------------------
@@ -185,8 +204,8 @@ def device_view(ptr, n, dtype, device):
 class ShardedPipeline(object):
     """threshold -> select -> halo -> split -> stats -> table all-gather on one rank's chunk.
 
-    The context must have been created on torch's current CUDA stream so that NCCL
-    operations and the library's kernels are ordered without extra synchronisation.
+    Every torch / NCCL operation of a step is issued on the context's own CUDA stream (wrapped as a
+    torch ExternalStream), so collectives and the library's kernels are ordered without extra synchronisation.
     """
 
     HALO_CAPACITY = 1 << 20
@@ -197,12 +216,14 @@ class ShardedPipeline(object):
         self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
         self.dist = dist
         self.device = torch.device("cuda", ctx.device)
+        self.stream = torch.cuda.ExternalStream(ctx.stream_handle, device=self.device)
         self.halo = torch.empty(self.HALO_CAPACITY, dtype=torch.float32, device=self.device)
         self.n_local = 0
         self.n_owned = 0
         self.offsets = None
         self.tables = None
         self.stage_ms = {}
+        self.rec = self.res = self.pack = None
 
     def load(self, host_chunk):
         self.ctx.upload_trace_async(host_chunk, extra_capacity=self.HALO_CAPACITY)
@@ -210,63 +231,60 @@ class ShardedPipeline(object):
 
     def step(self, threshold, rules, mw, MW, W, gain):
         import torch
-        ctx, dist = self.ctx, self.dist
-        ctx.truncate_trace(self.n_local)
-        n_runs = ctx.threshold_scan(threshold, scan_len=self.n_local)
-        if n_runs == 1:
-            first = last = [a[0] for a in ctx.runs_range(0, 1)]
+        with torch.cuda.stream(self.stream):
+            return self._step(threshold, rules, mw, MW, W, gain)
+
+    def _step(self, threshold, rules, mw, MW, W, gain):
+        """Two host synchronisations per step: after the all-gather of the boundary records (the plan is
+        host logic) and after the all-gather of the result records (table sizes)."""
+        import torch
+        ctx, dist, dev = self.ctx, self.dist, self.device
+        if self.rec is None:
+            self.rec = torch.zeros(INFO_LEN, dtype=torch.float64, device=dev)
+            self.res = torch.zeros(8, dtype=torch.int64, device=dev)
+        for attempt in range(2):
+            ctx.truncate_trace(self.n_local)
+            ctx.shard_scan(threshold, self.n_local, self.rec.data_ptr())
+            out = torch.empty(self.world * INFO_LEN, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(out, self.rec, group=self.group)
+            infos = out.cpu().numpy().reshape(self.world, INFO_LEN)      # host sync 1
+            if not infos[:, I_PAD].any():
+                break
+            # some rank's run table overflowed (very noisy chunk): grow it everywhere and scan again
+            ctx.threshold_scan(threshold, scan_len=self.n_local)
         else:
-            f = ctx.runs_range(0, 1)
-            l = ctx.runs_range(n_runs - 1, 1)
-            first, last = [a[0] for a in f], [a[0] for a in l]
-        infos = gather_infos(boundary_info(self.n_local, n_runs, first, last), dist, self.device, self.group)
+            raise RuntimeError("run table overflow")
+        n_runs = int(infos[self.rank, I_NRUNS])
         plan = plan_boundaries(infos, rules)[self.rank]
         lens = infos[:, I_N].astype(np.int64)
         self.offsets = np.concatenate(([0], np.cumsum(lens)))
         need = sum(c for _, c in plan["recv"])
         if need > self.halo.shape[0]:
             raise RuntimeError("halo of %d samples exceeds HALO_CAPACITY" % need)
-        chunk = device_view(ctx.trace_ptr, self.n_local, torch.float32, self.device)
+        chunk = device_view(ctx.trace_ptr, self.n_local, torch.float32, dev)
         got = exchange_halo(plan, chunk, self.halo, dist, self.group)
         if got:
             ctx.append_trace(self.halo.data_ptr(), got, True)
-        ne, ns = ctx.select_events(skip_first=plan["skip_first"], skip_last=plan["skip_last"], **rules)
-        if plan["event"] is not None:
-            ctx.append_event(*plan["event"])
-            ne += 1
-            ns += plan["event"][1]
-        n_seg = ctx.statsplit(mw, MW, W, gain)
-        self.stage_ms = ctx.stage_ms()   # prefix / split / compact of this step (the next call resets them)
-        ctx.segment_stats()
+        ctx.shard_finish(threshold, rules, mw, MW, W, gain, plan["skip_first"], plan["skip_last"], plan["event"],
+                         self.res.data_ptr())
+        allr = torch.empty(self.world * 8, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allr, self.res, group=self.group)
+        allr = allr.cpu().numpy().reshape(self.world, 8)                 # host sync 2
+        ctx.shard_commit(allr[self.rank])
+        self.stage_ms = ctx.stage_ms()
         self.n_owned = self.n_local
-        self._gather(ne, n_seg)
-        return dict(runs=n_runs, events=ne, event_samples=ns, segments=n_seg)
-
-    def _gather(self, ne, n_seg):
-        import torch
-        ctx, dist, dev = self.ctx, self.dist, self.device
-        cnt = torch.tensor([ne, n_seg], dtype=torch.int64, device=dev)
-        allc = torch.empty(2 * self.world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allc, cnt, group=self.group)
-        allc = allc.cpu().numpy().reshape(self.world, 2)
-        ev_counts, seg_counts = [int(v) for v in allc[:, 0]], [int(v) for v in allc[:, 1]]
-        ev_base = int(sum(ev_counts[:self.rank]))
-        # events: global start, length
-        ev_start = device_view(ctx.table_ptr(7), ne, torch.int64, dev) + int(self.offsets[self.rank])
-        ev_len = device_view(ctx.table_ptr(8), ne, torch.int64, dev)
-        ev_int = torch.stack([ev_start, ev_len], dim=1)
-        ev_flt = torch.zeros((ne, 1), dtype=torch.float64, device=dev)
-        g_ev, _ = gather_tables(ev_int, ev_flt, ev_counts, dist, self.group)
-        # segments: global event id, event-relative start / end, statistics
-        seg_ev = device_view(ctx.table_ptr(0), n_seg, torch.int32, dev).to(torch.int64) + ev_base
-        seg_int = torch.stack([seg_ev, device_view(ctx.table_ptr(1), n_seg, torch.int64, dev),
-                               device_view(ctx.table_ptr(2), n_seg, torch.int64, dev)], dim=1)
-        seg_flt = torch.stack([device_view(ctx.table_ptr(k), n_seg, torch.float64, dev) for k in (3, 4, 5, 6)],
-                              dim=1)
-        g_si, g_sf = gather_tables(seg_int, seg_flt, seg_counts, dist, self.group)
-        self.tables = dict(events=g_ev, seg_int=g_si, seg_flt=g_sf)
+        counts = [(int(r[1]), int(r[3])) for r in allr]
+        ne, n_seg = counts[self.rank]
+        words = 2 * ne + 7 * n_seg
+        if self.pack is None or self.pack.shape[0] < words:
+            self.pack = torch.empty(int(words * 1.25) + 64, dtype=torch.int64, device=dev)
+        ctx.pack_tables(int(self.offsets[self.rank]), sum(c[0] for c in counts[:self.rank]), self.pack.data_ptr(),
+                        self.pack.shape[0])
+        self.tables = gather_packed(self.pack, counts, dist, self.group)
+        return dict(runs=n_runs, events=ne, event_samples=int(allr[self.rank, 2]), segments=n_seg)
 
     def download(self):
         """Device-to-host read of the gathered tables (what a caller of the public API receives)."""
-        t = self.tables
-        return {k: v.cpu().numpy() for k, v in t.items()}
+        import torch
+        with torch.cuda.stream(self.stream):
+            return {k: v.cpu().numpy() for k, v in self.tables.items()}

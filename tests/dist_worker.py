@@ -19,7 +19,7 @@ def main():
     epr = int(sys.argv[1]) if len(sys.argv) > 1 else 30
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = _lib.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+    ctx = _lib.Context(local)
     chunk = ppdist.synthetic_chunk(rank, world, epr, seed0=70)
     shard = ppdist.ShardedPipeline(ctx, rank, world)
     pinned = torch.from_numpy(chunk).pin_memory()

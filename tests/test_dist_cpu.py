@@ -74,6 +74,20 @@ def _worker(rank, world, port, epr, q):
         ws, wl = oracle.events(glob.astype(np.float64), 110, PYRULES)
         assert np.array_equal(gi[:, 0].numpy(), ws) and np.array_equal(gi[:, 1].numpy(), wl)
         assert np.array_equal(gf[:, 0].numpy(), ws * 0.5)
+        # the packed single-collective gather used by ShardedPipeline (pp_pack_tables layout): events as above plus
+        # made-up segment rows {event id, start, end, mean, std, min, max}; ragged counts, one rank may be longer
+        nseg = 3 * len(keep) + rank
+        seg_i = torch.arange(nseg * 3, dtype=torch.int64).reshape(-1, 3) + 1000 * rank
+        seg_f = torch.arange(nseg * 4, dtype=torch.float64).reshape(-1, 4) * 0.25 - rank
+        words = torch.cat([ints.reshape(-1), torch.cat([seg_i, seg_f.view(torch.int64)], dim=1).reshape(-1),
+                           torch.zeros(5 * rank, dtype=torch.int64)])
+        pcounts = [None] * world
+        dist.all_gather_object(pcounts, (len(keep), nseg))
+        t = ppdist.gather_packed(words, pcounts, dist)
+        assert np.array_equal(t["events"].numpy()[:, 0], ws) and np.array_equal(t["events"].numpy()[:, 1], wl)
+        lo = sum(c[1] for c in pcounts[:rank])
+        assert t["seg_int"].shape == (sum(c[1] for c in pcounts), 3) and t["seg_flt"].dtype == torch.float64
+        assert torch.equal(t["seg_int"][lo:lo + nseg], seg_i) and torch.equal(t["seg_flt"][lo:lo + nseg], seg_f)
         # segments of the straddling event, split from chunk+halo, equal the oracle's on the global trace
         if plan["event"] is not None:
             s, n = plan["event"]
