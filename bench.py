@@ -339,7 +339,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k3_split", "achieved": split_gbs, "peak": peak,
                          "unit": "GB/s", "frac": split_gbs / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": split_bytes,
-                         "note": "fp64-pipe bound, not HBM bound: 2 log + 4 div per candidate (DESIGN.md)"},
+                         "note": "algorithmic bytes = one 16 B {c,c2} pair per candidate; the kernel itself is bound by "
+                                 "L2->SM traffic and instruction issue, DRAM traffic is ~0.8 GB (DESIGN.md 4)"},
             "pipeline_roofline": {"b_floor_bytes": b_floor, "achieved": b_floor / sec / 1e9 / world,
                                   "peak": peak, "unit": "GB/s per GPU",
                                   "frac": b_floor / sec / 1e9 / world / peak},

@@ -371,7 +371,7 @@ int enqueue_prefix(pp_ctx *ctx, int prefix_mode)
     const int64_t ncap = ctx->flat_cap;
     PPSource src = make_source(ctx);
     if (prefix_mode == PP_PREFIX_SEQUENTIAL) {
-        k2_prefix_sequential<<<ctx->sm_count * 16, 32, 0, ctx->stream>>>(
+        k2_prefix_sequential<<<ctx->sm_count * 4, K2S_WARPS * 32, 0, ctx->stream>>>(
             src, (const int64_t *)ctx->ev_len.p, ctx->ctr, nullptr, (double2 *)ctx->cc.p);
         LAUNCHED(ctx);
     } else {
@@ -411,7 +411,7 @@ int enqueue_prefix(pp_ctx *ctx, int prefix_mode)
                 (double2 *)ctx->cc.p);
         LAUNCHED(ctx);
         if (prefix_mode != PP_PREFIX_PARALLEL) {
-            k2_prefix_sequential<<<ctx->sm_count * 16, 32, 0, ctx->stream>>>(
+            k2_prefix_sequential<<<ctx->sm_count * 4, K2S_WARPS * 32, 0, ctx->stream>>>(
                 src, (const int64_t *)ctx->ev_len.p, ctx->ctr, (const unsigned *)ctx->inexact.p,
                 (double2 *)ctx->cc.p);
             LAUNCHED(ctx);

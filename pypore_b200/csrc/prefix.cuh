@@ -20,39 +20,65 @@
 #pragma once
 #include "common.cuh"
 
-// One thread per event, strict left-to-right order.
-__global__ void __launch_bounds__(128)
+// Strict left-to-right order (np.cumsum's), one WARP per event: the lanes stage a tile of
+// samples (and their squares) in shared memory with coalesced loads, lane 0 / lane 1 run the two
+// dependent addition chains  c += x  and  c2 += x*x  over the tile (operands come from shared
+// memory, so only the fp64 add latency is on the critical path), and all lanes write the tile
+// of prefix sums back coalesced.  Used for the events the tiled scan could not prove exact
+// (filtered float64 currents, raw non-ADC data) and for PP_PREFIX_SEQUENTIAL.
+constexpr int K2S_WARPS = 8;
+constexpr int K2S_TILE = 256;  // samples per warp tile
+
+__global__ void __launch_bounds__(K2S_WARPS * 32)
 k2_prefix_sequential(PPSource src, const int64_t *__restrict__ ev_len, PPCounters *ctr,
                      const unsigned *__restrict__ inexact /* nullable: redo only flagged events */,
                      double2 *__restrict__ cc)
 {
+    __shared__ double sv[K2S_WARPS][2][K2S_TILE];  // [warp][0: x -> c, 1: x*x -> c2][sample]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n_events = (int64_t)ctr->n_events;
-    for (int64_t e = (int64_t)ctr->ev_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_events;
-         e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t warps = (int64_t)gridDim.x * K2S_WARPS;
+    double (*v)[K2S_TILE] = sv[warp];
+    for (int64_t e = (int64_t)ctr->ev_begin + (int64_t)blockIdx.x * K2S_WARPS + warp; e < n_events; e += warps) {
         if (inexact) {
             if (inexact[e] == 0u) continue;
-            atomicAdd(&ctr->n_seq_redo, 1ull);
+            if (lane == 0) atomicAdd(&ctr->n_seq_redo, 1ull);
         }
         const int64_t len = ev_len[e];
         const int64_t off = src.ev_off[e];
-        double c = 0.0, c2 = 0.0;
-        int64_t j = 0;
-        for (; j + 8 <= len; j += 8) {
-            double xv[8];
+        double acc = 0.0;  // lane 0: c, lane 1: c2
+        for (int64_t base = 0; base < len; base += K2S_TILE) {
+            const int cnt = (int)((len - base) < K2S_TILE ? (len - base) : K2S_TILE);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) xv[k] = pp_sample(src, e, j + k);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                c = __dadd_rn(c, xv[k]);
-                c2 = __dadd_rn(c2, __dmul_rn(xv[k], xv[k]));
-                cc[off + j + k] = make_double2(c, c2);
+            for (int k = 0; k < K2S_TILE / 32; ++k) {
+                const int j = k * 32 + lane;
+                const double x = j < cnt ? pp_sample(src, e, base + j) : 0.0;
+                v[0][j] = x;
+                v[1][j] = __dmul_rn(x, x);
             }
-        }
-        for (; j < len; ++j) {
-            const double xv = pp_sample(src, e, j);
-            c = __dadd_rn(c, xv);
-            c2 = __dadd_rn(c2, __dmul_rn(xv, xv));
-            cc[off + j] = make_double2(c, c2);
+            __syncwarp();
+            if (lane < 2) {
+                double *p = v[lane];
+                for (int j0 = 0; j0 < K2S_TILE; j0 += 16) {
+                    double t[16];  // operands first: their loads do not wait for the chain's stores
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) t[k] = p[j0 + k];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        acc = __dadd_rn(acc, t[k]);
+                        t[k] = acc;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) p[j0 + k] = t[k];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < K2S_TILE / 32; ++k) {
+                const int j = k * 32 + lane;
+                if (j < cnt) cc[off + base + j] = make_double2(v[0][j], v[1][j]);
+            }
+            __syncwarp();
         }
     }
 }
