@@ -138,6 +138,16 @@ int pp_event_samples_download(pp_ctx *ctx, int64_t cap, double *out);
 /* min_gain is computed by the host exactly as cparsers.pyx:82-101. */
 int pp_statsplit(pp_ctx *ctx, int min_width, int max_width, int window_width, double min_gain,
                  int prefix_mode, int64_t *n_segments);
+/* Prefix sums only (cparsers.pyx:110-111 / :129-130), for pp_window_gains without a split. */
+int pp_prefix(pp_ctx *ctx, int prefix_mode);
+/* gain(i) in the reference's exact arithmetic for every candidate of a batch of windows
+ * [ps[w], pe[w]) of event `ev`: i = ps+min_width .. pe-min_width (the loop of
+ * _best_split_stepwise_score, cparsers.pyx:234-240; with ps=0, pe=len-1, min_width=2 the loop of
+ * _best_single_split, cparsers.pyx:142-151).  The gains of window w follow those of window w-1
+ * in `out` (host memory, `cap` doubles).  Needs resident prefix sums (pp_prefix / pp_statsplit). */
+int pp_window_gains(pp_ctx *ctx, int64_t ev, int n_windows, const int32_t *ps, const int32_t *pe, int min_width,
+                    double *out, int64_t cap);
+
 /* ---- K4: Segment.mean/std/min/max (core.py:209-223) ------------------- */
 int pp_segment_stats(pp_ctx *ctx);
 int pp_segments_download(pp_ctx *ctx, int64_t cap, int32_t *event, int64_t *start, int64_t *end,
@@ -205,12 +215,15 @@ int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_sa
  *   evaluations] to DEVICE memory, no host synchronisation.
  * pp_shard_commit: hands the (all-gathered, host-read) result record back so that downloads work.
  * pp_pack_tables: event rows {global start, length} and segment rows {global event id, start,
- *   end, mean, std, min, max} as 8-byte words in one device buffer (2 E + 7 S words). */
+ *   end, mean, std, min, max} as 8-byte words in one device buffer (2 E + 7 S words).  Counts and the
+ *   global event-id base are read on the DEVICE from the all-gathered result records (8 words per
+ *   rank), so the call needs no host knowledge of them; nothing is written if cap_words is too small. */
 int pp_shard_scan(pp_ctx *ctx, double threshold, int64_t scan_len, double *dev_record);
 int pp_shard_finish(pp_ctx *ctx, const pp_pipeline_params *p, int skip_first, int skip_last, int has_event,
                     int64_t ev_start, int64_t ev_len, int64_t *dev_record);
 int pp_shard_commit(pp_ctx *ctx, const int64_t rec[8]);
-int pp_pack_tables(pp_ctx *ctx, int64_t sample_offset, int64_t event_base, int64_t *dev_out, int64_t cap_words);
+int pp_pack_tables(pp_ctx *ctx, const int64_t *dev_records, int rank, int64_t sample_offset, int64_t *dev_out,
+                   int64_t cap_words);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,8 @@ def lib():
         L.orc_statsplit.restype = ctypes.c_int
         L.orc_statsplit.argtypes = [_f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                     ctypes.c_double, _i32p, ctypes.c_int, _i64p, _f64p, _f64p]
+        L.orc_window_gains.restype = None
+        L.orc_window_gains.argtypes = [_f64p, _f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f64p]
         L.orc_statsplit_events.restype = ctypes.c_int
         L.orc_statsplit_events.argtypes = [_f64p, _i64p, _i64p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_double, _i32p, _i64p, _i32p, _i64p,
@@ -193,6 +195,76 @@ def statsplit(event, min_width=100, max_width=1000000, window_width=10000, gain=
         return bp[:k].astype(np.int64), dict(ncand=int(st[0]), nscan=int(st[1]),
                                              gains=gains[:k].copy(), margins=margins[:k].copy())
     return bp[:k].astype(np.int64)
+
+
+def _window_gains(c, c2, start, end, first, last):
+    out = np.empty(max(last - first + 1, 0))
+    if out.shape[0]:
+        lib().orc_window_gains(_p(c, _f64p), _p(c2, _f64p), int(start), int(end), int(first), int(last),
+                               _p(out, _f64p))
+    return out
+
+
+def _sequential_best(gains, min_gain, first):
+    """`if gain > min_gain: min_gain = gain; x = i` over the candidates in order (cparsers.pyx:149-151,
+    238-240): the first occurrence of the largest gain above the threshold; NaN never wins."""
+    best, x = min_gain, -1
+    for j, g in enumerate(gains):
+        if g > best:
+            best, x = g, first + j
+    return float(best), x
+
+
+def best_single_split(event):
+    """FastStatSplit.best_single_split (cparsers.pyx:120-155): window [0, len-1), candidates
+    2 .. len-4, threshold 0.  Returns (gain, index)."""
+    x = _f64(event)
+    c, c2 = cumsum(x)
+    end = x.shape[0] - 1
+    if end - 2 <= 2:
+        return 0., -1
+    return _sequential_best(_window_gains(c, c2, 0, end, 2, end - 3), 0., 2)
+
+
+def score_samples(event, no_split=False, min_width=100, max_width=1000000, window_width=10000, gain=None,
+                  **gain_kwargs):
+    """FastStatSplit.score_samples (cparsers.pyx:205-275): one length-len(event) score array per window
+    scan in recursion order, or list(scores of the single scan of [0, len)) with no_split."""
+    x = _f64(event)
+    if gain is None:
+        gain = min_gain(min_width, max_width, window_width, **gain_kwargs)
+    mw, MW, W = int(min_width), int(max_width), int(window_width)
+    c, c2 = cumsum(x)
+    L = x.shape[0]
+
+    def stepwise_score(start, end):           # _best_split_stepwise_score, cparsers.pyx:217-241
+        if end - start <= 2 * mw:
+            return -1, []
+        g = _window_gains(c, c2, start, end, start + mw, end - mw)
+        score = np.zeros(L)
+        score[start + mw:end + 1 - mw] = g
+        return _sequential_best(g, gain, start + mw)[1], score
+
+    def rec(start, end, no_split):            # _recursive_split_scoring, cparsers.pyx:243-275
+        scores, split_at = [], -1
+        if no_split:
+            return list(stepwise_score(start, end)[1])
+        for pseudostart in range(start, end - 2 * mw, W // 2):
+            if pseudostart > start + MW:
+                split_at = min(start + MW, end - mw)
+                return scores + rec(split_at, end, 0)
+            pseudoend = min(end, pseudostart + W)
+            split_at, score = stepwise_score(pseudostart, pseudoend)
+            scores.append(score)
+            if split_at >= 0:
+                break
+        if split_at == -1:
+            if end - start <= MW:
+                return scores
+            split_at = min(start + MW, end - mw)
+        return scores + rec(start, split_at, 0) + rec(split_at, end, 0)
+
+    return rec(0, L, no_split)
 
 
 def statsplit_events(trace, ev_start, ev_len, min_width=100, max_width=1000000, window_width=10000,

@@ -178,6 +178,21 @@ static void recursive_split(split_ctx *S, int start, int end)
     }
 }
 
+/* The scoring loop shared by _best_single_split (PyPore/cparsers.pyx:142-151, start = 0,
+ * end = len-1, candidates 2 .. end-3) and _best_split_stepwise_score (cparsers.pyx:234-240,
+ * candidates start+min_width .. end-min_width): gain of every candidate first .. last of window
+ * [start, end) in the reference's operation order.  out[i - first] = gain(i). */
+void orc_window_gains(const double *c, const double *c2, int start, int end, int first, int last,
+                      double *out)
+{
+    double var_summed = (end - start) * log(var_c(start, end, c, c2));
+    for (int i = first; i <= last; ++i) {
+        double low_var_summed = (i - start) * log(var_c(start, i, c, c2));
+        double high_var_summed = (end - i) * log(var_c(i, end, c, c2));
+        out[i - first] = var_summed - (low_var_summed + high_var_summed);
+    }
+}
+
 /* FastStatSplit.parse minus the Python object construction
  * (PyPore/cparsers.pyx:103-118).  x must be float64 like the reference
  * requires.  Returns the number of breakpoints (segments = n + 1), or -1 on

@@ -81,11 +81,13 @@ SIGNATURES = {
     "pp_stream": (_c.c_void_p, [_c.c_void_p]),
     "pp_host_alloc": (_c.c_int, [_c.c_void_p, _i64, _c.POINTER(_c.c_void_p)]),
     "pp_host_free": (None, [_c.c_void_p, _c.c_void_p]),
+    "pp_prefix": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "pp_window_gains": (_c.c_int, [_c.c_void_p, _i64, _c.c_int, _i32p, _i32p, _c.c_int, _f64p, _i64]),
     "pp_shard_scan": (_c.c_int, [_c.c_void_p, _c.c_double, _i64, _c.c_void_p]),
     "pp_shard_finish": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _c.c_int, _c.c_int, _c.c_int, _i64, _i64,
                                    _c.c_void_p]),
     "pp_shard_commit": (_c.c_int, [_c.c_void_p, _i64p]),
-    "pp_pack_tables": (_c.c_int, [_c.c_void_p, _i64, _i64, _c.c_void_p, _i64]),
+    "pp_pack_tables": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _i64, _c.c_void_p, _i64]),
     "pp_pipeline_host": (_c.c_int, [_c.c_void_p, _f32p, _i64, _i64, _c.POINTER(PipelineParams), _i64p]),
     "pp_pipeline": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _i64p]),
 }
@@ -324,6 +326,19 @@ class Context(object):
                                       float(min_gain), int(prefix_mode), _c.byref(n)))
         return int(n.value)
 
+    def prefix(self, prefix_mode=PREFIX_AUTO):
+        self._ck(self._L.pp_prefix(self._h, int(prefix_mode)))
+
+    def window_gains(self, ev, ps, pe, min_width):
+        """Exact gains of every candidate of the windows [ps[w], pe[w]) of event `ev` (list of arrays)."""
+        ps = np.ascontiguousarray(ps, np.int32)
+        pe = np.ascontiguousarray(pe, np.int32)
+        n = np.maximum(pe.astype(np.int64) - ps - 2 * int(min_width) + 1, 0)
+        out = np.empty(int(n.sum()), np.float64)
+        self._ck(self._L.pp_window_gains(self._h, int(ev), ps.shape[0], _ptr(ps, _i32p), _ptr(pe, _i32p),
+                                         int(min_width), _ptr(out, _f64p), out.shape[0]))
+        return np.split(out, np.cumsum(n)[:-1])
+
     def segment_stats(self):
         self._ck(self._L.pp_segment_stats(self._h))
 
@@ -435,8 +450,8 @@ class Context(object):
         rec = np.ascontiguousarray(rec, np.int64)
         self._ck(self._L.pp_shard_commit(self._h, _ptr(rec, _i64p)))
 
-    def pack_tables(self, sample_offset, event_base, dev_out_ptr, cap_words):
-        self._ck(self._L.pp_pack_tables(self._h, int(sample_offset), int(event_base),
+    def pack_tables(self, dev_records_ptr, rank, sample_offset, dev_out_ptr, cap_words):
+        self._ck(self._L.pp_pack_tables(self._h, _c.c_void_p(int(dev_records_ptr)), int(rank), int(sample_offset),
                                         _c.c_void_p(int(dev_out_ptr)), int(cap_words)))
 
 

@@ -66,6 +66,7 @@ struct pp_ctx {
     int64_t n_segments = -1;
     bool stats_valid = false;
     int64_t split_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool prefix_valid = false;  // cc holds the prefix sums of the current events
 
     // event stats
     DevBuf evs_mean, evs_std, evs_min, evs_max;
@@ -219,6 +220,7 @@ int begin_threshold(pp_ctx *ctx, int64_t scan_len)
     ctx->n_runs = -1;
     ctx->n_events = ctx->n_event_samples = ctx->n_segments = -1;
     ctx->stats_valid = false;
+    ctx->prefix_valid = false;
     return PP_OK;
 }
 
@@ -263,6 +265,7 @@ int enqueue_select(pp_ctx *ctx, int rule_mask, int64_t duration_gt, int64_t dura
     LAUNCHED(ctx);
     ctx->n_events = ctx->n_event_samples = ctx->n_segments = -1;
     ctx->stats_valid = false;
+    ctx->prefix_valid = false;
     return PP_OK;
 }
 
@@ -319,6 +322,7 @@ int enqueue_filter(pp_ctx *ctx, const double *b, const double *a, const double *
     ctx->stage_ran[ST_FILTER] = true;
     ctx->n_segments = -1;
     ctx->stats_valid = false;
+    ctx->prefix_valid = false;
     return PP_OK;
 }
 
@@ -478,6 +482,7 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
 {
     CKR(prepare_split(ctx, mw, MW, W));
     CKR(enqueue_prefix(ctx, prefix_mode));
+    ctx->prefix_valid = true;
     CKR(record_boundary(ctx, ST_PREFIX + 1));
     ctx->stage_ran[ST_PREFIX] = true;
     CKR(enqueue_search(ctx, mw, MW, W, min_gain));
@@ -673,6 +678,7 @@ int pp_trace_upload(pp_ctx *ctx, const float *host, int64_t n, int64_t extra_cap
     ctx->trace_cap = (int64_t)(ctx->trace_buf.cap / sizeof(float));
     ctx->adopted = false;
     ctx->n_runs = ctx->n_events = ctx->n_event_samples = ctx->n_segments = -1;
+    ctx->prefix_valid = false;
     return PP_OK;
 }
 
@@ -685,6 +691,7 @@ int pp_trace_adopt(pp_ctx *ctx, const float *dev, int64_t n, int64_t capacity)
     ctx->trace_cap = capacity;
     ctx->adopted = true;
     ctx->n_runs = ctx->n_events = ctx->n_event_samples = ctx->n_segments = -1;
+    ctx->prefix_valid = false;
     return PP_OK;
 }
 
@@ -812,6 +819,7 @@ int pp_set_events(pp_ctx *ctx, const int64_t *start, const int64_t *length, int6
     ctx->n_event_samples = tot;
     ctx->n_segments = -1;
     ctx->stats_valid = false;
+    ctx->prefix_valid = false;
     return PP_OK;
 }
 
@@ -839,6 +847,7 @@ int pp_append_event(pp_ctx *ctx, int64_t start, int64_t length)
     LAUNCHED(ctx);
     ctx->n_events += 1;
     ctx->n_event_samples += length;
+    ctx->prefix_valid = false;
     if (ctx->flat_cap < ctx->n) ctx->flat_cap = ctx->n;
     return PP_OK;
 }
@@ -883,6 +892,7 @@ int pp_events_upload_f64(pp_ctx *ctx, const double *host, const int64_t *length,
     ctx->n_event_samples = tot;
     ctx->n_segments = -1;
     ctx->stats_valid = false;
+    ctx->prefix_valid = false;
     return PP_OK;
 }
 
@@ -929,6 +939,67 @@ int pp_statsplit(pp_ctx *ctx, int min_width, int max_width, int window_width, do
     ctx->n_segments = (int64_t)ctx->h_ctr->n_segments;
     if (n_segments) *n_segments = ctx->n_segments;
     return PP_OK;
+}
+
+int pp_prefix(pp_ctx *ctx, int prefix_mode)
+{
+    if (!ctx) return PP_ERR_ARG;
+    if (ctx->n_events < 0) return fail(ctx, PP_ERR_STATE, "no event table");
+    CKR(set_device(ctx));
+    const int64_t ncap = ctx->flat_cap;
+    if (ncap <= 0) return fail(ctx, PP_ERR_STATE, "no events selected");
+    CKR(ensure(ctx, ctx->cc, sizeof(double2) * ncap));
+    CKR(enqueue_prefix(ctx, prefix_mode));
+    CKR(fetch_counters(ctx));
+    ctx->split_counters[2] = (int64_t)ctx->h_ctr->n_seq_redo;
+    ctx->prefix_valid = true;
+    return PP_OK;
+}
+
+int pp_window_gains(pp_ctx *ctx, int64_t ev, int n_windows, const int32_t *ps, const int32_t *pe, int min_width,
+                    double *out, int64_t cap)
+{
+    if (!ctx || !ps || !pe || !out || n_windows <= 0 || min_width < 0) return fail(ctx, PP_ERR_ARG, "bad windows");
+    if (!ctx->prefix_valid) return fail(ctx, PP_ERR_STATE, "prefix sums are not resident (pp_prefix / pp_statsplit)");
+    if (ev < 0 || ev >= ctx->n_events) return fail(ctx, PP_ERR_ARG, "bad event index");
+    CKR(set_device(ctx));
+    int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (size_t)n_windows);
+    if (!off) return fail(ctx, PP_ERR_ARG, "out of host memory");
+    int64_t total = 0;
+    for (int w = 0; w < n_windows; ++w) {
+        off[w] = total;
+        const int64_t n = (int64_t)pe[w] - ps[w] - 2LL * min_width + 1;
+        if (ps[w] < 0 || pe[w] < ps[w]) { free(off); return fail(ctx, PP_ERR_ARG, "bad window %d", w); }
+        if (n > 0) total += n;
+    }
+    if (total > cap) { free(off); return fail(ctx, PP_ERR_CAPACITY, "gain buffer too small"); }
+    DevBuf d_ps, d_pe, d_off, d_out;
+    int rc = ensure(ctx, d_ps, 4 * (size_t)n_windows);
+    if (rc == PP_OK) rc = ensure(ctx, d_pe, 4 * (size_t)n_windows);
+    if (rc == PP_OK) rc = ensure(ctx, d_off, 8 * (size_t)n_windows);
+    if (rc == PP_OK) rc = ensure(ctx, d_out, 8 * (size_t)(total > 0 ? total : 1));
+    if (rc == PP_OK) {
+        cudaMemcpyAsync(d_ps.p, ps, 4 * (size_t)n_windows, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_pe.p, pe, 4 * (size_t)n_windows, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_off.p, off, 8 * (size_t)n_windows, cudaMemcpyHostToDevice, ctx->stream);
+        K3Global G;
+        memset(&G, 0, sizeof G);
+        G.cc = (const double2 *)ctx->cc.p;
+        G.ev_off = (const int64_t *)ctx->ev_off.p;
+        const dim3 grid(32, n_windows < 4096 ? n_windows : 4096);
+        k3_window_gains<<<grid, 256, 0, ctx->stream>>>(G, (int)ev, n_windows, (const int *)d_ps.p,
+                                                       (const int *)d_pe.p, min_width, (const int64_t *)d_off.p,
+                                                       (double *)d_out.p);
+        ctx->launches++;
+        if (total > 0)
+            cudaMemcpyAsync(out, d_out.p, 8 * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(ctx, PP_ERR_CUDA, "pp_window_gains: %s", cudaGetErrorString(e));
+    }
+    release(d_ps); release(d_pe); release(d_off); release(d_out);
+    free(off);
+    return rc;
 }
 
 int pp_segment_stats(pp_ctx *ctx)
@@ -1163,15 +1234,13 @@ int pp_shard_commit(pp_ctx *ctx, const int64_t rec[8])
     return PP_OK;
 }
 
-int pp_pack_tables(pp_ctx *ctx, int64_t sample_offset, int64_t event_base, int64_t *dev_out, int64_t cap_words)
+int pp_pack_tables(pp_ctx *ctx, const int64_t *dev_records, int rank, int64_t sample_offset, int64_t *dev_out,
+                   int64_t cap_words)
 {
-    if (!ctx || !dev_out) return PP_ERR_ARG;
-    if (ctx->n_events < 0 || ctx->n_segments < 0 || !ctx->stats_valid)
-        return fail(ctx, PP_ERR_STATE, "tables are not complete");
-    if (2 * ctx->n_events + 7 * ctx->n_segments > cap_words) return fail(ctx, PP_ERR_CAPACITY, "pack buffer too small");
+    if (!ctx || !dev_out || !dev_records || rank < 0) return PP_ERR_ARG;
     CKR(set_device(ctx));
     k_pack_tables<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(
-        ctx->n_events, ctx->n_segments, sample_offset, event_base, (const int64_t *)ctx->ev_start.p,
+        (const long long *)dev_records, rank, cap_words, sample_offset, (const int64_t *)ctx->ev_start.p,
         (const int64_t *)ctx->ev_len.p, (const int *)ctx->seg_event.p, (const int64_t *)ctx->seg_start.p,
         (const int64_t *)ctx->seg_end.p, (const double *)ctx->seg_mean.p, (const double *)ctx->seg_std.p,
         (const double *)ctx->seg_min.p, (const double *)ctx->seg_max.p, (long long *)dev_out);
@@ -1233,6 +1302,7 @@ int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_sa
     }
     absorb_counters(ctx);
     ctx->n_runs = runs;
+    ctx->prefix_valid = true;
     CKR(check_overflow(ctx));
     ctx->n_segments = (int64_t)ctx->h_ctr->n_segments;
     if (out) {

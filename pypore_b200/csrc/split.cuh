@@ -912,6 +912,29 @@ k3_debug_screen(K3Global G, int ev, int ps, int pe, int mw, double *h_screen, do
     }
 }
 
+// gain(i) in the reference's exact arithmetic for every candidate i = ps+mw .. pe-mw of a batch
+// of windows of one event (cparsers.pyx:224-240 _best_split_stepwise_score, :142-151
+// _best_single_split).  out[out_off[w] + j] = gain of candidate ps[w]+mw+j.
+__global__ void __launch_bounds__(256)
+k3_window_gains(K3Global G, int ev, int n_windows, const int *__restrict__ ps_a, const int *__restrict__ pe_a, int mw,
+                const int64_t *__restrict__ out_off, double *__restrict__ out)
+{
+    K3GlobalCC cc;
+    cc.g = G.cc + G.ev_off[ev];
+    for (int w = blockIdx.y; w < n_windows; w += gridDim.y) {
+        const int ps = ps_a[w], pe = pe_a[w];
+        const int n = pe - ps - 2 * mw + 1;
+        if (n <= 0) continue;
+        const double2 lo = cc.at(ps - 1), hi = cc.at(pe - 1);
+        const double tot = k3_exact_tot(lo, hi, ps, pe);
+        double *o = out + out_off[w];
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+            const int i = ps + mw + j;
+            o[j] = k3_exact_gain(lo, cc.at(i - 1), hi, ps, pe, i, tot);
+        }
+    }
+}
+
 // Exhaustive measurement of the hardware term of the screening bound: over all 2^23
 // float32 mantissas m in [1, 2), the largest | fixed23(1 + lg2.approx(m)) - 1 - log2(m) |
 // (MUFU.LG2 error plus the rounding of the +1.0f), returned as an ordered-u64 maximum.

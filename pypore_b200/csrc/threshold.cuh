@@ -439,14 +439,20 @@ __global__ void k_result_record(const PPCounters *ctr, long long *__restrict__ r
 // Multi-GPU: event and segment tables packed into 8-byte words for ONE all-gather:
 // n_events rows {global start, length}, then n_segments rows
 // {global event id, start, end, mean, std, min, max} (doubles as their bit patterns).
+// Counts and the global event-id base come from the all-gathered result records in DEVICE memory
+// (rec_all[r] = rank r's k_result_record), so the host does not have to know them yet.
 __global__ void __launch_bounds__(256)
-k_pack_tables(int64_t n_events, int64_t n_segments, int64_t sample_offset, int64_t event_base,
+k_pack_tables(const long long *__restrict__ rec_all, int rank, int64_t cap_words, int64_t sample_offset,
               const int64_t *__restrict__ ev_start, const int64_t *__restrict__ ev_len,
               const int *__restrict__ seg_event, const int64_t *__restrict__ seg_start,
               const int64_t *__restrict__ seg_end, const double *__restrict__ mean,
               const double *__restrict__ sd, const double *__restrict__ mn, const double *__restrict__ mx,
               long long *__restrict__ out)
 {
+    const int64_t n_events = rec_all[8 * rank + 1], n_segments = rec_all[8 * rank + 3];
+    if (2 * n_events + 7 * n_segments > cap_words) return;  // the host notices from the same records and retries
+    int64_t event_base = 0;
+    for (int r = 0; r < rank; ++r) event_base += rec_all[8 * r + 1];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (int64_t e = t0; e < n_events; e += stride) {

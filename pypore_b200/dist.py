@@ -134,23 +134,33 @@ def gather_tables(int_cols, flt_cols, counts, dist, group=None):
     return out[0], out[1]
 
 
-def gather_packed(words, counts, dist, group=None):
-    """All-gather the packed tables (pp_pack_tables layout: 2 words per event, then 7 per segment) with ONE
-    collective.  `words`: int64 tensor holding this rank's 2 E + 7 S words (it may be longer); `counts`: per-rank
-    (events, segments), known to every rank.  Returns dict(events int64 [sum E, 2], seg_int int64 [sum S, 3],
-    seg_flt float64 [sum S, 4])."""
+def gather_packed_raw(words, m, dist, group=None):
+    """ONE all-gather of the first m words of every rank's packed tables (pp_pack_tables layout: 2 words per
+    event, then 7 per segment).  Returns the int64 tensor [world, m]; row r holds rank r's words."""
     import torch
-    world = len(counts)
-    sizes = [2 * e + 7 * s for e, s in counts]
-    m = max(max(sizes), 1)
+    world = dist.get_world_size(group)
     if words.shape[0] < m:
         words = torch.cat([words, torch.zeros(m - words.shape[0], dtype=words.dtype, device=words.device)])
     g = torch.empty(world * m, dtype=torch.int64, device=words.device)
     dist.all_gather_into_tensor(g, words[:m].contiguous(), group=group)
-    g = g.view(world, m)
+    return g.view(world, m)
+
+
+def unpack_gathered(g, counts):
+    """Contiguous tables from gather_packed_raw's result; counts = per-rank (events, segments).
+    Returns dict(events int64 [sum E, 2], seg_int int64 [sum S, 3], seg_flt float64 [sum S, 4])."""
+    import torch
+    world = len(counts)
+    sizes = [2 * e + 7 * s for e, s in counts]
     ev = torch.cat([g[r, :2 * counts[r][0]].view(-1, 2) for r in range(world)], dim=0)
     seg = torch.cat([g[r, 2 * counts[r][0]:sizes[r]].view(-1, 7) for r in range(world)], dim=0)
     return dict(events=ev, seg_int=seg[:, :3].contiguous(), seg_flt=seg[:, 3:].contiguous().view(torch.float64))
+
+
+def gather_packed(words, counts, dist, group=None):
+    """gather_packed_raw + unpack_gathered for callers that know every rank's counts already."""
+    m = max(max(2 * e + 7 * s for e, s in counts), 1)
+    return unpack_gathered(gather_packed_raw(words, m, dist, group), counts)
 
 
 # ------------------------------------------------------------------------------------------
@@ -221,9 +231,10 @@ class ShardedPipeline(object):
         self.n_local = 0
         self.n_owned = 0
         self.offsets = None
-        self.tables = None
+        self.gathered = self.counts = self._tables = None
         self.stage_ms = {}
         self.rec = self.res = self.pack = None
+        self.pad_words = 0
 
     def load(self, host_chunk):
         self.ctx.upload_trace_async(host_chunk, extra_capacity=self.HALO_CAPACITY)
@@ -267,21 +278,44 @@ class ShardedPipeline(object):
             ctx.append_trace(self.halo.data_ptr(), got, True)
         ctx.shard_finish(threshold, rules, mw, MW, W, gain, plan["skip_first"], plan["skip_last"], plan["event"],
                          self.res.data_ptr())
-        allr = torch.empty(self.world * 8, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allr, self.res, group=self.group)
-        allr = allr.cpu().numpy().reshape(self.world, 8)                 # host sync 2
+        allr_dev = torch.empty(self.world * 8, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allr_dev, self.res, group=self.group)
+        # Speculative sizing: pack and all-gather with the padding of the previous step (+12.5 %) before the host
+        # knows this step's counts -- the pack kernel takes them from allr_dev on the device -- so the GPU is not
+        # idle during the second host round trip.  Every rank reads the same records and takes the same decision.
+        g = None
+        if self.pad_words:
+            if self.pack is None or self.pack.shape[0] < self.pad_words:
+                self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
+            ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
+                            self.pad_words)
+            g = gather_packed_raw(self.pack, self.pad_words, dist, self.group)
+        allr = allr_dev.cpu().numpy().reshape(self.world, 8)             # host sync 2 (nothing waits on it)
         ctx.shard_commit(allr[self.rank])
         self.stage_ms = ctx.stage_ms()
         self.n_owned = self.n_local
         counts = [(int(r[1]), int(r[3])) for r in allr]
+        need_words = max(max(2 * e + 7 * s for e, s in counts), 1)
+        if g is None or need_words > self.pad_words:
+            self.pad_words = int(need_words * 1.125) + 64
+            self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
+            ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
+                            self.pad_words)
+            g = gather_packed_raw(self.pack, self.pad_words, dist, self.group)
+        else:
+            self.pad_words = max(int(need_words * 1.125) + 64, 1)
+        self.gathered, self.counts, self._tables = g, counts, None
         ne, n_seg = counts[self.rank]
-        words = 2 * ne + 7 * n_seg
-        if self.pack is None or self.pack.shape[0] < words:
-            self.pack = torch.empty(int(words * 1.25) + 64, dtype=torch.int64, device=dev)
-        ctx.pack_tables(int(self.offsets[self.rank]), sum(c[0] for c in counts[:self.rank]), self.pack.data_ptr(),
-                        self.pack.shape[0])
-        self.tables = gather_packed(self.pack, counts, dist, self.group)
         return dict(runs=n_runs, events=ne, event_samples=int(allr[self.rank, 2]), segments=n_seg)
+
+    @property
+    def tables(self):
+        """The whole result on this GPU as contiguous tensors (built from the gathered buffer on first use)."""
+        if self._tables is None and self.gathered is not None:
+            import torch
+            with torch.cuda.stream(self.stream):
+                self._tables = unpack_gathered(self.gathered, self.counts)
+        return self._tables
 
     def download(self):
         """Device-to-host read of the gathered tables (what a caller of the public API receives)."""

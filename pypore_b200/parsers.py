@@ -237,6 +237,16 @@ def statsplit_min_gain(min_width=100, max_width=1000000, window_width=10000, min
     return mw, MW, W, gain * 2
 
 
+def _first_best(gains, min_gain, first_index):
+    """The sequential `if gain > best: best = gain; x = i` loop of the reference over an array of
+    gains: (best gain, index of its FIRST occurrence), or (min_gain, -1).  NaN never wins."""
+    ok = gains > min_gain
+    if not ok.any():
+        return min_gain, -1
+    best = gains[ok].max()
+    return float(best), int(first_index + np.flatnonzero(gains == best)[0])
+
+
 class SpeedyStatSplit(parser):
     """Recursive maximum-likelihood changepoint segmenter (parsers.py:505-528,
     cparsers.pyx:45-203) on the GPU."""
@@ -269,6 +279,99 @@ class SpeedyStatSplit(parser):
         """Segments of one event: ``current`` views, ``start``/``end``/``duration`` in
         samples (cparsers.pyx:115-116), statistics precomputed on the device."""
         return self.parse_many([current])[0]
+
+    @staticmethod
+    def _as_event(current):
+        cur = np.asarray(current)
+        if cur.dtype != np.float64:
+            # the reference assigns np.cumsum(current) to a double[:] memoryview (cparsers.pyx:53,110)
+            raise ValueError("Buffer dtype mismatch, expected 'double' but got '%s'" %
+                             {np.dtype(np.float32): 'float'}.get(cur.dtype, str(cur.dtype)))
+        return np.ascontiguousarray(cur)
+
+    def best_single_split(self, current):
+        """(gain, index) of the single best split of `current` (parsers.py:530-534 -> cparsers.pyx:120-155):
+        window [0, len-1), candidates 2 .. len-4, threshold 0, lowest index on ties; (0.0, -1) if no
+        candidate has a positive gain.  Exact reference arithmetic for every candidate on the device."""
+        # the reference builds a FastStatSplit first -- WITHOUT cutoff_freq (parsers.py:531-533): same assertions
+        statsplit_min_gain(self.min_width, self.max_width, self.window_width, self.min_gain_per_sample,
+                           self.false_positive_rate, self.prior_segments_per_second, self.sampling_freq)
+        cur = self._as_event(current)
+        end = cur.shape[0] - 1
+        if end - 4 < 1:  # xrange(2, end-2) is empty
+            return 0., -1
+        ctx = _lib.default_context()
+        ctx.upload_events_f64([cur])
+        ctx.prefix()
+        gains = ctx.window_gains(0, [0], [end], 2)[0][:end - 4]   # candidates 2 .. end-3
+        return _first_best(gains, 0., 2)
+
+    def score_samples(self, current, no_split=False):
+        """One length-len(current) score array per window scan, in the reference's recursion order
+        (cparsers.pyx:205-275 score_samples / _recursive_split_scoring); no_split=True: the scores of the
+        single scan of [0, len) as a plain list.  Exact reference arithmetic on the device, one batched
+        call per recursion depth; the recursion itself is replayed on the host."""
+        mw, MW, W, min_gain = self._params()
+        cur = self._as_event(current)
+        L = cur.shape[0]
+        ctx = _lib.default_context()
+        known = {}
+        if L > 0:
+            ctx.upload_events_f64([cur])
+            ctx.prefix()
+
+        def scan(ps, pe, missing):
+            """(split, score array) of window [ps, pe) -- _best_split_stepwise_score -- or None if not computed yet."""
+            if pe - ps <= 2 * mw:
+                return -1, []
+            if (ps, pe) not in known:
+                missing.add((ps, pe))
+                return None
+            return known[(ps, pe)]
+
+        def walk(start, end, missing):
+            """_recursive_split_scoring (cparsers.pyx:246-275); returns None while windows are missing."""
+            scores, split_at = [], -1
+            for pstart in range(start, end - 2 * mw, W // 2):
+                if pstart > start + MW:
+                    split_at = min(start + MW, end - mw)
+                    rest = walk(split_at, end, missing)
+                    return None if rest is None else scores + rest
+                r = scan(pstart, min(end, pstart + W), missing)
+                if r is None:
+                    return None
+                split_at, score = r
+                scores.append(score)
+                if split_at >= 0:
+                    break
+            if split_at == -1:
+                if end - start <= MW:
+                    return scores
+                split_at = min(start + MW, end - mw)
+            left, right = walk(start, split_at, missing), walk(split_at, end, missing)
+            return None if left is None or right is None else scores + left + right
+
+        def compute(windows):
+            windows = sorted(windows)
+            gains = ctx.window_gains(0, [w[0] for w in windows], [w[1] for w in windows], mw)
+            for (ps, pe), g in zip(windows, gains):
+                score = np.zeros(L)
+                score[ps + mw:ps + mw + g.shape[0]] = g
+                known[(ps, pe)] = (_first_best(g, min_gain, ps + mw)[1], score)
+
+        if no_split:
+            missing = set()
+            r = scan(0, L, missing)
+            if r is None:
+                compute(missing)
+                r = known[(0, L)]
+            return list(r[1])
+        while True:
+            missing = set()
+            out = walk(0, L, missing)
+            if out is not None:
+                return out
+            compute(missing)
 
     def parse_many(self, currents):
         """Segment many events in one device pass (list of float64 arrays)."""

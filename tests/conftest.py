@@ -29,3 +29,19 @@ def ctx():
     c = _lib.Context(0)
     yield c
     c.close()
+
+
+# FastStatSplit.best_single_split / score_samples fixture cases, shared by tests/golden/make_golden.py
+# (which runs the real reference) and the tests: name -> (length, seed, tier, FastStatSplit kwargs)
+SCORING_CASES = {
+    "psps10": (2500, 11, "A", dict(min_width=100, window_width=10000, prior_segments_per_second=10)),
+    "default_tierB": (1500, 12, "B", dict(min_width=100, window_width=10000)),
+    "narrow_forced": (6000, 13, "A", dict(min_width=50, max_width=2500, window_width=1000,
+                                          prior_segments_per_second=50)),
+}
+
+
+def sha(a):
+    import hashlib
+    import numpy as np
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()

@@ -25,6 +25,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 REFERENCE = "/root/reference"
 
+sys.path.insert(0, os.path.dirname(HERE))
+from conftest import SCORING_CASES  # noqa: E402
 from oracle import build_oracle  # noqa: E402
 from pypore_b200 import synth  # noqa: E402
 
@@ -204,8 +206,32 @@ def golden_params(parsers):
     return out
 
 
+def golden_scoring():
+    """FastStatSplit.best_single_split / score_samples of the compiled reference (cparsers.pyx:120-155,205-275)."""
+    from PyPore.cparsers import FastStatSplit
+    out = {}
+    for name, (length, seed, tier, kw) in SCORING_CASES.items():
+        x = synth.make_long_event(length, seed=seed, tier=tier).astype(np.float64)
+        out[name + "_input_sha256"] = np.array(sha(x))
+        g, i = FastStatSplit(**kw).best_single_split(x)
+        out[name + "_best_gain"], out[name + "_best_index"] = g, i
+        out[name + "_no_split"] = np.array(FastStatSplit(**kw).score_samples(x, no_split=True))
+        out[name + "_scores"] = np.array(FastStatSplit(**kw).score_samples(x))
+    for n in (0, 3, 5, 6, 7):   # too short for a candidate / the first lengths with one
+        x = synth.make_long_event(50, seed=14, tier="A").astype(np.float64)[:n]
+        with np.errstate(all="ignore"):
+            g, i = FastStatSplit().best_single_split(x)
+        out["short%d_best" % n] = np.array([g, i])
+    return out
+
+
 def main():
     dt, parsers, core = load_reference()
+    if "--scoring-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "scoring.npz"), **golden_scoring())
+        print("scoring.npz", os.path.getsize(os.path.join(HERE, "scoring.npz")))
+        return
+    np.savez_compressed(os.path.join(HERE, "scoring.npz"), **golden_scoring())
     np.savez_compressed(os.path.join(HERE, "pipeline_tierA.npz"), **golden_pipeline(dt, parsers, "A", 3, 12))
     np.savez_compressed(os.path.join(HERE, "pipeline_tierB.npz"), **golden_pipeline(dt, parsers, "B", 4, 8))
     np.savez_compressed(os.path.join(HERE, "filter_o1_100k.npz"), **golden_filter(dt, parsers, 1.e5, 1, 2000., 5))

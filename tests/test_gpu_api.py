@@ -152,3 +152,33 @@ def test_event_filter_then_parse_like_the_reference():
     assert ev.filtered and np.max(np.abs(ev.current - g["event1_filtered"]) / np.abs(g["event1_filtered"])) < 1e-5
     sel = f2.segment_table["event"] == 1
     assert np.array_equal(f2.segment_table["start"][sel], g["event1_seg_start"])
+
+
+def test_best_single_split_and_score_samples_match_reference():
+    """FastStatSplit.best_single_split / score_samples on the device, bit-equal to the
+    compiled reference's fixture and to the oracle (exact arithmetic, recursion order, dense score arrays)."""
+    from pypore_b200.cparsers import FastStatSplit
+    from conftest import SCORING_CASES
+    g = load_golden("scoring.npz")
+    for name, (length, seed, tier, kw) in SCORING_CASES.items():
+        x = synth.make_long_event(length, seed=seed, tier=tier).astype(np.float64)
+        gain, idx = FastStatSplit(**kw).best_single_split(x)
+        assert idx == int(g[name + "_best_index"]) and abs(gain - float(g[name + "_best_gain"])) <= 1e-9 * abs(gain)
+        ns = FastStatSplit(**kw).score_samples(x, no_split=True)
+        assert isinstance(ns, list) and len(ns) == length
+        ref = g[name + "_no_split"]
+        assert np.allclose(np.array(ns), ref, rtol=1e-9, atol=1e-9) and np.array_equal(np.array(ns) == 0, ref == 0)
+        sc = np.array(FastStatSplit(**kw).score_samples(x))
+        ref = g[name + "_scores"]
+        assert sc.shape == ref.shape                       # same scans, same recursion order
+        assert np.array_equal(sc == 0, ref == 0) and np.allclose(sc, ref, rtol=1e-9, atol=1e-9)
+    for n in (0, 3, 5, 6, 7):
+        x = synth.make_long_event(50, seed=14, tier="A").astype(np.float64)[:n]
+        gain, idx = SpeedyStatSplit().best_single_split(x)
+        assert idx == int(g["short%d_best" % n][1])
+        if idx >= 0:
+            assert abs(gain - g["short%d_best" % n][0]) <= 1e-9 * abs(gain)
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        SpeedyStatSplit().best_single_split(np.zeros(100, np.float32))
+    with pytest.raises(AssertionError):
+        FastStatSplit(min_width=100, max_width=50)

@@ -168,3 +168,23 @@ def test_threshold_edge_cases():
     t = 110.1
     xf = np.array([np.float32(110.1)], np.float32)  # float32(110.1) > 110.1 as doubles? check both ways
     assert (oracle.threshold_runs(xf.astype(np.float64), t)[4][0]) == (float(xf[0]) < t)
+
+
+def test_scoring_functions_match_reference_fixture():
+    """best_single_split / score_samples (cparsers.pyx:120-155, 205-275) of the restatement against the
+    compiled reference's outputs stored by tests/golden/make_golden.py."""
+    from conftest import SCORING_CASES, sha
+    g = load_golden("scoring.npz")
+    for name, (length, seed, tier, kw) in SCORING_CASES.items():
+        x = synth.make_long_event(length, seed=seed, tier=tier).astype(np.float64)
+        assert sha(x) == str(g[name + "_input_sha256"])
+        gain, idx = oracle.best_single_split(x)
+        assert gain == float(g[name + "_best_gain"]) and idx == int(g[name + "_best_index"])
+        assert np.array_equal(np.array(oracle.score_samples(x, no_split=True, **kw)), g[name + "_no_split"])
+        sc = np.array(oracle.score_samples(x, **kw))
+        assert sc.shape == g[name + "_scores"].shape and np.array_equal(sc, g[name + "_scores"])
+    assert len(g["narrow_forced_scores"]) > 10
+    for n in (0, 3, 5, 6, 7):
+        x = synth.make_long_event(50, seed=14, tier="A").astype(np.float64)[:n]
+        gain, idx = oracle.best_single_split(x)
+        assert [gain, idx] == list(g["short%d_best" % n])
