@@ -8,11 +8,14 @@ statistics in one device-resident pass, returning the same objects lazily built
 from the compact tables.  HMM-guided parsing, plotting, MySQL and .abf reading
 are out of scope.
 """
+import json
+from functools import reduce
+
 import numpy as np
 
 from . import _lib
-from .core import MetaSegment, Segment, ignored
-from .parsers import RuleSet, SpeedyStatSplit, lambda_event_parser, _as_float32_trace
+from .core import MetaSegment, Segment, ignored, _jsonable
+from .parsers import RuleSet, SpeedyStatSplit, lambda_event_parser, parser, _as_float32_trace
 
 
 class MetaEvent(MetaSegment):
@@ -27,6 +30,39 @@ class MetaEvent(MetaSegment):
         for segment in self.segments:
             segment.delete()
         del self
+
+    def to_dict(self):
+        """DataTypes.py:196-201 (no 'filtered' key, unlike Event.to_dict)."""
+        keys = ['mean', 'std', 'min', 'max', 'start', 'end', 'duration',
+                'filter_order', 'filter_cutoff', 'n', 'state_parser', 'segments']
+        d = {i: _jsonable(getattr(self, i)) for i in keys if hasattr(self, i)}
+        d['name'] = self.__class__.__name__
+        return d
+
+    def to_json(self, filename=None):
+        """DataTypes.py:203-216."""
+        d = self.to_dict()
+        with ignored(KeyError, AttributeError):
+            d['segments'] = [seg.to_dict() for seg in d['segments']]
+        with ignored(KeyError, AttributeError):
+            d['state_parser'] = d['state_parser'].to_dict()
+        _json = json.dumps(d, indent=4, separators=(',', ' : '))
+        if filename:
+            with open(filename, 'w') as out:
+                out.write(_json)
+        return _json
+
+    @classmethod
+    def from_json(cls, _json):
+        """DataTypes.py:218-225."""
+        if _json.endswith(".json"):
+            with open(_json, 'r') as infile:
+                _json = ''.join(line for line in infile)
+        return cls(**json.loads(_json))
+
+    @classmethod
+    def from_segments(cls, segments):
+        return cls(segments=segments)
 
     @property
     def n(self):
@@ -114,6 +150,41 @@ class Event(Segment):
         for segment in self.segments:
             segment.to_meta()
         self.__class__ = type("MetaEvent", (MetaEvent,), self.__dict__)
+
+    def to_dict(self):
+        """DataTypes.py:493-498."""
+        keys = ['mean', 'std', 'min', 'max', 'start', 'end', 'duration', 'filtered',
+                'filter_order', 'filter_cutoff', 'n', 'state_parser', 'segments']
+        d = {i: _jsonable(getattr(self, i)) for i in keys if hasattr(self, i)}
+        d['name'] = self.__class__.__name__
+        return d
+
+    def to_json(self, filename=None):
+        """DataTypes.py:500-513."""
+        d = self.to_dict()
+        with ignored(KeyError, AttributeError):
+            d['segments'] = [seg.to_dict() for seg in d['segments']]
+        with ignored(KeyError, AttributeError):
+            d['state_parser'] = d['state_parser'].to_dict()
+        _json = json.dumps(d, indent=4, separators=(',', ' : '))
+        if filename:
+            with open(filename, 'w') as out:
+                out.write(_json)
+        return _json
+
+    @classmethod
+    def from_json(cls, _json):
+        """DataTypes.py:515-529: a JSON without 'current' gives a MetaEvent."""
+        if _json.endswith(".json"):
+            with open(_json, 'r') as infile:
+                _json = ''.join(line for line in infile)
+        d = json.loads(_json)
+        event = MetaSegment()
+        if 'current' not in d.keys():
+            event.__class__ = type("MetaEvent", (MetaEvent,), d)
+        else:
+            event = cls(d['current'], start=d['start'])
+        return event
 
     @property
     def n(self):
@@ -263,6 +334,88 @@ class File(Segment):
         self.events = _LazyList(len(ev_start), make_event)
         self.event_parser = parser
 
+    def to_meta(self):
+        """Drop the ionic current of the file and of everything under it (DataTypes.py:683-693)."""
+        with ignored(AttributeError):
+            del self.current
+        events = list(self.events)  # lazily built events are materialised once, then reduced to metadata
+        for event in events:
+            event.to_meta()
+        self.events = events
+
+    def to_dict(self):
+        """DataTypes.py:695-706."""
+        keys = ['filename', 'n', 'event_parser', 'mean', 'std', 'duration', 'start', 'end', 'events']
+        if not hasattr(self, 'end') and (hasattr(self, 'start') and hasattr(self, 'duration')):
+            setattr(self, 'end', self.start + self.duration)
+        d = {i: _jsonable(getattr(self, i)) for i in keys if hasattr(self, i)}
+        d['name'] = self.__class__.__name__
+        return d
+
+    def to_json(self, filename=None):
+        """The file, its events and their segments as the reference's JSON (DataTypes.py:708-738)."""
+        d = self.to_dict()
+        devents = []
+        for event in d['events']:
+            devent = event.to_dict()
+            try:
+                devent['segments'] = [state.to_dict() for state in devent['segments']]
+                devent['state_parser'] = devent['state_parser'].to_dict()
+            except Exception:
+                with ignored(KeyError, AttributeError):
+                    del devent['segments']
+                    del devent['state_parser']
+            devents.append(devent)
+        d['events'] = devents
+        d['event_parser'] = d['event_parser'].to_dict()
+        _json = json.dumps(d, indent=4, separators=(',', ' : '))
+        if filename:
+            with open(filename, 'w') as outfile:
+                outfile.write(_json)
+        return _json
+
+    @classmethod
+    def from_json(cls, _json):
+        """Rebuild a file and its events from to_json's output (DataTypes.py:740-796).  Without the .abf
+        file -- always the case here, reading .abf is out of scope -- the result holds MetaEvents /
+        MetaSegments, exactly the reference's own fallback."""
+        if _json.endswith(".json"):
+            with open(_json, 'r') as infile:
+                _json = ''.join(line for line in infile)
+        d = json.loads(_json)
+        if d['name'] != "File":
+            raise TypeError("JSON does not encode a file")
+        try:
+            file = File(filename=d['filename'] + ".abf")
+            meta = False
+        except Exception:
+            file = File(current=[], timestep=1)
+            meta = True
+        file.event_parser = parser.from_json(json.dumps(d['event_parser']))
+        file.events = []
+        for _json in d['events']:
+            s, e = int(_json['start'] * file.second), int(_json['end'] * file.second)
+            if meta:
+                event = MetaEvent(**_json)
+            else:
+                current = file.current[s:e]
+                event = Event(current=current, start=s / file.second, end=e / file.second,
+                              duration=(e - s) / file.second, second=file.second, file=file)
+            if _json['filtered']:
+                if not meta:
+                    event.filter(order=_json['filter_order'], cutoff=_json['filter_cutoff'])
+            if meta:
+                event.segments = [MetaSegment(**s_json) for s_json in _json['segments']]
+            else:
+                event.segments = [Segment(current=event.current[int(s_json['start'] * file.second):
+                                                                int(s_json['end'] * file.second)],
+                                          second=file.second, event=event, **s_json)
+                                  for s_json in _json['segments']]
+            event.state_parser = parser.from_json(json.dumps(_json['state_parser']))
+            event.filtered = _json['filtered']
+            file.events.append(event)
+        return file
+
     def delete(self):
         with ignored(AttributeError):
             del self.current
@@ -274,3 +427,84 @@ class File(Segment):
 
     def close(self):
         self.delete()
+
+
+class Experiment(object):
+    """A series of files analysed together (DataTypes.py:938-1031).
+
+    ``filenames`` may hold ``File`` objects (``File(current=..., timestep=...)``: the only way to get data in
+    here, reading .abf is out of scope) next to file names; a name is handed to ``File(name)`` like the
+    reference does.  ``parse`` keeps the reference's signature, defaults, printed messages and results; each
+    file goes through ONE device-resident pass (threshold scan -> Event.filter -> segmenter -> statistics)
+    instead of the reference's per-event Python loop.
+    """
+
+    def __init__(self, filenames, name=None):
+        self.filenames = filenames
+        self.name = name or "Experiment"
+        self.files = []
+
+    def parse(self, event_detector=lambda_event_parser(threshold=90),
+              segmenter=SpeedyStatSplit(prior_segments_per_second=10, cutoff_freq=2000.),
+              filter_params=(1, 2000), verbose=True, meta=False):
+        for file in (f if isinstance(f, File) else File(f) for f in self.filenames):
+            if verbose:
+                print("Opening {}".format(file.filename))
+            batched = (isinstance(event_detector, lambda_event_parser) and event_detector._device_rules() is not None
+                       and (segmenter is None or isinstance(segmenter, SpeedyStatSplit)))
+            if batched and (segmenter is not None or filter_params is not None):
+                file.parse(parser=event_detector, segmenter=segmenter, filter_params=filter_params)
+            else:
+                # arbitrary Python rules or a foreign segmenter: the reference's own loop (DataTypes.py:972-982)
+                file.parse(parser=event_detector)
+                for event in file.events:
+                    if filter_params is not None:
+                        event.filter(*filter_params)
+                    if segmenter is not None:
+                        event.parse(parser=segmenter)
+            if verbose:
+                print("\tDetected {} Events".format(file.n))
+                if segmenter is not None:
+                    for i, event in enumerate(file.events):
+                        print("\t\tEvent {} has {} segments".format(i + 1, event.n))
+            if meta:
+                file.to_meta()
+            self.files.append(file)
+
+    def delete(self):
+        with ignored(AttributeError):
+            del self.events
+        with ignored(AttributeError):
+            del self.segments
+        for file in self.files:
+            file.delete()
+        del self
+
+    @property
+    def n(self):
+        return len(self.files)
+
+    @property
+    def events(self):
+        """All the events in all files."""
+        try:
+            return reduce(list.__add__, [list(file.events) for file in self.files])
+        except Exception:
+            return []
+
+    @property
+    def segments(self):
+        """All segments of all events."""
+        try:
+            return reduce(list.__add__, [list(event.segments) for event in self.events])
+        except Exception:
+            return []
+
+
+class Sample(object):
+    """A container for events all suggested to be from the same substrate (DataTypes.py:1034-1040)."""
+
+    def __init__(self, events=[], files=[], label=None):
+        self.events = events
+        self.files = files
+        self.label = label

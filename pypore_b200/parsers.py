@@ -24,8 +24,11 @@ class parser(object):
         return self.to_json()
 
     def to_dict(self):
+        # the reference drops Qt widgets and lambdas by their repr (parsers.py:42-49); a RuleSet is this
+        # repository's stand-in for the rule lambdas and is dropped the same way
         d = {key: val for key, val in self.__dict__.items() if key != 'param_dict' and not key.startswith('_')
-             if type(val) in (int, float) or ('Qt' not in repr(val)) and 'lambda' not in repr(val)}
+             if type(val) in (int, float) or (('Qt' not in repr(val)) and 'lambda' not in repr(val)
+                                              and not isinstance(val, RuleSet) and not callable(val))}
         d['name'] = self.__class__.__name__
         return d
 

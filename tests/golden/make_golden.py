@@ -225,13 +225,37 @@ def golden_scoring():
     return out
 
 
+def golden_json(dt, parsers):
+    """File.to_json of the real reference after File.parse -> Event.filter -> Event.parse (DataTypes.py:708-738),
+    the on-disk format of the result tables."""
+    x64 = synth.make_trace(4, seed=21, tier="A").astype(np.float64)
+    f = dt.File(current=x64, timestep=0.01)
+    f.parse(parser=parsers.lambda_event_parser(threshold=110, rules=[lambda e: e.duration > 1000,
+                                                                      lambda e: e.min > -0.5,
+                                                                      lambda e: e.max < 110]))
+    seg = parsers.SpeedyStatSplit(min_width=100, window_width=10000, prior_segments_per_second=10,
+                                  cutoff_freq=2000.)
+    for i, event in enumerate(f.events):
+        if i % 2 == 0:
+            event.filter(1, 2000.)
+        event.parse(parser=seg)
+    return f.to_json()
+
+
 def main():
     dt, parsers, core = load_reference()
+    if "--json-only" in sys.argv:
+        with open(os.path.join(HERE, "file_tierA.json"), "w") as out:
+            out.write(golden_json(dt, parsers))
+        print("file_tierA.json", os.path.getsize(os.path.join(HERE, "file_tierA.json")))
+        return
     if "--scoring-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "scoring.npz"), **golden_scoring())
         print("scoring.npz", os.path.getsize(os.path.join(HERE, "scoring.npz")))
         return
     np.savez_compressed(os.path.join(HERE, "scoring.npz"), **golden_scoring())
+    with open(os.path.join(HERE, "file_tierA.json"), "w") as out:
+        out.write(golden_json(dt, parsers))
     np.savez_compressed(os.path.join(HERE, "pipeline_tierA.npz"), **golden_pipeline(dt, parsers, "A", 3, 12))
     np.savez_compressed(os.path.join(HERE, "pipeline_tierB.npz"), **golden_pipeline(dt, parsers, "B", 4, 8))
     np.savez_compressed(os.path.join(HERE, "filter_o1_100k.npz"), **golden_filter(dt, parsers, 1.e5, 1, 2000., 5))

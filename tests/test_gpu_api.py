@@ -182,3 +182,76 @@ def test_best_single_split_and_score_samples_match_reference():
         SpeedyStatSplit().best_single_split(np.zeros(100, np.float32))
     with pytest.raises(AssertionError):
         FastStatSplit(min_width=100, max_width=50)
+
+
+def _close(a, b, rtol):
+    if isinstance(b, float):
+        return a == b or abs(a - b) <= rtol * max(abs(a), abs(b))
+    return a == b
+
+
+def test_file_to_json_matches_the_reference_format():
+    """File.parse -> Event.filter -> Event.parse -> File.to_json on the device against the
+    JSON the real reference wrote for the same trace (structure and keys equal, indices exact, statistics
+    1e-9, statistics of filtered events 1e-5 like the filtered current)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    ref = json.loads(open(os.path.join(GOLDEN, "file_tierA.json")).read())
+    x64 = synth.make_trace(4, seed=21, tier="A").astype(np.float64)
+    f = File(current=x64, timestep=0.01)
+    f.parse(parser=lambda_event_parser(threshold=110, rules=RULES_1000))
+    seg = SpeedyStatSplit(min_width=100, window_width=10000, prior_segments_per_second=10, cutoff_freq=2000.)
+    for i, event in enumerate(f.events):
+        if i % 2 == 0:
+            event.filter(1, 2000.)
+        event.parse(parser=seg)
+    ours = json.loads(f.to_json())
+    assert set(ours) == set(ref) and ours["n"] == ref["n"] and ours["event_parser"] == ref["event_parser"]
+    assert _close(ours["mean"], ref["mean"], 1e-9) and _close(ours["std"], ref["std"], 1e-9)
+    for a, b in zip(ours["events"], ref["events"]):
+        assert set(a) == set(b) and a["state_parser"] == b["state_parser"] and a["n"] == b["n"]
+        rtol = 1e-5 if b["filtered"] else 1e-9
+        for k in ("start", "end", "duration", "filtered", "filter_order", "filter_cutoff", "name"):
+            assert a.get(k) == b.get(k), k
+        for k in ("mean", "std", "min", "max"):
+            assert _close(a[k], b[k], rtol), (k, a[k], b[k])
+        assert len(a["segments"]) == len(b["segments"])
+        for sa, sb in zip(a["segments"], b["segments"]):
+            assert set(sa) == set(sb) and sa["name"] == sb["name"]
+            assert (sa["start"], sa["end"], sa["duration"]) == (sb["start"], sb["end"], sb["duration"])
+            assert all(_close(sa[k], sb[k], rtol) for k in ("mean", "std", "min", "max"))
+    # reload: metadata objects, like the reference without the .abf file
+    g = File.from_json(f.to_json())
+    assert g.n == 4 and [e.n for e in g.events] == [e.n for e in f.events]
+
+
+def test_experiment_parse_batch_driver(capsys):
+    """Experiment.parse (DataTypes.py:956-988) over File objects -- one device-resident pass
+    per file -- gives the events / segments of the reference's per-event loop; meta=True leaves metadata only."""
+    from pypore_b200.DataTypes import Experiment, MetaEvent
+    traces = [synth.make_trace(3, seed=31 + k, tier="A") for k in range(2)]
+    det = lambda_event_parser(threshold=110, rules=RuleSet(duration_gt=1000, min_gt=-0.5, max_lt=110))
+    seg = SpeedyStatSplit(prior_segments_per_second=10, cutoff_freq=2000.)
+    exp = Experiment([File(current=t, timestep=0.01) for t in traces], name="batch")
+    exp.parse(event_detector=det, segmenter=seg, filter_params=(1, 2000), verbose=True, meta=False)
+    out = capsys.readouterr().out
+    assert out.count("Opening") == 2 and "\tDetected 3 Events" in out and "\t\tEvent 1 has" in out
+    assert exp.n == 2 and len(exp.events) == 6 and len(exp.segments) == sum(e.n for e in exp.events)
+    # the same through the reference's own loop shape: File.parse, Event.filter, Event.parse
+    for t, file in zip(traces, exp.files):
+        f = File(current=t, timestep=0.01)
+        f.parse(parser=det)
+        for a, b in zip(f.events, file.events):
+            a.filter(1, 2000)
+            a.parse(parser=seg)
+            assert b.filtered and (a.start, a.end) == (b.start, b.end)
+            assert [(s.start, s.end) for s in a.segments] == [(s.start, s.end) for s in b.segments]
+            assert np.allclose([s.mean for s in a.segments], [s.mean for s in b.segments], rtol=1e-9, atol=0)
+    exp2 = Experiment([File(current=t, timestep=0.01) for t in traces])
+    exp2.parse(event_detector=det, segmenter=seg, filter_params=None, verbose=False, meta=True)
+    assert capsys.readouterr().out == ""
+    assert all(isinstance(e, MetaEvent) and not hasattr(e, "current") for e in exp2.events)
+    assert not hasattr(exp2.files[0], "current") and exp2.files[0].events[0].segments[0].mean > 0
+    with pytest.raises(NotImplementedError):
+        Experiment(["run1.abf"]).parse(verbose=False)

@@ -113,3 +113,40 @@ def test_float64_trace_must_be_float32_representable():
         parsers._as_float32_trace(np.array([0.1]))
     with pytest.raises(TypeError):
         parsers._as_float32_trace(np.array([1, 2, 3]))
+
+
+def test_file_json_round_trip_of_the_reference_format():
+    """the JSON written by the REAL reference's File.to_json (tests/golden/file_tierA.json)
+    is read by the mirror's File.from_json (MetaEvents / MetaSegments, the reference's own fallback without the
+    .abf file) and written back identically, parsers included."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from pypore_b200.DataTypes import File, MetaEvent
+    from pypore_b200.core import MetaSegment
+    from pypore_b200.parsers import SpeedyStatSplit, lambda_event_parser
+    text = open(os.path.join(GOLDEN, "file_tierA.json")).read()
+    ref = json.loads(text)
+    f = File.from_json(text)
+    assert f.n == ref["n"] == 4 and isinstance(f.event_parser, lambda_event_parser) and f.event_parser.threshold == 110
+    assert all(isinstance(e, MetaEvent) for e in f.events)
+    assert all(isinstance(s, MetaSegment) for e in f.events for s in e.segments)
+    assert isinstance(f.events[0].state_parser, SpeedyStatSplit) and f.events[0].state_parser.cutoff_freq == 2000.0
+    assert [e.filtered for e in f.events] == [True, False, True, False]
+    back = json.loads(f.to_json())
+    for key in ("filename", "n", "event_parser", "name"):
+        assert back[key] == ref[key]
+    assert len(back["events"]) == len(ref["events"])
+    for a, b in zip(back["events"], ref["events"]):
+        assert set(a) == set(b) - {"filtered"}      # MetaEvent.to_dict has no 'filtered' key (DataTypes.py:196-201)
+        for k in a:
+            if k == "name":
+                assert a[k] == "MetaEvent" and b[k] == "Event"      # what the reference's reload yields too
+            elif k == "segments":
+                assert [{**s, "name": "Segment"} for s in a[k]] == b[k]
+            else:
+                assert a[k] == b[k], k
+    # Event.to_json / from_json and the file-name form of from_json
+    ev = f.events[1]
+    again = MetaEvent.from_json(ev.to_json())
+    assert again.start == ev.start and again.n == ev.n and len(again.segments) == len(ev.segments)
