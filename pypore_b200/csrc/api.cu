@@ -375,7 +375,7 @@ int enqueue_prefix(pp_ctx *ctx, int prefix_mode)
     const int64_t ncap = ctx->flat_cap;
     PPSource src = make_source(ctx);
     if (prefix_mode == PP_PREFIX_SEQUENTIAL) {
-        k2_prefix_sequential<<<ctx->sm_count * 4, K2S_WARPS * 32, 0, ctx->stream>>>(
+        k2_prefix_sequential<<<ctx->sm_count * 3, K2S_WARPS * 32, 0, ctx->stream>>>(
             src, (const int64_t *)ctx->ev_len.p, ctx->ctr, nullptr, (double2 *)ctx->cc.p);
         LAUNCHED(ctx);
     } else {
@@ -415,7 +415,7 @@ int enqueue_prefix(pp_ctx *ctx, int prefix_mode)
                 (double2 *)ctx->cc.p);
         LAUNCHED(ctx);
         if (prefix_mode != PP_PREFIX_PARALLEL) {
-            k2_prefix_sequential<<<ctx->sm_count * 4, K2S_WARPS * 32, 0, ctx->stream>>>(
+            k2_prefix_sequential<<<ctx->sm_count * 3, K2S_WARPS * 32, 0, ctx->stream>>>(
                 src, (const int64_t *)ctx->ev_len.p, ctx->ctr, (const unsigned *)ctx->inexact.p,
                 (double2 *)ctx->cc.p);
             LAUNCHED(ctx);
@@ -1255,6 +1255,9 @@ int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_sa
 {
     if (!ctx || !p || !host || n <= 0) return fail(ctx, PP_ERR_ARG, "bad trace");
     CKR(set_device(ctx));
+    // 16 Mi samples measured best on B200 (scripts/e2e_breakdown.py: 1 Mi 17.9 ms, 4 Mi 5.9, 8 Mi 5.15, 16 Mi
+    // 4.92 for a 60 M-sample trace whose bare copy takes 4.32 ms; a shrinking schedule 24 -> 4 Mi was slower:
+    // every chunk pays a full split-search latency)
     if (chunk_samples <= 0) chunk_samples = (int64_t)16 << 20;
     chunk_samples = (chunk_samples + K1_TILE - 1) / K1_TILE * K1_TILE;
     if (p->filter_ncoef > 0 || n <= chunk_samples) {

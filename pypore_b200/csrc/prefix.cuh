@@ -29,7 +29,65 @@
 constexpr int K2S_WARPS = 8;
 constexpr int K2S_TILE = 256;  // samples per warp tile
 
-__global__ void __launch_bounds__(K2S_WARPS * 32)
+// one lane's samples of the tile starting at `base` (coalesced: sample k * 32 + lane), 0 past the end;
+// kept in their own type so that nothing waits for the loads until the values are used
+template <typename T>
+__device__ __forceinline__ void k2s_load(const T *__restrict__ p, int64_t base, int64_t len, int lane,
+                                         T (&xv)[K2S_TILE / 32])
+{
+#pragma unroll
+    for (int k = 0; k < K2S_TILE / 32; ++k) {
+        const int64_t j = base + k * 32 + lane;
+        xv[k] = j < len ? __ldg(p + j) : (T)0;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void k2s_event(const T *__restrict__ p, int64_t len, double2 *__restrict__ out,
+                                          double (*v)[K2S_TILE], int lane)
+{
+    double acc = 0.0;  // lane 0: c, lane 1: c2
+    T xv[K2S_TILE / 32], xn[K2S_TILE / 32];
+    k2s_load(p, 0, len, lane, xv);
+    for (int64_t base = 0; base < len; base += K2S_TILE) {
+        const int cnt = (int)((len - base) < K2S_TILE ? (len - base) : K2S_TILE);
+#pragma unroll
+        for (int k = 0; k < K2S_TILE / 32; ++k) {
+            const double x = (double)xv[k];
+            v[0][k * 32 + lane] = x;
+            v[1][k * 32 + lane] = __dmul_rn(x, x);
+        }
+        // the next tile's samples travel while lanes 0/1 walk the chain
+        if (base + K2S_TILE < len) k2s_load(p, base + K2S_TILE, len, lane, xn);
+        __syncwarp();
+        if (lane < 2) {
+            double *q = v[lane];
+            for (int j0 = 0; j0 < K2S_TILE; j0 += 16) {
+                double t[16];  // operands first: their loads do not wait for the chain's stores
+#pragma unroll
+                for (int k = 0; k < 16; ++k) t[k] = q[j0 + k];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    acc = __dadd_rn(acc, t[k]);
+                    t[k] = acc;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) q[j0 + k] = t[k];
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K2S_TILE / 32; ++k) {
+            const int j = k * 32 + lane;
+            if (j < cnt) out[base + j] = make_double2(v[0][j], v[1][j]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K2S_TILE / 32; ++k) xv[k] = xn[k];
+    }
+}
+
+__global__ void __launch_bounds__(K2S_WARPS * 32, 3)
 k2_prefix_sequential(PPSource src, const int64_t *__restrict__ ev_len, PPCounters *ctr,
                      const unsigned *__restrict__ inexact /* nullable: redo only flagged events */,
                      double2 *__restrict__ cc)
@@ -38,48 +96,16 @@ k2_prefix_sequential(PPSource src, const int64_t *__restrict__ ev_len, PPCounter
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n_events = (int64_t)ctr->n_events;
     const int64_t warps = (int64_t)gridDim.x * K2S_WARPS;
-    double (*v)[K2S_TILE] = sv[warp];
-    for (int64_t e = (int64_t)ctr->ev_begin + (int64_t)blockIdx.x * K2S_WARPS + warp; e < n_events; e += warps) {
+    // events are dealt to CTAs round-robin so that a few flagged events still spread over all SMs
+    for (int64_t e = (int64_t)ctr->ev_begin + (int64_t)warp * gridDim.x + blockIdx.x; e < n_events; e += warps) {
         if (inexact) {
             if (inexact[e] == 0u) continue;
             if (lane == 0) atomicAdd(&ctr->n_seq_redo, 1ull);
         }
         const int64_t len = ev_len[e];
         const int64_t off = src.ev_off[e];
-        double acc = 0.0;  // lane 0: c, lane 1: c2
-        for (int64_t base = 0; base < len; base += K2S_TILE) {
-            const int cnt = (int)((len - base) < K2S_TILE ? (len - base) : K2S_TILE);
-#pragma unroll
-            for (int k = 0; k < K2S_TILE / 32; ++k) {
-                const int j = k * 32 + lane;
-                const double x = j < cnt ? pp_sample(src, e, base + j) : 0.0;
-                v[0][j] = x;
-                v[1][j] = __dmul_rn(x, x);
-            }
-            __syncwarp();
-            if (lane < 2) {
-                double *p = v[lane];
-                for (int j0 = 0; j0 < K2S_TILE; j0 += 16) {
-                    double t[16];  // operands first: their loads do not wait for the chain's stores
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) t[k] = p[j0 + k];
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        acc = __dadd_rn(acc, t[k]);
-                        t[k] = acc;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) p[j0 + k] = t[k];
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < K2S_TILE / 32; ++k) {
-                const int j = k * 32 + lane;
-                if (j < cnt) cc[off + base + j] = make_double2(v[0][j], v[1][j]);
-            }
-            __syncwarp();
-        }
+        if (src.kind == 0) k2s_event(src.trace + src.ev_start[e], len, cc + off, sv[warp], lane);
+        else k2s_event(src.flat + off, len, cc + off, sv[warp], lane);
     }
 }
 

@@ -100,8 +100,49 @@ void run(const char *name, int ctas_per_sm, int threads)
     cudaFree(cyc);
 }
 
+// dependent-chain latency of one op (single warp, one chain per thread)
+template <int OP>
+__global__ void latency(double *out, const double *in, long long *cycles)
+{
+    double d = in[threadIdx.x & 63];
+    const double a = in[1];
+    __shared__ double sm[256];
+    sm[threadIdx.x] = a;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 16
+    for (int it = 0; it < 4096; ++it) {
+        if (OP == 0) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d) : "d"(a));
+        if (OP == 1) asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(d) : "d"(a));
+        if (OP == 2) { d = __dadd_rn(d, sm[(it + threadIdx.x) & 255]); }
+    }
+    const long long t1 = clock64();
+    out[threadIdx.x] = d;
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+template <int OP>
+void run_latency(const char *name)
+{
+    double *out, *in;
+    long long *cyc, h;
+    cudaMalloc(&out, 8 * 64);
+    cudaMalloc(&in, 8 * 64);
+    cudaMalloc(&cyc, 8);
+    double hin[64];
+    for (int i = 0; i < 64; ++i) hin[i] = 1.0 + i * 1e-3;
+    cudaMemcpy(in, hin, sizeof hin, cudaMemcpyHostToDevice);
+    latency<OP><<<1, 32>>>(out, in, cyc);
+    latency<OP><<<1, 32>>>(out, in, cyc);
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("%-26s %.2f cycles per dependent op\n", name, (double)h / 4096.0);
+}
+
 int main()
 {
+    run_latency<0>("latency DADD");
+    run_latency<1>("latency DFMA");
+    run_latency<2>("latency DADD + LDS operand");
     for (int pass = 0; pass < 2; ++pass) {
         const int c = pass == 0 ? 1 : 2, t = 512;
         run<0>("DFMA", c, t);
