@@ -349,6 +349,8 @@ def run_ours(args):
             "counts": {"samples": n_total, "events": ev_total, "event_samples": evs_total,
                        "segments": seg_total, "candidates_rank0": counters["candidates"]},
         }
+        if shard is not None:
+            line["host_planned_fallback_steps"] = int(shard.fallbacks)
         if world == 1 and not args.no_cpu_baseline:
             n_cpu = min(epg, 1500)
             xc = synth.make_trace(n_cpu, seed=1, tier="A").astype(np.float64)

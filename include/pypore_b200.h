@@ -95,6 +95,9 @@ int pp_trace_adopt(pp_ctx *ctx, const float *dev, int64_t n, int64_t capacity);
 int pp_trace_append(pp_ctx *ctx, const float *src, int64_t n, int src_is_device);
 /* Drop samples appended after position `n` (start of a new multi-GPU step). */
 int pp_trace_truncate(pp_ctx *ctx, int64_t n);
+/* Declare that the caller wrote `n` samples directly after the current trace end (NCCL recv or a
+ * peer copy into pp_trace_device_ptr() + pp_trace_len(), within the reserved capacity). */
+int pp_trace_extend(pp_ctx *ctx, int64_t n);
 int64_t pp_trace_len(pp_ctx *ctx);
 const float *pp_trace_device_ptr(pp_ctx *ctx);
 
@@ -215,12 +218,24 @@ int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_sa
  *   evaluations] to DEVICE memory, no host synchronisation.
  * pp_shard_commit: hands the (all-gathered, host-read) result record back so that downloads work.
  * pp_pack_tables: event rows {global start, length} and segment rows {global event id, start,
+ * pp_shard_plan / pp_shard_finish_planned: the same step without the host round trip between scan
+ *   and finish.  The caller placed `halo_avail` samples of the right neighbour's chunk after its own
+ *   (pp_trace_extend) before anything was known about the runs; pp_shard_plan derives this rank's part of
+ *   the boundary plan on the DEVICE from the all-gathered boundary records (world x 12 doubles) and writes
+ *   8 words [skip_first, skip_last, has_event, ev_start, ev_len, redo flags, halo samples needed, 0];
+ *   pp_shard_finish_planned reads them there.  Word 4 of the result record carries the redo flags
+ *   (16: a straddling event needs more than halo_avail samples or spans more than two chunks; 1: a rank's
+ *   run table overflowed) -- the caller then repeats the step with pp_shard_finish and a host-made plan.
+ * pp_pack_tables: event rows {global start, length} and segment rows {global event id, start,
  *   end, mean, std, min, max} as 8-byte words in one device buffer (2 E + 7 S words).  Counts and the
  *   global event-id base are read on the DEVICE from the all-gathered result records (8 words per
  *   rank), so the call needs no host knowledge of them; nothing is written if cap_words is too small. */
 int pp_shard_scan(pp_ctx *ctx, double threshold, int64_t scan_len, double *dev_record);
 int pp_shard_finish(pp_ctx *ctx, const pp_pipeline_params *p, int skip_first, int skip_last, int has_event,
                     int64_t ev_start, int64_t ev_len, int64_t *dev_record);
+int pp_shard_plan(pp_ctx *ctx, const double *dev_infos, int rank, int world, const pp_pipeline_params *p,
+                  int64_t halo_avail, int64_t *dev_plan);
+int pp_shard_finish_planned(pp_ctx *ctx, const pp_pipeline_params *p, const int64_t *dev_plan, int64_t *dev_record);
 int pp_shard_commit(pp_ctx *ctx, const int64_t rec[8]);
 int pp_pack_tables(pp_ctx *ctx, const int64_t *dev_records, int rank, int64_t sample_offset, int64_t *dev_out,
                    int64_t cap_words);

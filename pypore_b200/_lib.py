@@ -87,6 +87,10 @@ SIGNATURES = {
     "pp_shard_finish": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _c.c_int, _c.c_int, _c.c_int, _i64, _i64,
                                    _c.c_void_p]),
     "pp_shard_commit": (_c.c_int, [_c.c_void_p, _i64p]),
+    "pp_shard_plan": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.POINTER(PipelineParams), _i64,
+                                 _c.c_void_p]),
+    "pp_shard_finish_planned": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _c.c_void_p, _c.c_void_p]),
+    "pp_trace_extend": (_c.c_int, [_c.c_void_p, _i64]),
     "pp_pack_tables": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _i64, _c.c_void_p, _i64]),
     "pp_pipeline_host": (_c.c_int, [_c.c_void_p, _f32p, _i64, _i64, _c.POINTER(PipelineParams), _i64p]),
     "pp_pipeline": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _i64p]),
@@ -216,6 +220,10 @@ class Context(object):
 
     def truncate_trace(self, n):
         self._ck(self._L.pp_trace_truncate(self._h, int(n)))
+
+    def extend_trace(self, n):
+        """`n` samples were written by the caller directly after the trace end (halo received in place)."""
+        self._ck(self._L.pp_trace_extend(self._h, int(n)))
 
     @property
     def trace_len(self):
@@ -445,6 +453,19 @@ class Context(object):
         self._ck(self._L.pp_shard_finish(self._h, _c.byref(p), int(bool(skip_first)), int(bool(skip_last)),
                                          int(has), int(event[0]) if has else 0, int(event[1]) if has else 0,
                                          _c.c_void_p(int(dev_record_ptr))))
+
+    def shard_plan(self, dev_infos_ptr, rank, world, threshold, rules, halo_avail, dev_plan_ptr):
+        """This rank's boundary plan derived on the device from the all-gathered boundary records."""
+        p, keep = self._params(threshold, min_width=0, max_width=0, window_width=2, min_gain=0.0, **rules)
+        self._ck(self._L.pp_shard_plan(self._h, _c.c_void_p(int(dev_infos_ptr)), int(rank), int(world), _c.byref(p),
+                                       int(halo_avail), _c.c_void_p(int(dev_plan_ptr))))
+
+    def shard_finish_planned(self, threshold, rules, min_width, max_width, window_width, min_gain, dev_plan_ptr,
+                             dev_record_ptr):
+        p, keep = self._params(threshold, min_width=min_width, max_width=max_width, window_width=window_width,
+                               min_gain=min_gain, **rules)
+        self._ck(self._L.pp_shard_finish_planned(self._h, _c.byref(p), _c.c_void_p(int(dev_plan_ptr)),
+                                                 _c.c_void_p(int(dev_record_ptr))))
 
     def shard_commit(self, rec):
         rec = np.ascontiguousarray(rec, np.int64)

@@ -253,7 +253,8 @@ int enqueue_threshold(pp_ctx *ctx, double threshold, int64_t scan_len)
 }
 
 int enqueue_select(pp_ctx *ctx, int rule_mask, int64_t duration_gt, int64_t duration_lt,
-                   double min_gt, double max_lt, int skip_first, int skip_last, int incremental = 0)
+                   double min_gt, double max_lt, int skip_first, int skip_last, int incremental = 0,
+                   const long long *dev_plan = nullptr)
 {
     ctx->src_kind = 0;
     ctx->flat_cap = ctx->n;
@@ -261,7 +262,7 @@ int enqueue_select(pp_ctx *ctx, int rule_mask, int64_t duration_gt, int64_t dura
         ctx->ctr, (const int64_t *)ctx->run_start.p, (const int64_t *)ctx->run_len.p,
         (const double *)ctx->run_min.p, (const double *)ctx->run_max.p, ctx->cap_runs, rule_mask,
         duration_gt, duration_lt, min_gt, max_lt, skip_first, skip_last, (int64_t *)ctx->ev_start.p,
-        (int64_t *)ctx->ev_len.p, (int64_t *)ctx->ev_off.p, ctx->cap_events, incremental);
+        (int64_t *)ctx->ev_len.p, (int64_t *)ctx->ev_off.p, ctx->cap_events, incremental, dev_plan);
     LAUNCHED(ctx);
     ctx->n_events = ctx->n_event_samples = ctx->n_segments = -1;
     ctx->stats_valid = false;
@@ -711,6 +712,15 @@ int pp_trace_truncate(pp_ctx *ctx, int64_t n)
 {
     if (!ctx || n <= 0 || n > ctx->n) return fail(ctx, PP_ERR_ARG, "bad truncate");
     ctx->n = n;
+    return PP_OK;
+}
+
+int pp_trace_extend(pp_ctx *ctx, int64_t n)
+{
+    if (!ctx || n < 0) return fail(ctx, PP_ERR_ARG, "bad extend");
+    if (!ctx->trace) return fail(ctx, PP_ERR_STATE, "no trace resident");
+    if (ctx->n + n > ctx->trace_cap) return fail(ctx, PP_ERR_CAPACITY, "trace capacity exceeded");
+    ctx->n += n;
     return PP_OK;
 }
 
@@ -1213,6 +1223,38 @@ int pp_shard_finish(pp_ctx *ctx, const pp_pipeline_params *p, int skip_first, in
     CKR(enqueue_split(ctx, p->min_width, p->max_width, p->window_width, p->min_gain, p->prefix_mode));
     if (p->with_stats) CKR(enqueue_stats(ctx));
     k_result_record<<<1, 32, 0, ctx->stream>>>(ctx->ctr, (long long *)dev_record);
+    LAUNCHED(ctx);
+    return PP_OK;
+}
+
+int pp_shard_plan(pp_ctx *ctx, const double *dev_infos, int rank, int world, const pp_pipeline_params *p,
+                  int64_t halo_avail, int64_t *dev_plan)
+{
+    if (!ctx || !p || !dev_infos || !dev_plan || world < 1 || rank < 0 || rank >= world || halo_avail < 0)
+        return fail(ctx, PP_ERR_ARG, "bad shard plan arguments");
+    CKR(set_device(ctx));
+    k_shard_plan<<<1, 32, 0, ctx->stream>>>(dev_infos, rank, world, p->rule_mask, p->duration_gt, p->duration_lt,
+                                            p->min_gt, p->max_lt, halo_avail, (long long *)dev_plan);
+    LAUNCHED(ctx);
+    return PP_OK;
+}
+
+int pp_shard_finish_planned(pp_ctx *ctx, const pp_pipeline_params *p, const int64_t *dev_plan, int64_t *dev_record)
+{
+    if (!ctx || !p || !dev_plan || !dev_record) return PP_ERR_ARG;
+    if (p->filter_ncoef > 0) return fail(ctx, PP_ERR_ARG, "the sharded path does not filter");
+    CKR(set_device(ctx));
+    CKR(enqueue_select(ctx, p->rule_mask, p->duration_gt, p->duration_lt, p->min_gt, p->max_lt, 0, 0, 0,
+                       (const long long *)dev_plan));
+    k_append_planned_event<<<1, 32, 0, ctx->stream>>>(ctx->ctr, (int64_t *)ctx->ev_start.p, (int64_t *)ctx->ev_len.p,
+                                                      (int64_t *)ctx->ev_off.p, ctx->cap_events,
+                                                      (const long long *)dev_plan);
+    LAUNCHED(ctx);
+    CKR(record_boundary(ctx, ST_SELECT + 1));
+    ctx->stage_ran[ST_SELECT] = true;
+    CKR(enqueue_split(ctx, p->min_width, p->max_width, p->window_width, p->min_gain, p->prefix_mode));
+    if (p->with_stats) CKR(enqueue_stats(ctx));
+    k_result_record<<<1, 32, 0, ctx->stream>>>(ctx->ctr, (long long *)dev_record, (const long long *)dev_plan);
     LAUNCHED(ctx);
     return PP_OK;
 }

@@ -38,7 +38,8 @@ struct PPCounters {
     unsigned int first_below;         // below-threshold bit of sample 0
 };
 
-enum { PP_OVF_RUNS = 1, PP_OVF_QUEUE = 2, PP_OVF_SEGS = 4, PP_OVF_FILTER_SHORT = 8 };
+enum { PP_OVF_RUNS = 1, PP_OVF_QUEUE = 2, PP_OVF_SEGS = 4, PP_OVF_FILTER_SHORT = 8,
+       PP_OVF_HALO = 16 /* multi-GPU: the speculative halo did not cover a straddling event */ };
 
 // Where an event's samples live.
 //   kind 0: float32 trace, sample j of event e = trace[ev_start[e] + j]

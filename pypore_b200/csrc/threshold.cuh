@@ -284,8 +284,11 @@ k1_select_events(PPCounters *ctr, const int64_t *__restrict__ run_start,
                  int skip_first, int skip_last, int64_t *__restrict__ ev_start,
                  int64_t *__restrict__ ev_len, int64_t *__restrict__ ev_off, int64_t cap_events,
                  int incremental /* 0: whole run table; 1: append the runs completed since the last call,
-                                    the still open last run excluded; 2: same, last call (open run included) */)
+                                    the still open last run excluded; 2: same, last call (open run included) */,
+                 const long long *__restrict__ plan = nullptr /* multi-GPU: k_shard_plan's record overrides
+                                                                 skip_first / skip_last */)
 {
+    if (plan) { skip_first = (int)plan[0]; skip_last = (int)plan[1]; }
     __shared__ unsigned wcnt[SEL_THREADS / 32];
     __shared__ long long wlen[SEL_THREADS / 32];
     __shared__ unsigned long long s_cnt_carry;
@@ -422,15 +425,99 @@ __global__ void k1_boundary_record(int64_t n_local, const PPCounters *ctr, const
     rec[11] = ovf ? 1.0 : 0.0;
 }
 
+// Multi-GPU: this rank's row of dist.py plan_boundaries, derived on the DEVICE from the all-gathered
+// boundary records (infos[q] = rank q's k1_boundary_record), so that a step needs no host round trip
+// between the threshold scan and the split search.  `halo_avail` continuation samples of the right
+// neighbour were placed after the chunk speculatively, before anything was known about the runs.
+// plan = [skip_first, skip_last, has_event, ev_start, ev_len, redo, halo samples needed, 0]:
+//   redo = PP_OVF_HALO when the straddling event this rank owns needs more than halo_avail samples
+//          (or continues past the right neighbour), PP_OVF_RUNS when any rank's run table overflowed;
+//          the host then repeats the step with the host-planned exchange (dist.py).
+constexpr int PP_PLAN_WORDS = 8;
+
+__device__ __forceinline__ double pp_nan_min(double a, double b) { return (a != a || b != b) ? a + b : (a < b ? a : b); }
+__device__ __forceinline__ double pp_nan_max(double a, double b) { return (a != a || b != b) ? a + b : (a > b ? a : b); }
+
+__global__ void k_shard_plan(const double *__restrict__ infos, int rank, int world, int rule_mask,
+                             int64_t duration_gt, int64_t duration_lt, double min_gt, double max_lt,
+                             int64_t halo_avail, long long *__restrict__ plan)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int L = 12;
+    auto joins = [&](int q) { return infos[q * L + 6] == infos[(q + 1) * L + 2]; };  // last_below == next first_below
+    long long redo = 0;
+    for (int q = 0; q < world; ++q)
+        if (infos[q * L + 11] != 0.0) redo |= PP_OVF_RUNS;
+    const bool skip_first = rank > 0 && joins(rank - 1);
+    bool skip_last = false;
+    long long has_event = 0, ev_start = 0, ev_len = 0, need = 0;
+    if (rank < world - 1 && joins(rank)) {
+        skip_last = true;
+        const double *me = infos + rank * L;
+        const bool owns = !(me[1] == 1.0 && skip_first);  // else the run started further left
+        if (owns) {
+            long long length = (long long)me[8];
+            double mn = me[9], mx = me[10];
+            int q = rank + 1;
+            for (;;) {
+                const double *o = infos + q * L;
+                length += (long long)o[3];
+                mn = pp_nan_min(mn, o[4]);
+                mx = pp_nan_max(mx, o[5]);
+                if (o[1] == 1.0 && q < world - 1 && joins(q)) { ++q; continue; }
+                break;
+            }
+            bool ok = true;
+            if (rule_mask & PP_RULE_DURATION_GT) ok = ok && (length > duration_gt);
+            if (rule_mask & PP_RULE_DURATION_LT) ok = ok && (length < duration_lt);
+            if (rule_mask & PP_RULE_MIN_GT) ok = ok && (mn > min_gt);
+            if (rule_mask & PP_RULE_MAX_LT) ok = ok && (mx < max_lt);
+            if (ok) {
+                need = length - (long long)me[8];
+                if (q == rank + 1 && need <= halo_avail) {
+                    has_event = 1;
+                    ev_start = (long long)me[7];
+                    ev_len = length;
+                } else {
+                    redo |= PP_OVF_HALO;
+                }
+            }
+        }
+    }
+    plan[0] = skip_first;
+    plan[1] = skip_last;
+    plan[2] = has_event;
+    plan[3] = ev_start;
+    plan[4] = ev_len;
+    plan[5] = redo;
+    plan[6] = need;
+    plan[7] = 0;
+}
+
+// The straddling event of k_shard_plan appended after the selected events.
+__global__ void k_append_planned_event(PPCounters *ctr, int64_t *ev_start, int64_t *ev_len, int64_t *ev_off,
+                                       int64_t cap_events, const long long *__restrict__ plan)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0 || !plan[2]) return;
+    const unsigned long long e = ctr->n_events;
+    if ((int64_t)e >= cap_events) { atomicOr(&ctr->overflow, PP_OVF_RUNS); return; }
+    ev_start[e] = plan[3];
+    ev_len[e] = plan[4];
+    ev_off[e + 1] = ev_off[e] + plan[4];  // ev_off[e] already holds the running total
+    ctr->n_events = e + 1;
+    ctr->n_event_samples += (unsigned long long)plan[4];
+}
+
 // Multi-GPU: [n_runs, n_events, n_event_samples, n_segments, overflow flags, candidates, scans, exact]
-__global__ void k_result_record(const PPCounters *ctr, long long *__restrict__ rec)
+__global__ void k_result_record(const PPCounters *ctr, long long *__restrict__ rec,
+                                const long long *__restrict__ plan = nullptr)
 {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     rec[0] = (long long)ctr->n_runs;
     rec[1] = (long long)ctr->n_events;
     rec[2] = (long long)ctr->n_event_samples;
     rec[3] = (long long)ctr->n_segments;
-    rec[4] = (long long)ctr->overflow;
+    rec[4] = (long long)ctr->overflow | (plan ? plan[5] : 0);
     rec[5] = (long long)ctr->n_cand;
     rec[6] = (long long)ctr->n_scan;
     rec[7] = (long long)ctr->n_exact;

@@ -17,6 +17,7 @@ with NCCL, which is how tests/test_dist_cpu.py covers them without a GPU.
 import numpy as np
 
 INFO_LEN = 12
+_REDO_MASK = 16 | 1   # result-record flags of the device-planned step: PP_OVF_HALO | PP_OVF_RUNS (include/pypore_b200.h)
 (I_N, I_NRUNS, I_FIRST_BELOW, I_FIRST_LEN, I_FIRST_MIN, I_FIRST_MAX,
  I_LAST_BELOW, I_LAST_START, I_LAST_LEN, I_LAST_MIN, I_LAST_MAX, I_PAD) = range(INFO_LEN)
 
@@ -219,6 +220,7 @@ class ShardedPipeline(object):
     """
 
     HALO_CAPACITY = 1 << 20
+    HALO_SPECULATIVE = 1 << 16   # samples every rank ships to its left neighbour up front (256 KB over NVLink)
 
     def __init__(self, ctx, rank, world, group=None):
         import torch
@@ -233,21 +235,118 @@ class ShardedPipeline(object):
         self.offsets = None
         self.gathered = self.counts = self._tables = None
         self.stage_ms = {}
-        self.rec = self.res = self.pack = None
+        self.rec = self.res = self.pack = self.plan = self.infos_dev = None
         self.pad_words = 0
+        self.lens = None
+        self._p2p = None     # cached halo send / receive descriptors of the device-planned step
+        self.fallbacks = 0   # steps that had to be repeated with the host-made plan
 
     def load(self, host_chunk):
-        self.ctx.upload_trace_async(host_chunk, extra_capacity=self.HALO_CAPACITY)
+        """Upload this rank's chunk; ranks exchange their chunk lengths once (sample offsets of the global
+        trace and the size of the speculative halo each neighbour sends)."""
+        import torch
         self.n_local = int(host_chunk.shape[0])
+        with torch.cuda.stream(self.stream):
+            mine = torch.tensor([self.n_local], dtype=torch.int64, device=self.device)
+            lens = torch.empty(self.world, dtype=torch.int64, device=self.device)
+            self.dist.all_gather_into_tensor(lens, mine, group=self.group)
+            self.lens = lens.cpu().numpy()
+        self.ctx.upload_trace_async(host_chunk, extra_capacity=self.HALO_CAPACITY)   # after the read-back: not waited on
+        self.offsets = np.concatenate(([0], np.cumsum(self.lens)))
 
-    def step(self, threshold, rules, mw, MW, W, gain):
+    def step(self, threshold, rules, mw, MW, W, gain, host_planned=False):
+        """One pass over the sharded trace.  Default: the device-planned step (one host synchronisation, at the
+        end); `host_planned=True`, or a straddling event the speculative halo does not cover, takes the step
+        with the host-made plan (two more round trips)."""
         import torch
         with torch.cuda.stream(self.stream):
-            return self._step(threshold, rules, mw, MW, W, gain)
+            if not host_planned:
+                r = self._step_device_planned(threshold, rules, mw, MW, W, gain)
+                if r is not None:
+                    return r
+                self.fallbacks += 1
+            return self._step_host_planned(threshold, rules, mw, MW, W, gain)
 
-    def _step(self, threshold, rules, mw, MW, W, gain):
-        """Two host synchronisations per step: after the all-gather of the boundary records (the plan is
-        host logic) and after the all-gather of the result records (table sizes)."""
+    def _spec_halo(self, q):
+        """Samples rank q sends to rank q-1 before anything is known about the runs."""
+        return int(min(self.HALO_SPECULATIVE, self.lens[q]))
+
+    def _step_device_planned(self, threshold, rules, mw, MW, W, gain):
+        """scan -> all-gather of the boundary records -> k_shard_plan on the device -> select/prefix/split/
+        stats -> all-gather of the result records -> packed table all-gather: no host synchronisation until
+        the result records are read.  The head of every chunk travels to the left neighbour up front (it is
+        input data, independent of the scan), directly into the room reserved after that rank's chunk.
+        Returns None when the records ask for the host-planned step."""
+        import torch
+        ctx, dist, dev = self.ctx, self.dist, self.device
+        if self.rec is None:
+            self.rec = torch.zeros(INFO_LEN, dtype=torch.float64, device=dev)
+            self.res = torch.zeros(8, dtype=torch.int64, device=dev)
+        if self.plan is None:
+            self.plan = torch.zeros(8, dtype=torch.int64, device=dev)
+            self.infos_dev = torch.empty(self.world * INFO_LEN, dtype=torch.float64, device=dev)
+        ctx.truncate_trace(self.n_local)
+        # the scan is launched first: the GPU works on it while the host sets up the exchanges
+        ctx.shard_scan(threshold, self.n_local, self.rec.data_ptr())
+        if self._p2p is None or self._p2p[0] != (ctx.trace_ptr, self.n_local):
+            ops, halo = [], 0
+            if self.rank < self.world - 1:
+                halo = self._spec_halo(self.rank + 1)
+                room = device_view(ctx.trace_ptr + 4 * self.n_local, halo, torch.float32, dev)
+                ops.append(dist.P2POp(dist.irecv, room, self.rank + 1, self.group))
+            if self.rank > 0:
+                chunk = device_view(ctx.trace_ptr, self._spec_halo(self.rank), torch.float32, dev)
+                ops.append(dist.P2POp(dist.isend, chunk, self.rank - 1, self.group))
+            self._p2p = ((ctx.trace_ptr, self.n_local), ops, halo)
+        _, ops, halo = self._p2p
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        dist.all_gather_into_tensor(self.infos_dev, self.rec, group=self.group)
+        for w in reqs:
+            w.wait()                                          # stream-level wait, the host goes on
+        ctx.extend_trace(halo)
+        ctx.shard_plan(self.infos_dev.data_ptr(), self.rank, self.world, threshold, rules, halo, self.plan.data_ptr())
+        ctx.shard_finish_planned(threshold, rules, mw, MW, W, gain, self.plan.data_ptr(), self.res.data_ptr())
+        return self._gather_results(redo_mask=_REDO_MASK)
+
+    def _gather_results(self, redo_mask=0):
+        """All-gather of the result records and of the packed tables; the only host synchronisation."""
+        import torch
+        ctx, dist, dev = self.ctx, self.dist, self.device
+        allr_dev = torch.empty(self.world * 8, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allr_dev, self.res, group=self.group)
+        # Speculative sizing: pack and all-gather with the padding of the previous step (+12.5 %) before the host
+        # knows this step's counts -- the pack kernel takes them from allr_dev on the device -- so the GPU is not
+        # idle during the host round trip.  Every rank reads the same records and takes the same decision.
+        g = None
+        if self.pad_words:
+            if self.pack is None or self.pack.shape[0] < self.pad_words:
+                self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
+            ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
+                            self.pad_words)
+            g = gather_packed_raw(self.pack, self.pad_words, dist, self.group)
+        allr = allr_dev.cpu().numpy().reshape(self.world, 8)             # host sync (nothing waits on it)
+        if redo_mask and (allr[:, 4] & redo_mask).any():
+            return None
+        ctx.shard_commit(allr[self.rank])
+        self.stage_ms = ctx.stage_ms()
+        self.n_owned = self.n_local
+        counts = [(int(r[1]), int(r[3])) for r in allr]
+        need_words = max(max(2 * e + 7 * s for e, s in counts), 1)
+        if g is None or need_words > self.pad_words:
+            self.pad_words = int(need_words * 1.125) + 64
+            self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
+            ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
+                            self.pad_words)
+            g = gather_packed_raw(self.pack, self.pad_words, dist, self.group)
+        else:
+            self.pad_words = max(int(need_words * 1.125) + 64, 1)
+        self.gathered, self.counts, self._tables = g, counts, None
+        ne, n_seg = counts[self.rank]
+        return dict(runs=int(allr[self.rank, 0]), events=ne, event_samples=int(allr[self.rank, 2]), segments=n_seg)
+
+    def _step_host_planned(self, threshold, rules, mw, MW, W, gain):
+        """Two more host synchronisations: after the all-gather of the boundary records the plan is made on
+        the host (plan_boundaries) and halos of any length travel point-to-point from any number of ranks."""
         import torch
         ctx, dist, dev = self.ctx, self.dist, self.device
         if self.rec is None:
@@ -265,10 +364,7 @@ class ShardedPipeline(object):
             ctx.threshold_scan(threshold, scan_len=self.n_local)
         else:
             raise RuntimeError("run table overflow")
-        n_runs = int(infos[self.rank, I_NRUNS])
         plan = plan_boundaries(infos, rules)[self.rank]
-        lens = infos[:, I_N].astype(np.int64)
-        self.offsets = np.concatenate(([0], np.cumsum(lens)))
         need = sum(c for _, c in plan["recv"])
         if need > self.halo.shape[0]:
             raise RuntimeError("halo of %d samples exceeds HALO_CAPACITY" % need)
@@ -278,35 +374,7 @@ class ShardedPipeline(object):
             ctx.append_trace(self.halo.data_ptr(), got, True)
         ctx.shard_finish(threshold, rules, mw, MW, W, gain, plan["skip_first"], plan["skip_last"], plan["event"],
                          self.res.data_ptr())
-        allr_dev = torch.empty(self.world * 8, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allr_dev, self.res, group=self.group)
-        # Speculative sizing: pack and all-gather with the padding of the previous step (+12.5 %) before the host
-        # knows this step's counts -- the pack kernel takes them from allr_dev on the device -- so the GPU is not
-        # idle during the second host round trip.  Every rank reads the same records and takes the same decision.
-        g = None
-        if self.pad_words:
-            if self.pack is None or self.pack.shape[0] < self.pad_words:
-                self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
-            ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
-                            self.pad_words)
-            g = gather_packed_raw(self.pack, self.pad_words, dist, self.group)
-        allr = allr_dev.cpu().numpy().reshape(self.world, 8)             # host sync 2 (nothing waits on it)
-        ctx.shard_commit(allr[self.rank])
-        self.stage_ms = ctx.stage_ms()
-        self.n_owned = self.n_local
-        counts = [(int(r[1]), int(r[3])) for r in allr]
-        need_words = max(max(2 * e + 7 * s for e, s in counts), 1)
-        if g is None or need_words > self.pad_words:
-            self.pad_words = int(need_words * 1.125) + 64
-            self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
-            ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
-                            self.pad_words)
-            g = gather_packed_raw(self.pack, self.pad_words, dist, self.group)
-        else:
-            self.pad_words = max(int(need_words * 1.125) + 64, 1)
-        self.gathered, self.counts, self._tables = g, counts, None
-        ne, n_seg = counts[self.rank]
-        return dict(runs=n_runs, events=ne, event_samples=int(allr[self.rank, 2]), segments=n_seg)
+        return self._gather_results()
 
     @property
     def tables(self):
