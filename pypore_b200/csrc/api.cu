@@ -389,6 +389,17 @@ int enqueue_prefix(pp_ctx *ctx, int prefix_mode)
                                                      (int64_t *)ctx->ev_tile_off.p, (K2EventBits *)ctx->k2_bits.p,
                                                      (unsigned *)ctx->inexact.p);
         LAUNCHED(ctx);
+        // short events: one pass, one warp per event
+        if (ctx->src_kind == 0)
+            k2_event_scan<float><<<ctx->sm_count * 4, K2F_WARPS * 32, 0, ctx->stream>>>(
+                src, ctx->trace, (const int64_t *)ctx->ev_len.p, ctx->ctr, (unsigned *)ctx->inexact.p,
+                (double2 *)ctx->cc.p, prefix_mode != PP_PREFIX_PARALLEL);
+        else
+            k2_event_scan<double><<<ctx->sm_count * 4, K2F_WARPS * 32, 0, ctx->stream>>>(
+                src, (const double *)ctx->flat64.p, (const int64_t *)ctx->ev_len.p, ctx->ctr,
+                (unsigned *)ctx->inexact.p, (double2 *)ctx->cc.p, prefix_mode != PP_PREFIX_PARALLEL);
+        LAUNCHED(ctx);
+        // long events: multi-CTA reduce / carries / scan over their tiles
         const int grid = ctx->sm_count * 8;
         if (ctx->src_kind == 0)
             k2_tile_reduce<float><<<grid, K2_THREADS, 0, ctx->stream>>>(

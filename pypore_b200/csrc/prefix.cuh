@@ -214,6 +214,157 @@ struct K2Exp {
     }
 };
 
+// ---------------------------------------------------------------------------
+// Short events (<= K2F_MAX_LEN samples -- every event of the C1/C2/C3/C5 workloads): ONE pass, one
+// WARP per event, no CTA barrier and no inter-CTA dependency.  The warp walks its event in steps of
+// 256 samples: coalesced loads -> per-warp shared-memory transpose -> 8 consecutive samples per lane
+// -> warp scan of the lane totals -> running carry in registers -> per-warp transpose -> coalesced
+// 16 B stores.  The samples are read once (4 + 16 B per sample instead of 4 + 4 + 16), the exponent
+// statistics of the exactness proof are gathered in the same pass and the verdict is written when the
+// event ends.  Longer events keep the multi-CTA reduce / carries / scan kernels below (a single warp
+// would serialise them); k2_tile_offsets gives short events no tiles.
+// ---------------------------------------------------------------------------
+constexpr int K2F_WARPS = 8;
+constexpr int K2F_ITEMS = 8;                      // consecutive samples per lane
+constexpr int K2F_TILE = 32 * K2F_ITEMS;           // samples per warp step
+constexpr int K2F_PAD = K2F_ITEMS + 1;
+constexpr int K2F_MAX_LEN = 32768;
+
+// exponent statistics of the event's float32 samples from their bit patterns: the magnitude exponent is
+// that of the largest |x| (integer max of the bits), the quantum exponent is E + ctz(mantissa with its
+// implicit one); zeros contribute nothing, inf/NaN poison the verdict through the magnitude.
+struct K2FBits {
+    unsigned amax;  // max over samples of bits(|x|)
+    int elow;       // min over non-zero samples of (biased E, denormals as 1) + ctz(24-bit significand)
+    __device__ __forceinline__ void init() { amax = 0u; elow = K2_ELOW_INIT; }
+    __device__ __forceinline__ void add(float x)
+    {
+        const unsigned a = __float_as_uint(x) & 0x7fffffffu;
+        amax = max(amax, a);
+        const unsigned E = a >> 23;
+        const unsigned sig = E ? (a | 0x00800000u) : a;       // denormal: no implicit one, exponent as for E = 1
+        const int q = (int)(E ? E : 1u) + (__ffs((int)(sig & 0x00ffffffu)) - 1);
+        if (a) elow = min(elow, q);
+    }
+    __device__ __forceinline__ void add(double) {}
+};
+
+template <typename T>
+__global__ void __launch_bounds__(K2F_WARPS * 32)
+k2_event_scan(PPSource src, const T *__restrict__ samples, const int64_t *__restrict__ ev_len, const PPCounters *ctr,
+              unsigned *__restrict__ inexact, double2 *__restrict__ cc, int check)
+{
+    // per-warp staging; the input transpose (T) and the output transpose (double2) share it
+    __shared__ __align__(16) double2 s_stage[K2F_WARPS][32 * K2F_PAD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2 *sout = s_stage[warp];
+    T *sin = reinterpret_cast<T *>(sout);
+    const int64_t n_events = (int64_t)ctr->n_events;
+    const int64_t warps = (int64_t)gridDim.x * K2F_WARPS;
+    // events are dealt to CTAs round-robin so that a handful of events still spreads over all SMs
+    for (int64_t e = (int64_t)ctr->ev_begin + (int64_t)warp * gridDim.x + blockIdx.x; e < n_events; e += warps) {
+        const int64_t len = ev_len[e];
+        if (len > K2F_MAX_LEN) continue;
+        const int64_t off = src.ev_off[e];
+        const T *in = samples + (src.kind == 0 ? src.ev_start[e] : off);
+        double2 *out = cc + off;
+        double carry_c = 0.0, carry_c2 = 0.0;
+        K2FBits fb;
+        fb.init();
+        K2Exp ex;   // float64 source: both x and x*x are analysed
+        ex.init();
+        T xv[K2F_ITEMS], xn[K2F_ITEMS];
+#pragma unroll
+        for (int k = 0; k < K2F_ITEMS; ++k) {
+            const int q = k * 32 + lane;
+            xv[k] = q < len ? __ldg(in + q) : (T)0;
+        }
+        for (int64_t base = 0; base < len; base += K2F_TILE) {
+            const int cnt = (int)((len - base) < K2F_TILE ? (len - base) : K2F_TILE);
+            // the next step's samples travel while this one is scanned
+            const int64_t nb = base + K2F_TILE;
+#pragma unroll
+            for (int k = 0; k < K2F_ITEMS; ++k) {
+                const int64_t q = nb + k * 32 + lane;
+                xn[k] = q < len ? __ldg(in + q) : (T)0;
+            }
+#pragma unroll
+            for (int k = 0; k < K2F_ITEMS; ++k) {
+                const int q = k * 32 + lane;
+                sin[(q / K2F_ITEMS) * K2F_PAD + (q % K2F_ITEMS)] = xv[k];
+            }
+            __syncwarp();
+            double pc[K2F_ITEMS], pc2[K2F_ITEMS];
+            double c = 0.0, c2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < K2F_ITEMS; ++k) {
+                const T xs = sin[lane * K2F_PAD + k];
+                if (sizeof(T) == 4) fb.add(xs); else ex.add(xs);
+                const double x = (double)xs;
+                c = __dadd_rn(c, x);
+                c2 = __dadd_rn(c2, __dmul_rn(x, x));
+                pc[k] = c; pc2[k] = c2;
+            }
+            double ic = c, ic2 = c2;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double t1 = __shfl_up_sync(PP_FULL, ic, d), t2 = __shfl_up_sync(PP_FULL, ic2, d);
+                if (lane >= d) { ic = __dadd_rn(t1, ic); ic2 = __dadd_rn(t2, ic2); }
+            }
+            __syncwarp();  // every lane has taken its inputs out of the staging area
+            // exclusive prefix of this lane = carry + earlier lanes
+            const double ec = __dadd_rn(carry_c, __dsub_rn(ic, c));
+            const double ec2 = __dadd_rn(carry_c2, __dsub_rn(ic2, c2));
+#pragma unroll
+            for (int k = 0; k < K2F_ITEMS; ++k)
+                sout[lane * K2F_PAD + k] = make_double2(__dadd_rn(ec, pc[k]), __dadd_rn(ec2, pc2[k]));
+            carry_c = __dadd_rn(carry_c, __shfl_sync(PP_FULL, ic, 31));
+            carry_c2 = __dadd_rn(carry_c2, __shfl_sync(PP_FULL, ic2, 31));
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < K2F_ITEMS; ++k) {
+                const int q = k * 32 + lane;
+                if (q < cnt) out[base + q] = sout[(q / K2F_ITEMS) * K2F_PAD + (q % K2F_ITEMS)];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < K2F_ITEMS; ++k) xv[k] = xn[k];
+        }
+        if (check) {
+            int el1, em1, el2, em2;
+            if (sizeof(T) == 4) {
+                unsigned amax = fb.amax;
+                int elow = fb.elow;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    amax = max(amax, __shfl_xor_sync(PP_FULL, amax, d));
+                    elow = min(elow, __shfl_xor_sync(PP_FULL, elow, d));
+                }
+                if (amax == 0u) { el1 = el2 = K2_ELOW_INIT; em1 = em2 = K2_EMAX_INIT; }  // all zeros: nothing to prove
+                else if (amax >= 0x7f800000u) { el1 = el2 = -K2_BAD_EXP; em1 = em2 = K2_BAD_EXP; }
+                else {
+                    const int E = (int)(amax >> 23);
+                    em1 = (E ? E : 1) - 127;          // |x| < 2^(em1 + 1)
+                    el1 = elow - 127 - 23;
+                    el2 = 2 * el1;                      // x*x is exact in fp64: quantum and magnitude follow from x
+                    em2 = 2 * em1 + 1;
+                }
+            } else {
+                ex.warp_reduce();
+                el1 = ex.el1; em1 = ex.em1; el2 = ex.el2; em2 = ex.em2;
+            }
+            if (lane == 0) {
+                int lg = 0;
+                while ((1LL << lg) < len) ++lg;
+                bool ok = true;
+                if (em1 != K2_EMAX_INIT) ok = ok && ((long long)lg + em1 + 1 - el1 <= 53);
+                if (em2 != K2_EMAX_INIT) ok = ok && ((long long)lg + em2 + 1 - el2 <= 53);
+                inexact[e] = ok ? 0u : 1u;
+            }
+        }
+    }
+}
+
 // exclusive prefix of tiles per event (one CTA; the event table is small)
 __global__ void __launch_bounds__(1024)
 k2_tile_offsets(PPCounters *ctr, const int64_t *__restrict__ ev_len, int64_t *__restrict__ ev_tile_off,
@@ -229,7 +380,7 @@ k2_tile_offsets(PPCounters *ctr, const int64_t *__restrict__ ev_len, int64_t *__
     __syncthreads();
     for (int64_t c0 = ev_begin; c0 < n_events; c0 += 1024) {
         const int64_t e = c0 + tid;
-        long long v = e < n_events ? (ev_len[e] + K2_TILE - 1) / K2_TILE : 0;
+        long long v = (e < n_events && ev_len[e] > K2F_MAX_LEN) ? (ev_len[e] + K2_TILE - 1) / K2_TILE : 0;  // short events: k2_event_scan
         long long inc = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -352,6 +503,7 @@ k2_event_carries(const PPCounters *ctr, const int64_t *__restrict__ ev_len, cons
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t e = (int64_t)ctr->ev_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < n_events;
          e += warps) {
+        if (ev_len[e] <= K2F_MAX_LEN) continue;  // scanned and judged by k2_event_scan
         const int64_t t0 = ev_tile_off[e], t1 = ev_tile_off[e + 1];
         double carry_c = 0.0, carry_c2 = 0.0;
         for (int64_t b = t0; b < t1; b += 32) {

@@ -42,7 +42,7 @@
 #define K3_CFG_THREADS 128
 #endif
 #ifndef K3_CFG_CTAS
-#define K3_CFG_CTAS 6
+#define K3_CFG_CTAS 7   // 72 registers; measured 6: 1.183 ms, 7: 1.097 ms (5: 1.297)
 #endif
 constexpr int K3_THREADS = K3_CFG_THREADS;
 constexpr int K3_CTAS_PER_SM = K3_CFG_CTAS;
@@ -56,6 +56,12 @@ constexpr int K3_PIECES = K3_LIST + K3_WARPS;  // (warp, window) screening recor
 // prefix sums, and both widen a CTA's working set), so the defaults keep one event per CTA.
 #ifndef K3_CFG_BATCH
 #define K3_CFG_BATCH 1
+#endif
+#ifndef K3_CFG_WINLH
+#define K3_CFG_WINLH 0   // per-window {lo, hi} staged in shared memory: measured no gain (1.199 vs 1.183 ms)
+#endif
+#ifndef K3_CFG_PREFETCH
+#define K3_CFG_PREFETCH 1
 #endif
 #ifndef K3_CFG_DONATE
 #define K3_CFG_DONATE 0
@@ -105,6 +111,10 @@ struct K3Shared {
     unsigned long long win_thr[K3_LIST];   // min key + 2 eps
     unsigned long long best_key[K3_LIST];  // ordered key of the best exact gain (0 = none beats min_gain)
     int best_idx[K3_LIST];
+#if K3_CFG_WINLH
+    double2 win_lo[K3_LIST];               // {c, c2} just before the window and at its last sample, loaded once per
+    double2 win_hi[K3_LIST];               // level by the bookkeeping thread instead of once per (warp, window) piece
+#endif
     unsigned long long pc_k1[K3_PIECES];   // smallest key of the piece
     unsigned long long pc_k2[K3_PIECES];   // second smallest (== k1 on a tie)
     int pc_i1[K3_PIECES];                  // candidate index of k1 | K3_BAD_FLAG | K3_RESCAN_FLAG
@@ -286,9 +296,27 @@ __device__ __forceinline__ void k3_scr_init(K3Scr &a)
     a.bad = 0;
 }
 
+__device__ __forceinline__ void k3_scr_update(K3Scr &a, bool ok, unsigned long long key, int i)
+{
+    if (!ok) a.bad = 1;
+    else if (key < a.k2) {
+        if (key < a.k1) { a.k2 = a.k1; a.k1 = key; a.i1 = i; }
+        else a.k2 = key;
+    }
+}
+
+#ifndef K3_CFG_UNROLL
+#define K3_CFG_UNROLL 2
+#endif
+#if K3_CFG_LDCS
+#define K3_LD_MID(p) __ldcs(p)
+#else
+#define K3_LD_MID(p) __ldg(p)
+#endif
+
 // Screen candidates i, i+stride, ... <= i_last of window [ps,pe) (requires mw >= 1 so that
-// n1, n2 >= 1 and i >= 1).  Plain pointer increments; the operands of the next candidate are
-// requested before the current one is evaluated.
+// n1, n2 >= 1 and i >= 1).  Plain pointer increments; two candidates per trip (four independent
+// fp64 chains in flight), the operands of the next pair requested before the current one is evaluated.
 __device__ __forceinline__ void k3_screen_lane(const double2 *__restrict__ ccg, const double2 lo, const double2 hi,
                                                int ps, int pe, int ebase, const double *__restrict__ RN, int i,
                                                int i_last, int stride, K3Scr &a)
@@ -297,11 +325,78 @@ __device__ __forceinline__ void k3_screen_lane(const double2 *__restrict__ ccg, 
     const double2 *pm = ccg + (i - 1);
     const double *p1 = RN + (i - ps), *p2 = RN + (pe - i);
     unsigned n1 = (unsigned)(i - ps), n2 = (unsigned)(pe - i);
-#if K3_CFG_LDCS
-#define K3_LD_MID(p) __ldcs(p)
-#else
-#define K3_LD_MID(p) __ldg(p)
+#if K3_CFG_UNROLL == 2
+    const int s2 = 2 * stride;
+    if (i + stride <= i_last) {
+        double2 mA = K3_LD_MID(pm), mB = K3_LD_MID(pm + stride);
+        double rA1 = __ldg(p1), rA2 = __ldg(p2), rB1 = __ldg(p1 + stride), rB2 = __ldg(p2 - stride);
+        for (;;) {
+            const bool more = i + s2 + stride <= i_last;
+#if !K3_CFG_PREFETCH
+            if (true) {
+                unsigned long long keyA, keyB;
+                const bool okA = k3_screen_key(mA, rA1, rA2, lo, hi, n1, n2, ebase, keyA);
+                const bool okB = k3_screen_key(mB, rB1, rB2, lo, hi, n1 + (unsigned)stride, n2 - (unsigned)stride, ebase, keyB);
+                k3_scr_update(a, okA, keyA, i);
+                k3_scr_update(a, okB, keyB, i + stride);
+                pm += s2; p1 += s2; p2 -= s2;
+                n1 += (unsigned)s2; n2 -= (unsigned)s2;
+                i += s2;
+                if (!more) break;
+                mA = K3_LD_MID(pm); mB = K3_LD_MID(pm + stride);
+                rA1 = __ldg(p1); rA2 = __ldg(p2); rB1 = __ldg(p1 + stride); rB2 = __ldg(p2 - stride);
+                continue;
+            }
 #endif
+            double2 mA_n = mA, mB_n = mB;
+#if K3_CFG_PREFETCH == 2
+            // only the prefix sums (L2 latency) are requested a trip ahead; the 1/n table is L1-resident
+            if (more) {
+                mA_n = K3_LD_MID(pm + s2);
+                mB_n = K3_LD_MID(pm + s2 + stride);
+            }
+            unsigned long long keyA, keyB;
+            const bool okA = k3_screen_key(mA, rA1, rA2, lo, hi, n1, n2, ebase, keyA);
+            const bool okB = k3_screen_key(mB, rB1, rB2, lo, hi, n1 + (unsigned)stride, n2 - (unsigned)stride, ebase, keyB);
+            k3_scr_update(a, okA, keyA, i);
+            k3_scr_update(a, okB, keyB, i + stride);
+            pm += s2; p1 += s2; p2 -= s2;
+            n1 += (unsigned)s2; n2 -= (unsigned)s2;
+            i += s2;
+            if (!more) break;
+            rA1 = __ldg(p1); rA2 = __ldg(p2); rB1 = __ldg(p1 + stride); rB2 = __ldg(p2 - stride);
+            mA = mA_n; mB = mB_n;
+#else
+            double rA1_n = rA1, rA2_n = rA2, rB1_n = rB1, rB2_n = rB2;
+            if (more) {
+                mA_n = K3_LD_MID(pm + s2);
+                mB_n = K3_LD_MID(pm + s2 + stride);
+                rA1_n = __ldg(p1 + s2);
+                rB1_n = __ldg(p1 + s2 + stride);
+                rA2_n = __ldg(p2 - s2);
+                rB2_n = __ldg(p2 - s2 - stride);
+            }
+            unsigned long long keyA, keyB;
+            const bool okA = k3_screen_key(mA, rA1, rA2, lo, hi, n1, n2, ebase, keyA);
+            const bool okB = k3_screen_key(mB, rB1, rB2, lo, hi, n1 + (unsigned)stride, n2 - (unsigned)stride, ebase, keyB);
+            k3_scr_update(a, okA, keyA, i);
+            k3_scr_update(a, okB, keyB, i + stride);
+            pm += s2; p1 += s2; p2 -= s2;
+            n1 += (unsigned)s2; n2 -= (unsigned)s2;
+            i += s2;
+            if (!more) break;
+            mA = mA_n; mB = mB_n; rA1 = rA1_n; rA2 = rA2_n; rB1 = rB1_n; rB2 = rB2_n;
+#endif
+        }
+        if (i > i_last) return;
+    }
+    // at most one candidate is left
+    {
+        unsigned long long key;
+        const bool ok = k3_screen_key(K3_LD_MID(pm), __ldg(p1), __ldg(p2), lo, hi, n1, n2, ebase, key);
+        k3_scr_update(a, ok, key, i);
+    }
+#else
     double2 mid = K3_LD_MID(pm);
     double r1 = __ldg(p1), r2 = __ldg(p2);
     for (;;) {
@@ -315,17 +410,14 @@ __device__ __forceinline__ void k3_screen_lane(const double2 *__restrict__ ccg, 
         }
         unsigned long long key;
         const bool ok = k3_screen_key(mid, r1, r2, lo, hi, n1, n2, ebase, key);
-        if (!ok) a.bad = 1;
-        else if (key < a.k2) {
-            if (key < a.k1) { a.k2 = a.k1; a.k1 = key; a.i1 = i; }
-            else a.k2 = key;
-        }
+        k3_scr_update(a, ok, key, i);
         if (!more) break;
         mid = mid_n; r1 = r1_n; r2 = r2_n;
         pm += stride; p1 += stride; p2 -= stride;
         n1 += (unsigned)stride; n2 -= (unsigned)stride;
         i += stride;
     }
+#endif
 }
 
 // 2 eps of a window of n samples, in key units (rounded up)
@@ -696,6 +788,12 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                             S.win_chunk0[slot] = ok ? (pe - it.ps - 2 * mw + 1 + 31) >> 5 : 0;  // chunk count for now
                             S.best_key[slot] = 0ull;
                             S.best_idx[slot] = 0x7fffffff;
+#if K3_CFG_WINLH
+                            K3GlobalCC wacc;
+                            wacc.g = G.cc + off;
+                            S.win_lo[slot] = wacc.at(it.ps - 1);
+                            S.win_hi[slot] = wacc.at(pe - 1);
+#endif
                         }
                     }
                 }
@@ -736,7 +834,11 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                         const int w_pe = k3_window_end(P, it);
                         const int w_last = w_pe - mw;
                         const int i_end = it.ps + mw + cb * 32 - 1;
+#if K3_CFG_WINLH
+                        const double2 w_lo = S.win_lo[slot], w_hi = S.win_hi[slot];
+#else
                         const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
+#endif
                         K3Scr a;
                         k3_scr_init(a);
                         k3_screen_lane(ccg, w_lo, w_hi, it.ps, w_pe, S.b_ebase[it.b], G.RN,
@@ -792,7 +894,11 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                             const int w_last = w_pe - mw;
                             int i_end = it.ps + mw + cb * 32 - 1;
                             i_end = i_end < w_last ? i_end : w_last;
+#if K3_CFG_WINLH
+                            const double2 w_lo = S.win_lo[slot], w_hi = S.win_hi[slot];
+#else
                             const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
+#endif
                             const unsigned long long thr = S.win_thr[slot];
                             const int ebase = S.b_ebase[it.b];
                             for (int i = it.ps + mw + ca * 32 + lane; i <= i_end; i += 32) {
@@ -819,7 +925,11 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                             acc.g = G.cc + S.b_off[it.b];
                             w_ps = it.ps;
                             w_pe = k3_window_end(P, it);
+#if K3_CFG_WINLH
+                            const double2 lo = S.win_lo[k], hi = S.win_hi[k], mid = acc.at(i - 1);
+#else
                             const double2 lo = acc.at(w_ps - 1), hi = acc.at(w_pe - 1), mid = acc.at(i - 1);
+#endif
                             if (part == 0) v = k3_exact_tot(lo, hi, w_ps, w_pe);
                             else if (part == 1) v = __dmul_rn((double)(i - w_ps), log(k3_var(mid, lo, i - w_ps)));
                             else v = __dmul_rn((double)(w_pe - i), log(k3_var(hi, mid, w_pe - i)));
