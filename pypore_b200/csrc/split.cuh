@@ -48,14 +48,25 @@ constexpr int K3_THREADS = K3_CFG_THREADS;
 constexpr int K3_CTAS_PER_SM = K3_CFG_CTAS;
 constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int K3_CAP = 10240;   // longest interval resolved level by level inside one CTA
-constexpr int K3_LIST = 256;    // items per level list
-constexpr int K3_REQ = 256;     // exact-evaluation requests per level
+#ifndef K3_CFG_LIST
+#define K3_CFG_LIST 128
+#endif
+#ifndef K3_CFG_SURE
+#define K3_CFG_SURE 1
+#endif
+#ifndef K3_CFG_SHARE
+#define K3_CFG_SHARE 0
+#endif
+constexpr int K3_LIST = K3_CFG_LIST;  // windows per level (more go to the global queue)
+constexpr int K3_REQ = K3_CFG_LIST;   // exact-evaluation requests per level
+constexpr int K3_SHARE = K3_CFG_SHARE; // both children of a split at least this long: the right one goes to the
+                                       // global queue for another CTA (finer tasks, shorter tail); 0 = keep both
 constexpr int K3_PIECES = K3_LIST + K3_WARPS;  // (warp, window) screening records per level
 // Measured on B200 at BASELINE configs[1] (profiles/r01f_k3_variants.txt): taking 2 events per CTA
-// or handing intervals to idle CTAs both LOSE time (the search is bound by L2 -> SM traffic of the
-// prefix sums, and both widen a CTA's working set), so the defaults keep one event per CTA.
-#ifndef K3_CFG_BATCH
-#define K3_CFG_BATCH 1
+// or handing intervals to idle CTAs both LOST time (the search is bound by L2 -> SM traffic of the
+// prefix sums, and both widen a CTA's working set); those knobs are gone, a CTA resolves one task at a time.
+#ifndef K3_CFG_LDCS
+#define K3_CFG_LDCS 0
 #endif
 #ifndef K3_CFG_WINLH
 #define K3_CFG_WINLH 0   // per-window {lo, hi} staged in shared memory: measured no gain (1.199 vs 1.183 ms)
@@ -63,17 +74,11 @@ constexpr int K3_PIECES = K3_LIST + K3_WARPS;  // (warp, window) screening recor
 #ifndef K3_CFG_PREFETCH
 #define K3_CFG_PREFETCH 1
 #endif
-#ifndef K3_CFG_DONATE
-#define K3_CFG_DONATE 0
-#endif
-#ifndef K3_CFG_LDCS
-#define K3_CFG_LDCS 0
-#endif
-constexpr int K3_BATCH = K3_CFG_BATCH;  // events a CTA resolves together (amortises the per-level latencies)
-constexpr int K3_DONATE_MIN = 8; // fresh intervals of at least this many min_widths may go to idle CTAs
 constexpr int K3_NO_EBASE = 0x7fffffff;
 constexpr unsigned long long K3_NO_TICKET = ~0ull;
-constexpr int K3_FULL_FLAG = 0x40000000;  // window entry: screening inconclusive / list overflow, scan exactly
+constexpr int K3_FULL_FLAG = 0x40000000;  // window flag: screening impossible / inconclusive / request overflow, scan exactly
+constexpr int K3_MULTI_FLAG = 0x20000000; // window flag: several exact evaluations compete (two-phase argmax)
+constexpr unsigned K3_ALLOC_SLOT = 1u << 20;  // level allocator: windows in the high 12 bits, 32-candidate chunks below
 constexpr int K3_BAD_FLAG = 0x40000000;    // piece record: a candidate failed the validity test
 constexpr int K3_RESCAN_FLAG = (int)0x80000000;  // piece record: several candidates within 2 eps of the minimum
 constexpr int K3_MAX_SCREEN_W = 1 << 24;   // keys stay below 2^56
@@ -86,7 +91,7 @@ constexpr double K3_HUGE = 1e280;
 constexpr unsigned long long K3_NOKEY = ~0ull;
 
 struct PPTask { int ev, s, e, flags; };
-struct K3Item { int s, e, ps, b; };  // interval, next window start, batch slot of its event
+struct K3Item { int s, e, ps, pad; };  // interval and the start of the window to scan next
 struct K3Params { int mw, MW, W; double min_gain; };
 struct K3Best { double g; int x; };
 struct K3Scr { unsigned long long k1, k2; int i1, bad; };  // per-lane screening state: two smallest keys
@@ -104,35 +109,46 @@ struct K3Global {
     int screen;        // 0: exact evaluation of every candidate (validation mode)
 };
 
+// The windows one level of the local search scans.  A level is filled while the previous one is
+// resolved: the thread that decides a window runs the bookkeeping of _recursive_split for its
+// children right away (k3_place) and registers their first scannable windows here.
+struct K3Level {
+    K3Item item[K3_LIST];
+    int c0[K3_LIST];      // first 32-candidate chunk of the window in the level's chunk space
+    int cn[K3_LIST];      // chunk count (0: exact scan)
+    int flag[K3_LIST];    // K3_FULL_FLAG | K3_MULTI_FLAG
+};
+
+// Per-level counters.  Three sets rotate (level mod 3): while level L is resolved its own set collects
+// requests, set L+1 collects the registrations of the next level, and set L+2 -- last read right after the
+// barrier that ended level L-1 -- is zeroed behind the first barrier of level L.
+struct K3Count {
+    unsigned alloc;       // (windows << 20) | chunks handed out so far
+    int nfull;            // windows flagged K3_FULL_FLAG
+    int nreq, nrescan, nmulti;
+};
+
 struct K3Shared {
-    K3Item list[2][K3_LIST];
-    int win_item[K3_LIST];                 // scan window slot -> index into the level list (| K3_FULL_FLAG)
-    int win_chunk0[K3_LIST + 1];           // first chunk of the window (exclusive prefix of chunk counts)
+    K3Level lv[2];
+    K3Count cnt[3];
     unsigned long long win_thr[K3_LIST];   // min key + 2 eps
     unsigned long long best_key[K3_LIST];  // ordered key of the best exact gain (0 = none beats min_gain)
     int best_idx[K3_LIST];
-#if K3_CFG_WINLH
-    double2 win_lo[K3_LIST];               // {c, c2} just before the window and at its last sample, loaded once per
-    double2 win_hi[K3_LIST];               // level by the bookkeeping thread instead of once per (warp, window) piece
-#endif
     unsigned long long pc_k1[K3_PIECES];   // smallest key of the piece
     unsigned long long pc_k2[K3_PIECES];   // second smallest (== k1 on a tie)
     int pc_i1[K3_PIECES];                  // candidate index of k1 | K3_BAD_FLAG | K3_RESCAN_FLAG
+    unsigned long long pc_kt[K3_PIECES];   // screening key of the window's own n log V (K3_NOKEY: not valid)
     int req_k[K3_REQ];
     int req_i[K3_REQ];
     double req_g[K3_REQ];
     double red_g[K3_WARPS];
     unsigned long long red_k[K3_WARPS];
     int red_x[K3_WARPS];
-    int nA, nB, nwin, nchunk, nreq, nrescan;
-    int nb;                                // tasks of the current batch
-    int batch;                             // tasks a CTA takes at once (1 .. K3_BATCH)
-    int donate;                            // fresh intervals this level may hand to idle CTAs
-    int b_ev[K3_BATCH];                    // per batch slot: event, flat offset, screening exponent base
-    long long b_off[K3_BATCH];
-    int b_ebase[K3_BATCH];                 // biased exponent of the event's variance - 127, or K3_NO_EBASE
-    PPTask b_task[K3_BATCH];
-    unsigned long long carry;              // claimed global ticket that was not served yet
+    int have;                              // a task was taken
+    int ev;                                // current task: event, flat offset, screening exponent base
+    long long off;
+    int ebase;                             // biased exponent of the task's variance - 127, or K3_NO_EBASE
+    PPTask task;
     unsigned long long cand, scans, exact;
 };
 
@@ -542,24 +558,6 @@ __device__ void k3_push_global(const K3Global &G, int ev, int s, int e)
     atomicExch(&G.ready[slot], 1);
 }
 
-__device__ __forceinline__ void k3_push_local(const K3Global &G, K3Shared &S, K3Item *next, const K3Params &P,
-                                              int b, int s, int e, int ps)
-{
-    // idle CTAs are waiting: a fresh, big enough interval goes to the global queue instead
-    if (ps == s && S.donate > 0 && e - s >= K3_DONATE_MIN * P.mw && atomicSub(&S.donate, 1) > 0) {
-        k3_push_global(G, S.b_ev[b], s, e);
-        return;
-    }
-    const int idx = atomicAdd(&S.nB, 1);
-    if (idx < K3_LIST) {
-        K3Item it;
-        it.s = s; it.e = e; it.ps = ps; it.b = b;
-        next[idx] = it;
-    } else {
-        k3_push_global(G, S.b_ev[b], s, e);  // restart at ps = s elsewhere: redundant scans, same result
-    }
-}
-
 __device__ __forceinline__ int k3_forced(const K3Params &P, int s, int e)
 {
     const long long a = (long long)s + P.MW, b = (long long)e - P.mw;
@@ -578,46 +576,128 @@ __device__ __forceinline__ int k3_window_end(const K3Params &P, const K3Item &it
     return (int)(pe_l < it.e ? pe_l : it.e);
 }
 
-// Apply a scan result to an item in local mode (cparsers.pyx:194-203).
-__device__ __forceinline__ void k3_resolve_local(const K3Global &G, K3Shared &S, K3Item *next,
-                                                 const K3Params &P, const K3Item it, int x)
+__device__ __forceinline__ void k3_mark_full(K3Level &L, K3Count &C, int k)
 {
-    if (x >= 0) {
-        k3_emit(G, (int64_t)S.b_off[it.b], x);
-        if (k3_worth(P, it.s, x)) k3_push_local(G, S, next, P, it.b, it.s, x, it.s);
-        if (k3_worth(P, x, it.e)) k3_push_local(G, S, next, P, it.b, x, it.e, x);
-    } else {
-        k3_push_local(G, S, next, P, it.b, it.s, it.e, k3_next_ps(P, it.ps, it.e));
+    if (!(atomicOr(&L.flag[k], K3_FULL_FLAG) & K3_FULL_FLAG)) atomicAdd(&C.nfull, 1);
+}
+
+// The window loop of _recursive_split (cparsers.pyx:186-203) for interval `it` up to its next
+// scannable window, which is registered in level `nx`; forced max_width splits on the way are
+// emitted and their children handled the same way.  Run by ONE thread (many threads concurrently
+// for different intervals).  A level that is full hands the interval to the global queue.
+__device__ __noinline__ void k3_place(const K3Global *Gp, K3Shared *Sp, K3Level *nxp, K3Count *ncp,
+                                      const K3Params *Pp, int screen, K3Item it)
+{
+    const K3Global &G = *Gp;
+    K3Shared &S = *Sp;
+    K3Level &nx = *nxp;
+    K3Count &nc = *ncp;
+    const K3Params &P = *Pp;
+    const int mw = P.mw, MW = P.MW;
+    const int64_t off = (int64_t)S.off;
+    K3Item st[4];
+    int sp = 0;
+    for (;;) {
+        // ---- one interval ----
+        for (;;) {
+            const long long lim = (long long)it.e - 2LL * mw;
+            if (it.ps >= lim) {
+                if (it.e - it.s > MW) {
+                    const int x = k3_forced(P, it.s, it.e);
+                    k3_emit(G, off, x);
+                    K3Item l, r;
+                    l.s = it.s; l.e = x; l.ps = it.s; l.pad = 0;
+                    r.s = x; r.e = it.e; r.ps = x; r.pad = 0;
+                    const bool wl = k3_worth(P, l.s, l.e), wr = k3_worth(P, r.s, r.e);
+                    if (wl && wr) {
+                        if (sp < 4) st[sp++] = r; else k3_push_global(G, S.ev, r.s, r.e);
+                        it = l;
+                        continue;
+                    }
+                    if (wl) { it = l; continue; }
+                    if (wr) { it = r; continue; }
+                }
+                break;
+            }
+            if (it.ps > (long long)it.s + MW) {
+                const int x = k3_forced(P, it.s, it.e);
+                k3_emit(G, off, x);  // the left part is not revisited (cparsers.pyx:189-191)
+                if (!k3_worth(P, x, it.e)) break;
+                it.s = x; it.ps = x;
+                continue;
+            }
+            const int pe = k3_window_end(P, it);
+            if (pe - it.ps <= 2 * mw) { it.ps = k3_next_ps(P, it.ps, it.e); continue; }
+            // a window to scan: register it
+            const bool ok = screen && S.ebase != K3_NO_EBASE;
+            const unsigned nch = ok ? (unsigned)((pe - it.ps - 2 * mw + 1 + 31) >> 5) : 0u;
+            const unsigned old = atomicAdd(&nc.alloc, K3_ALLOC_SLOT | nch);
+            const unsigned slot = old >> 20;
+            if (slot >= (unsigned)K3_LIST) {
+                k3_push_global(G, S.ev, it.s, it.e);  // restart at ps = s elsewhere: redundant scans, same result
+                break;
+            }
+            nx.item[slot] = it;
+            nx.c0[slot] = (int)(old & (K3_ALLOC_SLOT - 1u));
+            nx.cn[slot] = (int)nch;
+            nx.flag[slot] = ok ? 0 : K3_FULL_FLAG;
+            if (!ok) atomicAdd(&nc.nfull, 1);
+            break;
+        }
+        if (sp == 0) break;
+        it = st[--sp];
     }
 }
 
-__device__ __forceinline__ void k3_request(K3Shared &S, int k, int i)
+// Apply the decision of a window scan (x = split position or -1) to its interval (cparsers.pyx:194-203).
+__device__ __forceinline__ void k3_resolve(const K3Global &G, K3Shared &S, K3Level &nx, K3Count &nc,
+                                           const K3Params &P, int screen, const K3Item it, int x)
 {
-    const int r = atomicAdd(&S.nreq, 1);
+    const int pe = k3_window_end(P, it);
+    atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * P.mw + 1));
+    atomicAdd(&S.scans, 1ull);
+    K3Item c;
+    c.pad = 0;
+    if (x >= 0) {
+        k3_emit(G, (int64_t)S.off, x);
+        if (k3_worth(P, it.s, x)) { c.s = it.s; c.e = x; c.ps = it.s; k3_place(&G, &S, &nx, &nc, &P, screen, c); }
+        if (k3_worth(P, x, it.e)) {
+            if (K3_SHARE > 0 && x - it.s >= K3_SHARE && it.e - x >= K3_SHARE) k3_push_global(G, S.ev, x, it.e);
+            else { c.s = x; c.e = it.e; c.ps = x; k3_place(&G, &S, &nx, &nc, &P, screen, c); }
+        }
+    } else {
+        c.s = it.s; c.e = it.e; c.ps = k3_next_ps(P, it.ps, it.e);
+        k3_place(&G, &S, &nx, &nc, &P, screen, c);
+    }
+}
+
+__device__ __forceinline__ void k3_request(K3Shared &S, K3Level &L, K3Count &C, int k, int i)
+{
+    const int r = atomicAdd(&C.nreq, 1);
     if (r < K3_REQ) { S.req_k[r] = k; S.req_i[r] = i; }
-    else atomicOr(&S.win_item[k], K3_FULL_FLAG);
+    else k3_mark_full(L, C, k);
 }
 
 // The (warp, window) pieces of a level: the level's chunks [0, nchunk) are dealt to
 // the warps in equal contiguous shares; f(slot, first_chunk_in_window, end_chunk_in_window)
 // is called for every window a warp's share touches.  Piece id = slot + warp.
 template <class F>
-__device__ __forceinline__ void k3_for_pieces(const K3Shared &S, int warp, int nwin, int nchunk, F f)
+__device__ __forceinline__ void k3_for_pieces(const K3Level &L, int warp, int nwin, int nchunk, F f)
 {
     const int per = (nchunk + K3_WARPS - 1) / K3_WARPS;
     const int c_lo = warp * per;
     const int c_hi = c_lo + per < nchunk ? c_lo + per : nchunk;
     if (c_lo >= c_hi) return;
-    int lo_s = 0, hi_s = nwin;  // largest slot with win_chunk0[slot] <= c_lo
+    int lo_s = 0, hi_s = nwin;  // largest slot with c0[slot] <= c_lo (the non-empty one among equals is the last)
     while (hi_s - lo_s > 1) {
         const int mid = (lo_s + hi_s) >> 1;
-        if (S.win_chunk0[mid] <= c_lo) lo_s = mid; else hi_s = mid;
+        if (L.c0[mid] <= c_lo) lo_s = mid; else hi_s = mid;
     }
     int slot = lo_s;
     int c = c_lo;
     while (c < c_hi) {
-        while (S.win_chunk0[slot + 1] <= c) ++slot;
-        const int w_c0 = S.win_chunk0[slot], w_c1 = S.win_chunk0[slot + 1];
+        while (L.c0[slot] + L.cn[slot] <= c) ++slot;
+        const int w_c0 = L.c0[slot], w_c1 = w_c0 + L.cn[slot];
         const int cb = w_c1 < c_hi ? w_c1 : c_hi;
         f(slot, c - w_c0, cb - w_c0);
         c = cb;
@@ -630,73 +710,52 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
     K3Shared &S = *reinterpret_cast<K3Shared *>(k3_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mw = P.mw, MW = P.MW, W = P.W;
-    const bool screen = G.screen && mw >= 1 && W <= K3_MAX_SCREEN_W;
-
-    if (tid == 0) {
-        S.carry = K3_NO_TICKET;
-        // few events per CTA: take them one at a time so that every CTA gets some
-        const long long cnt = (long long)G.ctr->n_events - (long long)G.ctr->ev_begin;
-        const long long per = cnt / (2LL * gridDim.x);
-        S.batch = per < 1 ? 1 : (per > K3_BATCH ? K3_BATCH : (int)per);
-    }
+    const int screen = (G.screen && mw >= 1 && W <= K3_MAX_SCREEN_W) ? 1 : 0;
 
     for (;;) {
         __syncthreads();
-        // ---- take up to S.batch tasks; wait only while holding none ------------------------
+        // ---- take a task -------------------------------------------------------------------
         if (tid == 0) {
-            int nb = 0;
-            while (nb < S.batch) {
-                unsigned long long h = S.carry;
-                if (h == K3_NO_TICKET) {
-                    if (nb > 0 && *((volatile unsigned long long *)&G.ctr->q_head) >=
-                                      *((volatile unsigned long long *)&G.ctr->q_tail))
-                        break;  // nothing is waiting right now
-                    h = atomicAdd(&G.ctr->q_head, 1ull);
-                }
-                bool ok = false;
-                for (;;) {
-                    if ((int64_t)h < G.q_cap && *((volatile int *)&G.ready[h]) != 0) { ok = true; break; }
-                    if (nb > 0) break;
-                    if (*((volatile long long *)&G.ctr->q_pending) <= 0) break;
-                    __nanosleep(256);
-                }
-                if (!ok) { S.carry = nb > 0 ? h : K3_NO_TICKET; break; }
-                S.carry = K3_NO_TICKET;
+            const unsigned long long h = atomicAdd(&G.ctr->q_head, 1ull);
+            bool ok = false;
+            for (;;) {
+                if ((int64_t)h < G.q_cap && *((volatile int *)&G.ready[h]) != 0) { ok = true; break; }
+                if (*((volatile long long *)&G.ctr->q_pending) <= 0) break;
+                __nanosleep(256);
+            }
+            S.have = ok ? 1 : 0;
+            if (ok) {
                 __threadfence();
                 const int4 t = __ldcg(reinterpret_cast<const int4 *>(&G.tasks[h]));
                 PPTask tk;
                 tk.ev = t.x; tk.s = t.y; tk.e = t.z; tk.flags = t.w;
-                S.b_task[nb] = tk;
-                S.b_ev[nb] = t.x;
-                S.b_off[nb] = (long long)G.ev_off[t.x];
-                ++nb;
+                S.task = tk;
+                S.ev = t.x;
+                S.off = (long long)G.ev_off[t.x];
+                // screening exponent base of the task: the variance of its whole interval (any value within
+                // 2^+-127 of the candidates' variances will do; the validity test checks each candidate)
+                K3GlobalCC a;
+                a.g = G.cc + S.off;
+                int ebase = 0;
+                const bool eok = screen && k3_window_ebase(k3_var(a.at(tk.e - 1), a.at(tk.s - 1), tk.e - tk.s), ebase);
+                S.ebase = eok ? ebase : K3_NO_EBASE;
             }
-            S.nb = nb;
             S.cand = 0;
             S.scans = 0;
             S.exact = 0;
-            S.nA = 0;
+            for (int q = 0; q < 3; ++q) {
+                S.cnt[q].alloc = 0; S.cnt[q].nfull = 0; S.cnt[q].nreq = 0; S.cnt[q].nrescan = 0; S.cnt[q].nmulti = 0;
+            }
         }
         __syncthreads();
-        const int nb = S.nb;
-        if (nb == 0) break;
-        // screening exponent base of every task: the variance of its whole interval (any value
-        // within 2^+-127 of the candidates' variances will do; the validity test checks each one)
-        if (tid < nb) {
-            const PPTask tk = S.b_task[tid];
-            K3GlobalCC a;
-            a.g = G.cc + S.b_off[tid];
-            int ebase = 0;
-            const bool ok = screen && k3_window_ebase(k3_var(a.at(tk.e - 1), a.at(tk.s - 1), tk.e - tk.s), ebase);
-            S.b_ebase[tid] = ok ? ebase : K3_NO_EBASE;
-        }
+        if (!S.have) break;
 
-        // ---- spine mode: intervals too long to resolve locally, one task after the other ---
-        for (int bt = 0; bt < nb; ++bt) {
-            const int ev = S.b_ev[bt];
-            const int64_t off = (int64_t)S.b_off[bt];
-            int s = S.b_task[bt].s;
-            const int e = S.b_task[bt].e;
+        // ---- spine mode: an interval too long to resolve locally ---------------------------------
+        {
+            const int ev = S.ev;
+            const int64_t off = (int64_t)S.off;
+            int s = S.task.s;
+            const int e = S.task.e;
             K3GlobalCC acc;
             acc.g = G.cc + off;
             int ps = s;
@@ -739,258 +798,218 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
             }
             if (!done && tid == 0) {
                 K3Item it;
-                it.s = s; it.e = e; it.ps = ps; it.b = bt;
-                S.list[0][S.nA++] = it;
+                it.s = s; it.e = e; it.ps = ps; it.pad = 0;
+                k3_place(&G, &S, &S.lv[0], &S.cnt[0], &P, screen, it);
             }
         }
 
-        // ---- local mode: the subtrees of all tasks of the batch, level by level ---------------
-        {
-            int cur = 0;
+        // ---- local mode: the subtree of the task, level by level.  A level normally costs two barriers:
+        //      SCREEN | barrier | DECIDE (+ resolve, which registers the next level's windows) | barrier ----
+        int cur = 0, ci = 0;
+        __syncthreads();  // the spine's registration into level 0
+        for (;;) {
+            K3Level &L = S.lv[cur], &NX = S.lv[cur ^ 1];
+            K3Count &C = S.cnt[ci], &NC = S.cnt[ci == 2 ? 0 : ci + 1];
+            const unsigned al = C.alloc;
+            int nwin = (int)(al >> 20);
+            int nchunk = (int)(al & (K3_ALLOC_SLOT - 1u));
+            if (nwin == 0) break;
+            if (nwin > K3_LIST) {  // the windows past the list went to the global queue; their chunks are the tail
+                nwin = K3_LIST;
+                nchunk = L.c0[K3_LIST - 1] + L.cn[K3_LIST - 1];
+            }
+            const int per = (nchunk + K3_WARPS - 1) / K3_WARPS;
+            const double2 *ccg = G.cc + S.off;
+            K3GlobalCC acc;
+            acc.g = ccg;
+            const int ebase = S.ebase;
+            // step 1: SCREEN -- every lane keeps the two smallest keys of its candidates of a piece
+            k3_for_pieces(L, warp, nwin, nchunk, [&](int slot, int ca, int cb) {
+                const K3Item it = L.item[slot];
+                const int w_pe = k3_window_end(P, it);
+                const int w_last = w_pe - mw;
+                const int i_end = it.ps + mw + cb * 32 - 1;
+                const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
+                K3Scr a;
+                k3_scr_init(a);
+                k3_screen_lane(ccg, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, it.ps + mw + ca * 32 + lane,
+                               i_end < w_last ? i_end : w_last, 32, a);
+                unsigned long long K1, K2;
+                int I1;
+                bool bad;
+                k3_warp_summary(a, K1, K2, I1, bad);
+                // the window's own n log V in the same fixed-point units (same error bound as a candidate side)
+                unsigned long long kt = 0ull;
+                const unsigned nw = (unsigned)(w_pe - it.ps);
+                const bool tok = k3_side(__dsub_rn(w_hi.x, w_lo.x), __dsub_rn(w_hi.y, w_lo.y), __ldg(G.RN + nw), nw,
+                                         ebase, kt);
+                if (lane == 0) {
+                    S.pc_k1[slot + warp] = K1;
+                    S.pc_k2[slot + warp] = K2;
+                    S.pc_i1[slot + warp] = ((I1 - it.ps) & 0x1fffffff) | (bad ? K3_BAD_FLAG : 0);
+                    S.pc_kt[slot + warp] = tok ? kt : K3_NOKEY;
+                }
+            });
             __syncthreads();
-            for (;;) {
-                const int nA = S.nA;
-                if (nA == 0) break;
-                K3Item *A = S.list[cur], *Bn = S.list[cur ^ 1];
-                __syncthreads();  // everyone has read nA
-                if (tid == 0) { S.nB = 0; S.nwin = 0; S.nreq = 0; S.nchunk = 0; S.nrescan = 0; }
-                if (tid == K3_THREADS - 1) {
-                    // CTAs waiting for work (claimed tickets without a task)
-                    const long long d = (long long)*((volatile unsigned long long *)&G.ctr->q_head) -
-                                        (long long)*((volatile unsigned long long *)&G.ctr->q_tail);
-                    S.donate = (K3_CFG_DONATE && d > 0) ? (int)(d > 16 ? 16 : d) : 0;
+            // step 2: DECIDE -- thread per window.  Minimum over the window's pieces; one contender within 2 eps of
+            // it whose screened gain is clear of min_gain by more than the bound is decided without any exact
+            // arithmetic and resolved on the spot; everything else asks for exact values.
+            if (tid == 0) {  // the set level L+2 will register into; its last readers passed the barrier above
+                K3Count &Z = S.cnt[ci == 0 ? 2 : ci - 1];
+                Z.alloc = 0; Z.nfull = 0; Z.nreq = 0; Z.nrescan = 0; Z.nmulti = 0;
+            }
+            for (int k = tid; k < nwin; k += K3_THREADS) {
+                const int c0 = L.c0[k], cn = L.cn[k];
+                if (cn == 0) continue;  // registered for the exact scan
+                const int w_first = c0 / per, w_last = (c0 + cn - 1) / per;
+                unsigned long long gmin = K3_NOKEY;
+                bool bad = false;
+                for (int w = w_first; w <= w_last; ++w) {
+                    const unsigned long long k1 = S.pc_k1[k + w];
+                    gmin = k1 < gmin ? k1 : gmin;
+                    bad = bad || (S.pc_i1[k + w] & K3_BAD_FLAG);
                 }
-                __syncthreads();
-                // step 1: the window-loop bookkeeping of _recursive_split per item
-                for (int t = tid; t < nA; t += K3_THREADS) {
-                    const K3Item it = A[t];
-                    const int64_t off = (int64_t)S.b_off[it.b];
-                    const long long lim = (long long)it.e - 2LL * mw;
-                    if (it.ps >= lim) {
-                        if (it.e - it.s > MW) {
-                            const int x = k3_forced(P, it.s, it.e);
-                            k3_emit(G, off, x);
-                            if (k3_worth(P, it.s, x)) k3_push_local(G, S, Bn, P, it.b, it.s, x, it.s);
-                            if (k3_worth(P, x, it.e)) k3_push_local(G, S, Bn, P, it.b, x, it.e, x);
-                        }
-                    } else if (it.ps > (long long)it.s + MW) {
-                        const int x = k3_forced(P, it.s, it.e);
-                        k3_emit(G, off, x);
-                        if (k3_worth(P, x, it.e)) k3_push_local(G, S, Bn, P, it.b, x, it.e, x);
-                    } else {
-                        const int pe = k3_window_end(P, it);
-                        if (pe - it.ps <= 2 * mw) {
-                            k3_push_local(G, S, Bn, P, it.b, it.s, it.e, k3_next_ps(P, it.ps, it.e));
-                        } else {
-                            const int slot = atomicAdd(&S.nwin, 1);
-                            const bool ok = screen && S.b_ebase[it.b] != K3_NO_EBASE;
-                            S.win_item[slot] = ok ? t : (t | K3_FULL_FLAG);
-                            S.win_chunk0[slot] = ok ? (pe - it.ps - 2 * mw + 1 + 31) >> 5 : 0;  // chunk count for now
-                            S.best_key[slot] = 0ull;
-                            S.best_idx[slot] = 0x7fffffff;
-#if K3_CFG_WINLH
-                            K3GlobalCC wacc;
-                            wacc.g = G.cc + off;
-                            S.win_lo[slot] = wacc.at(it.ps - 1);
-                            S.win_hi[slot] = wacc.at(pe - 1);
-#endif
-                        }
+                if (bad || gmin == K3_NOKEY) { k3_mark_full(L, C, k); continue; }
+                const K3Item it = L.item[k];
+                const int nw = k3_window_end(P, it) - it.ps;
+                const unsigned long long eps2 = k3_eps2_key(nw);
+                const unsigned long long thr = gmin + eps2;
+                S.win_thr[k] = thr;
+                int nr = 0, i_one = 0;
+                bool rescan = false;
+                for (int w = w_first; w <= w_last; ++w) {
+                    if (S.pc_k2[k + w] <= thr) rescan = true;
+                    else if (S.pc_k1[k + w] <= thr) { ++nr; i_one = it.ps + (S.pc_i1[k + w] & 0x1fffffff); }
+                }
+#if K3_CFG_SURE
+                if (!rescan && nr == 1) {
+                    // i_one is the argmax (every other candidate is more than 2 eps worse).  Its gain is
+                    // tot - (low + high); screened: (kt - gmin) * ln2 / 2^23 with error <= 2 eps (+ conversions).
+                    const unsigned long long kt = S.pc_kt[k + w_first];
+                    if (kt != K3_NOKEY) {
+                        const double d = (double)(long long)(kt - gmin);
+                        const double want = P.min_gain * K3_KEY_PER_NAT;
+                        const double margin = (double)eps2 + 64.0;
+                        if (d > want + margin) { k3_resolve(G, S, NX, NC, P, screen, it, i_one); continue; }
+                        if (d < want - margin) { k3_resolve(G, S, NX, NC, P, screen, it, -1); continue; }
                     }
                 }
+#endif
+                if (rescan || nr > 1) {  // several contenders: two-phase argmax over their exact gains
+                    atomicOr(&L.flag[k], K3_MULTI_FLAG);
+                    atomicAdd(&C.nmulti, 1);
+                    S.best_key[k] = 0ull;
+                    S.best_idx[k] = 0x7fffffff;
+                }
+                if (rescan) atomicAdd(&C.nrescan, 1);
+                for (int w = w_first; w <= w_last; ++w) {
+                    if (S.pc_k2[k + w] <= thr) S.pc_i1[k + w] |= K3_RESCAN_FLAG;
+                    else if (S.pc_k1[k + w] <= thr) k3_request(S, L, C, k, it.ps + (S.pc_i1[k + w] & 0x1fffffff));
+                }
+            }
+            __syncthreads();
+            bool more_work = false;
+            // step 2': pieces with several contenders are screened again, every contender is requested
+            if (C.nrescan) {
+                more_work = true;
+                k3_for_pieces(L, warp, nwin, nchunk, [&](int slot, int ca, int cb) {
+                    if (!(S.pc_i1[slot + warp] & K3_RESCAN_FLAG)) return;
+                    if (L.flag[slot] & K3_FULL_FLAG) return;  // request list overflowed: exact scan decides
+                    const K3Item it = L.item[slot];
+                    const int w_pe = k3_window_end(P, it);
+                    const int w_last = w_pe - mw;
+                    int i_end = it.ps + mw + cb * 32 - 1;
+                    i_end = i_end < w_last ? i_end : w_last;
+                    const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
+                    const unsigned long long thr = S.win_thr[slot];
+                    for (int i = it.ps + mw + ca * 32 + lane; i <= i_end; i += 32) {
+                        unsigned long long key;
+                        k3_screen_key_at(ccg, w_lo, w_hi, it.ps, w_pe, i, G.RN, ebase, key);
+                        if (key <= thr) k3_request(S, L, C, slot, i);
+                    }
+                });
                 __syncthreads();
-                const int nwin = S.nwin;
-                if (screen) {
-                    // exclusive prefix of the chunk counts (warp 0), in place; other warps clear the piece records
-                    if (warp == 0) {
-                        int carry = 0;
-                        for (int b0 = 0; b0 < nwin; b0 += 32) {
-                            const int v = b0 + lane < nwin ? S.win_chunk0[b0 + lane] : 0;
-                            int inc = v;
-#pragma unroll
-                            for (int d = 1; d < 32; d <<= 1) {
-                                const int t = __shfl_up_sync(PP_FULL, inc, d);
-                                if (lane >= d) inc += t;
-                            }
-                            if (b0 + lane < nwin) S.win_chunk0[b0 + lane] = carry + inc - v;
-                            carry += __shfl_sync(PP_FULL, inc, 31);
-                        }
-                        if (lane == 0) { S.win_chunk0[nwin] = carry; S.nchunk = carry; }
-                    } else {
-                        for (int p = tid - 32; p < nwin + K3_WARPS; p += K3_THREADS - 32) {
-                            S.pc_k1[p] = K3_NOKEY;
-                            S.pc_k2[p] = K3_NOKEY;
-                            S.pc_i1[p] = 0;
-                        }
+            }
+            // step 3: EXACT evaluation of the requests, 3 lanes per request (tot / low / high).  A window with a
+            // single contender is resolved on the spot.
+            const int nreq = C.nreq < K3_REQ ? C.nreq : K3_REQ;
+            if (nreq) {
+                more_work = true;
+                for (int r0 = 0; r0 < nreq; r0 += 10 * K3_WARPS) {
+                    const int part = lane % 3;
+                    const int r = r0 + warp * 10 + lane / 3;
+                    const bool act = lane < 30 && r < nreq;
+                    double v = 0.0;
+                    int k = 0, i = 0, fl = 0;
+                    K3Item it;
+                    it.s = it.e = it.ps = it.pad = 0;
+                    if (act) {
+                        k = S.req_k[r];
+                        i = S.req_i[r];
+                        it = L.item[k];
+                        fl = L.flag[k];
+                        const int w_ps = it.ps, w_pe = k3_window_end(P, it);
+                        const double2 lo = acc.at(w_ps - 1), hi = acc.at(w_pe - 1), mid = acc.at(i - 1);
+                        if (part == 0) v = k3_exact_tot(lo, hi, w_ps, w_pe);
+                        else if (part == 1) v = __dmul_rn((double)(i - w_ps), log(k3_var(mid, lo, i - w_ps)));
+                        else v = __dmul_rn((double)(w_pe - i), log(k3_var(hi, mid, w_pe - i)));
                     }
-                    __syncthreads();
-                    const int nchunk = S.nchunk;
-                    const int per = (nchunk + K3_WARPS - 1) / K3_WARPS;
-                    // step 2: SCREEN -- every lane keeps the two smallest keys of its candidates of a piece
-                    k3_for_pieces(S, warp, nwin, nchunk, [&](int slot, int ca, int cb) {
-                        const K3Item it = A[S.win_item[slot]];
-                        const double2 *ccg = G.cc + S.b_off[it.b];
-                        K3GlobalCC acc;
-                        acc.g = ccg;
-                        const int w_pe = k3_window_end(P, it);
-                        const int w_last = w_pe - mw;
-                        const int i_end = it.ps + mw + cb * 32 - 1;
-#if K3_CFG_WINLH
-                        const double2 w_lo = S.win_lo[slot], w_hi = S.win_hi[slot];
-#else
-                        const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
-#endif
-                        K3Scr a;
-                        k3_scr_init(a);
-                        k3_screen_lane(ccg, w_lo, w_hi, it.ps, w_pe, S.b_ebase[it.b], G.RN,
-                                       it.ps + mw + ca * 32 + lane, i_end < w_last ? i_end : w_last, 32, a);
-                        unsigned long long K1, K2;
-                        int I1;
-                        bool bad;
-                        k3_warp_summary(a, K1, K2, I1, bad);
-                        if (lane == 0) {
-                            S.pc_k1[slot + warp] = K1;
-                            S.pc_k2[slot + warp] = K2;
-                            S.pc_i1[slot + warp] = ((I1 - it.ps) & 0x3fffffff) | (bad ? K3_BAD_FLAG : 0);
-                        }
-                    });
-                    __syncthreads();
-                    // step 3a: window minimum over its pieces; pieces within 2 eps of it ask for exact values
-                    for (int k = tid; k < nwin; k += K3_THREADS) {
-                        const int c0 = S.win_chunk0[k], c1 = S.win_chunk0[k + 1];
-                        if (c1 == c0) continue;  // already marked for the exact scan
-                        const int w_first = c0 / per, w_last = (c1 - 1) / per;
-                        unsigned long long gmin = K3_NOKEY;
-                        bool bad = false;
-                        for (int w = w_first; w <= w_last; ++w) {
-                            const unsigned long long k1 = S.pc_k1[k + w];
-                            gmin = k1 < gmin ? k1 : gmin;
-                            bad = bad || (S.pc_i1[k + w] & K3_BAD_FLAG);
-                        }
-                        if (bad || gmin == K3_NOKEY) { S.win_item[k] |= K3_FULL_FLAG; continue; }
-                        const K3Item it = A[S.win_item[k]];
-                        const unsigned long long thr = gmin + k3_eps2_key(k3_window_end(P, it) - it.ps);
-                        S.win_thr[k] = thr;
-                        for (int w = w_first; w <= w_last; ++w) {
-                            if (S.pc_k2[k + w] <= thr) {
-                                S.pc_i1[k + w] |= K3_RESCAN_FLAG;
-                                atomicAdd(&S.nrescan, 1);
-                            } else if (S.pc_k1[k + w] <= thr) {
-                                k3_request(S, k, it.ps + (S.pc_i1[k + w] & 0x3fffffff));
-                            }
-                        }
-                    }
-                    __syncthreads();
-                    // step 3a': pieces with several contenders are screened again, every contender is requested
-                    if (S.nrescan) {
-                        k3_for_pieces(S, warp, nwin, nchunk, [&](int slot, int ca, int cb) {
-                            if (!(S.pc_i1[slot + warp] & K3_RESCAN_FLAG)) return;
-                            const int entry = S.win_item[slot];
-                            if (entry & K3_FULL_FLAG) return;  // request list overflowed: exact scan decides
-                            const K3Item it = A[entry & ~K3_FULL_FLAG];
-                            const double2 *ccg = G.cc + S.b_off[it.b];
-                            K3GlobalCC acc;
-                            acc.g = ccg;
-                            const int w_pe = k3_window_end(P, it);
-                            const int w_last = w_pe - mw;
-                            int i_end = it.ps + mw + cb * 32 - 1;
-                            i_end = i_end < w_last ? i_end : w_last;
-#if K3_CFG_WINLH
-                            const double2 w_lo = S.win_lo[slot], w_hi = S.win_hi[slot];
-#else
-                            const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
-#endif
-                            const unsigned long long thr = S.win_thr[slot];
-                            const int ebase = S.b_ebase[it.b];
-                            for (int i = it.ps + mw + ca * 32 + lane; i <= i_end; i += 32) {
-                                unsigned long long key;
-                                k3_screen_key_at(ccg, w_lo, w_hi, it.ps, w_pe, i, G.RN, ebase, key);
-                                if (key <= thr) k3_request(S, slot, i);
-                            }
-                        });
-                        __syncthreads();
-                    }
-                    // step 3b: EXACT evaluation of the requests; 3 lanes per request (tot / low / high)
-                    const int nreq = S.nreq < K3_REQ ? S.nreq : K3_REQ;
-                    for (int r0 = 0; r0 < nreq; r0 += 10 * K3_WARPS) {
-                        const int part = lane % 3;
-                        const int r = r0 + warp * 10 + lane / 3;
-                        const bool act = lane < 30 && r < nreq;
-                        double v = 0.0;
-                        int k = 0, i = 0, w_ps = 0, w_pe = 0;
-                        if (act) {
-                            k = S.req_k[r];
-                            i = S.req_i[r];
-                            const K3Item it = A[S.win_item[k] & ~K3_FULL_FLAG];
-                            K3GlobalCC acc;
-                            acc.g = G.cc + S.b_off[it.b];
-                            w_ps = it.ps;
-                            w_pe = k3_window_end(P, it);
-#if K3_CFG_WINLH
-                            const double2 lo = S.win_lo[k], hi = S.win_hi[k], mid = acc.at(i - 1);
-#else
-                            const double2 lo = acc.at(w_ps - 1), hi = acc.at(w_pe - 1), mid = acc.at(i - 1);
-#endif
-                            if (part == 0) v = k3_exact_tot(lo, hi, w_ps, w_pe);
-                            else if (part == 1) v = __dmul_rn((double)(i - w_ps), log(k3_var(mid, lo, i - w_ps)));
-                            else v = __dmul_rn((double)(w_pe - i), log(k3_var(hi, mid, w_pe - i)));
-                        }
-                        const double low = __shfl_down_sync(PP_FULL, v, 1), high = __shfl_down_sync(PP_FULL, v, 2);
-                        if (act && part == 0) {
-                            const double g = __dsub_rn(v, __dadd_rn(low, high));   // cparsers.pyx:174
+                    const double low = __shfl_down_sync(PP_FULL, v, 1), high = __shfl_down_sync(PP_FULL, v, 2);
+                    if (act && part == 0) {
+                        const double g = __dsub_rn(v, __dadd_rn(low, high));   // cparsers.pyx:174
+                        if (fl & K3_MULTI_FLAG) {
                             S.req_g[r] = g;
                             if (g > P.min_gain) atomicMax(&S.best_key[k], k3_okey(g));
+                        } else if (!(fl & K3_FULL_FLAG)) {
+                            k3_resolve(G, S, NX, NC, P, screen, it, g > P.min_gain ? i : -1);
                         }
                     }
-                    if (tid == 0) atomicAdd(&S.exact, (unsigned long long)nreq);
+                }
+                if (tid == 0) atomicAdd(&S.exact, (unsigned long long)nreq);
+                if (C.nmulti) {
                     __syncthreads();
                     for (int r = tid; r < nreq; r += K3_THREADS) {
-                        const double g = S.req_g[r];
                         const int k = S.req_k[r];
+                        if (!(L.flag[k] & K3_MULTI_FLAG)) continue;
+                        const double g = S.req_g[r];
                         if (g > P.min_gain && k3_okey(g) == S.best_key[k]) atomicMin(&S.best_idx[k], S.req_i[r]);
                     }
                     __syncthreads();
-                    // step 4: resolve every window whose screening was conclusive
                     for (int k = tid; k < nwin; k += K3_THREADS) {
-                        const int entry = S.win_item[k];
-                        if (entry & K3_FULL_FLAG) continue;
-                        const K3Item it = A[entry];
-                        const int pe = k3_window_end(P, it);
-                        atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
-                        atomicAdd(&S.scans, 1ull);
-                        k3_resolve_local(G, S, Bn, P, it, S.best_key[k] ? S.best_idx[k] : -1);
+                        const int fl = L.flag[k];
+                        if ((fl & K3_MULTI_FLAG) && !(fl & K3_FULL_FLAG))
+                            k3_resolve(G, S, NX, NC, P, screen, L.item[k], S.best_key[k] ? S.best_idx[k] : -1);
                     }
                 }
-                // step 5: windows left for the exact scan (validation mode: all of them), whole CTA each
+            }
+            // step 4: windows left for the exact scan (validation mode: all of them), whole CTA each
+            if (C.nfull) {
+                more_work = true;
+                __syncthreads();
                 for (int k = 0; k < nwin; ++k) {
-                    const int entry = S.win_item[k];
-                    if (screen && !(entry & K3_FULL_FLAG)) continue;
-                    const K3Item it = A[entry & ~K3_FULL_FLAG];
-                    K3GlobalCC acc;
-                    acc.g = G.cc + S.b_off[it.b];
+                    if (!(L.flag[k] & K3_FULL_FLAG)) continue;
+                    const K3Item it = L.item[k];
                     const int pe = k3_window_end(P, it);
                     K3Best b = k3_scan_range(acc, it.ps, pe, mw, P.min_gain, tid, K3_THREADS);
                     b = k3_cta_reduce(b, S);
                     if (tid == 0) {
-                        atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * mw + 1));
-                        atomicAdd(&S.scans, 1ull);
                         if (screen) atomicAdd(&S.exact, (unsigned long long)(pe - it.ps - 2 * mw + 1));
-                        k3_resolve_local(G, S, Bn, P, it, b.x);
+                        k3_resolve(G, S, NX, NC, P, screen, it, b.x);
                     }
                 }
-                __syncthreads();
-                if (tid == 0) S.nA = S.nB < K3_LIST ? S.nB : K3_LIST;
-                cur ^= 1;
-                __syncthreads();
             }
+            if (more_work) __syncthreads();  // the next level is complete
+            cur ^= 1;
+            ci = ci == 2 ? 0 : ci + 1;
         }
         __syncthreads();
         if (tid == 0) {
             atomicAdd(&G.ctr->n_cand, S.cand);
             atomicAdd(&G.ctr->n_scan, S.scans);
             atomicAdd(&G.ctr->n_exact, S.exact);
-            atomicAdd(&G.ctr->n_tasks, (unsigned long long)nb);
+            atomicAdd(&G.ctr->n_tasks, 1ull);
             __threadfence();
-            atomicAdd((unsigned long long *)&G.ctr->q_pending, (unsigned long long)(-(long long)nb));
+            atomicAdd((unsigned long long *)&G.ctr->q_pending, (unsigned long long)(-1LL));
         }
     }
 }

@@ -20,7 +20,10 @@ def line_map(lib, kernel):
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=d, stdout=subprocess.DEVNULL)
     cubin = [os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cubin")][0]
     txt = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
-    out, active, loc = [], False, None
+    # a group of "//## File" lines (innermost inlined location first, outermost last) precedes the
+    # instructions it applies to; SASS_DEPTH picks the entry (0 = innermost, -1 = outermost call site)
+    depth = int(os.environ.get("SASS_DEPTH", "0"))
+    out, active, loc, group, in_group = [], False, None, [], False
     for ln in txt:
         if ln.startswith("//---") and ".text." in ln:
             active = kernel in ln
@@ -29,9 +32,15 @@ def line_map(lib, kernel):
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', ln)
         if m:
-            loc = (os.path.basename(m.group(1)), int(m.group(2)), m.group(3))
+            if not in_group:
+                group, in_group = [], True
+            group.append((os.path.basename(m.group(1)), int(m.group(2)), m.group(3)))
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
+            if in_group:
+                own = [g for g in group if g[0].endswith((".cuh", ".cu"))] or group
+                loc = own[depth] if -len(own) <= depth < len(own) else own[-1]
+                in_group = False
             out.append(loc)
     return out
 
@@ -62,7 +71,7 @@ def main():
     ts = sum(a[1] for a in agg.values())
     print("total warp instructions %.0f, samples %.0f" % (ti, ts))
     srcs = {}
-    for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][1 if os.environ.get('SASS_SORT') == 'samples' else 0])[:top]:
         if f not in srcs:
             p = os.path.join(os.path.dirname(os.path.abspath(lib)), "csrc", f)
             srcs[f] = open(p).read().splitlines() if os.path.exists(p) else []
