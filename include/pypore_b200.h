@@ -74,7 +74,12 @@ void pp_host_free(pp_ctx *ctx, void *p);
 /* Options: PP_OPT_SCREEN (default 1) -- 1: two-stage split search (bounded-error
  * screening of every candidate, exact arithmetic for the contenders); 0: exact
  * arithmetic for every candidate (validation mode, same results, many times slower). */
-enum pp_option { PP_OPT_SCREEN = 0 };
+enum pp_option {
+    PP_OPT_SCREEN = 0,
+    /* PP_OPT_SPINE (default 1) -- 1: events longer than the locally resolvable interval are first walked window by
+     * window by a whole 1024-thread CTA each (k3_spine); 0: the 128-thread work-queue CTAs walk them (same results). */
+    PP_OPT_SPINE = 1
+};
 int pp_set_option(pp_ctx *ctx, int option, int64_t value);
 /* Number of kernel launches this context has issued since creation. */
 int64_t pp_launch_count(pp_ctx *ctx);

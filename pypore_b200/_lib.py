@@ -248,6 +248,10 @@ class Context(object):
         """Two-stage split search (default on); off = exact arithmetic for every candidate."""
         self.set_option(0, 1 if on else 0)
 
+    def set_spine_kernel(self, on):
+        """Long events walked by the 1024-thread spine kernel first (default on); off = by the work-queue CTAs."""
+        self.set_option(1, 1 if on else 0)
+
     @property
     def launch_count(self):
         return int(self._L.pp_launch_count(self._h))

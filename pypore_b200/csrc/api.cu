@@ -58,6 +58,7 @@ struct pp_ctx {
 
     // K2/K3
     DevBuf cc, bits, tasks, ready, block_count, block_off, inexact, Ttab, ev_tile_off, k2_bits, k2_tiles;
+    int opt_spine = 1;
     int T_len = 0;
     int opt_screen = 1;
     int64_t q_cap = 0;
@@ -460,8 +461,12 @@ int enqueue_search(pp_ctx *ctx, int mw, int MW, int W, double min_gain)
     G.screen = ctx->opt_screen;
     K3Params P;
     P.mw = mw; P.MW = MW; P.W = W; P.min_gain = min_gain;
-    k3_init_queue<<<ctx->sm_count, 256, 0, ctx->stream>>>(G);
+    k3_init_queue<<<ctx->sm_count, 256, 0, ctx->stream>>>(G, ctx->opt_spine);
     LAUNCHED(ctx);
+    if (ctx->opt_spine) {  // events longer than K3_CAP: their window chain first, a whole CTA per scan
+        k3_spine<<<ctx->sm_count, K3S_THREADS, 0, ctx->stream>>>(G, P);
+        LAUNCHED(ctx);
+    }
     k3_split<<<ctx->sm_count * K3_CTAS_PER_SM, K3_THREADS, K3_SMEM_BYTES, ctx->stream>>>(G, P);
     LAUNCHED(ctx);
     return PP_OK;
@@ -659,6 +664,7 @@ int pp_set_option(pp_ctx *ctx, int option, int64_t value)
     if (!ctx) return PP_ERR_ARG;
     switch (option) {
     case PP_OPT_SCREEN: ctx->opt_screen = value ? 1 : 0; return PP_OK;
+    case PP_OPT_SPINE: ctx->opt_spine = value ? 1 : 0; return PP_OK;
     default: return fail(ctx, PP_ERR_ARG, "unknown option %d", option);
     }
 }

@@ -34,6 +34,7 @@ struct PPCounters {
     unsigned long long sel_next_run;  // first run the next incremental select looks at
     unsigned long long ev_begin;
     unsigned long long tile_begin;
+    unsigned long long n_long;        // events of the current search that k3_spine walks first
     unsigned int overflow;            // bit0 runs, bit1 queue, bit2 segments, bit3 filter-too-short
     unsigned int first_below;         // below-threshold bit of sample 0
 };

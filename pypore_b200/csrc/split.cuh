@@ -61,6 +61,13 @@ constexpr int K3_LIST = K3_CFG_LIST;  // windows per level (more go to the globa
 constexpr int K3_REQ = K3_CFG_LIST;   // exact-evaluation requests per level
 constexpr int K3_SHARE = K3_CFG_SHARE; // both children of a split at least this long: the right one goes to the
                                        // global queue for another CTA (finer tasks, shorter tail); 0 = keep both
+#ifndef K3_CFG_IDLE_SHARE
+#define K3_CFG_IDLE_SHARE 512
+#endif
+constexpr int K3_IDLE_SHARE = K3_CFG_IDLE_SHARE;  // while CTAs are waiting for work: right children of splits whose
+                                                  // halves are both at least this long go to the global queue; 0 = off.
+// Only acts when the launch starts with fewer than two tasks per CTA (measured with 512: 500 events 0.252 -> 0.216 ms;
+// with a full queue sharing loses: the pushes' gpu-scope fences cost more than the tail they fill).
 constexpr int K3_PIECES = K3_LIST + K3_WARPS;  // (warp, window) screening records per level
 // Measured on B200 at BASELINE configs[1] (profiles/r01f_k3_variants.txt): taking 2 events per CTA
 // or handing intervals to idle CTAs both LOST time (the search is bound by L2 -> SM traffic of the
@@ -144,12 +151,16 @@ struct K3Shared {
     double red_g[K3_WARPS];
     unsigned long long red_k[K3_WARPS];
     int red_x[K3_WARPS];
+    int share;                             // right children this level may hand to CTAs that wait for work
+    int few;                               // the launch started with fewer than two tasks per CTA
     int have;                              // a task was taken
     int ev;                                // current task: event, flat offset, screening exponent base
     long long off;
     int ebase;                             // biased exponent of the task's variance - 127, or K3_NO_EBASE
     PPTask task;
     unsigned long long cand, scans, exact;
+    K3Global G;                            // copies of the kernel parameters for the out-of-line bookkeeping
+    K3Params P;
 };
 
 constexpr size_t K3_SMEM_BYTES = sizeof(K3Shared);
@@ -585,14 +596,15 @@ __device__ __forceinline__ void k3_mark_full(K3Level &L, K3Count &C, int k)
 // scannable window, which is registered in level `nx`; forced max_width splits on the way are
 // emitted and their children handled the same way.  Run by ONE thread (many threads concurrently
 // for different intervals).  A level that is full hands the interval to the global queue.
-__device__ __noinline__ void k3_place(const K3Global *Gp, K3Shared *Sp, K3Level *nxp, K3Count *ncp,
-                                      const K3Params *Pp, int screen, K3Item it)
+__device__ __noinline__ void k3_place(K3Shared *Sp, K3Level *nxp, K3Count *ncp, int screen, K3Item it)
 {
-    const K3Global &G = *Gp;
+    // the kernel parameters are read from their shared-memory copy: taking the address of the parameter structs
+    // themselves would force a local-memory copy that the whole kernel then reads instead of the constant bank
     K3Shared &S = *Sp;
+    const K3Global &G = S.G;
+    const K3Params &P = S.P;
     K3Level &nx = *nxp;
     K3Count &nc = *ncp;
-    const K3Params &P = *Pp;
     const int mw = P.mw, MW = P.MW;
     const int64_t off = (int64_t)S.off;
     K3Item st[4];
@@ -650,7 +662,15 @@ __device__ __noinline__ void k3_place(const K3Global *Gp, K3Shared *Sp, K3Level 
 }
 
 // Apply the decision of a window scan (x = split position or -1) to its interval (cparsers.pyx:194-203).
-__device__ __forceinline__ void k3_resolve(const K3Global &G, K3Shared &S, K3Level &nx, K3Count &nc,
+#ifndef K3_CFG_NOINLINE_RESOLVE
+#define K3_CFG_NOINLINE_RESOLVE 0  // measured: out of line 1.20 ms vs 1.15 ms inline
+#endif
+#if K3_CFG_NOINLINE_RESOLVE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void k3_resolve(const K3Global &G, K3Shared &S, K3Level &nx, K3Count &nc,
                                            const K3Params &P, int screen, const K3Item it, int x)
 {
     const int pe = k3_window_end(P, it);
@@ -660,14 +680,17 @@ __device__ __forceinline__ void k3_resolve(const K3Global &G, K3Shared &S, K3Lev
     c.pad = 0;
     if (x >= 0) {
         k3_emit(G, (int64_t)S.off, x);
-        if (k3_worth(P, it.s, x)) { c.s = it.s; c.e = x; c.ps = it.s; k3_place(&G, &S, &nx, &nc, &P, screen, c); }
+        if (k3_worth(P, it.s, x)) { c.s = it.s; c.e = x; c.ps = it.s; k3_place(&S, &nx, &nc, screen, c); }
         if (k3_worth(P, x, it.e)) {
-            if (K3_SHARE > 0 && x - it.s >= K3_SHARE && it.e - x >= K3_SHARE) k3_push_global(G, S.ev, x, it.e);
-            else { c.s = x; c.e = it.e; c.ps = x; k3_place(&G, &S, &nx, &nc, &P, screen, c); }
+            bool away = K3_SHARE > 0 && x - it.s >= K3_SHARE && it.e - x >= K3_SHARE;
+            if (!away && K3_IDLE_SHARE > 0 && S.share > 0 && x - it.s >= K3_IDLE_SHARE && it.e - x >= K3_IDLE_SHARE)
+                away = atomicSub(&S.share, 1) > 0;
+            if (away) k3_push_global(G, S.ev, x, it.e);
+            else { c.s = x; c.e = it.e; c.ps = x; k3_place(&S, &nx, &nc, screen, c); }
         }
     } else {
         c.s = it.s; c.e = it.e; c.ps = k3_next_ps(P, it.ps, it.e);
-        k3_place(&G, &S, &nx, &nc, &P, screen, c);
+        k3_place(&S, &nx, &nc, screen, c);
     }
 }
 
@@ -704,6 +727,52 @@ __device__ __forceinline__ void k3_for_pieces(const K3Level &L, int warp, int nw
     }
 }
 
+// Step 1 of a level: SCREEN.  Kept out of line so that the hot loop has the whole register budget to itself
+// (the level loop's long-lived values are saved once per level at the call, not spilled inside the loop).
+#ifndef K3_CFG_NOINLINE_SCREEN
+#define K3_CFG_NOINLINE_SCREEN 0   // measured: out of line 1.33 ms vs 1.20 ms inline
+#endif
+#if K3_CFG_NOINLINE_SCREEN
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void k3_screen_level(const K3Global &G, const K3Params &P, K3Shared &S, int cur, int nwin, int nchunk)
+{
+    const K3Level &L = S.lv[cur];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int mw = P.mw;
+    const double2 *ccg = G.cc + S.off;
+    K3GlobalCC acc;
+    acc.g = ccg;
+    const int ebase = S.ebase;
+    k3_for_pieces(L, warp, nwin, nchunk, [&](int slot, int ca, int cb) {
+        const K3Item it = L.item[slot];
+        const int w_pe = k3_window_end(P, it);
+        const int w_last = w_pe - mw;
+        const int i_end = it.ps + mw + cb * 32 - 1;
+        const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
+        K3Scr a;
+        k3_scr_init(a);
+        k3_screen_lane(ccg, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, it.ps + mw + ca * 32 + lane,
+                       i_end < w_last ? i_end : w_last, 32, a);
+        unsigned long long K1, K2;
+        int I1;
+        bool bad;
+        k3_warp_summary(a, K1, K2, I1, bad);
+        // the window's own n log V in the same fixed-point units (same error bound as a candidate side)
+        unsigned long long kt = 0ull;
+        const unsigned nw = (unsigned)(w_pe - it.ps);
+        const bool tok = k3_side(__dsub_rn(w_hi.x, w_lo.x), __dsub_rn(w_hi.y, w_lo.y), __ldg(G.RN + nw), nw, ebase, kt);
+        if (lane == 0) {
+            S.pc_k1[slot + warp] = K1;
+            S.pc_k2[slot + warp] = K2;
+            S.pc_i1[slot + warp] = ((I1 - it.ps) & 0x1fffffff) | (bad ? K3_BAD_FLAG : 0);
+            S.pc_kt[slot + warp] = tok ? kt : K3_NOKEY;
+        }
+    });
+}
+
 __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global G, K3Params P)
 {
     extern __shared__ __align__(16) unsigned char k3_smem[];
@@ -712,6 +781,12 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
     const int mw = P.mw, MW = P.MW, W = P.W;
     const int screen = (G.screen && mw >= 1 && W <= K3_MAX_SCREEN_W) ? 1 : 0;
 
+    if (tid == 0) {
+        S.G = G;
+        S.P = P;
+        S.few = ((long long)G.ctr->n_events - (long long)G.ctr->ev_begin) < 2LL * gridDim.x ? 1 : 0;
+    }
+    if (tid == 0 && blockIdx.x == 0) G.ctr->n_long = 0ull;  // k3_spine is done with it; ready for the next search
     for (;;) {
         __syncthreads();
         // ---- take a task -------------------------------------------------------------------
@@ -740,6 +815,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                 const bool eok = screen && k3_window_ebase(k3_var(a.at(tk.e - 1), a.at(tk.s - 1), tk.e - tk.s), ebase);
                 S.ebase = eok ? ebase : K3_NO_EBASE;
             }
+            S.share = 0;
             S.cand = 0;
             S.scans = 0;
             S.exact = 0;
@@ -758,7 +834,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
             const int e = S.task.e;
             K3GlobalCC acc;
             acc.g = G.cc + off;
-            int ps = s;
+            int ps = s + S.task.flags;  // k3_spine hands over the remainder of an event with its window position
             bool done = false;
             while ((long long)e - s > K3_CAP) {
                 const long long lim = (long long)e - 2LL * mw;
@@ -799,7 +875,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
             if (!done && tid == 0) {
                 K3Item it;
                 it.s = s; it.e = e; it.ps = ps; it.pad = 0;
-                k3_place(&G, &S, &S.lv[0], &S.cnt[0], &P, screen, it);
+                k3_place(&S, &S.lv[0], &S.cnt[0], screen, it);
             }
         }
 
@@ -823,33 +899,18 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
             K3GlobalCC acc;
             acc.g = ccg;
             const int ebase = S.ebase;
+            // CTAs waiting for work hold tickets past the queue's tail; the two loads complete behind the screening
+            unsigned long long qh = 0ull, qt = 0ull;
+            if (K3_IDLE_SHARE > 0 && tid == 0 && S.few) {
+                qh = *((volatile unsigned long long *)&G.ctr->q_head);
+                qt = *((volatile unsigned long long *)&G.ctr->q_tail);
+            }
             // step 1: SCREEN -- every lane keeps the two smallest keys of its candidates of a piece
-            k3_for_pieces(L, warp, nwin, nchunk, [&](int slot, int ca, int cb) {
-                const K3Item it = L.item[slot];
-                const int w_pe = k3_window_end(P, it);
-                const int w_last = w_pe - mw;
-                const int i_end = it.ps + mw + cb * 32 - 1;
-                const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
-                K3Scr a;
-                k3_scr_init(a);
-                k3_screen_lane(ccg, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, it.ps + mw + ca * 32 + lane,
-                               i_end < w_last ? i_end : w_last, 32, a);
-                unsigned long long K1, K2;
-                int I1;
-                bool bad;
-                k3_warp_summary(a, K1, K2, I1, bad);
-                // the window's own n log V in the same fixed-point units (same error bound as a candidate side)
-                unsigned long long kt = 0ull;
-                const unsigned nw = (unsigned)(w_pe - it.ps);
-                const bool tok = k3_side(__dsub_rn(w_hi.x, w_lo.x), __dsub_rn(w_hi.y, w_lo.y), __ldg(G.RN + nw), nw,
-                                         ebase, kt);
-                if (lane == 0) {
-                    S.pc_k1[slot + warp] = K1;
-                    S.pc_k2[slot + warp] = K2;
-                    S.pc_i1[slot + warp] = ((I1 - it.ps) & 0x1fffffff) | (bad ? K3_BAD_FLAG : 0);
-                    S.pc_kt[slot + warp] = tok ? kt : K3_NOKEY;
-                }
-            });
+            k3_screen_level(G, P, S, cur, nwin, nchunk);
+            if (K3_IDLE_SHARE > 0 && tid == 0 && S.few) {
+                const long long waiting = (long long)(qh - qt);
+                S.share = waiting > 0 ? (int)(waiting > 64 ? 64 : waiting) : 0;
+            }
             __syncthreads();
             // step 2: DECIDE -- thread per window.  Minimum over the window's pieces; one contender within 2 eps of
             // it whose screened gain is clear of min_gain by more than the bound is decided without any exact
@@ -1014,6 +1075,227 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Long events: the right spine of _recursive_split, one 1024-thread CTA per event.
+//
+// The window loop over an interval longer than K3_CAP is sequential (the next window starts at
+// the split the current one finds), so its speed is the latency of ONE window
+// scan.  k3_spine runs before k3_split: every event longer than K3_CAP is walked by a whole
+// 1024-thread CTA (about ten candidates per thread and window, one barrier per scan in the common
+// case: per-warp summaries in shared memory, every thread derives the decision from them, and a
+// single contender whose screened gain clears min_gain by the error bound needs no exact
+// arithmetic).  Left children go to the global queue, the remainder (<= K3_CAP) follows as an
+// ordinary task with its window position; k3_split then resolves all of them.
+// ---------------------------------------------------------------------------
+constexpr int K3S_THREADS = 1024;
+constexpr int K3S_WARPS = K3S_THREADS / 32;
+
+struct K3SpineShared {
+    unsigned long long wk1[2][K3S_WARPS], wk2[2][K3S_WARPS];
+    int wi1[2][K3S_WARPS];
+    int wbad[2][K3S_WARPS];
+    double red_g[K3S_WARPS];
+    int red_x[K3S_WARPS];
+};
+
+// exact decision over per-thread partial results (rare path; two barriers)
+__device__ __forceinline__ K3Best k3_spine_reduce(K3Best b, K3SpineShared &S)
+{
+    const int tid = threadIdx.x;
+    b = k3_warp_reduce(b);
+    __syncthreads();
+    if ((tid & 31) == 0) { S.red_g[tid >> 5] = b.g; S.red_x[tid >> 5] = b.x; }
+    __syncthreads();
+    K3Best r;
+    r.g = S.red_g[0];
+    r.x = S.red_x[0];
+    for (int w = 1; w < K3S_WARPS; ++w) {
+        K3Best o;
+        o.g = S.red_g[w];
+        o.x = S.red_x[w];
+        r = k3_better(r, o);
+    }
+    return r;
+}
+
+// One window [ps,pe) scanned by the whole CTA; every thread returns the same split position (or -1).
+__device__ __forceinline__ int k3_spine_scan(const K3GlobalCC &acc, int ps, int pe, const K3Params &P, const K3Global &G,
+                                             K3SpineShared &S, int ebase, bool screen, int par, unsigned &nexact)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double2 lo = acc.at(ps - 1), hi = acc.at(pe - 1);
+    if (screen) {
+        K3Scr a;
+        k3_scr_init(a);
+        k3_screen_lane(acc.g, lo, hi, ps, pe, ebase, G.RN, ps + P.mw + tid, pe - P.mw, K3S_THREADS, a);
+        unsigned long long K1, K2;
+        int I1;
+        bool bad;
+        k3_warp_summary(a, K1, K2, I1, bad);
+        unsigned long long kt = 0ull;
+        const unsigned nw = (unsigned)(pe - ps);
+        const bool tok = k3_side(__dsub_rn(hi.x, lo.x), __dsub_rn(hi.y, lo.y), __ldg(G.RN + nw), nw, ebase, kt);
+        if (lane == 0) { S.wk1[par][warp] = K1; S.wk2[par][warp] = K2; S.wi1[par][warp] = I1; S.wbad[par][warp] = bad; }
+        __syncthreads();
+        unsigned long long gmin = K3_NOKEY;
+        bool anybad = false;
+#pragma unroll 8
+        for (int w = 0; w < K3S_WARPS; ++w) {
+            const unsigned long long k1 = S.wk1[par][w];
+            gmin = k1 < gmin ? k1 : gmin;
+            anybad = anybad || S.wbad[par][w];
+        }
+        if (!anybad && gmin != K3_NOKEY) {
+            const unsigned long long eps2 = k3_eps2_key(pe - ps);
+            const unsigned long long thr = gmin + eps2;
+            int nr = 0, i_one = -1;
+            bool rescan = false;
+#pragma unroll 8
+            for (int w = 0; w < K3S_WARPS; ++w) {
+                if (S.wk2[par][w] <= thr) rescan = true;
+                else if (S.wk1[par][w] <= thr) { ++nr; i_one = S.wi1[par][w]; }
+            }
+            if (!rescan && nr == 1 && tok) {
+                const double d = (double)(long long)(kt - gmin);
+                const double want = P.min_gain * K3_KEY_PER_NAT;
+                const double margin = (double)eps2 + 64.0;
+                if (d > want + margin) return i_one;
+                if (d < want - margin) return -1;
+            }
+            // contenders in the reference's exact arithmetic
+            K3Best b;
+            b.g = P.min_gain;
+            b.x = -1;
+            const double tot = k3_exact_tot(lo, hi, ps, pe);
+            if (a.k2 <= thr) {
+                const int last = pe - P.mw;
+                for (int i = ps + P.mw + tid; i <= last; i += K3S_THREADS) {
+                    unsigned long long key;
+                    k3_screen_key_at(acc.g, lo, hi, ps, pe, i, G.RN, ebase, key);
+                    if (key <= thr) {
+                        const double g = k3_exact_gain(lo, acc.at(i - 1), hi, ps, pe, i, tot);
+                        ++nexact;
+                        if (g > b.g) { b.g = g; b.x = i; }
+                    }
+                }
+            } else if (a.k1 <= thr) {
+                const double g = k3_exact_gain(lo, acc.at(a.i1 - 1), hi, ps, pe, a.i1, tot);
+                ++nexact;
+                if (g > b.g) { b.g = g; b.x = a.i1; }
+            }
+            return k3_spine_reduce(b, S).x;
+        }
+    }
+    // exact scan of every candidate (validation mode, or a candidate failed the validity test)
+    K3Best b = k3_scan_range(acc, ps, pe, P.mw, P.min_gain, tid, K3S_THREADS);
+    nexact += (unsigned)((pe - P.mw - (ps + P.mw + tid)) / K3S_THREADS + 1) * (ps + P.mw + tid <= pe - P.mw ? 1u : 0u);
+    return k3_spine_reduce(b, S).x;
+}
+
+__device__ __forceinline__ void k3_push_global_at(const K3Global &G, int ev, int s, int e, int ps)
+{
+    atomicAdd((unsigned long long *)&G.ctr->q_pending, 1ull);
+    const unsigned long long slot = atomicAdd(&G.ctr->q_tail, 1ull);
+    if ((int64_t)slot >= G.q_cap) {
+        atomicOr(&G.ctr->overflow, (unsigned)PP_OVF_QUEUE);
+        atomicAdd((unsigned long long *)&G.ctr->q_pending, (unsigned long long)(-1LL));
+        return;
+    }
+    PPTask t;
+    t.ev = ev; t.s = s; t.e = e; t.flags = ps - s;  // the windows before ps were scanned without a split
+    *reinterpret_cast<int4 *>(&G.tasks[slot]) = *reinterpret_cast<int4 *>(&t);
+    __threadfence();
+    atomicExch(&G.ready[slot], 1);
+}
+
+__global__ void __launch_bounds__(K3S_THREADS, 1) k3_spine(K3Global G, K3Params P)
+{
+    __shared__ K3SpineShared S;
+    const int tid = threadIdx.x;
+    const int mw = P.mw, MW = P.MW, W = P.W;
+    const bool screen_ok = G.screen && mw >= 1 && W <= K3_MAX_SCREEN_W;
+    if (G.ctr->n_long == 0ull) return;  // counted by k3_init_queue: the usual case costs one load
+    const int64_t n_events = (int64_t)G.ctr->n_events, ev_begin = (int64_t)G.ctr->ev_begin;
+    __shared__ int s_list[K3S_THREADS];
+    __shared__ int s_n;
+    // CTA b owns the long events among b, b + grid, ...; a round looks at 1024 of them at once
+    for (int64_t base = ev_begin + blockIdx.x; base < n_events; base += (int64_t)K3S_THREADS * gridDim.x) {
+    __syncthreads();
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    {
+        const int64_t cand_ev = base + (int64_t)tid * gridDim.x;
+        if (cand_ev < n_events) {
+            const int64_t l = G.ev_len[cand_ev];
+            if (l > K3_CAP && l < 0x7fffffffLL) s_list[atomicAdd(&s_n, 1)] = (int)cand_ev;
+        }
+    }
+    __syncthreads();
+    const int n_mine = s_n;
+    for (int q = 0; q < n_mine; ++q) {
+        const int64_t ev64 = s_list[q];
+        const int64_t len = G.ev_len[ev64];
+        __syncthreads();  // the previous event's readers of S are done
+        const int ev = (int)ev64;
+        const int64_t off = G.ev_off[ev];
+        const int e = (int)len;
+        K3GlobalCC acc;
+        acc.g = G.cc + off;
+        // screening exponent base: the variance of the whole event (the validity test checks every candidate)
+        int ebase = 0;
+        const bool screen = screen_ok && k3_window_ebase(k3_var(acc.at(e - 1), acc.at(-1), e), ebase);
+        int s = 0, ps = 0, par = 0;
+        unsigned long long cand = 0, scans = 0;
+        unsigned nexact = 0;
+        while ((long long)e - s > K3_CAP) {
+            const long long lim = (long long)e - 2LL * mw;
+            if (ps >= lim) {
+                if (e - s <= MW) { s = e; break; }  // a leaf
+                const int x = k3_forced(P, s, e);
+                if (tid == 0) {
+                    k3_emit(G, off, x);
+                    if (k3_worth(P, s, x)) k3_push_global(G, ev, s, x);
+                }
+                s = x; ps = s;
+                continue;
+            }
+            if (ps > (long long)s + MW) {
+                const int x = k3_forced(P, s, e);
+                if (tid == 0) k3_emit(G, off, x);
+                s = x; ps = s;  // the left part is not revisited (cparsers.pyx:189-191)
+                continue;
+            }
+            const long long pe_l = (long long)ps + W;
+            const int pe = (int)(pe_l < e ? pe_l : e);
+            if (pe - ps <= 2 * mw) { ps = k3_next_ps(P, ps, e); continue; }
+            const int x = k3_spine_scan(acc, ps, pe, P, G, S, ebase, screen, par, nexact);
+            par ^= 1;
+            cand += (unsigned long long)(pe - ps - 2 * mw + 1);
+            scans += 1;
+            if (x >= 0) {
+                if (tid == 0) {
+                    k3_emit(G, off, x);
+                    if (k3_worth(P, s, x)) k3_push_global(G, ev, s, x);
+                }
+                s = x; ps = s;
+            } else {
+                ps = k3_next_ps(P, ps, e);
+            }
+        }
+        // the remainder is an ordinary task
+        if (tid == 0 && s < e && k3_worth(P, s, e)) k3_push_global_at(G, ev, s, e, ps);
+        // work counters: cand / scans are uniform, exact evaluations are per thread
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nexact += __shfl_xor_sync(PP_FULL, nexact, d);
+        if ((tid & 31) == 0 && nexact) atomicAdd(&G.ctr->n_exact, (unsigned long long)nexact);
+        if (tid == 0) {
+            atomicAdd(&G.ctr->n_cand, cand);
+            atomicAdd(&G.ctr->n_scan, scans);
+        }
+    }
+    }
+}
+
 // Debug / validation: for window [ps,pe) of event `ev`, write per candidate the screened
 // value (key converted to nats), the reference-arithmetic value fl(low + high) and the
 // validity flag.
@@ -1091,7 +1373,7 @@ __global__ void __launch_bounds__(256) k3_fill_RN(double *RN, int len)
 
 // One initial task per event of [ev_begin, n_events); event starts are segment starts.
 __global__ void __launch_bounds__(256)
-k3_init_queue(K3Global G)
+k3_init_queue(K3Global G, int use_spine)
 {
     const int64_t n_events = (int64_t)G.ctr->n_events;
     const int64_t ev_begin = (int64_t)G.ctr->ev_begin;
@@ -1104,6 +1386,10 @@ k3_init_queue(K3Global G)
         if (slot < G.q_cap && len < 0x7fffffffLL) {
             PPTask t;
             t.ev = (int)e; t.s = 0; t.e = (int)len; t.flags = 0;
+            if (use_spine && len > K3_CAP) {  // walked by k3_spine first; the slot keeps an empty task
+                t.e = 0;
+                atomicAdd(&G.ctr->n_long, 1ull);
+            }
             G.tasks[slot] = t;
             G.ready[slot] = 1;
         } else {

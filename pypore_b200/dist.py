@@ -238,7 +238,7 @@ class ShardedPipeline(object):
         self.rec = self.res = self.pack = self.plan = self.infos_dev = None
         self.pad_words = 0
         self.lens = None
-        self._p2p = None     # cached halo send / receive descriptors of the device-planned step
+        self._halo = 0       # speculative halo samples resident after the chunk
         self.fallbacks = 0   # steps that had to be repeated with the host-made plan
 
     def load(self, host_chunk):
@@ -252,6 +252,28 @@ class ShardedPipeline(object):
             self.dist.all_gather_into_tensor(lens, mine, group=self.group)
             self.lens = lens.cpu().numpy()
         self.ctx.upload_trace_async(host_chunk, extra_capacity=self.HALO_CAPACITY)   # after the read-back: not waited on
+        self._exchange_speculative_halo()
+
+    def _exchange_speculative_halo(self):
+        """The head of every chunk travels to the left neighbour as soon as the chunk is on the device -- it is
+        input data, independent of any scan -- directly into the room reserved after that rank's chunk (256 KB
+        per boundary over NVLink).  Steps on the resident trace find it there; k_shard_plan decides on the
+        device whether it covers the straddling event."""
+        import torch
+        ctx, dist, dev = self.ctx, self.dist, self.device
+        with torch.cuda.stream(self.stream):
+            ops, halo = [], 0
+            if self.rank < self.world - 1:
+                halo = self._spec_halo(self.rank + 1)
+                room = device_view(ctx.trace_ptr + 4 * self.n_local, halo, torch.float32, dev)
+                ops.append(dist.P2POp(dist.irecv, room, self.rank + 1, self.group))
+            if self.rank > 0:
+                chunk = device_view(ctx.trace_ptr, self._spec_halo(self.rank), torch.float32, dev)
+                ops.append(dist.P2POp(dist.isend, chunk, self.rank - 1, self.group))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()                                  # stream-level wait, the host goes on
+            self._halo = halo
         self.offsets = np.concatenate(([0], np.cumsum(self.lens)))
 
     def step(self, threshold, rules, mw, MW, W, gain, host_planned=False):
@@ -274,9 +296,8 @@ class ShardedPipeline(object):
     def _step_device_planned(self, threshold, rules, mw, MW, W, gain):
         """scan -> all-gather of the boundary records -> k_shard_plan on the device -> select/prefix/split/
         stats -> all-gather of the result records -> packed table all-gather: no host synchronisation until
-        the result records are read.  The head of every chunk travels to the left neighbour up front (it is
-        input data, independent of the scan), directly into the room reserved after that rank's chunk.
-        Returns None when the records ask for the host-planned step."""
+        the result records are read.  The head of the right neighbour's chunk is already resident behind this
+        rank's chunk (load() put it there).  Returns None when the records ask for the host-planned step."""
         import torch
         ctx, dist, dev = self.ctx, self.dist, self.device
         if self.rec is None:
@@ -286,23 +307,9 @@ class ShardedPipeline(object):
             self.plan = torch.zeros(8, dtype=torch.int64, device=dev)
             self.infos_dev = torch.empty(self.world * INFO_LEN, dtype=torch.float64, device=dev)
         ctx.truncate_trace(self.n_local)
-        # the scan is launched first: the GPU works on it while the host sets up the exchanges
         ctx.shard_scan(threshold, self.n_local, self.rec.data_ptr())
-        if self._p2p is None or self._p2p[0] != (ctx.trace_ptr, self.n_local):
-            ops, halo = [], 0
-            if self.rank < self.world - 1:
-                halo = self._spec_halo(self.rank + 1)
-                room = device_view(ctx.trace_ptr + 4 * self.n_local, halo, torch.float32, dev)
-                ops.append(dist.P2POp(dist.irecv, room, self.rank + 1, self.group))
-            if self.rank > 0:
-                chunk = device_view(ctx.trace_ptr, self._spec_halo(self.rank), torch.float32, dev)
-                ops.append(dist.P2POp(dist.isend, chunk, self.rank - 1, self.group))
-            self._p2p = ((ctx.trace_ptr, self.n_local), ops, halo)
-        _, ops, halo = self._p2p
-        reqs = dist.batch_isend_irecv(ops) if ops else []
         dist.all_gather_into_tensor(self.infos_dev, self.rec, group=self.group)
-        for w in reqs:
-            w.wait()                                          # stream-level wait, the host goes on
+        halo = self._halo
         ctx.extend_trace(halo)
         ctx.shard_plan(self.infos_dev.data_ptr(), self.rank, self.world, threshold, rules, halo, self.plan.data_ptr())
         ctx.shard_finish_planned(threshold, rules, mw, MW, W, gain, self.plan.data_ptr(), self.res.data_ptr())

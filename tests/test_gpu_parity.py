@@ -48,6 +48,14 @@ def check_split_f64(ctx, arrays, **kw):
     ctx.set_screening(True)
     tab = gpu_split_f64(ctx, arrays, **kw)
     assert all(np.array_equal(ref_tab[k], tab[k]) for k in ("event", "start", "end"))
+    if max(len(a) for a in arrays) > 10240:
+        # long events: the 1024-thread spine kernel (default) against the work-queue CTAs walking the spine
+        ctx.set_option(1, 0)
+        try:
+            alt = gpu_split_f64(ctx, arrays, **kw)
+        finally:
+            ctx.set_option(1, 1)
+        assert all(np.array_equal(alt[k], tab[k]) for k in ("event", "start", "end"))
     k = 0
     for e, a in enumerate(arrays):
         bp = oracle.statsplit(a, **kw)
