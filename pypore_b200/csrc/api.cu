@@ -392,11 +392,11 @@ int enqueue_prefix(pp_ctx *ctx, int prefix_mode)
         LAUNCHED(ctx);
         // short events: one pass, one warp per event
         if (ctx->src_kind == 0)
-            k2_event_scan<float><<<ctx->sm_count * 4, K2F_WARPS * 32, 0, ctx->stream>>>(
+            k2_event_scan<float><<<ctx->sm_count * K2F_CFG_CTAS * 2, K2F_WARPS * 32, 0, ctx->stream>>>(
                 src, ctx->trace, (const int64_t *)ctx->ev_len.p, ctx->ctr, (unsigned *)ctx->inexact.p,
                 (double2 *)ctx->cc.p, prefix_mode != PP_PREFIX_PARALLEL);
         else
-            k2_event_scan<double><<<ctx->sm_count * 4, K2F_WARPS * 32, 0, ctx->stream>>>(
+            k2_event_scan<double><<<ctx->sm_count * K2F_CFG_CTAS * 2, K2F_WARPS * 32, 0, ctx->stream>>>(
                 src, (const double *)ctx->flat64.p, (const int64_t *)ctx->ev_len.p, ctx->ctr,
                 (unsigned *)ctx->inexact.p, (double2 *)ctx->cc.p, prefix_mode != PP_PREFIX_PARALLEL);
         LAUNCHED(ctx);

@@ -249,8 +249,11 @@ struct K2FBits {
     __device__ __forceinline__ void add(double) {}
 };
 
+#ifndef K2F_CFG_CTAS
+#define K2F_CFG_CTAS 2
+#endif
 template <typename T>
-__global__ void __launch_bounds__(K2F_WARPS * 32)
+__global__ void __launch_bounds__(K2F_WARPS * 32, K2F_CFG_CTAS)
 k2_event_scan(PPSource src, const T *__restrict__ samples, const int64_t *__restrict__ ev_len, const PPCounters *ctr,
               unsigned *__restrict__ inexact, double2 *__restrict__ cc, int check)
 {
