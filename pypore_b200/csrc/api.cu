@@ -464,7 +464,7 @@ int enqueue_search(pp_ctx *ctx, int mw, int MW, int W, double min_gain)
     k3_init_queue<<<ctx->sm_count, 256, 0, ctx->stream>>>(G, ctx->opt_spine);
     LAUNCHED(ctx);
     if (ctx->opt_spine) {  // events longer than K3_CAP: their window chain first, a whole CTA per scan
-        k3_spine<<<ctx->sm_count, K3S_THREADS, 0, ctx->stream>>>(G, P);
+        k3_spine<<<(ctx->sm_count / K3S_CLUSTER) * K3S_CLUSTER, K3S_THREADS, 0, ctx->stream>>>(G, P);
         LAUNCHED(ctx);
     }
     k3_split<<<ctx->sm_count * K3_CTAS_PER_SM, K3_THREADS, K3_SMEM_BYTES, ctx->stream>>>(G, P);

@@ -37,6 +37,7 @@
 // (__dsub_rn/__ddiv_rn/__dmul_rn/__dadd_rn are never contracted to FMA).
 #pragma once
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 #ifndef K3_CFG_THREADS  // development knobs: -DK3_CFG_THREADS=.. -DK3_CFG_CTAS=..
 #define K3_CFG_THREADS 128
@@ -1076,58 +1077,102 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
 }
 
 // ---------------------------------------------------------------------------
-// Long events: the right spine of _recursive_split, one 1024-thread CTA per event.
+// Long events: the right spine of _recursive_split, one thread-block CLUSTER per event.
 //
 // The window loop over an interval longer than K3_CAP is sequential (the next window starts at
 // the split the current one finds), so its speed is the latency of ONE window
-// scan.  k3_spine runs before k3_split: every event longer than K3_CAP is walked by a whole
-// 1024-thread CTA (about ten candidates per thread and window, one barrier per scan in the common
-// case: per-warp summaries in shared memory, every thread derives the decision from them, and a
-// single contender whose screened gain clears min_gain by the error bound needs no exact
-// arithmetic).  Left children go to the global queue, the remainder (<= K3_CAP) follows as an
-// ordinary task with its window position; k3_split then resolves all of them.
+// scan -- and a scan of ~10^4 candidates is ~26 k warp instructions, i.e. issue-bound on a single
+// SM.  k3_spine runs before k3_split: every event longer than K3_CAP is walked by a cluster of
+// K3S_CLUSTER CTAs on as many SMs.  The cluster's threads share a window's candidates; every warp
+// writes its summary (two smallest keys, argmin, validity) into the shared memory of ALL CTAs of
+// the cluster (distributed shared memory), one cluster barrier makes them visible, and every thread
+// of every CTA derives the same decision from them -- a single contender whose screened gain clears
+// min_gain by the error bound needs no exact arithmetic.  Rank 0 records breakpoints and pushes the
+// left children to the global queue; the remainder (<= K3_CAP) follows as an ordinary task with its
+// window position; k3_split then resolves all of them.
 // ---------------------------------------------------------------------------
-constexpr int K3S_THREADS = 1024;
+#ifndef K3S_CFG_CLUSTER
+#define K3S_CFG_CLUSTER 4
+#endif
+#ifndef K3S_CFG_THREADS
+#define K3S_CFG_THREADS 512
+#endif
+constexpr int K3S_CLUSTER = K3S_CFG_CLUSTER;
+constexpr int K3S_THREADS = K3S_CFG_THREADS;
 constexpr int K3S_WARPS = K3S_THREADS / 32;
+constexpr int K3S_TOTAL = K3S_CLUSTER * K3S_THREADS; // threads that share a window
 
 struct K3SpineShared {
-    unsigned long long wk1[2][K3S_WARPS], wk2[2][K3S_WARPS];
-    int wi1[2][K3S_WARPS];
-    int wbad[2][K3S_WARPS];
-    double red_g[K3S_WARPS];
-    int red_x[K3S_WARPS];
+    // per-warp summaries of this CTA (reduced by warp 0), then per-CTA summaries of the whole cluster
+    unsigned long long wk1[K3S_WARPS], wk2[K3S_WARPS];
+    int wi1[K3S_WARPS];
+    int wbad[K3S_WARPS];
+    unsigned long long ck1[2][K3S_CLUSTER], ck2[2][K3S_CLUSTER];
+    int ci1[2][K3S_CLUSTER];
+    int cbad[2][K3S_CLUSTER];
+    double wred_g[K3S_WARPS];
+    int wred_x[K3S_WARPS];
+    double cred_g[2][K3S_CLUSTER];
+    int cred_x[2][K3S_CLUSTER];
+    int list[K3S_THREADS];
+    unsigned char flag[K3S_THREADS];
+    int n_list;
 };
 
-// exact decision over per-thread partial results (rare path; two barriers)
-__device__ __forceinline__ K3Best k3_spine_reduce(K3Best b, K3SpineShared &S)
+// exact decision over per-thread partial results, cluster-wide (rare path): warps -> CTA -> cluster
+__device__ __forceinline__ K3Best k3_spine_reduce(K3Best b, K3SpineShared &S, int par)
 {
-    const int tid = threadIdx.x;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     b = k3_warp_reduce(b);
+    if (lane == 0) { S.wred_g[warp] = b.g; S.wred_x[warp] = b.x; }
     __syncthreads();
-    if ((tid & 31) == 0) { S.red_g[tid >> 5] = b.g; S.red_x[tid >> 5] = b.x; }
-    __syncthreads();
+    if (warp == 0) {
+        K3Best c;
+        c.g = lane < K3S_WARPS ? S.wred_g[lane] : 0.0;
+        c.x = lane < K3S_WARPS ? S.wred_x[lane] : -1;
+        c = k3_warp_reduce(c);
+        if (lane == 0) {
+            const int rank = (int)cluster.block_rank();
+            for (int r = 0; r < K3S_CLUSTER; ++r) {
+                K3SpineShared *R = cluster.map_shared_rank(&S, r);
+                R->cred_g[par][rank] = c.g;
+                R->cred_x[par][rank] = c.x;
+            }
+        }
+    }
+    cluster.sync();
     K3Best r;
-    r.g = S.red_g[0];
-    r.x = S.red_x[0];
-    for (int w = 1; w < K3S_WARPS; ++w) {
+    r.g = S.cred_g[par][0];
+    r.x = S.cred_x[par][0];
+#pragma unroll
+    for (int w = 1; w < K3S_CLUSTER; ++w) {
         K3Best o;
-        o.g = S.red_g[w];
-        o.x = S.red_x[w];
+        o.g = S.cred_g[par][w];
+        o.x = S.cred_x[par][w];
         r = k3_better(r, o);
     }
     return r;
 }
 
-// One window [ps,pe) scanned by the whole CTA; every thread returns the same split position (or -1).
+// One window [ps,pe) scanned by the whole cluster; every thread returns the same split position (or -1).
 __device__ __forceinline__ int k3_spine_scan(const K3GlobalCC &acc, int ps, int pe, const K3Params &P, const K3Global &G,
                                              K3SpineShared &S, int ebase, bool screen, int par, unsigned &nexact)
 {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)cluster.block_rank();
+    const int gtid = rank * K3S_THREADS + tid;
     const double2 lo = acc.at(ps - 1), hi = acc.at(pe - 1);
+    // the window front only moves forward: pull the prefix sums behind the current window's end into L2 now
+    // (one 128 B line per thread), so that the next windows' new samples are L2 hits instead of HBM misses
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(acc.g + pe + (long long)gtid * 8));
     if (screen) {
         K3Scr a;
         k3_scr_init(a);
-        k3_screen_lane(acc.g, lo, hi, ps, pe, ebase, G.RN, ps + P.mw + tid, pe - P.mw, K3S_THREADS, a);
+        k3_screen_lane(acc.g, lo, hi, ps, pe, ebase, G.RN, ps + P.mw + gtid, pe - P.mw, K3S_TOTAL, a);
         unsigned long long K1, K2;
         int I1;
         bool bad;
@@ -1135,25 +1180,45 @@ __device__ __forceinline__ int k3_spine_scan(const K3GlobalCC &acc, int ps, int 
         unsigned long long kt = 0ull;
         const unsigned nw = (unsigned)(pe - ps);
         const bool tok = k3_side(__dsub_rn(hi.x, lo.x), __dsub_rn(hi.y, lo.y), __ldg(G.RN + nw), nw, ebase, kt);
-        if (lane == 0) { S.wk1[par][warp] = K1; S.wk2[par][warp] = K2; S.wi1[par][warp] = I1; S.wbad[par][warp] = bad; }
+        // warps -> CTA (warp 0, the same two-smallest summary over the warps' records) -> every CTA of the cluster
+        if (lane == 0) { S.wk1[warp] = K1; S.wk2[warp] = K2; S.wi1[warp] = I1; S.wbad[warp] = bad ? 1 : 0; }
         __syncthreads();
+        if (warp == 0) {
+            K3Scr c;
+            k3_scr_init(c);
+            if (lane < K3S_WARPS) { c.k1 = S.wk1[lane]; c.k2 = S.wk2[lane]; c.i1 = S.wi1[lane]; c.bad = S.wbad[lane]; }
+            unsigned long long C1, C2;
+            int CI;
+            bool cbad;
+            k3_warp_summary(c, C1, C2, CI, cbad);
+            if (lane == 0) {
+                for (int r = 0; r < K3S_CLUSTER; ++r) {
+                    K3SpineShared *R = cluster.map_shared_rank(&S, r);
+                    R->ck1[par][rank] = C1;
+                    R->ck2[par][rank] = C2;
+                    R->ci1[par][rank] = CI;
+                    R->cbad[par][rank] = cbad ? 1 : 0;
+                }
+            }
+        }
+        cluster.sync();
         unsigned long long gmin = K3_NOKEY;
         bool anybad = false;
-#pragma unroll 8
-        for (int w = 0; w < K3S_WARPS; ++w) {
-            const unsigned long long k1 = S.wk1[par][w];
+#pragma unroll
+        for (int w = 0; w < K3S_CLUSTER; ++w) {
+            const unsigned long long k1 = S.ck1[par][w];
             gmin = k1 < gmin ? k1 : gmin;
-            anybad = anybad || S.wbad[par][w];
+            anybad = anybad || S.cbad[par][w];
         }
         if (!anybad && gmin != K3_NOKEY) {
             const unsigned long long eps2 = k3_eps2_key(pe - ps);
             const unsigned long long thr = gmin + eps2;
             int nr = 0, i_one = -1;
             bool rescan = false;
-#pragma unroll 8
-            for (int w = 0; w < K3S_WARPS; ++w) {
-                if (S.wk2[par][w] <= thr) rescan = true;
-                else if (S.wk1[par][w] <= thr) { ++nr; i_one = S.wi1[par][w]; }
+#pragma unroll
+            for (int w = 0; w < K3S_CLUSTER; ++w) {
+                if (S.ck2[par][w] <= thr) rescan = true;
+                else if (S.ck1[par][w] <= thr) { ++nr; i_one = S.ci1[par][w]; }
             }
             if (!rescan && nr == 1 && tok) {
                 const double d = (double)(long long)(kt - gmin);
@@ -1169,7 +1234,7 @@ __device__ __forceinline__ int k3_spine_scan(const K3GlobalCC &acc, int ps, int 
             const double tot = k3_exact_tot(lo, hi, ps, pe);
             if (a.k2 <= thr) {
                 const int last = pe - P.mw;
-                for (int i = ps + P.mw + tid; i <= last; i += K3S_THREADS) {
+                for (int i = ps + P.mw + gtid; i <= last; i += K3S_TOTAL) {
                     unsigned long long key;
                     k3_screen_key_at(acc.g, lo, hi, ps, pe, i, G.RN, ebase, key);
                     if (key <= thr) {
@@ -1183,117 +1248,142 @@ __device__ __forceinline__ int k3_spine_scan(const K3GlobalCC &acc, int ps, int 
                 ++nexact;
                 if (g > b.g) { b.g = g; b.x = a.i1; }
             }
-            return k3_spine_reduce(b, S).x;
+            return k3_spine_reduce(b, S, par).x;
         }
     }
     // exact scan of every candidate (validation mode, or a candidate failed the validity test)
-    K3Best b = k3_scan_range(acc, ps, pe, P.mw, P.min_gain, tid, K3S_THREADS);
-    nexact += (unsigned)((pe - P.mw - (ps + P.mw + tid)) / K3S_THREADS + 1) * (ps + P.mw + tid <= pe - P.mw ? 1u : 0u);
-    return k3_spine_reduce(b, S).x;
+    K3Best b = k3_scan_range(acc, ps, pe, P.mw, P.min_gain, gtid, K3S_TOTAL);
+    if (ps + P.mw + gtid <= pe - P.mw) nexact += (unsigned)((pe - P.mw - (ps + P.mw + gtid)) / K3S_TOTAL + 1);
+    return k3_spine_reduce(b, S, par).x;
 }
 
-__device__ __forceinline__ void k3_push_global_at(const K3Global &G, int ev, int s, int e, int ps)
-{
-    atomicAdd((unsigned long long *)&G.ctr->q_pending, 1ull);
-    const unsigned long long slot = atomicAdd(&G.ctr->q_tail, 1ull);
-    if ((int64_t)slot >= G.q_cap) {
-        atomicOr(&G.ctr->overflow, (unsigned)PP_OVF_QUEUE);
-        atomicAdd((unsigned long long *)&G.ctr->q_pending, (unsigned long long)(-1LL));
-        return;
+// Queue slots of the spine kernel's leader thread.  Nothing consumes the queue before k3_spine has finished
+// (k3_split is the next kernel on the stream), so a push is two plain stores into a slot reserved in bulk -- no
+// fence, no atomic round trip on the window chain's critical path.  Slots left over are filled with empty tasks.
+struct K3SpineQueue {
+    long long next, end;
+    __device__ __forceinline__ void push(const K3Global &G, int ev, int s, int e, int ps)
+    {
+        if (next == end) {
+            next = (long long)atomicAdd(&G.ctr->q_tail, 32ull);
+            atomicAdd((unsigned long long *)&G.ctr->q_pending, 32ull);
+            end = next + 32;
+        }
+        if (next < G.q_cap) {
+            PPTask t;
+            t.ev = ev; t.s = s; t.e = e; t.flags = ps - s;  // the windows before ps were scanned without a split
+            *reinterpret_cast<int4 *>(&G.tasks[next]) = *reinterpret_cast<int4 *>(&t);
+            G.ready[next] = 1;
+        } else {
+            atomicOr(&G.ctr->overflow, (unsigned)PP_OVF_QUEUE);
+            atomicAdd((unsigned long long *)&G.ctr->q_pending, (unsigned long long)(-1LL));
+        }
+        ++next;
     }
-    PPTask t;
-    t.ev = ev; t.s = s; t.e = e; t.flags = ps - s;  // the windows before ps were scanned without a split
-    *reinterpret_cast<int4 *>(&G.tasks[slot]) = *reinterpret_cast<int4 *>(&t);
-    __threadfence();
-    atomicExch(&G.ready[slot], 1);
-}
+    __device__ __forceinline__ void flush(const K3Global &G, int ev)
+    {
+        while (next < end) push(G, ev, 0, 0, 0);
+    }
+};
 
-__global__ void __launch_bounds__(K3S_THREADS, 1) k3_spine(K3Global G, K3Params P)
+__global__ void __cluster_dims__(K3S_CLUSTER, 1, 1) __launch_bounds__(K3S_THREADS, 1) k3_spine(K3Global G, K3Params P)
 {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ K3SpineShared S;
     const int tid = threadIdx.x;
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / K3S_CLUSTER, ncl = gridDim.x / K3S_CLUSTER;
+    const bool leader = rank == 0 && tid == 0;
     const int mw = P.mw, MW = P.MW, W = P.W;
     const bool screen_ok = G.screen && mw >= 1 && W <= K3_MAX_SCREEN_W;
-    if (G.ctr->n_long == 0ull) return;  // counted by k3_init_queue: the usual case costs one load
+    if (G.ctr->n_long == 0ull) return;  // counted by k3_init_queue: the usual case costs one load (whole cluster leaves)
     const int64_t n_events = (int64_t)G.ctr->n_events, ev_begin = (int64_t)G.ctr->ev_begin;
-    __shared__ int s_list[K3S_THREADS];
-    __shared__ int s_n;
-    // CTA b owns the long events among b, b + grid, ...; a round looks at 1024 of them at once
-    for (int64_t base = ev_begin + blockIdx.x; base < n_events; base += (int64_t)K3S_THREADS * gridDim.x) {
-    __syncthreads();
-    if (tid == 0) s_n = 0;
-    __syncthreads();
-    {
-        const int64_t cand_ev = base + (int64_t)tid * gridDim.x;
-        if (cand_ev < n_events) {
-            const int64_t l = G.ev_len[cand_ev];
-            if (l > K3_CAP && l < 0x7fffffffLL) s_list[atomicAdd(&s_n, 1)] = (int)cand_ev;
+    int par = 0;
+    K3SpineQueue Q;
+    Q.next = Q.end = 0;
+    // cluster c owns the long events among c, c + ncl, ...; every CTA of the cluster builds the same ordered list
+    for (int64_t base = ev_begin + cid; base < n_events; base += (int64_t)K3S_THREADS * ncl) {
+        __syncthreads();
+        {
+            const int64_t cand_ev = base + (int64_t)tid * ncl;
+            bool is_long = false;
+            if (cand_ev < n_events) {
+                const int64_t l = G.ev_len[cand_ev];
+                is_long = l > K3_CAP && l < 0x7fffffffLL;
+            }
+            S.flag[tid] = is_long ? 1 : 0;
         }
-    }
-    __syncthreads();
-    const int n_mine = s_n;
-    for (int q = 0; q < n_mine; ++q) {
-        const int64_t ev64 = s_list[q];
-        const int64_t len = G.ev_len[ev64];
-        __syncthreads();  // the previous event's readers of S are done
-        const int ev = (int)ev64;
-        const int64_t off = G.ev_off[ev];
-        const int e = (int)len;
-        K3GlobalCC acc;
-        acc.g = G.cc + off;
-        // screening exponent base: the variance of the whole event (the validity test checks every candidate)
-        int ebase = 0;
-        const bool screen = screen_ok && k3_window_ebase(k3_var(acc.at(e - 1), acc.at(-1), e), ebase);
-        int s = 0, ps = 0, par = 0;
-        unsigned long long cand = 0, scans = 0;
-        unsigned nexact = 0;
-        while ((long long)e - s > K3_CAP) {
-            const long long lim = (long long)e - 2LL * mw;
-            if (ps >= lim) {
-                if (e - s <= MW) { s = e; break; }  // a leaf
-                const int x = k3_forced(P, s, e);
-                if (tid == 0) {
-                    k3_emit(G, off, x);
-                    if (k3_worth(P, s, x)) k3_push_global(G, ev, s, x);
-                }
-                s = x; ps = s;
-                continue;
-            }
-            if (ps > (long long)s + MW) {
-                const int x = k3_forced(P, s, e);
-                if (tid == 0) k3_emit(G, off, x);
-                s = x; ps = s;  // the left part is not revisited (cparsers.pyx:189-191)
-                continue;
-            }
-            const long long pe_l = (long long)ps + W;
-            const int pe = (int)(pe_l < e ? pe_l : e);
-            if (pe - ps <= 2 * mw) { ps = k3_next_ps(P, ps, e); continue; }
-            const int x = k3_spine_scan(acc, ps, pe, P, G, S, ebase, screen, par, nexact);
-            par ^= 1;
-            cand += (unsigned long long)(pe - ps - 2 * mw + 1);
-            scans += 1;
-            if (x >= 0) {
-                if (tid == 0) {
-                    k3_emit(G, off, x);
-                    if (k3_worth(P, s, x)) k3_push_global(G, ev, s, x);
-                }
-                s = x; ps = s;
-            } else {
-                ps = k3_next_ps(P, ps, e);
-            }
-        }
-        // the remainder is an ordinary task
-        if (tid == 0 && s < e && k3_worth(P, s, e)) k3_push_global_at(G, ev, s, e, ps);
-        // work counters: cand / scans are uniform, exact evaluations are per thread
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) nexact += __shfl_xor_sync(PP_FULL, nexact, d);
-        if ((tid & 31) == 0 && nexact) atomicAdd(&G.ctr->n_exact, (unsigned long long)nexact);
+        __syncthreads();
         if (tid == 0) {
-            atomicAdd(&G.ctr->n_cand, cand);
-            atomicAdd(&G.ctr->n_scan, scans);
+            int n = 0;
+            for (int t = 0; t < K3S_THREADS; ++t)
+                if (S.flag[t]) S.list[n++] = (int)(base + (int64_t)t * ncl);
+            S.n_list = n;
+        }
+        __syncthreads();
+        const int n_mine = S.n_list;
+        for (int q = 0; q < n_mine; ++q) {
+            const int ev = S.list[q];
+            const int64_t off = G.ev_off[ev];
+            const int e = (int)G.ev_len[ev];
+            K3GlobalCC acc;
+            acc.g = G.cc + off;
+            // screening exponent base: the variance of the whole event (the validity test checks every candidate)
+            int ebase = 0;
+            const bool screen = screen_ok && k3_window_ebase(k3_var(acc.at(e - 1), acc.at(-1), e), ebase);
+            int s = 0, ps = 0;
+            unsigned long long cand = 0, scans = 0;
+            unsigned nexact = 0;
+            while ((long long)e - s > K3_CAP) {
+                const long long lim = (long long)e - 2LL * mw;
+                if (ps >= lim) {
+                    if (e - s <= MW) { s = e; break; }  // a leaf
+                    const int x = k3_forced(P, s, e);
+                    if (leader) {
+                        k3_emit(G, off, x);
+                        if (k3_worth(P, s, x)) Q.push(G, ev, s, x, s);
+                    }
+                    s = x; ps = s;
+                    continue;
+                }
+                if (ps > (long long)s + MW) {
+                    const int x = k3_forced(P, s, e);
+                    if (leader) k3_emit(G, off, x);
+                    s = x; ps = s;  // the left part is not revisited (cparsers.pyx:189-191)
+                    continue;
+                }
+                const long long pe_l = (long long)ps + W;
+                const int pe = (int)(pe_l < e ? pe_l : e);
+                if (pe - ps <= 2 * mw) { ps = k3_next_ps(P, ps, e); continue; }
+                const int x = k3_spine_scan(acc, ps, pe, P, G, S, ebase, screen, par, nexact);
+                par ^= 1;
+                cand += (unsigned long long)(pe - ps - 2 * mw + 1);
+                scans += 1;
+                if (x >= 0) {
+                    if (leader) {
+                        k3_emit(G, off, x);
+                        if (k3_worth(P, s, x)) Q.push(G, ev, s, x, s);
+                    }
+                    s = x; ps = s;
+                } else {
+                    ps = k3_next_ps(P, ps, e);
+                }
+            }
+            // the remainder is an ordinary task
+            if (leader && s < e && k3_worth(P, s, e)) Q.push(G, ev, s, e, ps);
+            if (leader) Q.flush(G, ev);
+            // work counters: cand / scans are uniform, exact evaluations are per thread
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) nexact += __shfl_xor_sync(PP_FULL, nexact, d);
+            if ((tid & 31) == 0 && nexact) atomicAdd(&G.ctr->n_exact, (unsigned long long)nexact);
+            if (leader) {
+                atomicAdd(&G.ctr->n_cand, cand);
+                atomicAdd(&G.ctr->n_scan, scans);
+            }
         }
     }
-    }
+    cluster.sync();  // nobody leaves while a peer may still write into its shared memory
 }
 
 // Debug / validation: for window [ps,pe) of event `ev`, write per candidate the screened
