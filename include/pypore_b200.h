@@ -221,8 +221,6 @@ int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_sa
  *   straddling event appended, prefix + split + compaction + statistics; writes the 8-word result
  *   record [runs, events, event samples, segments, overflow flags, candidates, scans, exact
  *   evaluations] to DEVICE memory, no host synchronisation.
- * pp_shard_commit: hands the (all-gathered, host-read) result record back so that downloads work.
- * pp_pack_tables: event rows {global start, length} and segment rows {global event id, start,
  * pp_shard_plan / pp_shard_finish_planned: the same step without the host round trip between scan
  *   and finish.  The caller placed `halo_avail` samples of the right neighbour's chunk after its own
  *   (pp_trace_extend) before anything was known about the runs; pp_shard_plan derives this rank's part of
@@ -231,10 +229,15 @@ int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_sa
  *   pp_shard_finish_planned reads them there.  Word 4 of the result record carries the redo flags
  *   (16: a straddling event needs more than halo_avail samples or spans more than two chunks; 1: a rank's
  *   run table overflowed) -- the caller then repeats the step with pp_shard_finish and a host-made plan.
- * pp_pack_tables: event rows {global start, length} and segment rows {global event id, start,
- *   end, mean, std, min, max} as 8-byte words in one device buffer (2 E + 7 S words).  Counts and the
- *   global event-id base are read on the DEVICE from the all-gathered result records (8 words per
- *   rank), so the call needs no host knowledge of them; nothing is written if cap_words is too small. */
+ * pp_shard_commit: hands the (all-gathered, host-read) result record back so that downloads work.
+ * pp_pack_tables: the tables as 8-byte words in one device buffer for ONE all-gather: event rows {global start,
+ *   length} (2 words), then segment rows of 4 words {global event id | event-relative start << 32, mean, std,
+ *   min | max << 32 as float32 bit patterns} -- 32 B instead of the table's 56: `end` is the next row's start (or
+ *   the event's length) and is rebuilt after the gather, and the sharded path works on float32 traces, whose
+ *   extrema are float32 values.  2 E + 4 S words.  Counts and the global event-id base are read on the DEVICE
+ *   from the all-gathered result records (8 words per rank), so the call needs no host knowledge of them;
+ *   nothing is written if cap_words is too small.
+ */
 int pp_shard_scan(pp_ctx *ctx, double threshold, int64_t scan_len, double *dev_record);
 int pp_shard_finish(pp_ctx *ctx, const pp_pipeline_params *p, int skip_first, int skip_last, int has_event,
                     int64_t ev_start, int64_t ev_len, int64_t *dev_record);

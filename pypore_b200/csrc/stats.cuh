@@ -14,6 +14,7 @@
 #include "common.cuh"
 
 constexpr int K4_ONE_PASS = 4096;
+constexpr int K4_U = 4;  // independent loads per lane and trip
 
 template <int G>
 __device__ __forceinline__ double k4_group_sum(double v)
@@ -82,21 +83,36 @@ __device__ __forceinline__ void k4_rows(const T *__restrict__ samples, const int
             p = samples + ev_base[ev] + (f0 - ev_off[ev]);
         }
         const int n0 = (int)(len < G ? len : G);
-        double K = k4_group_sum<G>(gl < n0 ? (double)p[gl] : 0.0) / (double)(n0 > 0 ? n0 : 1);
+        // the lane's first K4_U samples are requested together (a row of ~130 samples is 4 trips of 8 lanes x 4
+        // loads instead of 16 dependent round trips); the very first one also serves the shift K
+        T xq[K4_U];
+#pragma unroll
+        for (int u = 0; u < K4_U; ++u) xq[u] = (gl + u * G) < len ? p[gl + u * G] : (T)0;
+        double K = k4_group_sum<G>(gl < n0 ? (double)xq[0] : 0.0) / (double)(n0 > 0 ? n0 : 1);
         if (!(fabs(K) <= 1.7e308)) K = 0.0;  // inf / NaN among the first samples: plain sums below
         double s1 = 0.0, s2 = 0.0;
         T mn = inf, mx = -inf;
         int nan = 0;
         double mean, var;
         if (__all_sync(PP_FULL, len <= K4_ONE_PASS)) {
-            for (int64_t j = gl; j < len; j += G) {
-                const T x = p[j];
-                const double d = (double)x - K;
-                s1 += d;
-                s2 = fma(d, d, s2);
-                mn = k4_min(mn, x);
-                mx = k4_max(mx, x);
-                nan |= (x != x);
+            for (int64_t j = gl; j < len; j += K4_U * G) {
+                T xn[K4_U];
+#pragma unroll
+                for (int u = 0; u < K4_U; ++u) xn[u] = (j + (K4_U + u) * G) < len ? p[j + (K4_U + u) * G] : (T)0;
+#pragma unroll
+                for (int u = 0; u < K4_U; ++u) {
+                    if (j + u * G < len) {
+                        const T x = xq[u];
+                        const double d = (double)x - K;
+                        s1 += d;
+                        s2 = fma(d, d, s2);
+                        mn = k4_min(mn, x);
+                        mx = k4_max(mx, x);
+                        nan |= (x != x);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < K4_U; ++u) xq[u] = xn[u];
             }
             s1 = k4_group_sum<G>(s1);
             s2 = k4_group_sum<G>(s2);

@@ -524,10 +524,14 @@ __global__ void k_result_record(const PPCounters *ctr, long long *__restrict__ r
 }
 
 // Multi-GPU: event and segment tables packed into 8-byte words for ONE all-gather:
-// n_events rows {global start, length}, then n_segments rows
-// {global event id, start, end, mean, std, min, max} (doubles as their bit patterns).
-// Counts and the global event-id base come from the all-gathered result records in DEVICE memory
-// (rec_all[r] = rank r's k_result_record), so the host does not have to know them yet.
+// n_events rows {global start, length}, then n_segments rows of PP_SEG_WORDS words
+//   { global event id (low 32 bits) | event-relative start (high 32 bits),  mean,  std,  min | max as float32 }
+// -- 32 B instead of the table's 56: `end` is the next row's start (or the event's length) and is rebuilt
+// after the gather, the sharded path works on float32 traces so min / max are float32 values, and an event
+// is shorter than 2^31 samples.  Counts and the global event-id base come from the all-gathered result
+// records in DEVICE memory (rec_all[r] = rank r's k_result_record), so the host does not have to know them yet.
+constexpr int PP_SEG_WORDS = 4;
+
 __global__ void __launch_bounds__(256)
 k_pack_tables(const long long *__restrict__ rec_all, int rank, int64_t cap_words, int64_t sample_offset,
               const int64_t *__restrict__ ev_start, const int64_t *__restrict__ ev_len,
@@ -537,7 +541,7 @@ k_pack_tables(const long long *__restrict__ rec_all, int rank, int64_t cap_words
               long long *__restrict__ out)
 {
     const int64_t n_events = rec_all[8 * rank + 1], n_segments = rec_all[8 * rank + 3];
-    if (2 * n_events + 7 * n_segments > cap_words) return;  // the host notices from the same records and retries
+    if (2 * n_events + PP_SEG_WORDS * n_segments > cap_words) return;  // the host notices from the same records and retries
     int64_t event_base = 0;
     for (int r = 0; r < rank; ++r) event_base += rec_all[8 * r + 1];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -546,15 +550,13 @@ k_pack_tables(const long long *__restrict__ rec_all, int rank, int64_t cap_words
         out[2 * e] = ev_start[e] + sample_offset;
         out[2 * e + 1] = ev_len[e];
     }
-    long long *seg = out + 2 * n_events;
+    longlong2 *seg = reinterpret_cast<longlong2 *>(out + 2 * n_events);  // 16-byte aligned: 2 words per event
     for (int64_t k = t0; k < n_segments; k += stride) {
-        long long *row = seg + 7 * k;
-        row[0] = (long long)seg_event[k] + event_base;
-        row[1] = seg_start[k];
-        row[2] = seg_end[k];
-        row[3] = __double_as_longlong(mean[k]);
-        row[4] = __double_as_longlong(sd[k]);
-        row[5] = __double_as_longlong(mn[k]);
-        row[6] = __double_as_longlong(mx[k]);
+        const unsigned long long id = (unsigned long long)((long long)seg_event[k] + event_base) & 0xffffffffull;
+        const unsigned long long st = (unsigned long long)seg_start[k] << 32;
+        const unsigned long long lo = (unsigned long long)__float_as_uint((float)mn[k]);
+        const unsigned long long hi = (unsigned long long)__float_as_uint((float)mx[k]) << 32;
+        seg[2 * k] = make_longlong2((long long)(id | st), __double_as_longlong(mean[k]));
+        seg[2 * k + 1] = make_longlong2(__double_as_longlong(sd[k]), (long long)(lo | hi));
     }
 }

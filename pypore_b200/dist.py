@@ -17,6 +17,7 @@ with NCCL, which is how tests/test_dist_cpu.py covers them without a GPU.
 import numpy as np
 
 INFO_LEN = 12
+SEG_WORDS = 4         # 8-byte words per packed segment row (pp_pack_tables): id|start, mean, std, min|max as float32
 _REDO_MASK = 16 | 1   # result-record flags of the device-planned step: PP_OVF_HALO | PP_OVF_RUNS (include/pypore_b200.h)
 (I_N, I_NRUNS, I_FIRST_BELOW, I_FIRST_LEN, I_FIRST_MIN, I_FIRST_MAX,
  I_LAST_BELOW, I_LAST_START, I_LAST_LEN, I_LAST_MIN, I_LAST_MAX, I_PAD) = range(INFO_LEN)
@@ -137,7 +138,7 @@ def gather_tables(int_cols, flt_cols, counts, dist, group=None):
 
 def gather_packed_raw(words, m, dist, group=None):
     """ONE all-gather of the first m words of every rank's packed tables (pp_pack_tables layout: 2 words per
-    event, then 7 per segment).  Returns the int64 tensor [world, m]; row r holds rank r's words."""
+    event, then SEG_WORDS per segment).  Returns the int64 tensor [world, m]; row r holds rank r's words."""
     import torch
     world = dist.get_world_size(group)
     if words.shape[0] < m:
@@ -147,21 +148,45 @@ def gather_packed_raw(words, m, dist, group=None):
     return g.view(world, m)
 
 
-def unpack_gathered(g, counts):
-    """Contiguous tables from gather_packed_raw's result; counts = per-rank (events, segments).
-    Returns dict(events int64 [sum E, 2], seg_int int64 [sum S, 3], seg_flt float64 [sum S, 4])."""
+def split_gathered(g, counts):
+    """Contiguous raw rows from gather_packed_raw's result; counts = per-rank (events, segments).
+    Returns (events int64 [sum E, 2], segment words int64 [sum S, SEG_WORDS])."""
     import torch
     world = len(counts)
-    sizes = [2 * e + 7 * s for e, s in counts]
+    sizes = [2 * e + SEG_WORDS * s for e, s in counts]
     ev = torch.cat([g[r, :2 * counts[r][0]].view(-1, 2) for r in range(world)], dim=0)
-    seg = torch.cat([g[r, 2 * counts[r][0]:sizes[r]].view(-1, 7) for r in range(world)], dim=0)
-    return dict(events=ev, seg_int=seg[:, :3].contiguous(), seg_flt=seg[:, 3:].contiguous().view(torch.float64))
+    seg = torch.cat([g[r, 2 * counts[r][0]:sizes[r]].view(-1, SEG_WORDS) for r in range(world)], dim=0)
+    return ev, seg
+
+
+def unpack_gathered(g, counts):
+    """The whole result as contiguous tables: dict(events int64 [sum E, 2] {global start, length},
+    seg_int int64 [sum S, 3] {global event id, start, end}, seg_flt float64 [sum S, 4] {mean, std, min, max}).
+    Undoes the packing of pp_pack_tables: `end` is the next row's start inside the same event, else the
+    event's length; min / max come back from their float32 bit patterns."""
+    import torch
+    ev, seg = split_gathered(g, counts)
+    w0 = seg[:, 0]
+    event = w0 & 0xffffffff
+    start = w0 >> 32
+    n = seg.shape[0]
+    if n:
+        nxt_same = torch.zeros(n, dtype=torch.bool, device=seg.device)
+        nxt_same[:-1] = event[1:] == event[:-1]
+        nxt_start = torch.cat([start[1:], start[:1]])
+        end = torch.where(nxt_same, nxt_start, ev[:, 1][event])
+    else:
+        end = start
+    mnmx = seg[:, 3].contiguous().view(torch.int32).view(-1, 2).view(torch.float32).to(torch.float64)
+    flt = torch.stack([seg[:, 1].contiguous().view(torch.float64), seg[:, 2].contiguous().view(torch.float64),
+                       mnmx[:, 0], mnmx[:, 1]], dim=1)
+    return dict(events=ev, seg_int=torch.stack([event, start, end], dim=1), seg_flt=flt)
 
 
 def gather_packed(words, counts, dist, group=None):
-    """gather_packed_raw + unpack_gathered for callers that know every rank's counts already."""
-    m = max(max(2 * e + 7 * s for e, s in counts), 1)
-    return unpack_gathered(gather_packed_raw(words, m, dist, group), counts)
+    """gather_packed_raw + split_gathered for callers that know every rank's counts already."""
+    m = max(max(2 * e + SEG_WORDS * s for e, s in counts), 1)
+    return split_gathered(gather_packed_raw(words, m, dist, group), counts)
 
 
 # ------------------------------------------------------------------------------------------
@@ -234,7 +259,6 @@ class ShardedPipeline(object):
         self.n_owned = 0
         self.offsets = None
         self.gathered = self.counts = self._tables = None
-        self.stage_ms = {}
         self.rec = self.res = self.pack = self.plan = self.infos_dev = None
         self.pad_words = 0
         self.lens = None
@@ -335,10 +359,9 @@ class ShardedPipeline(object):
         if redo_mask and (allr[:, 4] & redo_mask).any():
             return None
         ctx.shard_commit(allr[self.rank])
-        self.stage_ms = ctx.stage_ms()
         self.n_owned = self.n_local
         counts = [(int(r[1]), int(r[3])) for r in allr]
-        need_words = max(max(2 * e + 7 * s for e, s in counts), 1)
+        need_words = max(max(2 * e + SEG_WORDS * s for e, s in counts), 1)
         if g is None or need_words > self.pad_words:
             self.pad_words = int(need_words * 1.125) + 64
             self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
@@ -382,6 +405,11 @@ class ShardedPipeline(object):
         ctx.shard_finish(threshold, rules, mw, MW, W, gain, plan["skip_first"], plan["skip_last"], plan["event"],
                          self.res.data_ptr())
         return self._gather_results()
+
+    @property
+    def stage_ms(self):
+        """Stage times of the last step (read on demand: seven event queries are host time between steps)."""
+        return self.ctx.stage_ms()
 
     @property
     def tables(self):

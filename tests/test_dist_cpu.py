@@ -75,19 +75,40 @@ def _worker(rank, world, port, epr, q):
         assert np.array_equal(gi[:, 0].numpy(), ws) and np.array_equal(gi[:, 1].numpy(), wl)
         assert np.array_equal(gf[:, 0].numpy(), ws * 0.5)
         # the packed single-collective gather used by ShardedPipeline (pp_pack_tables layout): events as above plus
-        # made-up segment rows {event id, start, end, mean, std, min, max}; ragged counts, one rank may be longer
-        nseg = 3 * len(keep) + rank
-        seg_i = torch.arange(nseg * 3, dtype=torch.int64).reshape(-1, 3) + 1000 * rank
-        seg_f = torch.arange(nseg * 4, dtype=torch.float64).reshape(-1, 4) * 0.25 - rank
-        words = torch.cat([ints.reshape(-1), torch.cat([seg_i, seg_f.view(torch.int64)], dim=1).reshape(-1),
+        # segment rows {event id | start << 32, mean, std, min | max as float32}; ragged counts, one rank may be
+        # longer; unpack_gathered rebuilds `end` from the next row / the event length
+        k0 = sum(c for c in counts[:rank])
+        seg_ev, seg_st, seg_en = [], [], []
+        for j, (s0, n0) in enumerate(keep):
+            cuts = [0, n0 // 3, n0 // 2 + rank, n0]
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                seg_ev.append(k0 + j); seg_st.append(a); seg_en.append(b)
+        nseg = len(seg_ev)
+        mean = np.arange(nseg) * 0.25 - rank
+        sd = np.arange(nseg) * 0.5 + 1
+        mn = (np.arange(nseg) - 3.5).astype(np.float32)
+        mx = (np.arange(nseg) + 0.125).astype(np.float32)
+        if nseg:
+            mn[0] = np.nan
+        w0 = np.asarray(seg_ev, np.int64) | (np.asarray(seg_st, np.int64) << 32)
+        w3 = mn.view(np.uint32).astype(np.int64) | (mx.view(np.uint32).astype(np.int64) << 32)
+        rows = np.stack([w0, mean.view(np.int64), sd.view(np.int64), w3], axis=1) if nseg else np.zeros((0, 4), np.int64)
+        words = torch.cat([ints.reshape(-1), torch.from_numpy(rows.reshape(-1)),
                            torch.zeros(5 * rank, dtype=torch.int64)])
         pcounts = [None] * world
         dist.all_gather_object(pcounts, (len(keep), nseg))
-        t = ppdist.gather_packed(words, pcounts, dist)
+        m = max(max(2 * e + ppdist.SEG_WORDS * s for e, s in pcounts), 1)
+        t = ppdist.unpack_gathered(ppdist.gather_packed_raw(words, m, dist), pcounts)
         assert np.array_equal(t["events"].numpy()[:, 0], ws) and np.array_equal(t["events"].numpy()[:, 1], wl)
         lo = sum(c[1] for c in pcounts[:rank])
         assert t["seg_int"].shape == (sum(c[1] for c in pcounts), 3) and t["seg_flt"].dtype == torch.float64
-        assert torch.equal(t["seg_int"][lo:lo + nseg], seg_i) and torch.equal(t["seg_flt"][lo:lo + nseg], seg_f)
+        mine_i = t["seg_int"][lo:lo + nseg].numpy()
+        mine_f = t["seg_flt"][lo:lo + nseg].numpy()
+        assert np.array_equal(mine_i[:, 0], seg_ev) and np.array_equal(mine_i[:, 1], seg_st)
+        assert np.array_equal(mine_i[:, 2], seg_en)
+        assert np.array_equal(mine_f[:, 0], mean) and np.array_equal(mine_f[:, 1], sd)
+        assert np.array_equal(mine_f[:, 2], mn.astype(np.float64), equal_nan=True)
+        assert np.array_equal(mine_f[:, 3], mx.astype(np.float64))
         # segments of the straddling event, split from chunk+halo, equal the oracle's on the global trace
         if plan["event"] is not None:
             s, n = plan["event"]
