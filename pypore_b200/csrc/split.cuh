@@ -76,9 +76,6 @@ constexpr int K3_PIECES = K3_LIST + K3_WARPS;  // (warp, window) screening recor
 #ifndef K3_CFG_LDCS
 #define K3_CFG_LDCS 0
 #endif
-#ifndef K3_CFG_WINLH
-#define K3_CFG_WINLH 0   // per-window {lo, hi} staged in shared memory: measured no gain (1.199 vs 1.183 ms)
-#endif
 #ifndef K3_CFG_PREFETCH
 #define K3_CFG_PREFETCH 1
 #endif

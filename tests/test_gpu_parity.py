@@ -152,6 +152,35 @@ def test_split_short_and_degenerate_events(ctx):
     check_split_f64(ctx, arrays, min_width=1, max_width=50, window_width=2)
 
 
+def test_min_gain_exactly_at_a_decision_boundary(ctx):
+    """Windows with one contender are decided from the SCREENED gain when it clears min_gain by more than the
+    error bound, and in exact arithmetic otherwise.  Here min_gain is set to gains the reference itself computed
+    (and to their floating-point neighbours), so that a decision sits exactly on `gain > min_gain`; the device must
+    fall back to exact arithmetic there and reproduce the reference's strict comparison."""
+    arrays = [synth.make_long_event(7000, seed=41, tier="A").astype(np.float64),
+              synth.make_long_event(5000, seed=42, tier="B").astype(np.float64),
+              synth.make_long_event(30000, seed=43, tier="A").astype(np.float64)]   # through the spine kernel
+    picked = []
+    for a in arrays:
+        _, info = oracle.statsplit(a, min_width=100, window_width=10000, return_info=True)
+        g = np.sort(info["gains"][np.isfinite(info["gains"])])
+        picked += [g[0], g[len(g) // 3], g[len(g) // 2], g[-1]]
+    for g in picked:
+        for mg in (g, np.nextafter(g, -np.inf), np.nextafter(g, np.inf)):
+            ctx.upload_events_f64(arrays)
+            n = ctx.statsplit(100, 1000000, 10000, float(mg))
+            tab = ctx.segments(n, stats=False)
+            k = 0
+            for e, a in enumerate(arrays):
+                bp = oracle.statsplit(a, min_width=100, window_width=10000, gain=float(mg))
+                edges = np.concatenate(([0], bp, [len(a)]))
+                m = len(edges) - 1
+                assert np.array_equal(tab["start"][k:k + m], edges[:-1]), (g, mg, e)
+                assert np.array_equal(tab["end"][k:k + m], edges[1:]), (g, mg, e)
+                k += m
+            assert k == n
+
+
 def test_split_long_event_spine_and_forced(ctx):
     """Intervals longer than the shared-memory slab: window chain, queue hand-off, max_width forcing."""
     g = load_golden("long_event.npz")
