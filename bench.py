@@ -265,11 +265,12 @@ def run_ours(args):
 
     def step_e2e():
         if shard is None:
-            # public host-memory entry point: chunked H2D copy overlapped with the stages, then table download
+            # public host-memory entry point (pp_pipeline_host_tables): chunked H2D copy overlapped with the stages;
+            # the event / segment rows a chunk has finalised are written into page-locked host tables while the
+            # next chunk is still on its way, so the call returns with the whole result in host memory
             r = ctx.pipeline(THRESHOLD, min_width=mw, max_width=MW, window_width=W, min_gain=gain,
-                             with_stats=True, host_trace=xp, **rules)
-            ctx.events(r["events"])
-            ctx.segments(r["segments"], pinned=True)
+                             with_stats=True, host_trace=xp, export=True, **rules)
+            assert len(r["segment_table"]["mean"]) == r["segments"]
             return r
         shard.load(xp)
         r = shard.step(THRESHOLD, rules, mw, MW, W, gain)

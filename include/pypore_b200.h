@@ -77,7 +77,8 @@ void pp_host_free(pp_ctx *ctx, void *p);
 enum pp_option {
     PP_OPT_SCREEN = 0,
     /* PP_OPT_SPINE (default 1) -- 1: events longer than the locally resolvable interval are first walked window by
-     * window by a whole 1024-thread CTA each (k3_spine); 0: the 128-thread work-queue CTAs walk them (same results). */
+     * window by a thread-block cluster each (k3_spine: 4 CTAs x 512 threads, summaries through distributed shared
+     * memory); 0: the 128-thread work-queue CTAs walk them (same results). */
     PP_OPT_SPINE = 1
 };
 int pp_set_option(pp_ctx *ctx, int option, int64_t value);
@@ -210,6 +211,22 @@ int pp_pipeline(pp_ctx *ctx, const pp_pipeline_params *p, int64_t out[4]);
  * With a filter, or a trace of at most one chunk, it is exactly that sequence. */
 int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_samples,
                      const pp_pipeline_params *p, int64_t out[4]);
+/* pp_pipeline_host that also delivers the event and segment tables to HOST memory: compaction, statistics and
+ * the copy-out of the rows a chunk has finalised run per chunk, overlapped with the copy of the next chunk in the
+ * other direction, so that only the last chunk's rows are outstanding when the last samples have landed (the
+ * rows are written by a kernel straight into the page-locked buffers).  All buffers must come from pp_host_alloc;
+ * the statistics columns may be NULL when p->with_stats == 0.  PP_ERR_CAPACITY: the tables were too small --
+ * nothing of them is valid, the counts in `out` and the device tables are (download them the usual way). */
+typedef struct pp_host_tables {
+    int64_t cap_events;
+    int64_t *ev_start, *ev_len;
+    int64_t cap_segments;
+    int32_t *seg_event;
+    int64_t *seg_start, *seg_end;
+    double *mean, *std, *min, *max;
+} pp_host_tables;
+int pp_pipeline_host_tables(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_samples,
+                            const pp_pipeline_params *p, const pp_host_tables *tables, int64_t out[4]);
 
 /* ---- multi-GPU: one context per rank, contiguous trace chunks -------------
  * The exchange itself (NCCL all-gathers of the records / tables, point-to-point halos) is

@@ -42,6 +42,15 @@ class PipelineParams(_c.Structure):
     ]
 
 
+class HostTables(_c.Structure):
+    """pp_host_tables: page-locked host buffers pp_pipeline_host_tables fills chunk by chunk."""
+    _fields_ = [
+        ("cap_events", _i64), ("ev_start", _c.c_void_p), ("ev_len", _c.c_void_p),
+        ("cap_segments", _i64), ("seg_event", _c.c_void_p), ("seg_start", _c.c_void_p), ("seg_end", _c.c_void_p),
+        ("mean", _c.c_void_p), ("std", _c.c_void_p), ("min", _c.c_void_p), ("max", _c.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/pypore_b200.h declares
 SIGNATURES = {
     "pp_version": (_c.c_int, []),
@@ -93,6 +102,8 @@ SIGNATURES = {
     "pp_trace_extend": (_c.c_int, [_c.c_void_p, _i64]),
     "pp_pack_tables": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _i64, _c.c_void_p, _i64]),
     "pp_pipeline_host": (_c.c_int, [_c.c_void_p, _f32p, _i64, _i64, _c.POINTER(PipelineParams), _i64p]),
+    "pp_pipeline_host_tables": (_c.c_int, [_c.c_void_p, _f32p, _i64, _i64, _c.POINTER(PipelineParams),
+                                           _c.POINTER(HostTables), _i64p]),
     "pp_pipeline": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _i64p]),
 }
 
@@ -408,20 +419,56 @@ class Context(object):
 
     def pipeline(self, threshold, rule_mask, duration_gt, duration_lt, min_gt, max_lt, min_width,
                  max_width, window_width, min_gain, filter_ba=None, prefix_mode=PREFIX_AUTO,
-                 with_stats=True, host_trace=None, chunk_samples=0):
+                 with_stats=True, host_trace=None, chunk_samples=0, export=False):
         """Whole pipeline on the resident trace, or -- with `host_trace` (float32, ideally pinned) --
-        streamed from host memory in chunks that overlap the copy with the computation."""
+        streamed from host memory in chunks that overlap the copy with the computation.  With `export=True`
+        the event and segment tables also arrive in page-locked host memory chunk by chunk (keys `event_table`,
+        `segment_table` of the result: views of the context's pinned arena, valid until its next pinned use)."""
         p, keep = self._params(threshold, rule_mask, duration_gt, duration_lt, min_gt, max_lt, min_width,
                                max_width, window_width, min_gain, filter_ba, prefix_mode, with_stats)
         out = np.zeros(4, np.int64)
+        views = None
         if host_trace is None:
             self._ck(self._L.pp_pipeline(self._h, _c.byref(p), _ptr(out, _i64p)))
         else:
             x = np.ascontiguousarray(host_trace, np.float32)
-            self._ck(self._L.pp_pipeline_host(self._h, _ptr(x, _f32p), x.shape[0], int(chunk_samples),
-                                              _c.byref(p), _ptr(out, _i64p)))
+            if export:
+                # upper bounds: an event is a run (>= 1 sample each, in practice far fewer); a segment is at least
+                # min_width samples unless it is a whole event
+                cap_e = int(x.shape[0] // 256 + 4096)
+                cap_s = int(x.shape[0] // max(int(min_width), 1) + cap_e)
+                spec = [("ev_start", cap_e, np.int64), ("ev_len", cap_e, np.int64), ("event", cap_s, np.int32),
+                        ("start", cap_s, np.int64), ("end", cap_s, np.int64)]
+                if with_stats:
+                    spec += [(k, cap_s, np.float64) for k in ("mean", "std", "min", "max")]
+                views = self._arena_views(spec)
+                t = HostTables()
+                t.cap_events, t.cap_segments = cap_e, cap_s
+                t.ev_start, t.ev_len = views["ev_start"].ctypes.data, views["ev_len"].ctypes.data
+                t.seg_event, t.seg_start, t.seg_end = (views["event"].ctypes.data, views["start"].ctypes.data,
+                                                       views["end"].ctypes.data)
+                if with_stats:
+                    t.mean, t.std, t.min, t.max = (views[k].ctypes.data for k in ("mean", "std", "min", "max"))
+                r = self._L.pp_pipeline_host_tables(self._h, _ptr(x, _f32p), x.shape[0], int(chunk_samples),
+                                                    _c.byref(p), _c.byref(t), _ptr(out, _i64p))
+                if r == PP_ERR_CAPACITY and int(out[3]) > 0:
+                    views = None   # the host tables were too small: the device tables are complete, fetch them
+                else:
+                    self._ck(r)
+            else:
+                self._ck(self._L.pp_pipeline_host(self._h, _ptr(x, _f32p), x.shape[0], int(chunk_samples),
+                                                  _c.byref(p), _ptr(out, _i64p)))
         del keep
-        return dict(runs=int(out[0]), events=int(out[1]), event_samples=int(out[2]), segments=int(out[3]))
+        res = dict(runs=int(out[0]), events=int(out[1]), event_samples=int(out[2]), segments=int(out[3]))
+        if export and host_trace is not None:
+            if views is None:
+                res["event_table"] = self.events(res["events"])
+                res["segment_table"] = self.segments(res["segments"], stats=with_stats)
+            else:
+                ne, ns = res["events"], res["segments"]
+                res["event_table"] = (views["ev_start"][:ne], views["ev_len"][:ne])
+                res["segment_table"] = {k: views[k][:ns] for k in views if not k.startswith("ev_")}
+        return res
 
     @staticmethod
     def _params(threshold, rule_mask, duration_gt, duration_lt, min_gt, max_lt, min_width, max_width,

@@ -368,6 +368,7 @@ int prepare_split(pp_ctx *ctx, int mw, int MW, int W)
         ctx->T_len = W + 1;
     }
     CK(cudaMemsetAsync(ctx->bits.p, 0, sizeof(unsigned) * n_words, ctx->stream));
+    CK(cudaMemsetAsync(&ctx->ctr->seg_done, 0, 3 * sizeof(unsigned long long), ctx->stream));  // seg/flat/ev_done
     return PP_OK;
 }
 
@@ -472,18 +473,19 @@ int enqueue_search(pp_ctx *ctx, int mw, int MW, int W, double min_gain)
     return PP_OK;
 }
 
-// bitmap -> segment table (all events)
+// bitmap -> segment table over the flat range not finalised yet (all events unless the streamed pipeline exports
+// per chunk)
 int enqueue_compact(pp_ctx *ctx)
 {
-    const int64_t n_words = ctx->n_words, n_blocks = ctx->n_blocks;
-    k3c_count<<<(unsigned)n_blocks, CP_THREADS, 0, ctx->stream>>>((const unsigned *)ctx->bits.p, n_words,
+    const int64_t n_blocks = ctx->n_blocks;
+    k3c_count<<<(unsigned)n_blocks, CP_THREADS, 0, ctx->stream>>>((const unsigned *)ctx->bits.p, ctx->ctr,
                                                                  (unsigned *)ctx->block_count.p);
     LAUNCHED(ctx);
-    k3c_scan<<<1, 1024, 0, ctx->stream>>>((const unsigned *)ctx->block_count.p, n_blocks,
+    k3c_scan<<<1, 1024, 0, ctx->stream>>>((const unsigned *)ctx->block_count.p,
                                           (unsigned long long *)ctx->block_off.p, ctx->ctr, ctx->cap_segs);
     LAUNCHED(ctx);
     k3c_write<<<(unsigned)n_blocks, CP_THREADS, 0, ctx->stream>>>(
-        (const unsigned *)ctx->bits.p, n_words, (const unsigned long long *)ctx->block_off.p,
+        (const unsigned *)ctx->bits.p, (const unsigned long long *)ctx->block_off.p,
         (const int64_t *)ctx->ev_off.p, ctx->ctr, (int64_t *)ctx->seg_flat.p, (int *)ctx->seg_event.p,
         (int64_t *)ctx->seg_start.p, ctx->cap_segs);
     LAUNCHED(ctx);
@@ -491,6 +493,19 @@ int enqueue_compact(pp_ctx *ctx)
                                                      (const int *)ctx->seg_event.p,
                                                      (const int64_t *)ctx->ev_off.p,
                                                      (int64_t *)ctx->seg_end.p, ctx->cap_segs);
+    LAUNCHED(ctx);
+    return PP_OK;
+}
+
+// rows / events finalised since the last call -> page-locked host tables, then the range advances
+int enqueue_export(pp_ctx *ctx, const PPHostTables &H, int with_stats)
+{
+    k_export_tables<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(
+        ctx->ctr, H, (const int64_t *)ctx->ev_start.p, (const int64_t *)ctx->ev_len.p, (const int *)ctx->seg_event.p,
+        (const int64_t *)ctx->seg_start.p, (const int64_t *)ctx->seg_end.p, (const double *)ctx->seg_mean.p,
+        (const double *)ctx->seg_std.p, (const double *)ctx->seg_min.p, (const double *)ctx->seg_max.p, with_stats);
+    LAUNCHED(ctx);
+    k_tables_advance<<<1, 32, 0, ctx->stream>>>(ctx->ctr);
     LAUNCHED(ctx);
     return PP_OK;
 }
@@ -1309,11 +1324,35 @@ int pp_pack_tables(pp_ctx *ctx, const int64_t *dev_records, int rank, int64_t sa
 
 // Same pipeline fed from host memory: the trace is copied in chunks on a second stream and every
 // stage up to the split search runs on the events completed so far while the next chunk is in flight.
-int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_samples,
-                     const pp_pipeline_params *p, int64_t out[4])
+// With host tables (pp_pipeline_host_tables) compaction, statistics and the copy-out of the finished rows also
+// run per chunk, so that only the last chunk's rows are left when the last copy has landed.
+static int pipeline_host_impl(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_samples,
+                              const pp_pipeline_params *p, const pp_host_tables *tables, int64_t out[4])
 {
     if (!ctx || !p || !host || n <= 0) return fail(ctx, PP_ERR_ARG, "bad trace");
     CKR(set_device(ctx));
+    PPHostTables H;
+    memset(&H, 0, sizeof H);
+    if (tables) {
+        if (tables->cap_events < 0 || tables->cap_segments < 0 || !tables->ev_start || !tables->ev_len ||
+            !tables->seg_event || !tables->seg_start || !tables->seg_end ||
+            (p->with_stats && (!tables->mean || !tables->std || !tables->min || !tables->max)))
+            return fail(ctx, PP_ERR_ARG, "incomplete host tables");
+        H.cap_events = tables->cap_events;
+        H.cap_segments = tables->cap_segments;
+        // device-visible aliases of the page-locked buffers (pp_host_alloc); fails for pageable memory
+        CK(cudaHostGetDevicePointer((void **)&H.ev_start, tables->ev_start, 0));
+        CK(cudaHostGetDevicePointer((void **)&H.ev_len, tables->ev_len, 0));
+        CK(cudaHostGetDevicePointer((void **)&H.seg_event, tables->seg_event, 0));
+        CK(cudaHostGetDevicePointer((void **)&H.seg_start, tables->seg_start, 0));
+        CK(cudaHostGetDevicePointer((void **)&H.seg_end, tables->seg_end, 0));
+        if (p->with_stats) {
+            CK(cudaHostGetDevicePointer((void **)&H.mean, tables->mean, 0));
+            CK(cudaHostGetDevicePointer((void **)&H.sd, tables->std, 0));
+            CK(cudaHostGetDevicePointer((void **)&H.mn, tables->min, 0));
+            CK(cudaHostGetDevicePointer((void **)&H.mx, tables->max, 0));
+        }
+    }
     // 16 Mi samples measured best on B200 (scripts/e2e_breakdown.py: 1 Mi 17.9 ms, 4 Mi 5.9, 8 Mi 5.15, 16 Mi
     // 4.92 for a 60 M-sample trace whose bare copy takes 4.32 ms; a shrinking schedule 24 -> 4 Mi was slower:
     // every chunk pays a full split-search latency)
@@ -1322,7 +1361,13 @@ int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_sa
     if (p->filter_ncoef > 0 || n <= chunk_samples) {
         // filtering needs every event before the split; a short trace gains nothing from chunking
         CKR(pp_trace_upload(ctx, host, n, 0));
-        return pp_pipeline(ctx, p, out);
+        CKR(pp_pipeline(ctx, p, out));
+        if (tables) {
+            CKR(enqueue_export(ctx, H, p->with_stats));
+            CKR(fetch_counters(ctx));
+            if (ctx->h_ctr->overflow & PP_OVF_EXPORT) return fail(ctx, PP_ERR_CAPACITY, "host tables too small");
+        }
+        return PP_OK;
     }
     if (!ctx->copy_stream) {
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -1353,27 +1398,55 @@ int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_sa
                            b == n ? 2 : 1));
         CKR(enqueue_prefix(ctx, p->prefix_mode));
         CKR(enqueue_search(ctx, p->min_width, p->max_width, p->window_width, p->min_gain));
+        if (tables) {  // the events of this chunk are final: their rows leave for the host now
+            CKR(enqueue_compact(ctx));
+            if (p->with_stats) CKR(enqueue_stats(ctx));
+            CKR(enqueue_export(ctx, H, p->with_stats));
+        }
     }
-    CKR(enqueue_compact(ctx));
-    if (p->with_stats) CKR(enqueue_stats(ctx));
+    if (!tables) {
+        CKR(enqueue_compact(ctx));
+        if (p->with_stats) CKR(enqueue_stats(ctx));
+    }
     CKR(fetch_counters(ctx));
     const int64_t runs = (int64_t)ctx->h_ctr->n_runs;
     if (runs > ctx->cap_runs) {  // rare: noisy trace with many crossings; the trace is resident now, redo it whole
         CKR(ensure_run_buffers(ctx, runs + 16));
-        return pp_pipeline(ctx, p, out);
+        CKR(pp_pipeline(ctx, p, out));
+        if (tables) {
+            CKR(enqueue_export(ctx, H, p->with_stats));
+            CKR(fetch_counters(ctx));
+            if (ctx->h_ctr->overflow & PP_OVF_EXPORT) return fail(ctx, PP_ERR_CAPACITY, "host tables too small");
+        }
+        return PP_OK;
     }
     absorb_counters(ctx);
     ctx->n_runs = runs;
     ctx->prefix_valid = true;
     CKR(check_overflow(ctx));
     ctx->n_segments = (int64_t)ctx->h_ctr->n_segments;
+    ctx->stats_valid = p->with_stats != 0;
     if (out) {
         out[0] = runs;
         out[1] = ctx->n_events;
         out[2] = ctx->n_event_samples;
         out[3] = ctx->n_segments;
     }
+    if (ctx->h_ctr->overflow & PP_OVF_EXPORT) return fail(ctx, PP_ERR_CAPACITY, "host tables too small");
     return PP_OK;
+}
+
+int pp_pipeline_host(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_samples,
+                     const pp_pipeline_params *p, int64_t out[4])
+{
+    return pipeline_host_impl(ctx, host, n, chunk_samples, p, nullptr, out);
+}
+
+int pp_pipeline_host_tables(pp_ctx *ctx, const float *host, int64_t n, int64_t chunk_samples,
+                            const pp_pipeline_params *p, const pp_host_tables *tables, int64_t out[4])
+{
+    if (!tables) return fail(ctx, PP_ERR_ARG, "no host tables");
+    return pipeline_host_impl(ctx, host, n, chunk_samples, p, tables, out);
 }
 
 }  // extern "C"

@@ -35,12 +35,18 @@ struct PPCounters {
     unsigned long long ev_begin;
     unsigned long long tile_begin;
     unsigned long long n_long;        // events of the current search that k3_spine walks first
+    // tables finalised so far (streamed pipeline with host export: compaction, statistics and the copy-out run per
+    // chunk on the flat range [flat_done, n_event_samples) / the events [ev_done, n_events)); all zero otherwise
+    unsigned long long seg_done;
+    unsigned long long flat_done;
+    unsigned long long ev_done;
     unsigned int overflow;            // bit0 runs, bit1 queue, bit2 segments, bit3 filter-too-short
     unsigned int first_below;         // below-threshold bit of sample 0
 };
 
 enum { PP_OVF_RUNS = 1, PP_OVF_QUEUE = 2, PP_OVF_SEGS = 4, PP_OVF_FILTER_SHORT = 8,
-       PP_OVF_HALO = 16 /* multi-GPU: the speculative halo did not cover a straddling event */ };
+       PP_OVF_HALO = 16 /* multi-GPU: the speculative halo did not cover a straddling event */,
+       PP_OVF_EXPORT = 32 /* host tables of pp_pipeline_host_tables too small */ };
 
 // Where an event's samples live.
 //   kind 0: float32 trace, sample j of event e = trace[ev_start[e] + j]

@@ -1499,22 +1499,37 @@ k3_init_queue(K3Global G, int use_spine)
 }
 
 // ---------------------------------------------------------------------------
-// Bitmap -> sorted segment table (flat start, event id, event-relative start).
+// Bitmap -> sorted segment table (flat start, event id, event-relative start), for the flat range
+// [ctr->flat_done, ctr->n_event_samples): the whole table in one go (flat_done = seg_done = 0), or -- streamed
+// pipeline with host export -- one range per chunk, appended behind the ctr->seg_done rows already written.
 // ---------------------------------------------------------------------------
 constexpr int CP_THREADS = 256;
 constexpr int CP_WPT = 4;                           // words per thread
 constexpr int CP_BLOCK_WORDS = CP_THREADS * CP_WPT;  // 1024 words = 32768 samples
 
+// word w of the bitmap restricted to the flat range [lo, hi)
+__device__ __forceinline__ unsigned k3c_word(const unsigned *__restrict__ bits, int64_t w, int64_t lo, int64_t hi)
+{
+    const int64_t b0 = w << 5;
+    if (b0 + 32 <= lo || b0 >= hi) return 0u;
+    unsigned v = bits[w];
+    if (b0 < lo) v &= ~0u << (unsigned)(lo - b0);
+    if (b0 + 32 > hi) v &= ~0u >> (unsigned)(b0 + 32 - hi);
+    return v;
+}
+
 __global__ void __launch_bounds__(CP_THREADS)
-k3c_count(const unsigned *__restrict__ bits, int64_t n_words, unsigned *__restrict__ block_count)
+k3c_count(const unsigned *__restrict__ bits, const PPCounters *ctr, unsigned *__restrict__ block_count)
 {
     __shared__ unsigned wsum[CP_THREADS / 32];
     const int tid = threadIdx.x;
-    const int64_t w0 = (int64_t)blockIdx.x * CP_BLOCK_WORDS + tid * CP_WPT;
+    const int64_t lo = (int64_t)ctr->flat_done, hi = (int64_t)ctr->n_event_samples;
+    const int64_t blk0 = (int64_t)blockIdx.x * CP_BLOCK_WORDS;
+    if ((blk0 + CP_BLOCK_WORDS) * 32 <= lo || blk0 * 32 >= hi) return;  // outside the range: not looked at by the scan
+    const int64_t w0 = blk0 + tid * CP_WPT;
     unsigned c = 0;
 #pragma unroll
-    for (int k = 0; k < CP_WPT; ++k)
-        if (w0 + k < n_words) c += __popc(bits[w0 + k]);
+    for (int k = 0; k < CP_WPT; ++k) c += __popc(k3c_word(bits, w0 + k, lo, hi));
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(PP_FULL, c, d);
     if ((tid & 31) == 0) wsum[tid >> 5] = c;
@@ -1527,17 +1542,20 @@ k3c_count(const unsigned *__restrict__ bits, int64_t n_words, unsigned *__restri
 }
 
 __global__ void __launch_bounds__(1024)
-k3c_scan(const unsigned *__restrict__ block_count, int64_t n_blocks,
-         unsigned long long *__restrict__ block_off, PPCounters *ctr, int64_t cap_segs)
+k3c_scan(const unsigned *__restrict__ block_count, unsigned long long *__restrict__ block_off, PPCounters *ctr,
+         int64_t cap_segs)
 {
     __shared__ unsigned long long wtot[32];
     __shared__ unsigned long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    const int64_t lo = (int64_t)ctr->flat_done, hi = (int64_t)ctr->n_event_samples;
+    const int64_t b_lo = lo / (CP_BLOCK_WORDS * 32);
+    const int64_t b_hi = hi > lo ? (hi - 1) / (CP_BLOCK_WORDS * 32) + 1 : b_lo;  // blocks [b_lo, b_hi) touch the range
+    if (tid == 0) s_carry = ctr->seg_done;
     __syncthreads();
-    for (int64_t c0 = 0; c0 < n_blocks; c0 += 1024) {
+    for (int64_t c0 = b_lo; c0 < b_hi; c0 += 1024) {
         const int64_t b = c0 + tid;
-        const unsigned long long v = b < n_blocks ? block_count[b] : 0ull;
+        const unsigned long long v = b < b_hi ? block_count[b] : 0ull;
         unsigned long long inc = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -1549,7 +1567,7 @@ k3c_scan(const unsigned *__restrict__ block_count, int64_t n_blocks,
         unsigned long long add = 0;
         for (int w = 0; w < warp; ++w) add += wtot[w];
         const unsigned long long excl = s_carry + add + inc - v;
-        if (b < n_blocks) block_off[b] = excl;
+        if (b < b_hi) block_off[b] = excl;
         __syncthreads();
         if (tid == 1023) s_carry = excl + v;
         __syncthreads();
@@ -1561,19 +1579,21 @@ k3c_scan(const unsigned *__restrict__ block_count, int64_t n_blocks,
 }
 
 __global__ void __launch_bounds__(CP_THREADS)
-k3c_write(const unsigned *__restrict__ bits, int64_t n_words,
-          const unsigned long long *__restrict__ block_off, const int64_t *__restrict__ ev_off,
-          const PPCounters *ctr, int64_t *__restrict__ seg_flat, int *__restrict__ seg_event,
-          int64_t *__restrict__ seg_start, int64_t cap_segs)
+k3c_write(const unsigned *__restrict__ bits, const unsigned long long *__restrict__ block_off,
+          const int64_t *__restrict__ ev_off, const PPCounters *ctr, int64_t *__restrict__ seg_flat,
+          int *__restrict__ seg_event, int64_t *__restrict__ seg_start, int64_t cap_segs)
 {
     __shared__ unsigned wsum[CP_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t w0 = (int64_t)blockIdx.x * CP_BLOCK_WORDS + tid * CP_WPT;
+    const int64_t lo = (int64_t)ctr->flat_done, hi = (int64_t)ctr->n_event_samples;
+    const int64_t blk0 = (int64_t)blockIdx.x * CP_BLOCK_WORDS;
+    if ((blk0 + CP_BLOCK_WORDS) * 32 <= lo || blk0 * 32 >= hi) return;
+    const int64_t w0 = blk0 + tid * CP_WPT;
     unsigned wv[CP_WPT];
     unsigned c = 0;
 #pragma unroll
     for (int k = 0; k < CP_WPT; ++k) {
-        wv[k] = (w0 + k < n_words) ? bits[w0 + k] : 0u;
+        wv[k] = k3c_word(bits, w0 + k, lo, hi);
         c += __popc(wv[k]);
     }
     unsigned inc = c;
@@ -1621,9 +1641,61 @@ k3c_ends(const PPCounters *ctr, const int64_t *__restrict__ seg_flat,
     int64_t S = (int64_t)ctr->n_segments;
     if (S > cap_segs) S = cap_segs;
     const int64_t total = (int64_t)ctr->n_event_samples;
-    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < S;
+    for (int64_t k = (int64_t)ctr->seg_done + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < S;
          k += (int64_t)gridDim.x * blockDim.x) {
         const int64_t fe = (k + 1 < S) ? seg_flat[k + 1] : total;
         seg_end[k] = fe - ev_off[seg_event[k]];
     }
+}
+
+// Streamed pipeline with host export: rows [seg_done, n_segments) and events [ev_done, n_events) written straight
+// into page-locked host memory (device-visible alias), coalesced per column, while the next chunk is being copied
+// in the other direction.  Nothing is written (and PP_OVF_EXPORT is raised) if the host tables are too small.
+struct PPHostTables {
+    int64_t cap_events;
+    int64_t *ev_start, *ev_len;
+    int64_t cap_segments;
+    int *seg_event;
+    int64_t *seg_start, *seg_end;
+    double *mean, *sd, *mn, *mx;
+};
+
+__global__ void __launch_bounds__(256)
+k_export_tables(PPCounters *ctr, PPHostTables H, const int64_t *__restrict__ ev_start,
+                const int64_t *__restrict__ ev_len, const int *__restrict__ seg_event,
+                const int64_t *__restrict__ seg_start, const int64_t *__restrict__ seg_end,
+                const double *__restrict__ mean, const double *__restrict__ sd, const double *__restrict__ mn,
+                const double *__restrict__ mx, int with_stats)
+{
+    const int64_t S = (int64_t)ctr->n_segments, E = (int64_t)ctr->n_events;
+    if (S > H.cap_segments || E > H.cap_events) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&ctr->overflow, (unsigned)PP_OVF_EXPORT);
+        return;
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t e = (int64_t)ctr->ev_done + t0; e < E; e += stride) {
+        H.ev_start[e] = ev_start[e];
+        H.ev_len[e] = ev_len[e];
+    }
+    for (int64_t k = (int64_t)ctr->seg_done + t0; k < S; k += stride) {
+        H.seg_event[k] = seg_event[k];
+        H.seg_start[k] = seg_start[k];
+        H.seg_end[k] = seg_end[k];
+        if (with_stats) {
+            H.mean[k] = mean[k];
+            H.sd[k] = sd[k];
+            H.mn[k] = mn[k];
+            H.mx[k] = mx[k];
+        }
+    }
+}
+
+// the next range starts where this one ended
+__global__ void k_tables_advance(PPCounters *ctr)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    ctr->seg_done = ctr->n_segments;
+    ctr->flat_done = ctr->n_event_samples;
+    ctr->ev_done = ctr->n_events;
 }

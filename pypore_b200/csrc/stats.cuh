@@ -60,7 +60,7 @@ __device__ __forceinline__ double k4_max(double a, double b) { return fmax(a, b)
 // so that the full-mask shuffles stay convergent (inactive groups work on an empty row).
 template <typename T, int G>
 __device__ __forceinline__ void k4_rows(const T *__restrict__ samples, const int64_t *__restrict__ ev_base,
-                                        const int64_t *__restrict__ ev_off, int64_t rows, int64_t total,
+                                        const int64_t *__restrict__ ev_off, int64_t row0, int64_t rows, int64_t total,
                                         const int64_t *__restrict__ flat_start, const int *__restrict__ row_event,
                                         double *__restrict__ o_mean, double *__restrict__ o_std,
                                         double *__restrict__ o_min, double *__restrict__ o_max)
@@ -70,7 +70,7 @@ __device__ __forceinline__ void k4_rows(const T *__restrict__ samples, const int
     const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
     const int64_t warp_first = group0 - ((threadIdx.x & 31) / G);  // row of the warp's first group
     const T inf = (T)__longlong_as_double(0x7ff0000000000000LL);
-    for (int64_t kw = warp_first; kw < rows; kw += ngroups) {
+    for (int64_t kw = row0 + warp_first; kw < rows; kw += ngroups) {  // rows [row0, rows)
         const int64_t k = kw + ((threadIdx.x & 31) / G);
         const bool live = k < rows;
         int64_t len = 0;
@@ -161,9 +161,11 @@ k4_segment_stats(const T *__restrict__ samples, const int64_t *__restrict__ ev_b
     int64_t rows = rows_are_events ? (int64_t)ctr->n_events : (int64_t)ctr->n_segments;
     if (rows > cap_rows) rows = cap_rows;
     const int64_t total = (int64_t)ctr->n_event_samples;
-    if (rows <= 0) return;
+    // segments: only the rows not finalised yet (the whole table unless the streamed pipeline exports per chunk)
+    const int64_t row0 = rows_are_events ? 0 : (int64_t)ctr->seg_done;
+    if (rows <= row0) return;
     if (total / rows < 512)
-        k4_rows<T, 8>(samples, ev_base, ev_off, rows, total, flat_start, row_event, o_mean, o_std, o_min, o_max);
+        k4_rows<T, 8>(samples, ev_base, ev_off, row0, rows, total, flat_start, row_event, o_mean, o_std, o_min, o_max);
     else
-        k4_rows<T, 32>(samples, ev_base, ev_off, rows, total, flat_start, row_event, o_mean, o_std, o_min, o_max);
+        k4_rows<T, 32>(samples, ev_base, ev_off, row0, rows, total, flat_start, row_event, o_mean, o_std, o_min, o_max);
 }

@@ -24,5 +24,8 @@ r = ctx.pipeline(110.0, min_width=mw, max_width=MW, window_width=W, min_gain=gai
 print("resident pipeline      %.3f ms" % t(lambda: ctx.pipeline(110.0, min_width=mw, max_width=MW, window_width=W, min_gain=gain, with_stats=True, **rules)))
 for ch in (1 << 20, 2 << 20, 4 << 20, 8 << 20, 16 << 20):
     print("host pipeline chunk %3dM %.3f ms" % (ch >> 20, t(lambda: ctx.pipeline(110.0, min_width=mw, max_width=MW, window_width=W, min_gain=gain, with_stats=True, host_trace=xp, chunk_samples=ch, **rules))))
+for ch in (4 << 20, 8 << 20, 12 << 20, 16 << 20, 20 << 20, 30 << 20):
+    print("host pipeline + host tables, chunk %3dM %.3f ms" % (ch >> 20, t(lambda: ctx.pipeline(110.0, min_width=mw, max_width=MW, window_width=W, min_gain=gain, with_stats=True, host_trace=xp, chunk_samples=ch, export=True, **rules))))
 print("events download        %.3f ms" % t(lambda: ctx.events(r["events"])))
 print("segments download      %.3f ms" % t(lambda: ctx.segments(r["segments"])))
+print("segments download (pinned) %.3f ms" % t(lambda: ctx.segments(r["segments"], pinned=True)))

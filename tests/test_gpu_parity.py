@@ -493,6 +493,33 @@ def test_streamed_host_pipeline_equals_resident(ctx, chunk):
         assert np.array_equal(ev1[0], ws) and np.array_equal(ev1[1], wl)
         oe, ost, oen, _ = oracle.statsplit_events(x64, ws, wl, gain=gain)
         assert np.array_equal(tab1["event"], oe) and np.array_equal(tab1["start"], ost) and np.array_equal(tab1["end"], oen)
+        # pp_pipeline_host_tables: compaction / statistics / copy-out per chunk into page-locked host tables
+        r2 = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, gain, host_trace=x,
+                          chunk_samples=chunk, export=True)
+        assert {k: r2[k] for k in r0} == r0
+        assert np.array_equal(r2["event_table"][0], ev0[0]) and np.array_equal(r2["event_table"][1], ev0[1])
+        assert set(r2["segment_table"]) == set(tab0)
+        assert all(np.array_equal(tab0[k], r2["segment_table"][k]) for k in tab0)
+        # ... and the device tables it leaves behind are the same ones
+        tab2 = ctx.segments(r2["segments"])
+        assert all(np.array_equal(tab0[k], tab2[k]) for k in tab0)
+
+
+def test_host_tables_too_small_fall_back_to_downloads(ctx):
+    """More events than the exporting call reserves host rows for: the C call reports PP_ERR_CAPACITY, the Python
+    layer fetches the (complete) device tables instead."""
+    n = 1200000
+    x = np.where((np.arange(n) // 50) % 2 == 0, 50.0, 120.0).astype(np.float32)   # 12,000 events of 50 samples
+    x += (np.arange(n) % 7).astype(np.float32) * 0.125
+    gain = oracle.min_gain()
+    kw = dict(host_trace=x, chunk_samples=1 << 18)
+    r = ctx.pipeline(110.0, 5, 20, 0, 0.0, 110.0, 10, 1000000, 40, gain, export=True, **kw)
+    assert r["events"] == 12000 and r["events"] > n // 256 + 4096
+    ctx.upload_trace(x)
+    r0 = ctx.pipeline(110.0, 5, 20, 0, 0.0, 110.0, 10, 1000000, 40, gain)
+    tab0 = ctx.segments(r0["segments"])
+    assert {k: r[k] for k in r0} == r0
+    assert all(np.array_equal(tab0[k], r["segment_table"][k]) for k in tab0)
 
 
 def test_streamed_host_pipeline_no_events_and_single_chunk(ctx):
@@ -503,8 +530,13 @@ def test_streamed_host_pipeline_no_events_and_single_chunk(ctx):
     assert (r["runs"], r["events"], r["segments"]) == (1, 0, 0)
     x = synth.make_trace(5, seed=2, tier="A")                               # shorter than one chunk
     r = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, oracle.min_gain(), host_trace=x)
+    r2 = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, oracle.min_gain(), host_trace=x,
+                      export=True)
     ctx.upload_trace(x)
-    assert r == ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, oracle.min_gain())
+    r0 = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, oracle.min_gain())
+    assert r == r0 and {k: r2[k] for k in r0} == r0
+    tab0 = ctx.segments(r0["segments"])
+    assert all(np.array_equal(tab0[k], r2["segment_table"][k]) for k in tab0)
 
 
 def test_pinned_downloads_and_pinned_trace(ctx):
