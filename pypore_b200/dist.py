@@ -136,16 +136,17 @@ def gather_tables(int_cols, flt_cols, counts, dist, group=None):
     return out[0], out[1]
 
 
-def gather_packed_raw(words, m, dist, group=None):
+def gather_packed_raw(words, m, dist, group=None, async_op=False):
     """ONE all-gather of the first m words of every rank's packed tables (pp_pack_tables layout: 2 words per
-    event, then SEG_WORDS per segment).  Returns the int64 tensor [world, m]; row r holds rank r's words."""
+    event, then SEG_WORDS per segment).  Returns the int64 tensor [world, m]; row r holds rank r's words.
+    With async_op the collective is only enqueued: returns (tensor, work) and the caller waits on `work`."""
     import torch
     world = dist.get_world_size(group)
     if words.shape[0] < m:
         words = torch.cat([words, torch.zeros(m - words.shape[0], dtype=words.dtype, device=words.device)])
     g = torch.empty(world * m, dtype=torch.int64, device=words.device)
-    dist.all_gather_into_tensor(g, words[:m].contiguous(), group=group)
-    return g.view(world, m)
+    work = dist.all_gather_into_tensor(g, words[:m].contiguous(), group=group, async_op=async_op)
+    return (g.view(world, m), work) if async_op else g.view(world, m)
 
 
 def split_gathered(g, counts):
@@ -263,6 +264,10 @@ class ShardedPipeline(object):
         self.pad_words = 0
         self.lens = None
         self._halo = 0       # speculative halo samples resident after the chunk
+        self._table_work = None   # outstanding asynchronous table all-gather
+        # the tiny control collectives (chunk lengths, boundary records, result records) get their own communicator:
+        # they sit on every step's critical path and must not queue behind the previous step's table all-gather
+        self.ctl_group = dist.new_group() if world > 1 and dist.is_initialized() else group
         self.fallbacks = 0   # steps that had to be repeated with the host-made plan
 
     def load(self, host_chunk):
@@ -273,7 +278,7 @@ class ShardedPipeline(object):
         with torch.cuda.stream(self.stream):
             mine = torch.tensor([self.n_local], dtype=torch.int64, device=self.device)
             lens = torch.empty(self.world, dtype=torch.int64, device=self.device)
-            self.dist.all_gather_into_tensor(lens, mine, group=self.group)
+            self.dist.all_gather_into_tensor(lens, mine, group=self.ctl_group)
             self.lens = lens.cpu().numpy()
         self.ctx.upload_trace_async(host_chunk, extra_capacity=self.HALO_CAPACITY)   # after the read-back: not waited on
         self._exchange_speculative_halo()
@@ -332,7 +337,7 @@ class ShardedPipeline(object):
             self.infos_dev = torch.empty(self.world * INFO_LEN, dtype=torch.float64, device=dev)
         ctx.truncate_trace(self.n_local)
         ctx.shard_scan(threshold, self.n_local, self.rec.data_ptr())
-        dist.all_gather_into_tensor(self.infos_dev, self.rec, group=self.group)
+        dist.all_gather_into_tensor(self.infos_dev, self.rec, group=self.ctl_group)
         halo = self._halo
         ctx.extend_trace(halo)
         ctx.shard_plan(self.infos_dev.data_ptr(), self.rank, self.world, threshold, rules, halo, self.plan.data_ptr())
@@ -344,32 +349,41 @@ class ShardedPipeline(object):
         import torch
         ctx, dist, dev = self.ctx, self.dist, self.device
         allr_dev = torch.empty(self.world * 8, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allr_dev, self.res, group=self.group)
+        dist.all_gather_into_tensor(allr_dev, self.res, group=self.ctl_group)
         # Speculative sizing: pack and all-gather with the padding of the previous step (+12.5 %) before the host
         # knows this step's counts -- the pack kernel takes them from allr_dev on the device -- so the GPU is not
         # idle during the host round trip.  Every rank reads the same records and takes the same decision.
-        g = None
+        # The table all-gather is asynchronous: the context's stream does not wait for it here, so the next step's
+        # scan (or whatever the caller enqueues next) overlaps it; `tables` / `download()` and the next step's pack
+        # kernel wait for it.
+        self._wait_tables()                      # the previous step's gather still reads self.pack
+        g = work = None
         if self.pad_words:
             if self.pack is None or self.pack.shape[0] < self.pad_words:
                 self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
             ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
                             self.pad_words)
-            g = gather_packed_raw(self.pack, self.pad_words, dist, self.group)
+            g, work = gather_packed_raw(self.pack, self.pad_words, dist, self.group, async_op=True)
         allr = allr_dev.cpu().numpy().reshape(self.world, 8)             # host sync (nothing waits on it)
         if redo_mask and (allr[:, 4] & redo_mask).any():
+            if work is not None:
+                work.wait()
             return None
         ctx.shard_commit(allr[self.rank])
         self.n_owned = self.n_local
         counts = [(int(r[1]), int(r[3])) for r in allr]
         need_words = max(max(2 * e + SEG_WORDS * s for e, s in counts), 1)
         if g is None or need_words > self.pad_words:
+            if work is not None:
+                work.wait()
             self.pad_words = int(need_words * 1.125) + 64
             self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
             ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
                             self.pad_words)
-            g = gather_packed_raw(self.pack, self.pad_words, dist, self.group)
+            g, work = gather_packed_raw(self.pack, self.pad_words, dist, self.group, async_op=True)
         else:
             self.pad_words = max(int(need_words * 1.125) + 64, 1)
+        self._table_work = work
         self.gathered, self.counts, self._tables = g, counts, None
         ne, n_seg = counts[self.rank]
         return dict(runs=int(allr[self.rank, 0]), events=ne, event_samples=int(allr[self.rank, 2]), segments=n_seg)
@@ -386,7 +400,7 @@ class ShardedPipeline(object):
             ctx.truncate_trace(self.n_local)
             ctx.shard_scan(threshold, self.n_local, self.rec.data_ptr())
             out = torch.empty(self.world * INFO_LEN, dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(out, self.rec, group=self.group)
+            dist.all_gather_into_tensor(out, self.rec, group=self.ctl_group)
             infos = out.cpu().numpy().reshape(self.world, INFO_LEN)      # host sync 1
             if not infos[:, I_PAD].any():
                 break
@@ -411,11 +425,24 @@ class ShardedPipeline(object):
         """Stage times of the last step (read on demand: seven event queries are host time between steps)."""
         return self.ctx.stage_ms()
 
+    def wait(self):
+        """The context's stream waits for everything the last step left in flight (the table all-gather)."""
+        self._wait_tables()
+
+    def _wait_tables(self):
+        """Make the context's stream wait for the outstanding table all-gather (stream-level, the host goes on)."""
+        if self._table_work is not None:
+            import torch
+            with torch.cuda.stream(self.stream):
+                self._table_work.wait()
+            self._table_work = None
+
     @property
     def tables(self):
         """The whole result on this GPU as contiguous tensors (built from the gathered buffer on first use)."""
         if self._tables is None and self.gathered is not None:
             import torch
+            self._wait_tables()
             with torch.cuda.stream(self.stream):
                 self._tables = unpack_gathered(self.gathered, self.counts)
         return self._tables
