@@ -28,9 +28,17 @@ def main():
     for kw in (dict(min_width=100, max_width=1000000, window_width=10000),
                dict(min_width=100, max_width=1000000, window_width=10000, prior_segments_per_second=10)):
         mw, MW, W, gain = statsplit_min_gain(**kw)
-        for _ in range(2):  # twice: the halo is dropped and re-fetched on every step
+        for _ in range(2):  # twice: buffers, counters and the asynchronous table gather are reused across steps
             shard.step(110.0, rules, mw, MW, W, gain)
         tabs = shard.download()
+        assert shard.fallbacks == 0
+        # the host-planned step (the fallback of the device-planned one) must give the same tables
+        shard.step(110.0, rules, mw, MW, W, gain, host_planned=True)
+        alt = shard.download()
+        assert all(np.array_equal(tabs[k], alt[k], equal_nan=True) for k in tabs), "host-planned step differs"
+        shard.step(110.0, rules, mw, MW, W, gain)   # and back: the speculative halo is still in place
+        alt = shard.download()
+        assert all(np.array_equal(tabs[k], alt[k], equal_nan=True) for k in tabs), "device-planned step after it differs"
         glob = ppdist.synthetic_global(world, epr, seed0=70).astype(np.float64)
         pyrules = [lambda e: e.duration > 1000, lambda e: e.min > -0.5, lambda e: e.max < 110]
         ws, wl = oracle.events(glob, 110, pyrules)
