@@ -410,3 +410,41 @@ class SpeedyStatSplit(parser):
                 segs.append(seg)
             out[i] = segs
         return out
+
+
+class FilterDerivativeSegmenter(parser):
+    """Filter-derivative segmenter (PyPore/parsers.py:609-656): zero-phase order-1 Bessel low-pass, absolute
+    first difference, blocks where it exceeds ``low_threshold``, split points from those blocks.
+
+    Same constructor, attributes and results as the reference, its quirks included: a block is kept when the
+    *position* of its largest derivative (``np.argmax``) exceeds ``high_threshold`` (parsers.py:645), and a
+    Segment is built for every second pair of split points only (parsers.py:655-656).  The filtfilt -- the
+    O(n) arithmetic of the method -- runs on the device through the K5 scan (pp_filter_events, the kernel behind
+    Event.filter); the thresholding of the derivative is the reference's own NumPy statements."""
+
+    def __init__(self, low_threshold=1, high_threshold=2, cutoff_freq=1000., sampling_freq=1.e5):
+        self.low_threshold = low_threshold
+        self.high_threshold = high_threshold
+        self.cutoff_freq = cutoff_freq
+        self.sampling_freq = sampling_freq
+
+    def parse(self, current):
+        from .DataTypes import bessel_coefficients
+        x = np.ascontiguousarray(np.array(current), np.float64)
+        ctx = _lib.default_context()
+        ctx.upload_events_f64([x])
+        ctx.filter_events(*bessel_coefficients(1, self.cutoff_freq, self.sampling_freq))   # scipy raises for len <= padlen
+        filtered_current = ctx.event_samples(x.shape[0])
+
+        deriv = np.abs(np.diff(filtered_current))
+        blocks = np.where(deriv > self.low_threshold, 1, 0)
+        block_edges = np.abs(np.diff(blocks))
+        tics = np.where(block_edges == 1)[0] + 1
+
+        split_points = [0]
+        for start, end in zip(tics[:-1:2], tics[1::2]):
+            segment = deriv[start:end]
+            if np.argmax(segment) > self.high_threshold:
+                split_points = np.concatenate((split_points, [start, end]))
+        tics = [int(t) for t in np.concatenate((split_points, [current.shape[0]]))]
+        return [Segment(current=current[tics[i]:tics[i + 1]], start=tics[i]) for i in range(0, len(tics) - 1, 2)]

@@ -36,6 +36,7 @@ def _shim(src):
     src = src.replace("from itertools import tee,izip,chain", "from itertools import tee,chain; izip=zip")
     src = src.replace("from itertools import chain, izip, tee, combinations",
                       "from itertools import chain, tee, combinations; izip=zip")
+    src = src.replace("tics = map( int, tics )", "tics = list( map( int, tics ) )")   # Python-2 map returned a list
     src = re.sub(r'^(\s*)print "(.*)"\.format\((.*)\)\s*$', r'\1print("\2".format(\3))', src, flags=re.M)
     src = re.sub(r'^(\s*)print "(.*)"\s*$', r'\1print("\2")', src, flags=re.M)
     return src
@@ -225,6 +226,22 @@ def golden_scoring():
     return out
 
 
+from make_golden_cases import FDS_CASES  # noqa: E402  (shared with tests/test_gpu_api.py)
+
+
+def golden_fds(parsers):
+    """FilterDerivativeSegmenter.parse (parsers.py:609-656) of the real reference, quirks included (np.argmax
+    compared with high_threshold; a Segment for every SECOND pair of tics only)."""
+    out = {}
+    for name, (length, seed, tier, kw) in FDS_CASES.items():
+        x = synth.make_long_event(length, seed=seed, tier=tier).astype(np.float64)
+        segs = parsers.FilterDerivativeSegmenter(**kw).parse(x)
+        out[name + "_start"] = np.array([s.start for s in segs], np.int64)
+        out[name + "_n"] = np.array([len(s.current) for s in segs], np.int64)
+        out[name + "_mean"] = np.array([s.mean for s in segs], np.float64)
+    return out
+
+
 def golden_json(dt, parsers):
     """File.to_json of the real reference after File.parse -> Event.filter -> Event.parse (DataTypes.py:708-738),
     the on-disk format of the result tables."""
@@ -249,6 +266,10 @@ def main():
             out.write(golden_json(dt, parsers))
         print("file_tierA.json", os.path.getsize(os.path.join(HERE, "file_tierA.json")))
         return
+    if "--fds-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "fds.npz"), **golden_fds(parsers))
+        print("fds.npz", os.path.getsize(os.path.join(HERE, "fds.npz")))
+        return
     if "--scoring-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "scoring.npz"), **golden_scoring())
         print("scoring.npz", os.path.getsize(os.path.join(HERE, "scoring.npz")))
@@ -264,6 +285,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "filter_o4_100k.npz"), **golden_filter(dt, parsers, 1.e5, 4, 5000., 5))
     np.savez_compressed(os.path.join(HERE, "long_event.npz"), **golden_long(parsers))
     np.savez_compressed(os.path.join(HERE, "params.npz"), **golden_params(parsers))
+    np.savez_compressed(os.path.join(HERE, "fds.npz"), **golden_fds(parsers))
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith(".npz"):
             print(fn, os.path.getsize(os.path.join(HERE, fn)))

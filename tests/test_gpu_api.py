@@ -255,3 +255,24 @@ def test_experiment_parse_batch_driver(capsys):
     assert not hasattr(exp2.files[0], "current") and exp2.files[0].events[0].segments[0].mean > 0
     with pytest.raises(NotImplementedError):
         Experiment(["run1.abf"]).parse(verbose=False)
+
+
+def test_filter_derivative_segmenter_matches_reference():
+    """FilterDerivativeSegmenter (parsers.py:609-656) against what the real reference returned
+    (tests/golden/make_golden.py: golden_fds), its quirks included; the filtfilt runs on the device."""
+    from make_golden_cases import FDS_CASES
+    from pypore_b200.parsers import FilterDerivativeSegmenter
+    g = load_golden("fds.npz")
+    for name, (length, seed, tier, kw) in FDS_CASES.items():
+        x = synth.make_long_event(length, seed=seed, tier=tier).astype(np.float64)
+        p = FilterDerivativeSegmenter(**kw)
+        assert (p.low_threshold, p.high_threshold, p.cutoff_freq, p.sampling_freq) == \
+            (kw["low_threshold"], kw["high_threshold"], kw["cutoff_freq"], kw["sampling_freq"])
+        segs = p.parse(x)
+        assert np.array_equal([s.start for s in segs], g[name + "_start"]), name
+        assert np.array_equal([len(s.current) for s in segs], g[name + "_n"]), name
+        assert np.allclose([s.mean for s in segs], g[name + "_mean"], rtol=1e-9, atol=0), name
+        assert all(s.current.base is x or s.current is x for s in segs)      # views of the caller's array
+    assert p.to_dict()["name"] == "FilterDerivativeSegmenter"
+    with pytest.raises(ValueError):
+        FilterDerivativeSegmenter().parse(np.zeros(5))                         # not longer than filtfilt's padlen
