@@ -79,7 +79,13 @@ enum pp_option {
     /* PP_OPT_SPINE (default 1) -- 1: events longer than the locally resolvable interval are first walked window by
      * window by a thread-block cluster each (k3_spine: 4 CTAs x 512 threads, summaries through distributed shared
      * memory); 0: the 128-thread work-queue CTAs walk them (same results). */
-    PP_OPT_SPINE = 1
+    PP_OPT_SPINE = 1,
+    /* PP_OPT_SPLIT_CTAS (default 0) -- number of persistent CTAs the split search (k3_split) is launched with; 0 or
+     * anything above one full wave: one full wave (7 CTAs per SM).  The search is a work queue, any CTA count gives the
+     * same tables.  Contexts that share a GPU (pypore_b200/batch.py: several files in flight, each with a few
+     * hundred events) take a fraction of a wave each, so that their searches are resident side by side instead of
+     * one after the other. */
+    PP_OPT_SPLIT_CTAS = 2
 };
 int pp_set_option(pp_ctx *ctx, int option, int64_t value);
 /* Number of kernel launches this context has issued since creation. */

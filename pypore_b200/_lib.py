@@ -263,6 +263,11 @@ class Context(object):
         """Long events walked by the 1024-thread spine kernel first (default on); off = by the work-queue CTAs."""
         self.set_option(1, 1 if on else 0)
 
+    def set_split_ctas(self, n):
+        """Persistent CTAs of the split search (0 = one full wave).  Same tables for any value; contexts that share
+        a GPU take a fraction of a wave each (batch.FileBatch)."""
+        self.set_option(2, int(n))
+
     @property
     def launch_count(self):
         return int(self._L.pp_launch_count(self._h))

@@ -61,6 +61,7 @@ struct pp_ctx {
     int opt_spine = 1;
     int T_len = 0;
     int opt_screen = 1;
+    int opt_split_ctas = 0;  // 0: one full wave (K3_CTAS_PER_SM per SM)
     int64_t q_cap = 0;
     DevBuf seg_flat, seg_event, seg_start, seg_end, seg_mean, seg_std, seg_min, seg_max;
     int64_t cap_segs = 0;
@@ -468,7 +469,11 @@ int enqueue_search(pp_ctx *ctx, int mw, int MW, int W, double min_gain)
         k3_spine<<<(ctx->sm_count / K3S_CLUSTER) * K3S_CLUSTER, K3S_THREADS, 0, ctx->stream>>>(G, P);
         LAUNCHED(ctx);
     }
-    k3_split<<<ctx->sm_count * K3_CTAS_PER_SM, K3_THREADS, K3_SMEM_BYTES, ctx->stream>>>(G, P);
+    // the queue is served by however many CTAs there are; contexts that share the GPU (file batches) take a
+    // fraction of a wave each so that their searches are resident side by side
+    const int wave = ctx->sm_count * K3_CTAS_PER_SM;
+    const int k3_grid = ctx->opt_split_ctas > 0 && ctx->opt_split_ctas < wave ? ctx->opt_split_ctas : wave;
+    k3_split<<<k3_grid, K3_THREADS, K3_SMEM_BYTES, ctx->stream>>>(G, P);
     LAUNCHED(ctx);
     return PP_OK;
 }
@@ -680,6 +685,10 @@ int pp_set_option(pp_ctx *ctx, int option, int64_t value)
     switch (option) {
     case PP_OPT_SCREEN: ctx->opt_screen = value ? 1 : 0; return PP_OK;
     case PP_OPT_SPINE: ctx->opt_spine = value ? 1 : 0; return PP_OK;
+    case PP_OPT_SPLIT_CTAS:
+        if (value < 0 || value > (1 << 20)) return fail(ctx, PP_ERR_ARG, "bad CTA count %lld", (long long)value);
+        ctx->opt_split_ctas = (int)value;
+        return PP_OK;
     default: return fail(ctx, PP_ERR_ARG, "unknown option %d", option);
     }
 }

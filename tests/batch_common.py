@@ -1,0 +1,79 @@
+"""Shared by the file-batch tests (CPU gloo / GPU): a small C5-style batch (BASELINE configs[4]: 250 kHz
+files, Event.filter(1, 2000) then SpeedyStatSplit) and the oracle's version of one file's pass -- the
+reference's Experiment.parse loop body (DataTypes.py:972-982) stated over tables."""
+import numpy as np
+
+import oracle
+from pypore_b200 import synth
+from pypore_b200.parsers import RuleSet, SpeedyStatSplit, lambda_event_parser
+
+FS = 2.5e5
+TIMESTEP = 1000. / FS
+FILTER = (1, 2000.)
+PYRULES = [lambda e: e.duration > 1000, lambda e: e.min > -0.5, lambda e: e.max < 110]
+
+
+def detector():
+    return lambda_event_parser(threshold=110, rules=RuleSet(duration_gt=1000, min_gt=-0.5, max_lt=110))
+
+
+def segmenter():
+    return SpeedyStatSplit(min_width=100, window_width=10000, sampling_freq=FS, cutoff_freq=2000.,
+                           prior_segments_per_second=10)
+
+
+def make_files(n_files, seed0=300):
+    """Ragged batch: 2..7 events per file; one file without any event (open channel only)."""
+    files = []
+    for i in range(n_files):
+        if i == 2:
+            rng = np.random.RandomState(seed0 + i)
+            files.append(synth.quantise(rng.normal(synth.OPEN_MEAN, synth.OPEN_STD, 7000)))
+        else:
+            files.append(synth.make_trace(2 + (i * 3) % 6, seed=seed0 + i, tier="A"))
+    return files
+
+
+def oracle_file_pass(ctx, current, second, event_detector, seg, filter_params):
+    """Same contract as pypore_b200.batch.device_file_pass, computed by the oracle (tests only)."""
+    x = np.asarray(current, np.float64)
+    ws, wl = oracle.events(x, event_detector.threshold, PYRULES)
+    mw, MW, W, gain = seg._params()
+    ev_flt, seg_int, seg_flt = [], [], []
+    for e, (s, n) in enumerate(zip(ws, wl)):
+        cur = x[s:s + n]
+        if filter_params is not None:
+            cur = oracle.event_filter(cur, second, *filter_params)
+        bp = oracle.statsplit(cur, min_width=mw, max_width=MW, window_width=W, gain=gain)
+        edges = np.concatenate(([0], bp, [n])).astype(np.int64)
+        m, sd, mn, mx = oracle.segment_stats(cur, edges[:-1], edges[1:])
+        seg_int.append(np.stack([np.full(len(edges) - 1, e, np.int64), edges[:-1], edges[1:]], axis=1))
+        seg_flt.append(np.stack([m, sd, mn, mx], axis=1))
+        ev_flt.append([np.mean(cur), np.std(cur), np.min(cur), np.max(cur)])
+    E = len(ws)
+    return dict(ev_int=np.stack([ws, wl], axis=1).astype(np.int64).reshape(E, 2),
+                ev_flt=np.asarray(ev_flt, np.float64).reshape(E, 4),
+                seg_int=np.concatenate(seg_int, axis=0) if E else np.zeros((0, 3), np.int64),
+                seg_flt=np.concatenate(seg_flt, axis=0) if E else np.zeros((0, 4)))
+
+
+def oracle_tables(files):
+    """The whole batch through the oracle on one process: what every rank must end up with."""
+    from pypore_b200.batch import FileBatch
+    b = FileBatch(workers=1, file_pass=oracle_file_pass)
+    return b.parse(files, TIMESTEP, detector(), segmenter(), FILTER)
+
+
+def assert_tables_match(t, want, rtol_stats=1e-9, exact=False):
+    """Indices bit-exact; statistics within the north star's 1e-9 (1e-5 for filtered samples' extrema)."""
+    for k in ("file", "start", "length"):
+        assert np.array_equal(t.events[k], want.events[k]), "event column %s differs" % k
+    for k in ("file", "event", "start", "end"):
+        assert np.array_equal(t.segments[k], want.segments[k]), "segment column %s differs" % k
+    for tab, wtab in ((t.events, want.events), (t.segments, want.segments)):
+        for k in ("mean", "std", "min", "max"):
+            if exact:
+                assert np.array_equal(tab[k], wtab[k]), k
+            else:
+                tol = rtol_stats if k in ("mean", "std") else 1e-5
+                assert np.allclose(tab[k], wtab[k], rtol=tol, atol=0), k

@@ -1,0 +1,111 @@
+"""File batches (BASELINE configs[4], SURVEY 8e "files are the unit") -- host logic on CPU: round-robin
+ownership, worker threads, the ragged table all-gather over gloo (world_size 2 and 3) and the ordering of
+the gathered rows.  The per-file device pass is played by the oracle (tests may use it); tests/
+test_zz_gpu_batch.py runs the real one."""
+import json
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from batch_common import (FILTER, TIMESTEP, assert_tables_match, detector, make_files, oracle_file_pass,
+                          oracle_tables, segmenter)
+from pypore_b200.batch import BatchTables, FileBatch, assign_files
+
+
+def test_assign_files_partitions_the_batch():
+    for n, world in ((0, 2), (1, 4), (7, 2), (8, 8), (1000, 8), (5, 3)):
+        owned = [assign_files(n, r, world) for r in range(world)]
+        assert sorted(i for o in owned for i in o) == list(range(n))
+        assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+
+
+def test_worker_threads_give_the_single_thread_tables():
+    files = make_files(7)
+    want = oracle_tables(files)
+    assert want.n_files == 7 and want.n_events > 10 and want.n_segments > want.n_events
+    (e0, e1), (s0, s1) = want.file_rows(2)
+    assert e0 == e1 and s0 == s1                          # the file without events contributes no rows
+    got = FileBatch(workers=3, file_pass=oracle_file_pass).parse(files, [TIMESTEP] * 7, detector(), segmenter(),
+                                                                 FILTER)
+    assert_tables_match(got, want, exact=True)
+    with pytest.raises(ValueError):
+        FileBatch(workers=1, file_pass=oracle_file_pass).parse(files, [TIMESTEP] * 3, detector(), segmenter(), FILTER)
+
+    def failing(ctx, current, *a):
+        raise RuntimeError("boom")
+    with pytest.raises(RuntimeError, match="boom"):       # a worker's exception reaches the caller
+        FileBatch(workers=2, file_pass=failing).parse(files, TIMESTEP, detector(), segmenter(), FILTER)
+
+
+def test_tables_to_meta_files_like_the_reference():
+    """BatchTables.files(): what Experiment.parse(..., meta=True) leaves behind (DataTypes.py:956-988):
+    Files of MetaEvents of MetaSegments, times in seconds, JSON-serialisable like the reference's."""
+    files = make_files(4)
+    t = oracle_tables(files)
+    out = t.files(["f%d" % i for i in range(4)], detector(), segmenter(), FILTER)
+    assert [f.filename for f in out] == ["f0", "f1", "f2", "f3"] and out[2].n == 0
+    second = 1000. / TIMESTEP
+    k = 0
+    for i, f in enumerate(out):
+        assert not hasattr(f, "current")
+        for e, ev in enumerate(f.events):
+            assert type(ev).__name__ == "MetaEvent" and ev.filtered and ev.filter_order == 1
+            assert ev.start == t.events["start"][k] / second and ev.duration == t.events["length"][k] / second
+            assert ev.mean == t.events["mean"][k] and ev.n == len(ev.segments) > 0
+            assert ev.segments[0].start == 0.0 and abs(ev.segments[-1].end - ev.duration) < 1e-12
+            assert all(type(s).__name__ == "MetaSegment" for s in ev.segments)
+            k += 1
+        d = json.loads(f.to_json())
+        assert d["name"] == "File" and d["n"] == f.n and len(d["events"]) == f.n
+        if f.n:
+            assert d["events"][0]["name"] == "MetaEvent" and d["events"][0]["segments"][0]["name"] == "MetaSegment"
+            assert d["events"][0]["state_parser"]["name"] == "SpeedyStatSplit"
+    assert k == t.n_events
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_files, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        files = make_files(n_files)
+        want = oracle_tables(files)
+        owned = set(assign_files(n_files, rank, world))
+        mine = [f if i in owned else None for i, f in enumerate(files)]   # a rank only holds its own files
+        b = FileBatch(workers=2, rank=rank, world=world, file_pass=oracle_file_pass)
+        got = b.parse(mine, TIMESTEP, detector(), segmenter(), FILTER)
+        assert sorted(b.local) == sorted(owned)
+        assert_tables_match(got, want, exact=True)        # row for row the one-process table, on every rank
+        q.put((rank, "ok"))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_files", [(2, 5), (3, 4), (2, 1)])
+def test_file_batch_gloo(world, n_files):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_files, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", "rank %d: %s" % (rank, msg)
