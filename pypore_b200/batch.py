@@ -269,8 +269,28 @@ class FileBatch(object):
             gi, gf = gather_tables(torch.from_numpy(np.ascontiguousarray(ints)).to(dev),
                                    torch.from_numpy(np.ascontiguousarray(flts)).to(dev),
                                    [int(c) for c in counts[:, col]], dist, self.group)
-            gi, gf = gi.cpu().numpy(), gf.cpu().numpy()
-            # ranks hold interleaved files; rows of one file are contiguous and already ordered inside a rank
-            order = np.argsort(gi[:, 0], kind="stable")
-            out += [gi[order], gf[order]]
+            out += list(_merge_by_file(gi.cpu().numpy(), gf.cpu().numpy()))
         return out[0], out[1], out[2], out[3]
+
+
+def _merge_by_file(gi, gf):
+    """Rank-major gathered rows -> file order.  Ranks hold interleaved files, but the rows of one file are
+    contiguous and already ordered, so the merge moves whole per-file blocks (one memcpy each) instead of
+    sorting rows: a 1000-file batch has 1000 blocks and possibly 10^7 rows."""
+    n = gi.shape[0]
+    if n == 0:
+        return gi, gf
+    col = gi[:, 0]
+    starts = np.concatenate(([0], np.flatnonzero(col[1:] != col[:-1]) + 1))
+    ends = np.concatenate((starts[1:], [n]))
+    order = np.argsort(col[starts], kind="stable")
+    if np.array_equal(order, np.arange(order.shape[0])):
+        return gi, gf
+    oi, of = np.empty_like(gi), np.empty_like(gf)
+    pos = 0
+    for b in order:
+        a, e = int(starts[b]), int(ends[b])
+        oi[pos:pos + e - a] = gi[a:e]
+        of[pos:pos + e - a] = gf[a:e]
+        pos += e - a
+    return oi, of

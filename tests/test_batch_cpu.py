@@ -109,3 +109,19 @@ def test_file_batch_gloo(world, n_files):
         p.join(timeout=60)
     for rank, msg in results:
         assert msg == "ok", "rank %d: %s" % (rank, msg)
+
+
+def test_block_merge_equals_a_stable_row_sort():
+    """The gathered rows are rank-major; FileBatch moves whole per-file blocks into file order.  Must equal a
+    stable sort of the rows by file for any dealing of ragged (also empty) files over any number of ranks."""
+    from pypore_b200.batch import _merge_by_file
+    rng = np.random.RandomState(0)
+    for _ in range(60):
+        world, nf = rng.randint(1, 6), rng.randint(0, 14)
+        rows = [(f, rng.randint(100)) for r in range(world) for f in range(r, nf, world)
+                for _ in range(rng.randint(0, 4))]
+        gi = np.array(rows, np.int64).reshape(-1, 2)
+        gf = rng.rand(len(rows), 4)
+        oi, of = _merge_by_file(gi, gf)
+        o = np.argsort(gi[:, 0], kind="stable")
+        assert np.array_equal(oi, gi[o]) and np.array_equal(of, gf[o])
