@@ -156,6 +156,9 @@ class Context(object):
             if getattr(self, "_arena", None):
                 self._L.pp_host_free(self._h, self._arena[0])
                 self._arena = None
+            for p in getattr(self, "_pinned_keep", []):   # pinned_empty() arrays die with the context
+                self._L.pp_host_free(self._h, p)
+            self._pinned_keep = []
             self._L.pp_destroy(self._h)
             self._h = None
 

@@ -6,10 +6,12 @@ SURVEY 8e: "Files are the unit for C5, with no halo."  The reference's caller is
 the event / segment metadata (DataTypes.py:480-491,683-693; core.py:237-249).  Here
 
 * a rank owns the files ``rank, rank + world, ...`` (``assign_files``);
-* every file is ONE device-resident pass (threshold scan -> select -> Bessel filtfilt -> prefix sums ->
-  split search -> compaction -> segment and event statistics) through ``pp_pipeline_host``; a rank drives
-  ``workers`` contexts, each with its own CUDA stream and its own host thread (ctypes releases the GIL), so
-  the host->device copy of one file, the table read-back of another and the kernels of a third overlap;
+* a pass is device-resident from the threshold scan to the tables (scan -> select -> Bessel filtfilt -> prefix
+  sums -> split search -> compaction -> segment and event statistics) and serves SEVERAL files where the rules
+  allow it (``groupable``: the files sit behind each other in one trace, a +inf sample between them), else one;
+* a rank drives ``workers`` contexts, each with its own CUDA stream and its own host thread (ctypes releases
+  the GIL), so the host->device copies of one pass, the table read-back of another and the kernels of a third
+  overlap;
 * nothing but the compact tables leaves the device: no filtered current is downloaded, because ``meta=True``
   discards it anyway;
 * the ranks' tables are all-gathered (two ragged gathers: event rows, segment rows) and ordered by file, so
@@ -61,6 +63,89 @@ def device_file_pass(ctx, current, second, event_detector, segmenter, filter_par
                 ev_flt=np.stack([est[k] for k in STAT_KEYS], axis=1).reshape(ne, 4),
                 seg_int=np.stack([seg["event"].astype(np.int64), seg["start"], seg["end"]], axis=1).reshape(ns, 3),
                 seg_flt=np.stack([seg[k] for k in STAT_KEYS], axis=1).reshape(ns, 4))
+
+
+def groupable(event_detector):
+    """Several files can share one resident pass when no run above the threshold can ever be an event: the
+    files then sit behind each other in one device trace, separated by a single +inf sample.  A run below
+    the threshold cannot cross the separator; runs above it may merge across files or pick up the separator,
+    but `max < v` with v <= threshold rejects every one of them (max >= threshold, or NaN)."""
+    rs = event_detector._device_rules()
+    return (rs is not None and bool(rs.mask & _lib.RULE_MAX_LT)
+            and float(rs.max_lt) <= float(event_detector.threshold))
+
+
+def plan_groups(lengths, seconds, owned, group_samples, min_groups=1):
+    """Consecutive owned files with the same sampling rate, at most `group_samples` samples per group (a file
+    longer than that is a group of its own).  `min_groups` shrinks the budget so that every worker context
+    gets work.  Returns a list of lists of file indices, in file order."""
+    owned = list(owned)
+    if group_samples <= 0:
+        return [[i] for i in owned]
+    total = sum(int(lengths[i]) for i in owned)
+    budget = int(group_samples)
+    if min_groups > 1 and total > 0:
+        budget = max(1, min(budget, -(-total // int(min_groups))))
+    groups, cur, used = [], [], 0
+    for i in owned:
+        n = int(lengths[i])
+        if cur and (used + n + 1 > budget or seconds[i] != seconds[cur[0]] or n == 0 or lengths[cur[0]] == 0):
+            groups.append(cur)
+            cur, used = [], 0
+        cur.append(i)
+        used += n + 1
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+def device_group_pass(ctx, currents, second, event_detector, segmenter, filter_params):
+    """Several files in ONE device-resident pass (see `groupable`): the files are copied behind each other
+    into the context's trace (pp_trace_upload + pp_trace_append, asynchronous from pinned memory), one launch of
+    every stage serves all their events, and the tables are cut back into per-file results -- the same rows
+    device_file_pass gives file by file, because every stage after the threshold scan works per event."""
+    from .DataTypes import bessel_coefficients
+    if not groupable(event_detector):
+        raise TypeError("these rules could select a run above the threshold: files cannot share a pass")
+    if not isinstance(segmenter, SpeedyStatSplit):
+        raise TypeError("the batched pipeline needs a pypore_b200 SpeedyStatSplit")
+    rs = event_detector._device_rules()
+    mw, MW, W, gain = segmenter._params()
+    filt = bessel_coefficients(filter_params[0], filter_params[1], second) if filter_params is not None else None
+    xs = [_as_float32_trace(np.asarray(c)) for c in currents]
+    sep = getattr(ctx, "_batch_separator", None)
+    if sep is None:
+        sep = ctx._batch_separator = ctx.pinned_empty(1, np.float32)
+        sep[0] = np.inf
+    total = sum(x.shape[0] for x in xs) + len(xs) - 1
+    ctx.upload_trace_async(xs[0], extra_capacity=total - xs[0].shape[0])
+    offs = [0]
+    for x in xs[1:]:
+        ctx.append_trace(sep.ctypes.data, 1, False)
+        offs.append(ctx.trace_len)
+        ctx.append_trace(x.ctypes.data, x.shape[0], False)
+    c = ctx.pipeline(event_detector.threshold, min_width=mw, max_width=MW, window_width=W, min_gain=gain,
+                     filter_ba=filt, with_stats=True, **rs.device_args())     # ends with a sync: copies consumed
+    del xs
+    ne, ns = c["events"], c["segments"]
+    ev_start, ev_len = ctx.events(ne)
+    est = ctx.event_stats(ne)
+    seg = ctx.segments(ns)
+    offs = np.asarray(offs, np.int64)
+    e_bounds = np.searchsorted(ev_start, np.concatenate((offs, [total + 1])))   # events are ordered by start
+    s_bounds = np.searchsorted(seg["event"], e_bounds)
+    ev_flt = np.stack([est[k] for k in STAT_KEYS], axis=1).reshape(ne, 4)
+    seg_flt = np.stack([seg[k] for k in STAT_KEYS], axis=1).reshape(ns, 4)
+    seg_event = seg["event"].astype(np.int64)
+    out = []
+    for k in range(len(currents)):
+        e0, e1, s0, s1 = int(e_bounds[k]), int(e_bounds[k + 1]), int(s_bounds[k]), int(s_bounds[k + 1])
+        out.append(dict(ev_int=np.stack([ev_start[e0:e1] - offs[k], ev_len[e0:e1]], axis=1).reshape(e1 - e0, 2),
+                        ev_flt=ev_flt[e0:e1],
+                        seg_int=np.stack([seg_event[s0:s1] - e0, seg["start"][s0:s1], seg["end"][s0:s1]],
+                                         axis=1).reshape(s1 - s0, 3),
+                        seg_flt=seg_flt[s0:s1]))
+    return out
 
 
 class BatchTables(object):
@@ -150,10 +235,13 @@ class FileBatch(object):
     """
 
     def __init__(self, device=0, workers=4, rank=0, world=1, group=None, file_pass=None, contexts=None,
-                 share_split=True):
+                 share_split=True, group_samples=1 << 26, group_pass=None):
         self.rank, self.world, self.group = int(rank), int(world), group
         self.device = int(device)
         self.file_pass = file_pass or device_file_pass
+        # files that may share a pass (`groupable`) are packed `group_samples` samples at a time; 0: one file per pass
+        self.group_pass = group_pass or (device_group_pass if file_pass is None else None)
+        self.group_samples = int(group_samples) if self.group_pass is not None else 0
         if contexts is not None:
             self.contexts = list(contexts)
         elif file_pass is None:
@@ -161,7 +249,7 @@ class FileBatch(object):
         else:
             self.contexts = [None] * max(1, int(workers))
         self._owns_contexts = contexts is None and file_pass is None
-        if self._owns_contexts and share_split and len(self.contexts) > 1:
+        if self._owns_contexts and share_split and len(self.contexts) > 1 and self.group_samples <= 0:
             # a file holds a few hundred events: its split search cannot fill 1036 persistent CTAs, but a full wave
             # would keep every other context's kernels off the SMs until it ends.  Each context takes its share
             # of the wave (at least one CTA per SM), so the searches of the files in flight run side by side.
@@ -179,10 +267,17 @@ class FileBatch(object):
     def parse_local(self, traces, timestep, event_detector=lambda_event_parser(threshold=90),
                     segmenter=SpeedyStatSplit(prior_segments_per_second=10, cutoff_freq=2000.),
                     filter_params=(1, 2000)):
-        """The owned files through the worker contexts; returns {file index: file_pass result}."""
+        """The owned files through the worker contexts -- several files per pass where the rules allow it
+        (`groupable`) -- returns {file index: per-file result}."""
         n_files = len(traces)
         seconds = self._seconds(timestep, n_files)
         mine = assign_files(n_files, self.rank, self.world)
+        if self.group_samples > 0 and groupable(event_detector):
+            lengths = {i: len(traces[i]) for i in mine}
+            items = plan_groups(lengths, seconds, mine, self.group_samples, min_groups=2 * len(self.contexts))
+        else:
+            items = [[i] for i in mine]
+        self.groups = items
         results, errors = {}, []
         lock = threading.Lock()
         cursor = [0]
@@ -190,23 +285,28 @@ class FileBatch(object):
         def work(ctx):
             while True:
                 with lock:
-                    if cursor[0] >= len(mine) or errors:
+                    if cursor[0] >= len(items) or errors:
                         return
-                    i = mine[cursor[0]]
+                    item = items[cursor[0]]
                     cursor[0] += 1
                 try:
-                    r = self.file_pass(ctx, traces[i], float(seconds[i]), event_detector, segmenter, filter_params)
+                    if len(item) == 1:
+                        rs = [self.file_pass(ctx, traces[item[0]], float(seconds[item[0]]), event_detector,
+                                             segmenter, filter_params)]
+                    else:
+                        rs = self.group_pass(ctx, [traces[i] for i in item], float(seconds[item[0]]),
+                                             event_detector, segmenter, filter_params)
                 except BaseException as exc:  # surfaced on the calling thread
                     with lock:
                         errors.append(exc)
                     return
                 with lock:
-                    results[i] = r
+                    results.update(zip(item, rs))
 
-        if len(self.contexts) == 1 or len(mine) <= 1:
+        if len(self.contexts) == 1 or len(items) <= 1:
             work(self.contexts[0])
         else:
-            threads = [threading.Thread(target=work, args=(c,)) for c in self.contexts[:len(mine)]]
+            threads = [threading.Thread(target=work, args=(c,)) for c in self.contexts[:len(items)]]
             for t in threads:
                 t.start()
             for t in threads:

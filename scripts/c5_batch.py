@@ -48,12 +48,14 @@ def main():
                                                             cutoff_freq=2000., prior_segments_per_second=10), (1, 2000.)),
                 ("filter(1,2000)+default gain", SpeedyStatSplit(min_width=100, window_width=10000), (1, 2000.))]
     lines = []
-    combos = ((1, True), (2, True), (4, False), (4, True), (7, True))
+    G = 1 << 26
+    # (worker contexts, split-search wave shared, samples per resident pass: 0 = one file per pass)
+    combos = ((1, True, 0), (4, True, 0), (1, False, G), (2, False, G), (4, False, G))
     if len(sys.argv) > 3 and sys.argv[3] == "quick":
-        combos = ((1, True), (4, True))
+        combos = ((4, True, 0), (2, False, G))
     for name, seg, filt in settings:
-        for workers, share in combos:
-            b = FileBatch(device=local, workers=workers, rank=rank, world=world, share_split=share)
+        for workers, share, gs in combos:
+            b = FileBatch(device=local, workers=workers, rank=rank, world=world, share_split=share, group_samples=gs)
             b.parse_local(files, 1000. / FS, det, seg, filt)     # every context's buffers grown, kernels loaded
             t_local, t_all = [], []
             for _ in range(3):
@@ -76,6 +78,7 @@ def main():
                 t_local, t_all = tt.tolist()
             b.close()
             line = dict(config="C5", setting=name, n_gpus=world, workers_per_gpu=workers, split_ctas_shared=share,
+                        samples_per_pass=gs, passes=len(b.groups),
                         files=len(files), samples=n_samples, events=tables.n_events, segments=tables.n_segments,
                         ms_per_file=1e3 * t_local / len(files), files_per_s=len(files) / t_local,
                         msamples_per_s=n_samples / t_local / 1e6,

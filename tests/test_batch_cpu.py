@@ -125,3 +125,53 @@ def test_block_merge_equals_a_stable_row_sort():
         oi, of = _merge_by_file(gi, gf)
         o = np.argsort(gi[:, 0], kind="stable")
         assert np.array_equal(oi, gi[o]) and np.array_equal(of, gf[o])
+
+
+def test_plan_groups_and_groupable():
+    from pypore_b200.batch import groupable, plan_groups
+    from pypore_b200.parsers import RuleSet, lambda_event_parser
+    assert plan_groups({0: 10, 1: 10, 2: 10, 3: 0, 4: 50, 5: 5}, [1] * 6, range(6), 25) == [[0, 1], [2], [3], [4], [5]]
+    assert plan_groups({0: 10, 2: 10, 4: 10}, [1, 1, 2, 2, 2], [0, 2, 4], 100) == [[0], [2, 4]]   # sampling rates
+    assert plan_groups({i: 10 for i in range(10)}, [1] * 10, range(10), 1000, min_groups=4) == \
+        [[0, 1], [2, 3], [4, 5], [6, 7], [8, 9]]
+    assert plan_groups({0: 5, 1: 7}, [1, 1], [0, 1], 0) == [[0], [1]] and plan_groups({}, [], [], 10) == []
+    assert groupable(lambda_event_parser(threshold=110, rules=RuleSet(duration_gt=1000, min_gt=-0.5, max_lt=110)))
+    assert groupable(lambda_event_parser(threshold=110, rules=RuleSet(max_lt=90)))
+    assert groupable(lambda_event_parser(threshold=110))                                    # reference defaults
+    assert not groupable(lambda_event_parser(threshold=110, rules=RuleSet(duration_gt=1000, min_gt=-0.5)))
+    assert not groupable(lambda_event_parser(threshold=110, rules=RuleSet(max_lt=111)))    # a run above could pass
+    assert not groupable(lambda_event_parser(threshold=110, rules=[lambda e: e.max < 110]))  # opaque callables
+
+
+def test_grouped_passes_equal_file_by_file_passes():
+    """Several files behind each other in one trace with +inf separators (batch.device_group_pass), the
+    oracle playing the device on the concatenated trace: per-file rows must equal file-by-file passes."""
+    from batch_common import OracleContext
+    from pypore_b200.batch import device_file_pass, device_group_pass
+    from batch_common import edge_files
+    files = edge_files()
+    second = 1000. / TIMESTEP
+    ctx = OracleContext()
+    for filt in (FILTER, None):
+        single = [device_file_pass(ctx, x, second, detector(), segmenter(), filt) for x in files]
+        for cut in ([0, 7], [0, 3, 7], [0, 1, 2, 4, 7]):
+            grouped = []
+            for a, b in zip(cut[:-1], cut[1:]):
+                grouped += (device_group_pass(ctx, files[a:b], second, detector(), segmenter(), filt) if b - a > 1
+                            else [device_file_pass(ctx, files[a], second, detector(), segmenter(), filt)])
+            assert len(grouped) == len(single)
+            for g, w in zip(grouped, single):
+                for k in ("ev_int", "ev_flt", "seg_int", "seg_flt"):
+                    assert g[k].shape == w[k].shape and np.array_equal(g[k], w[k]), k
+    assert sum(r["ev_int"].shape[0] for r in single) >= 10 and single[4]["ev_int"].shape[0] == 0
+    from pypore_b200.parsers import RuleSet, lambda_event_parser
+    with pytest.raises(TypeError):
+        device_group_pass(ctx, files[:2], second, lambda_event_parser(threshold=110, rules=RuleSet(duration_gt=10)),
+                          segmenter(), None)
+    # FileBatch end to end with grouping on: same tables as without
+    fb = lambda gs: FileBatch(workers=2, contexts=[OracleContext(), OracleContext()], group_samples=gs)  # noqa: E731
+    want = fb(0).parse(files, TIMESTEP, detector(), segmenter(), FILTER)
+    b = fb(40000)
+    got = b.parse(files, TIMESTEP, detector(), segmenter(), FILTER)
+    assert any(len(g) > 1 for g in b.groups) and sorted(i for g in b.groups for i in g) == list(range(7))
+    assert_tables_match(got, want, exact=True)

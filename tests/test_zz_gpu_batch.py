@@ -29,16 +29,19 @@ def _single_file_tables(files):
 
 def test_file_batch_matches_oracle_and_single_file_path():
     from pypore_b200.batch import FileBatch
-    files = make_files(9)
+    from batch_common import edge_files
+    files = make_files(9) + edge_files()        # ragged files; files that start / end inside events
     want = oracle_tables(files)
-    for workers in (1, 3):
-        b = FileBatch(device=0, workers=workers)
+    # group_samples > 0 (default): several files per resident pass, +inf separators; 0: one file per pass
+    for workers, group_samples in ((1, 1 << 26), (3, 1 << 26), (3, 0)):
+        b = FileBatch(device=0, workers=workers, group_samples=group_samples)
         try:
             got = b.parse(files, TIMESTEP, detector(), segmenter(), FILTER)
+            assert any(len(g) > 1 for g in b.groups) == (group_samples > 0)
             assert_tables_match(got, want)
             again = b.parse(files, TIMESTEP, detector(), segmenter(), FILTER)   # contexts reused across batches
             assert_tables_match(again, got, exact=True)
-            if workers == 3:
+            if workers == 3 and group_samples:
                 for i, et, st in _single_file_tables(files):
                     (e0, e1), (s0, s1) = got.file_rows(i)
                     assert np.array_equal(got.events["start"][e0:e1], et["start"])
