@@ -166,3 +166,45 @@ class OracleContext(object):
         out = dict(event=self.rows[:, 0].astype(np.int32), start=self.rows[:, 1], end=self.rows[:, 2])
         out.update({k: self.flt[:, j] for j, k in enumerate(("mean", "std", "min", "max"))})
         return out
+
+
+def golden_experiment_inputs():
+    """The traces tests/golden/make_golden.py::golden_experiment fed to the real reference's Experiment.parse."""
+    traces = make_files(4) + edge_files()[1:4]
+    return traces, ["batch%d" % i for i in range(len(traces))]
+
+
+def assert_json_close(a, b, rtol, path="", time_rtol=1e-12):
+    """Same keys, same structure, same strings / ints; statistics (mean / std / min / max) within rtol, every
+    other float (start / end / duration in seconds, parser parameters) within time_rtol."""
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and sorted(a) == sorted(b), "%s: keys %s != %s" % (path, sorted(a), sorted(b))
+        for k in a:
+            assert_json_close(a[k], b[k], rtol, path + "/" + str(k), time_rtol)
+    elif isinstance(a, list):
+        assert isinstance(b, list) and len(a) == len(b), "%s: %d != %d items" % (path, len(a), len(b))
+        for i, (x, y) in enumerate(zip(a, b)):
+            assert_json_close(x, y, rtol, "%s[%d]" % (path, i), time_rtol)
+    elif isinstance(a, float) or isinstance(b, float):
+        tol = rtol if path.rsplit("/", 1)[-1] in ("mean", "std", "min", "max") else time_rtol
+        assert abs(a - b) <= tol * max(abs(a), abs(b)), "%s: %r != %r" % (path, a, b)
+    else:
+        assert a == b, "%s: %r != %r" % (path, a, b)
+
+
+def experiment_through_batch(batch, capsys=None):
+    """Experiment.parse(..., meta=True, batch=batch) on the golden inputs -> (list of per-file JSON dicts, stdout)."""
+    import contextlib
+    import io
+    import json
+    from pypore_b200.DataTypes import Experiment, File
+    traces, names = golden_experiment_inputs()
+    files = [File(current=x, timestep=TIMESTEP) for x in traces]
+    for f, n in zip(files, names):
+        f.filename = n
+    exp = Experiment(files)
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        exp.parse(event_detector=detector(), segmenter=segmenter(), filter_params=FILTER, verbose=True, meta=True,
+                  batch=batch)
+    return [json.loads(f.to_json()) for f in exp.files], out.getvalue()

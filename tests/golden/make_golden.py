@@ -259,8 +259,39 @@ def golden_json(dt, parsers):
     return f.to_json()
 
 
+def golden_experiment(dt, parsers):
+    """The real reference's batch driver, Experiment.parse(..., meta=True) (DataTypes.py:956-988), on the
+    file-batch test set of tests/batch_common.py (250 kHz, Event.filter(1, 2000) + SpeedyStatSplit per event):
+    every file's to_json after the run plus everything the run printed.  The only stand-ins are I/O:
+    read_abf (no .abf data offline) hands out the in-memory traces, itertools.imap is Python 3's map."""
+    import contextlib
+    import io
+    import json
+    from batch_common import FS, TIMESTEP, edge_files, make_files
+    traces = make_files(4) + edge_files()[1:4]
+    names = ["batch%d.abf" % i for i in range(len(traces))]
+    store = {n: x.astype(np.float64) for n, x in zip(names, traces)}
+    dt.read_abf = lambda filename: (TIMESTEP, store[filename])
+    itertools.imap = map
+    exp = dt.Experiment(names)
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        exp.parse(event_detector=parsers.lambda_event_parser(threshold=110, rules=[lambda e: e.duration > 1000,
+                                                                                    lambda e: e.min > -0.5,
+                                                                                    lambda e: e.max < 110]),
+                  segmenter=parsers.SpeedyStatSplit(min_width=100, window_width=10000, sampling_freq=FS,
+                                                    cutoff_freq=2000., prior_segments_per_second=10),
+                  filter_params=(1, 2000.), verbose=True, meta=True)
+    return json.dumps(dict(stdout=out.getvalue(), files=[json.loads(f.to_json()) for f in exp.files]), indent=1)
+
+
 def main():
     dt, parsers, core = load_reference()
+    if "--experiment-only" in sys.argv:
+        with open(os.path.join(HERE, "experiment_meta.json"), "w") as out:
+            out.write(golden_experiment(dt, parsers))
+        print("experiment_meta.json", os.path.getsize(os.path.join(HERE, "experiment_meta.json")))
+        return
     if "--json-only" in sys.argv:
         with open(os.path.join(HERE, "file_tierA.json"), "w") as out:
             out.write(golden_json(dt, parsers))
@@ -286,6 +317,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "long_event.npz"), **golden_long(parsers))
     np.savez_compressed(os.path.join(HERE, "params.npz"), **golden_params(parsers))
     np.savez_compressed(os.path.join(HERE, "fds.npz"), **golden_fds(parsers))
+    with open(os.path.join(HERE, "experiment_meta.json"), "w") as out:
+        out.write(golden_experiment(dt, parsers))
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith(".npz"):
             print(fn, os.path.getsize(os.path.join(HERE, fn)))

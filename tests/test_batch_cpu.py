@@ -175,3 +175,17 @@ def test_grouped_passes_equal_file_by_file_passes():
     got = b.parse(files, TIMESTEP, detector(), segmenter(), FILTER)
     assert any(len(g) > 1 for g in b.groups) and sorted(i for g in b.groups for i in g) == list(range(7))
     assert_tables_match(got, want, exact=True)
+
+
+def test_experiment_batch_reproduces_the_real_references_run():
+    """tests/golden/experiment_meta.json is what the REAL reference's Experiment.parse(..., meta=True) printed and
+    left behind (every file's to_json) on the batch test set.  Host side of the check: the batch driver with the
+    oracle playing the device must reproduce it -- file names, event / segment times, parser dictionaries, counts
+    and printed lines exactly, statistics to 1e-9."""
+    from batch_common import OracleContext, assert_json_close, experiment_through_batch
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "experiment_meta.json")) as f:
+        want = json.load(f)
+    got, printed = experiment_through_batch(FileBatch(workers=2, contexts=[OracleContext(), OracleContext()],
+                                                      group_samples=30000))
+    assert printed == want["stdout"]
+    assert_json_close(got, want["files"], 1e-9)

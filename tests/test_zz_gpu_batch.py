@@ -153,3 +153,22 @@ def test_split_cta_count_does_not_change_the_tables():
             c.set_split_ctas(-1)
     finally:
         c.close()
+
+
+def test_experiment_batch_reproduces_the_real_references_run():
+    """tests/golden/experiment_meta.json: what the REAL reference's Experiment.parse(..., meta=True) printed and left
+    behind on the batch test set (generated by tests/golden/make_golden.py --experiment-only).  The device batch
+    must reproduce it: names, counts, printed lines, event / segment times exactly (bit-exact indices), statistics of
+    the FILTERED events within the north star's 1e-5 (every event is filtered here; measured filter error 2e-9)."""
+    from batch_common import assert_json_close, experiment_through_batch
+    from pypore_b200.batch import FileBatch
+    with open(os.path.join(ROOT, "tests", "golden", "experiment_meta.json")) as f:
+        want = json.load(f)
+    for kw in (dict(workers=2), dict(workers=2, group_samples=0)):
+        b = FileBatch(device=0, **kw)
+        try:
+            got, printed = experiment_through_batch(b)
+        finally:
+            b.close()
+        assert printed == want["stdout"]
+        assert_json_close(got, want["files"], 1e-5)
