@@ -58,6 +58,7 @@ struct pp_ctx {
 
     // K2/K3
     DevBuf cc, bits, tasks, ready, block_count, block_off, inexact, Ttab, ev_tile_off, k2_bits, k2_tiles;
+    DevBuf hk;  // K3_CFG_HALFKEY development variant: half-keys, 2 x 8 B per flat sample
     int opt_spine = 1;
     int T_len = 0;
     int opt_screen = 1;
@@ -461,6 +462,11 @@ int enqueue_search(pp_ctx *ctx, int mw, int MW, int W, double min_gain)
     }
     G.RN = (const double *)ctx->Ttab.p;
     G.screen = ctx->opt_screen;
+#if K3_CFG_HALFKEY
+    CKR(ensure(ctx, ctx->hk, 2 * sizeof(unsigned long long) * (size_t)ctx->flat_cap));
+    G.hkL = (unsigned long long *)ctx->hk.p;
+    G.hkR = G.hkL + ctx->flat_cap;
+#endif
     K3Params P;
     P.mw = mw; P.MW = MW; P.W = W; P.min_gain = min_gain;
     k3_init_queue<<<ctx->sm_count, 256, 0, ctx->stream>>>(G, ctx->opt_spine);
@@ -640,7 +646,7 @@ void pp_destroy(pp_ctx *ctx)
                       &ctx->tasks, &ctx->ready, &ctx->block_count, &ctx->block_off, &ctx->inexact, &ctx->Ttab, &ctx->ev_tile_off, &ctx->k2_bits, &ctx->k2_tiles,
                       &ctx->seg_flat, &ctx->seg_event, &ctx->seg_start, &ctx->seg_end, &ctx->seg_mean,
                       &ctx->seg_std, &ctx->seg_min, &ctx->seg_max, &ctx->evs_mean, &ctx->evs_std,
-                      &ctx->evs_min, &ctx->evs_max, &ctx->filt_tmp, &ctx->filt_carry, &ctx->filt_coef};
+                      &ctx->evs_min, &ctx->evs_max, &ctx->filt_tmp, &ctx->filt_carry, &ctx->filt_coef, &ctx->hk};
     for (DevBuf *b : bufs) release(*b);
     if (ctx->ctr) cudaFree(ctx->ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);

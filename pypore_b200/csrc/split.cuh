@@ -79,6 +79,17 @@ constexpr int K3_PIECES = K3_LIST + K3_WARPS;  // (warp, window) screening recor
 #ifndef K3_CFG_PREFETCH
 #define K3_CFG_PREFETCH 1
 #endif
+#ifndef K3_CFG_HALFKEY
+// DEVELOPMENT VARIANT, off in the product build, not yet run on a GPU ("planned next"): a candidate's
+// screening key is L(s,i) + R(i,e) (left side, right side).  When [s,e) splits at x, the left child's candidates need
+// L(s,i) + R(i,x) -- and L(s,i) is the number the parent's scan computed -- the right child's need L(x,i) + R(i,e).
+// With K3_CFG_HALFKEY=1 every screened scan of the level loop stores both half-keys per flat candidate position
+// (K3Global::hkL / hkR, 8 B each) and a child whose first window is its whole interval loads the inherited half
+// instead of recomputing it (K3Item::pad bit 0: L valid, bit 1: R valid).  The half-keys are integers relative to the
+// task's exponent base, which is constant for a task's whole local subtree; anything that leaves the CTA (global
+// queue), every forced split and every window that was scanned exactly starts without inherited halves.
+#define K3_CFG_HALFKEY 0
+#endif
 constexpr int K3_NO_EBASE = 0x7fffffff;
 constexpr unsigned long long K3_NO_TICKET = ~0ull;
 constexpr int K3_FULL_FLAG = 0x40000000;  // window flag: screening impossible / inconclusive / request overflow, scan exactly
@@ -112,6 +123,9 @@ struct K3Global {
     PPCounters *ctr;
     const double *RN;  // RN[n] = 1/n for n in [1, W], RN[0] = 0
     int screen;        // 0: exact evaluation of every candidate (validation mode)
+#if K3_CFG_HALFKEY
+    unsigned long long *hkL, *hkR;  // half-keys per flat candidate position: n1 L(V(s,i)), n2 L(V(i,e))
+#endif
 };
 
 // The windows one level of the local search scans.  A level is filled while the previous one is
@@ -445,6 +459,75 @@ __device__ __forceinline__ void k3_screen_lane(const double2 *__restrict__ ccg, 
 #endif
 }
 
+#if K3_CFG_HALFKEY
+// k3_screen_lane with half-key reuse.  MODE 0: both sides computed and stored; 1: the left half is inherited
+// (loaded), the right one computed and stored; 2: the right half is inherited.  hkL / hkR are event-based.
+// Loads of half-keys written earlier in this launch by other warps of the CTA go through L2 (__ldcg / __stcg):
+// the level barriers order them, the non-coherent path would not see them.
+template <int MODE>
+__device__ __forceinline__ void k3_hk_load(const double2 *__restrict__ ccg, const unsigned long long *hkL,
+                                           const unsigned long long *hkR, const double *__restrict__ RN, int ps, int pe,
+                                           int j, double2 &m, double &r1, double &r2, unsigned long long &h)
+{
+    m = K3_LD_MID(ccg + (j - 1));
+    if (MODE != 1) r1 = __ldg(RN + (j - ps));
+    if (MODE != 2) r2 = __ldg(RN + (pe - j));
+    if (MODE == 1) h = __ldcg(hkL + j);
+    if (MODE == 2) h = __ldcg(hkR + j);
+}
+
+template <int MODE>
+__device__ __forceinline__ void k3_hk_eval(unsigned long long *hkL, unsigned long long *hkR, const double2 lo,
+                                           const double2 hi, int ps, int pe, int ebase, int j, const double2 m,
+                                           double r1, double r2, unsigned long long h, K3Scr &a)
+{
+    unsigned long long kl = 0ull, kr = 0ull;
+    bool ok = true;
+    if (MODE != 1) {
+        ok = k3_side(__dsub_rn(m.x, lo.x), __dsub_rn(m.y, lo.y), r1, (unsigned)(j - ps), ebase, kl);
+        __stcg(hkL + j, kl);
+    } else {
+        kl = h;
+    }
+    if (MODE != 2) {
+        ok = ok & k3_side(__dsub_rn(hi.x, m.x), __dsub_rn(hi.y, m.y), r2, (unsigned)(pe - j), ebase, kr);
+        __stcg(hkR + j, kr);
+    } else {
+        kr = h;
+    }
+    k3_scr_update(a, ok, kl + kr, j);
+}
+
+template <int MODE>
+__device__ __forceinline__ void k3_screen_lane_hk(const double2 *__restrict__ ccg, unsigned long long *hkL,
+                                                  unsigned long long *hkR, const double2 lo, const double2 hi, int ps,
+                                                  int pe, int ebase, const double *__restrict__ RN, int i, int i_last,
+                                                  int stride, K3Scr &a)
+{
+    if (i > i_last) return;
+    // two candidates per trip; the operands of the next pair are requested before the current pair is evaluated
+    double2 mA = make_double2(0.0, 0.0), mB = mA, mA_n = mA, mB_n = mA;
+    double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0, a1_n = 0.0, a2_n = 0.0, b1_n = 0.0, b2_n = 0.0;
+    unsigned long long hA = 0ull, hB = 0ull, hA_n = 0ull, hB_n = 0ull;
+    k3_hk_load<MODE>(ccg, hkL, hkR, RN, ps, pe, i, mA, a1, a2, hA);
+    bool haveB = i + stride <= i_last;
+    if (haveB) k3_hk_load<MODE>(ccg, hkL, hkR, RN, ps, pe, i + stride, mB, b1, b2, hB);
+    for (;;) {
+        const int in = i + 2 * stride;
+        const bool nextA = haveB && in <= i_last, nextB = nextA && in + stride <= i_last;
+        if (nextA) k3_hk_load<MODE>(ccg, hkL, hkR, RN, ps, pe, in, mA_n, a1_n, a2_n, hA_n);
+        if (nextB) k3_hk_load<MODE>(ccg, hkL, hkR, RN, ps, pe, in + stride, mB_n, b1_n, b2_n, hB_n);
+        k3_hk_eval<MODE>(hkL, hkR, lo, hi, ps, pe, ebase, i, mA, a1, a2, hA, a);
+        if (haveB) k3_hk_eval<MODE>(hkL, hkR, lo, hi, ps, pe, ebase, i + stride, mB, b1, b2, hB, a);
+        if (!nextA) break;
+        i = in;
+        mA = mA_n; a1 = a1_n; a2 = a2_n; hA = hA_n;
+        mB = mB_n; b1 = b1_n; b2 = b2_n; hB = hB_n;
+        haveB = nextB;
+    }
+}
+#endif
+
 // 2 eps of a window of n samples, in key units (rounded up)
 __device__ __forceinline__ unsigned long long k3_eps2_key(int n)
 {
@@ -634,6 +717,9 @@ __device__ __noinline__ void k3_place(K3Shared *Sp, K3Level *nxp, K3Count *ncp, 
                 k3_emit(G, off, x);  // the left part is not revisited (cparsers.pyx:189-191)
                 if (!k3_worth(P, x, it.e)) break;
                 it.s = x; it.ps = x;
+#if K3_CFG_HALFKEY
+                it.pad = 0;  // the anchor moved: nothing inherited
+#endif
                 continue;
             }
             const int pe = k3_window_end(P, it);
@@ -669,8 +755,10 @@ __device__ __noinline__
 __device__ __forceinline__
 #endif
 void k3_resolve(const K3Global &G, K3Shared &S, K3Level &nx, K3Count &nc,
-                                           const K3Params &P, int screen, const K3Item it, int x)
+                                           const K3Params &P, int screen, const K3Item it, int x, int reuse = 0)
 {
+    // reuse (K3_CFG_HALFKEY): the window was screened and every candidate passed the validity test, i.e. its
+    // half-keys are stored -- the children may inherit the half that keeps its anchor
     const int pe = k3_window_end(P, it);
     atomicAdd(&S.cand, (unsigned long long)(pe - it.ps - 2 * P.mw + 1));
     atomicAdd(&S.scans, 1ull);
@@ -678,7 +766,13 @@ void k3_resolve(const K3Global &G, K3Shared &S, K3Level &nx, K3Count &nc,
     c.pad = 0;
     if (x >= 0) {
         k3_emit(G, (int64_t)S.off, x);
+#if K3_CFG_HALFKEY
+        c.pad = (reuse && it.ps == it.s) ? 1 : 0;
+#endif
         if (k3_worth(P, it.s, x)) { c.s = it.s; c.e = x; c.ps = it.s; k3_place(&S, &nx, &nc, screen, c); }
+#if K3_CFG_HALFKEY
+        c.pad = (reuse && pe == it.e) ? 2 : 0;
+#endif
         if (k3_worth(P, x, it.e)) {
             bool away = K3_SHARE > 0 && x - it.s >= K3_SHARE && it.e - x >= K3_SHARE;
             if (!away && K3_IDLE_SHARE > 0 && S.share > 0 && x - it.s >= K3_IDLE_SHARE && it.e - x >= K3_IDLE_SHARE)
@@ -687,6 +781,9 @@ void k3_resolve(const K3Global &G, K3Shared &S, K3Level &nx, K3Count &nc,
             else { c.s = x; c.e = it.e; c.ps = x; k3_place(&S, &nx, &nc, screen, c); }
         }
     } else {
+#if K3_CFG_HALFKEY
+        c.pad = 0;
+#endif
         c.s = it.s; c.e = it.e; c.ps = k3_next_ps(P, it.ps, it.e);
         k3_place(&S, &nx, &nc, screen, c);
     }
@@ -752,8 +849,19 @@ void k3_screen_level(const K3Global &G, const K3Params &P, K3Shared &S, int cur,
         const double2 w_lo = acc.at(it.ps - 1), w_hi = acc.at(w_pe - 1);
         K3Scr a;
         k3_scr_init(a);
+#if K3_CFG_HALFKEY
+        {
+            unsigned long long *hl = G.hkL + S.off, *hr = G.hkR + S.off;
+            const int hmode = (it.ps == it.s && w_pe == it.e) ? (it.pad & 3) : 0;  // whole-interval windows only
+            const int i0 = it.ps + mw + ca * 32 + lane, i1 = i_end < w_last ? i_end : w_last;
+            if (hmode == 1) k3_screen_lane_hk<1>(ccg, hl, hr, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, i0, i1, 32, a);
+            else if (hmode == 2) k3_screen_lane_hk<2>(ccg, hl, hr, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, i0, i1, 32, a);
+            else k3_screen_lane_hk<0>(ccg, hl, hr, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, i0, i1, 32, a);
+        }
+#else
         k3_screen_lane(ccg, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, it.ps + mw + ca * 32 + lane,
                        i_end < w_last ? i_end : w_last, 32, a);
+#endif
         unsigned long long K1, K2;
         int I1;
         bool bad;
@@ -949,8 +1057,8 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                         const double d = (double)(long long)(kt - gmin);
                         const double want = P.min_gain * K3_KEY_PER_NAT;
                         const double margin = (double)eps2 + 64.0;
-                        if (d > want + margin) { k3_resolve(G, S, NX, NC, P, screen, it, i_one); continue; }
-                        if (d < want - margin) { k3_resolve(G, S, NX, NC, P, screen, it, -1); continue; }
+                        if (d > want + margin) { k3_resolve(G, S, NX, NC, P, screen, it, i_one, 1); continue; }
+                        if (d < want - margin) { k3_resolve(G, S, NX, NC, P, screen, it, -1, 1); continue; }
                     }
                 }
 #endif
@@ -1020,7 +1128,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                             S.req_g[r] = g;
                             if (g > P.min_gain) atomicMax(&S.best_key[k], k3_okey(g));
                         } else if (!(fl & K3_FULL_FLAG)) {
-                            k3_resolve(G, S, NX, NC, P, screen, it, g > P.min_gain ? i : -1);
+                            k3_resolve(G, S, NX, NC, P, screen, it, g > P.min_gain ? i : -1, 1);
                         }
                     }
                 }
@@ -1037,7 +1145,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3_CTAS_PER_SM) k3_split(K3Global 
                     for (int k = tid; k < nwin; k += K3_THREADS) {
                         const int fl = L.flag[k];
                         if ((fl & K3_MULTI_FLAG) && !(fl & K3_FULL_FLAG))
-                            k3_resolve(G, S, NX, NC, P, screen, L.item[k], S.best_key[k] ? S.best_idx[k] : -1);
+                            k3_resolve(G, S, NX, NC, P, screen, L.item[k], S.best_key[k] ? S.best_idx[k] : -1, 1);
                     }
                 }
             }
