@@ -354,6 +354,10 @@ def run_ours(args):
         split_gbs = split_bytes / (split_ms / 1e3) / 1e9
         traffic, traffic_src = ncu_traffic("k3_split") if world == 1 and epg == EVENTS_PER_GPU else (None, None)
         b_floor = 4.0 * n_total + 56.0 * seg_total + 24.0 * ev_total
+        # SURVEY 8d's second figure, the reference's data flow: threshold reads N, the prefix kernel reads N_ev and
+        # writes {c, c2}, the search touches one pair per candidate, statistics re-read N_ev, 56 B per segment row
+        # (candidates are counted on rank 0; every rank holds the same workload)
+        b_alg = 4.0 * n_total + 20.0 * evs_total + 16.0 * counters["candidates"] * world + 4.0 * evs_total + 56.0 * seg_total
         seg_row = 4 + 8 + 8 + 32
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -374,7 +378,9 @@ def run_ours(args):
                                  "(DESIGN.md 4)"},
             "pipeline_roofline": {"b_floor_bytes": b_floor, "achieved": b_floor / sec / 1e9 / world,
                                   "peak": peak, "unit": "GB/s per GPU",
-                                  "frac": b_floor / sec / 1e9 / world / peak},
+                                  "frac": b_floor / sec / 1e9 / world / peak,
+                                  "b_alg_bytes": b_alg, "achieved_b_alg": b_alg / sec / 1e9 / world,
+                                  "frac_b_alg": b_alg / sec / 1e9 / world / peak},
             "stage_ms": stage, "split_ms": split_ms,
             "counts": {"samples": n_total, "events": ev_total, "event_samples": evs_total,
                        "segments": seg_total, "candidates_rank0": counters["candidates"]},
