@@ -479,19 +479,19 @@ __device__ __forceinline__ void k3_hk_load(const double2 *__restrict__ ccg, cons
 template <int MODE>
 __device__ __forceinline__ void k3_hk_eval(unsigned long long *hkL, unsigned long long *hkR, const double2 lo,
                                            const double2 hi, int ps, int pe, int ebase, int j, const double2 m,
-                                           double r1, double r2, unsigned long long h, K3Scr &a)
+                                           double r1, double r2, unsigned long long h, bool store, K3Scr &a)
 {
     unsigned long long kl = 0ull, kr = 0ull;
     bool ok = true;
     if (MODE != 1) {
         ok = k3_side(__dsub_rn(m.x, lo.x), __dsub_rn(m.y, lo.y), r1, (unsigned)(j - ps), ebase, kl);
-        __stcg(hkL + j, kl);
+        if (store) __stcg(hkL + j, kl);
     } else {
         kl = h;
     }
     if (MODE != 2) {
         ok = ok & k3_side(__dsub_rn(hi.x, m.x), __dsub_rn(hi.y, m.y), r2, (unsigned)(pe - j), ebase, kr);
-        __stcg(hkR + j, kr);
+        if (store) __stcg(hkR + j, kr);
     } else {
         kr = h;
     }
@@ -502,8 +502,9 @@ template <int MODE>
 __device__ __forceinline__ void k3_screen_lane_hk(const double2 *__restrict__ ccg, unsigned long long *hkL,
                                                   unsigned long long *hkR, const double2 lo, const double2 hi, int ps,
                                                   int pe, int ebase, const double *__restrict__ RN, int i, int i_last,
-                                                  int stride, K3Scr &a)
+                                                  int stride, bool store, K3Scr &a)
 {
+    // store == false: no child of this window can be scanned (leaf scans), nobody will read the halves
     if (i > i_last) return;
     // two candidates per trip; the operands of the next pair are requested before the current pair is evaluated
     double2 mA = make_double2(0.0, 0.0), mB = mA, mA_n = mA, mB_n = mA;
@@ -517,8 +518,8 @@ __device__ __forceinline__ void k3_screen_lane_hk(const double2 *__restrict__ cc
         const bool nextA = haveB && in <= i_last, nextB = nextA && in + stride <= i_last;
         if (nextA) k3_hk_load<MODE>(ccg, hkL, hkR, RN, ps, pe, in, mA_n, a1_n, a2_n, hA_n);
         if (nextB) k3_hk_load<MODE>(ccg, hkL, hkR, RN, ps, pe, in + stride, mB_n, b1_n, b2_n, hB_n);
-        k3_hk_eval<MODE>(hkL, hkR, lo, hi, ps, pe, ebase, i, mA, a1, a2, hA, a);
-        if (haveB) k3_hk_eval<MODE>(hkL, hkR, lo, hi, ps, pe, ebase, i + stride, mB, b1, b2, hB, a);
+        k3_hk_eval<MODE>(hkL, hkR, lo, hi, ps, pe, ebase, i, mA, a1, a2, hA, store, a);
+        if (haveB) k3_hk_eval<MODE>(hkL, hkR, lo, hi, ps, pe, ebase, i + stride, mB, b1, b2, hB, store, a);
         if (!nextA) break;
         i = in;
         mA = mA_n; a1 = a1_n; a2 = a2_n; hA = hA_n;
@@ -854,9 +855,11 @@ void k3_screen_level(const K3Global &G, const K3Params &P, K3Shared &S, int cur,
             unsigned long long *hl = G.hkL + S.off, *hr = G.hkR + S.off;
             const int hmode = (it.ps == it.s && w_pe == it.e) ? (it.pad & 3) : 0;  // whole-interval windows only
             const int i0 = it.ps + mw + ca * 32 + lane, i1 = i_end < w_last ? i_end : w_last;
-            if (hmode == 1) k3_screen_lane_hk<1>(ccg, hl, hr, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, i0, i1, 32, a);
-            else if (hmode == 2) k3_screen_lane_hk<2>(ccg, hl, hr, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, i0, i1, 32, a);
-            else k3_screen_lane_hk<0>(ccg, hl, hr, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, i0, i1, 32, a);
+            // a child is at most (window - min_width) long and is scanned only if longer than 2 min_width
+            const bool st = (long long)w_pe - it.ps > 3LL * mw;
+            if (hmode == 1) k3_screen_lane_hk<1>(ccg, hl, hr, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, i0, i1, 32, st, a);
+            else if (hmode == 2) k3_screen_lane_hk<2>(ccg, hl, hr, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, i0, i1, 32, st, a);
+            else k3_screen_lane_hk<0>(ccg, hl, hr, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, i0, i1, 32, st, a);
         }
 #else
         k3_screen_lane(ccg, w_lo, w_hi, it.ps, w_pe, ebase, G.RN, it.ps + mw + ca * 32 + lane,

@@ -99,9 +99,10 @@ def replay(x, mw, MW, W, gain, rng, p_full=0.0, p_away=0.0):
                     assert touched.get(j, k) == k and written.get(j, k) == k, "scans of one level overlap"
                     touched[j] = k
                     written[j] = k
-                if mode != 1:
+                store = pe - it.ps > 3 * mw                 # leaf scans (no child can be scanned) store nothing
+                if mode != 1 and store:
                     ancL[cand] = -1 if full else it.ps      # a failed validity test leaves garbage behind
-                if mode != 2:
+                if mode != 2 and store:
                     ancR[cand] = -1 if full else pe
             g = _window_gains(c, c2, it.ps, pe, it.ps + mw, pe - mw)
             decisions.append((it, pe, _sequential_best(g, gain, it.ps + mw)[1], not full))
