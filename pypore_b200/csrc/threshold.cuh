@@ -34,7 +34,11 @@ __device__ __forceinline__ void k1_local_update(unsigned rid, float m, float M, 
     atomicMax(&lmax[rid], kmax);
 }
 
+#ifdef K1_CFG_MINBLOCKS  // development knob: 8 = all 2048 threads of an SM resident (32 registers per thread)
+__global__ void __launch_bounds__(K1_THREADS, K1_CFG_MINBLOCKS)
+#else
 __global__ void __launch_bounds__(K1_THREADS)
+#endif
 k1_threshold_scan(const float *__restrict__ x, int64_t n, float thr_f,
                   unsigned long long *__restrict__ tile_state, PPCounters *ctr,
                   int64_t *__restrict__ run_start, unsigned *__restrict__ run_minkey,
