@@ -183,3 +183,63 @@ def test_plan_rejected_and_non_straddling_runs():
     infos = [_info(5000, [(False, 3000, 118, 125), (True, 2000, 30, 80)]),
              _info(4000, [(True, 900, np.nan, np.nan), (False, 3100, 117, 126)])]
     assert ppdist.plan_boundaries(infos, RULES)[0]["event"] is None
+
+
+def test_plan_boundaries_property_random_cuts():
+    """Random traces cut at random places (inside events, exactly on run edges, several cuts inside one run,
+    one-sample chunks): the events the ranks own under plan_boundaries -- their own accepted runs minus the
+    skipped first / last run, plus the straddling event each rank keeps -- must be exactly the events of the
+    uncut trace, each owned once, with recv counts that deliver exactly the continuation samples."""
+    rng = np.random.RandomState(11)
+    rules = dict(rule_mask=7, duration_gt=6, duration_lt=0, min_gt=-0.5, max_lt=110.0)
+    pyrules = [lambda e: e.duration > 6, lambda e: e.min > -0.5, lambda e: e.max < 110]
+    n_straddle = n_multi = 0
+    for case in range(300):
+        parts = []
+        for _ in range(rng.randint(1, 9)):
+            parts.append(rng.normal(120, 1.5, rng.randint(1, 12)))
+            body = rng.normal(rng.uniform(20, 90), 1.0, rng.randint(1, 25))
+            if rng.uniform() < 0.15:
+                body[rng.randint(len(body))] = -20.0          # sub-zero spike: the whole run is rejected
+            parts.append(body)
+        if rng.uniform() < 0.5:
+            parts.append(rng.normal(120, 1.5, rng.randint(1, 12)))
+        if rng.uniform() < 0.3:
+            parts = parts[1:]                                   # trace starts inside an event
+        x = np.concatenate(parts)
+        n = len(x)
+        world = int(rng.randint(2, 7))
+        if n < world:
+            continue
+        cuts = np.sort(rng.choice(np.arange(1, n), size=world - 1, replace=False))
+        bounds = np.concatenate(([0], cuts, [n]))
+        ws, wl = oracle.events(x, 110.0, pyrules)
+        want = sorted(zip(ws.tolist(), wl.tolist()))
+        infos, runs = [], []
+        for r in range(world):
+            chunk = x[bounds[r]:bounds[r + 1]]
+            rr = oracle.threshold_runs(chunk, 110.0)
+            runs.append(rr)
+            infos.append(ppdist.boundary_info(len(chunk), len(rr[0]), [a[0] for a in rr], [a[-1] for a in rr]))
+        plans = ppdist.plan_boundaries(infos, rules)
+        got = []
+        for r in range(world):
+            rr, plan = runs[r], plans[r]
+            k = len(rr[0])
+            for i in range(k):
+                if (i == 0 and plan["skip_first"]) or (i == k - 1 and plan["skip_last"]):
+                    continue
+                if ppdist.rules_accept(rules, rr[1][i], rr[2][i], rr[3][i]):
+                    got.append((int(bounds[r] + rr[0][i]), int(rr[1][i])))
+            if plan["event"] is not None:
+                s, length = plan["event"]
+                got.append((int(bounds[r] + s), int(length)))
+                n_straddle += 1
+                n_multi += len(plan["recv"]) > 1
+                # the halo pieces are the heads of the following chunks, in order, and end where the event ends
+                assert [q for q, _ in plan["recv"]] == list(range(r + 1, r + 1 + len(plan["recv"])))
+                assert bounds[r] + s + length == bounds[plan["recv"][-1][0]] + plan["recv"][-1][1]
+                for q, cnt in plan["recv"]:
+                    assert (r, cnt) in plans[q]["send"] and cnt <= bounds[q + 1] - bounds[q]
+        assert sorted(got) == want, "case %d world %d" % (case, world)
+    assert n_straddle > 50 and n_multi > 5      # the generator does produce the interesting cases
