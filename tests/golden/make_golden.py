@@ -188,6 +188,30 @@ def golden_long(parsers):
     return out
 
 
+def golden_c4_full(dt, parsers):
+    """BASELINE configs[3] at FULL size: 4 events of 10 M samples in one trace, SpeedyStatSplit with max_width=1e6,
+    through the real reference (File.parse + the compiled cparsers per event).  Too big to store: the fixture holds
+    the event table, the segment counts and a SHA-256 of the (event, start, end) int64 rows per setting."""
+    x64 = synth.make_long_trace(4, 10_000_000, seed0=100, tier="A").astype(np.float64)
+    f = dt.File(current=x64, timestep=0.01)
+    f.parse(parser=parsers.lambda_event_parser(threshold=110, rules=[lambda e: e.duration > 1000,
+                                                                      lambda e: e.min > -0.5,
+                                                                      lambda e: e.max < 110]))
+    out = dict(ev_start=np.array([int(round(e.start * f.second)) for e in f.events], np.int64),
+               ev_len=np.array([len(e.current) for e in f.events], np.int64), input_sha256=np.array(sha(x64)))
+    for name, kw in (("default", dict(min_width=100, max_width=1000000, window_width=10000)),
+                     ("psps10", dict(min_width=100, max_width=1000000, window_width=10000,
+                                     prior_segments_per_second=10))):
+        rows = []
+        for k, event in enumerate(f.events):
+            for seg in parsers.SpeedyStatSplit(**kw).parse(event.current):
+                rows.append((k, seg.start, seg.end))
+        rows = np.array(rows, np.int64).reshape(-1, 3)
+        out[name + "_segments"] = np.int64(len(rows))
+        out[name + "_sha"] = np.array(sha(rows))
+    return out
+
+
 def golden_params(parsers):
     """min_gain known answers and exception parity."""
     from PyPore.cparsers import FastStatSplit
@@ -287,6 +311,10 @@ def golden_experiment(dt, parsers):
 
 def main():
     dt, parsers, core = load_reference()
+    if "--c4-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "c4_full.npz"), **golden_c4_full(dt, parsers))
+        print("c4_full.npz", os.path.getsize(os.path.join(HERE, "c4_full.npz")))
+        return
     if "--experiment-only" in sys.argv:
         with open(os.path.join(HERE, "experiment_meta.json"), "w") as out:
             out.write(golden_experiment(dt, parsers))
@@ -319,6 +347,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "fds.npz"), **golden_fds(parsers))
     with open(os.path.join(HERE, "experiment_meta.json"), "w") as out:
         out.write(golden_experiment(dt, parsers))
+    np.savez_compressed(os.path.join(HERE, "c4_full.npz"), **golden_c4_full(dt, parsers))
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith(".npz"):
             print(fn, os.path.getsize(os.path.join(HERE, fn)))

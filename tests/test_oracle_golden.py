@@ -188,3 +188,20 @@ def test_scoring_functions_match_reference_fixture():
         x = synth.make_long_event(50, seed=14, tier="A").astype(np.float64)[:n]
         gain, idx = oracle.best_single_split(x)
         assert [gain, idx] == list(g["short%d_best" % n])
+
+
+def test_oracle_reproduces_the_full_size_long_event_fixture():
+    """BASELINE configs[3] at full size (4 events x 10 M samples, max_width=1e6): tests/golden/c4_full.npz was written by
+    the real reference; the oracle must hash to the same tables.  Its candidate counts are what the GPU test
+    (tests/test_zz_gpu_fullsize.py) expects of the device counters."""
+    g = load_golden("c4_full.npz")
+    x = synth.make_long_trace(4, 10_000_000, seed0=100, tier="A").astype(np.float64)
+    assert sha(x) == str(g["input_sha256"])
+    ws, wl = oracle.events(x, 110, RULES_1000)
+    assert np.array_equal(ws, g["ev_start"]) and np.array_equal(wl, g["ev_len"])
+    for name, kw, cand in (("default", dict(), 300443705), ("psps10", dict(prior_segments_per_second=10), 188617127)):
+        oe, ost, oen, nc = oracle.statsplit_events(x, ws, wl, min_width=100, max_width=1000000, window_width=10000,
+                                                   threads=8, **kw)
+        rows = np.stack([oe, ost, oen], axis=1).astype(np.int64)
+        assert len(rows) == int(g[name + "_segments"]) and nc == cand
+        assert sha(rows) == str(g[name + "_sha"])
