@@ -200,6 +200,30 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
+def parity_against_fixture(res_e2e):
+    """The tables the end-to-end call just delivered to host memory against tests/golden/c2_full.npz -- counts and
+    SHA-256 of the event rows (start, length) and segment rows (event, start, end) the REAL reference produced on this
+    exact workload (tests/golden/make_golden.py --c2-only).  Outside every timed region; never raises."""
+    try:
+        import hashlib
+        g = np.load(os.path.join(ROOT, "tests", "golden", "c2_full.npz"), allow_pickle=False)
+
+        def sha(a):
+            return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+        es, el = res_e2e["event_table"]
+        t = res_e2e["segment_table"]
+        ev = np.stack([np.asarray(es, np.int64), np.asarray(el, np.int64)], axis=1)
+        rows = np.stack([np.asarray(t["event"]).astype(np.int64), np.asarray(t["start"], np.int64),
+                         np.asarray(t["end"], np.int64)], axis=1)
+        return {"fixture": "tests/golden/c2_full.npz (real reference, full size)",
+                "events": int(len(ev)), "events_expected": int(g["events"]),
+                "segments": int(len(rows)), "segments_expected": int(g["default_segments"]),
+                "events_bit_exact": bool(sha(ev) == str(g["events_sha"])),
+                "segments_bit_exact": bool(sha(rows) == str(g["default_sha"]))}
+    except Exception as exc:  # a reporting extra must not cost the bench line
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+
 def ncu_traffic(kernel="k3_split"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
     capture of this same command (profiles/*_ncu_summary.csv, newest round); None without one."""
@@ -387,6 +411,8 @@ def run_ours(args):
         }
         if shard is not None:
             line["host_planned_fallback_steps"] = int(shard.fallbacks)
+        elif epg == EVENTS_PER_GPU:
+            line["parity"] = parity_against_fixture(res_e2e)
         if world == 1 and not args.no_cpu_baseline:
             n_cpu = min(epg, 1500)
             xc = synth.make_trace(n_cpu, seed=1, tier="A").astype(np.float64)

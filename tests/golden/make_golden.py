@@ -212,6 +212,31 @@ def golden_c4_full(dt, parsers):
     return out
 
 
+def golden_c2_full(dt, parsers):
+    """BASELINE configs[1] at FULL size -- exactly bench.py's single-GPU workload, synth.make_trace(5000, seed=1),
+    about 60 M samples -- through the real reference: File.parse(lambda_event_parser(threshold=110, rules=[duration >
+    1000, min > -0.5, max < 110])) then SpeedyStatSplit(min_width=100, window_width=10000) per event.  Counts and
+    SHA-256 of the event rows (start, length) and of the segment rows (event, start, end)."""
+    x64 = synth.make_trace(5000, seed=1, tier="A").astype(np.float64)
+    f = dt.File(current=x64, timestep=0.01)
+    f.parse(parser=parsers.lambda_event_parser(threshold=110, rules=[lambda e: e.duration > 1000,
+                                                                      lambda e: e.min > -0.5,
+                                                                      lambda e: e.max < 110]))
+    ev = np.array([(int(round(e.start * f.second)), len(e.current)) for e in f.events], np.int64).reshape(-1, 2)
+    out = dict(samples=np.int64(len(x64)), events=np.int64(len(ev)), event_samples=np.int64(ev[:, 1].sum()),
+               events_sha=np.array(sha(ev)), input_sha256=np.array(sha(x64)))
+    for name, kw in (("default", dict(min_width=100, window_width=10000)),
+                     ("psps10", dict(min_width=100, window_width=10000, prior_segments_per_second=10))):
+        rows = []
+        for k, event in enumerate(f.events):
+            for seg in parsers.SpeedyStatSplit(**kw).parse(event.current):
+                rows.append((k, seg.start, seg.end))
+        rows = np.array(rows, np.int64).reshape(-1, 3)
+        out[name + "_segments"] = np.int64(len(rows))
+        out[name + "_sha"] = np.array(sha(rows))
+    return out
+
+
 def golden_params(parsers):
     """min_gain known answers and exception parity."""
     from PyPore.cparsers import FastStatSplit
@@ -311,6 +336,10 @@ def golden_experiment(dt, parsers):
 
 def main():
     dt, parsers, core = load_reference()
+    if "--c2-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "c2_full.npz"), **golden_c2_full(dt, parsers))
+        print("c2_full.npz", os.path.getsize(os.path.join(HERE, "c2_full.npz")))
+        return
     if "--c4-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "c4_full.npz"), **golden_c4_full(dt, parsers))
         print("c4_full.npz", os.path.getsize(os.path.join(HERE, "c4_full.npz")))
@@ -348,6 +377,7 @@ def main():
     with open(os.path.join(HERE, "experiment_meta.json"), "w") as out:
         out.write(golden_experiment(dt, parsers))
     np.savez_compressed(os.path.join(HERE, "c4_full.npz"), **golden_c4_full(dt, parsers))
+    np.savez_compressed(os.path.join(HERE, "c2_full.npz"), **golden_c2_full(dt, parsers))
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith(".npz"):
             print(fn, os.path.getsize(os.path.join(HERE, fn)))

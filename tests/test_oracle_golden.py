@@ -205,3 +205,19 @@ def test_oracle_reproduces_the_full_size_long_event_fixture():
         rows = np.stack([oe, ost, oen], axis=1).astype(np.int64)
         assert len(rows) == int(g[name + "_segments"]) and nc == cand
         assert sha(rows) == str(g[name + "_sha"])
+
+
+def test_oracle_reproduces_the_full_size_bench_workload_fixture():
+    """BASELINE configs[1] at full size = bench.py's workload (make_trace(5000, seed=1), 59,883,057 samples):
+    tests/golden/c2_full.npz was written by the real reference; the oracle hashes to the same event and segment
+    tables, and its candidate counts are what the device counters must show (tests/test_zz_gpu_fullsize.py)."""
+    g = load_golden("c2_full.npz")
+    x = synth.make_trace(5000, seed=1, tier="A").astype(np.float64)
+    assert len(x) == int(g["samples"]) and sha(x) == str(g["input_sha256"])
+    ws, wl = oracle.events(x, 110, RULES_1000)
+    assert len(ws) == int(g["events"]) and int(wl.sum()) == int(g["event_samples"])
+    assert sha(np.stack([ws, wl], axis=1).astype(np.int64)) == str(g["events_sha"])
+    for name, kw, cand in (("default", dict(), 240399270), ("psps10", dict(prior_segments_per_second=10), 135656885)):
+        oe, ost, oen, nc = oracle.statsplit_events(x, ws, wl, min_width=100, window_width=10000, threads=8, **kw)
+        assert len(oe) == int(g[name + "_segments"]) and nc == cand
+        assert sha(np.stack([oe, ost, oen], axis=1).astype(np.int64)) == str(g[name + "_sha"])

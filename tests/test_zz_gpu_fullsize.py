@@ -46,3 +46,40 @@ def test_c4_full_size_tables_hash_to_the_references(ctx):
             assert abs(seg["mean"][k] - v.mean()) <= 1e-9 * abs(v.mean())
             assert abs(seg["std"][k] - v.std()) <= 1e-9 * v.std()
             assert seg["min"][k] == v.min() and seg["max"][k] == v.max()
+
+
+C2_CANDIDATES = {"default": 240399270, "psps10": 135656885}
+C2_SETTINGS = {"default": dict(min_width=100, max_width=1000000, window_width=10000),
+               "psps10": dict(min_width=100, max_width=1000000, window_width=10000, prior_segments_per_second=10)}
+
+
+def test_c2_full_size_tables_hash_to_the_references(ctx):
+    """BASELINE configs[1] at full size -- exactly bench.py's workload (60 M samples, 5000 events): the event and
+    segment tables, resident and streamed from host memory, hash to what the REAL reference produced
+    (tests/golden/c2_full.npz, make_golden.py --c2-only), and the device counted the oracle's candidates."""
+    g = load_golden("c2_full.npz")
+    x = synth.make_trace(5000, seed=1, tier="A")
+    assert len(x) == int(g["samples"])
+    rules = dict(rule_mask=7, duration_gt=1000, duration_lt=0, min_gt=-0.5, max_lt=110.0)
+    ctx.upload_trace(x)
+    for name, kw in C2_SETTINGS.items():
+        mw, MW, W, gain = statsplit_min_gain(**kw)
+        r = ctx.pipeline(110.0, min_width=mw, max_width=MW, window_width=W, min_gain=gain, **rules)
+        assert r["events"] == int(g["events"]) and r["event_samples"] == int(g["event_samples"])
+        es, el = ctx.events(r["events"])
+        assert sha(np.stack([es, el], axis=1)) == str(g["events_sha"])
+        seg = ctx.segments(r["segments"], stats=False)
+        rows = np.stack([seg["event"].astype(np.int64), seg["start"], seg["end"]], axis=1)
+        assert r["segments"] == int(g[name + "_segments"])
+        assert ctx.split_counters()["candidates"] == C2_CANDIDATES[name]
+        assert sha(rows) == str(g[name + "_sha"])
+    # the public host-memory call (what bench.py's e2e times), tables delivered to page-locked host memory
+    mw, MW, W, gain = statsplit_min_gain(**C2_SETTINGS["default"])
+    r = ctx.pipeline(110.0, min_width=mw, max_width=MW, window_width=W, min_gain=gain, host_trace=x, export=True,
+                     **rules)
+    es, el = r["event_table"]
+    t = r["segment_table"]
+    assert sha(np.stack([np.asarray(es, np.int64), np.asarray(el, np.int64)], axis=1)) == str(g["events_sha"])
+    rows = np.stack([np.asarray(t["event"]).astype(np.int64), np.asarray(t["start"], np.int64),
+                     np.asarray(t["end"], np.int64)], axis=1)
+    assert sha(rows) == str(g["default_sha"])
