@@ -224,6 +224,30 @@ def parity_against_fixture(res_e2e):
         return {"error": "%s: %s" % (type(exc).__name__, exc)}
 
 
+def parity_sharded(tables, world):
+    """The gathered tables rank 0 downloaded in the last end-to-end step (events {global start, length}, seg_int
+    {global event id, start, end}) against tests/golden/sharded_full.npz: the CPU oracle on the uncut world x 60 M-sample
+    trace (tests/golden/make_sharded_full.py).  Outside every timed region; never raises."""
+    try:
+        import hashlib
+        g = np.load(os.path.join(ROOT, "tests", "golden", "sharded_full.npz"), allow_pickle=False)
+        k = "w%d_" % world
+        if k + "events" not in g.files:
+            return {"error": "no fixture for %d GPUs" % world}
+
+        def sha(a):
+            return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+        ev = np.asarray(tables["events"], np.int64)
+        rows = np.asarray(tables["seg_int"], np.int64)
+        return {"fixture": "tests/golden/sharded_full.npz (CPU oracle on the uncut trace, full size)",
+                "events": int(len(ev)), "events_expected": int(g[k + "events"]),
+                "segments": int(len(rows)), "segments_expected": int(g[k + "segments"]),
+                "events_bit_exact": bool(sha(ev) == str(g[k + "events_sha"])),
+                "segments_bit_exact": bool(sha(rows) == str(g[k + "segments_sha"]))}
+    except Exception as exc:  # a reporting extra must not cost the bench line
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+
 def ncu_traffic(kernel="k3_split"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
     capture of this same command (profiles/*_ncu_summary.csv, newest round); None without one."""
@@ -287,6 +311,8 @@ def run_ours(args):
                                 with_stats=True, **rules)
         return shard.step(THRESHOLD, rules, mw, MW, W, gain)
 
+    last_download = {}
+
     def step_e2e():
         if shard is None:
             # public host-memory entry point (pp_pipeline_host_tables): chunked H2D copy overlapped with the stages;
@@ -299,7 +325,7 @@ def run_ours(args):
         shard.load(xp)
         r = shard.step(THRESHOLD, rules, mw, MW, W, gain)
         if rank == 0:
-            shard.download()  # every GPU holds the whole result; the caller reads it once
+            last_download["tables"] = shard.download()  # every GPU holds the whole result; the caller reads it once
         return r
 
     def barrier():
@@ -411,6 +437,8 @@ def run_ours(args):
         }
         if shard is not None:
             line["host_planned_fallback_steps"] = int(shard.fallbacks)
+            if epg == EVENTS_PER_GPU:
+                line["parity"] = parity_sharded(last_download.get("tables"), world)
         elif epg == EVENTS_PER_GPU:
             line["parity"] = parity_against_fixture(res_e2e)
         if world == 1 and not args.no_cpu_baseline:
