@@ -83,3 +83,30 @@ def test_c2_full_size_tables_hash_to_the_references(ctx):
     rows = np.stack([np.asarray(t["event"]).astype(np.int64), np.asarray(t["start"], np.int64),
                      np.asarray(t["end"], np.int64)], axis=1)
     assert sha(rows) == str(g["default_sha"])
+
+
+def test_c5_full_size_files_through_the_batch_driver():
+    """BASELINE configs[4] at full file size: eight 250 kHz files of 2.49 M samples, Event.filter(1, 2000) +
+    SpeedyStatSplit per event, through batch.FileBatch (grouped passes and one file per pass).  The tables hash to the
+    oracle's (tests/golden/c5_files.npz, made by tests/golden/make_c5_files.py) for the tutorial gain AND for the default
+    gain min_gain = -0.0, where every window of filtered samples splits down to 2 * min_width."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_c5_files import SETTINGS, table_hashes
+    from batch_common import FILTER, FS, detector
+    from pypore_b200.batch import FileBatch
+    from pypore_b200.parsers import SpeedyStatSplit
+    g = load_golden("c5_files.npz")
+    files = [synth.make_trace(208, seed=900 + i, tier="A") for i in range(8)]
+    assert sum(len(f) for f in files) == int(g["samples"])
+    for group_samples in (1 << 26, 0):
+        b = FileBatch(device=0, workers=2, group_samples=group_samples)
+        try:
+            for name, kw in SETTINGS.items():
+                t = b.parse(files, 1000. / FS, detector(), SpeedyStatSplit(**kw), FILTER)
+                ne, ns, he, hs = table_hashes(t)
+                assert (ne, ns) == (int(g[name + "_events"]), int(g[name + "_segments"])), name
+                assert he == str(g[name + "_events_sha"]) and hs == str(g[name + "_segments_sha"]), name
+        finally:
+            b.close()
