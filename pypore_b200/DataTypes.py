@@ -490,6 +490,10 @@ class Experiment(object):
             raise ValueError("batch= keeps only the event / segment tables on the host; use it with meta=True")
         if segmenter is None:
             raise ValueError("batch= runs the whole pipeline; it needs a segmenter")
+        if not (isinstance(event_detector, lambda_event_parser) and event_detector._device_rules() is not None
+                and isinstance(segmenter, SpeedyStatSplit)):
+            raise TypeError("batch= needs a lambda_event_parser with device-evaluable rules (parsers.RuleSet or the "
+                            "defaults) and a SpeedyStatSplit; other plug-ins go through the sequential loop")
         files = [f if isinstance(f, File) else File(f) for f in self.filenames]
         tables = batch.parse([f.current for f in files], [1000. / f.second for f in files], event_detector,
                              segmenter, filter_params)

@@ -189,3 +189,18 @@ def test_experiment_batch_reproduces_the_real_references_run():
                                                       group_samples=30000))
     assert printed == want["stdout"]
     assert_json_close(got, want["files"], 1e-9)
+
+
+def test_experiment_batch_argument_errors():
+    from batch_common import OracleContext
+    from pypore_b200.DataTypes import Experiment, File
+    from pypore_b200.parsers import lambda_event_parser
+    b = FileBatch(workers=1, contexts=[OracleContext()])
+    mk = lambda: Experiment([File(current=x, timestep=TIMESTEP) for x in make_files(2)])  # noqa: E731
+    with pytest.raises(ValueError, match="meta=True"):
+        mk().parse(event_detector=detector(), segmenter=segmenter(), meta=False, batch=b)
+    with pytest.raises(ValueError, match="segmenter"):
+        mk().parse(event_detector=detector(), segmenter=None, meta=True, batch=b)
+    with pytest.raises(TypeError, match="device-evaluable"):      # opaque Python rules cannot run on the device
+        mk().parse(event_detector=lambda_event_parser(threshold=110, rules=[lambda e: e.max < 110]),
+                   segmenter=segmenter(), meta=True, batch=b)
