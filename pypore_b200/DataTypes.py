@@ -1,75 +1,54 @@
-"""Container drivers: host-side mirror of the hot-path part of PyPore/DataTypes.py.
+"""Container drivers behind the reference's names: ``File``, ``Event``, ``MetaEvent``, ``Experiment``, ``Sample``.
 
-``File.parse(parser=...)``, ``Event.filter(order, cutoff)`` and
-``Event.parse(parser=...)`` keep the reference's signatures and side effects
-(DataTypes.py:258-289, 589-602).  On top of that, ``File.parse`` accepts
-``segmenter=`` / ``filter_params=`` to run threshold -> [filter] -> split ->
-statistics in one device-resident pass, returning the same objects lazily built
-from the compact tables.  HMM-guided parsing, plotting, MySQL and .abf reading
-are out of scope.
+``File.parse(parser=...)``, ``Event.filter(order, cutoff)`` and ``Event.parse(parser=...)`` keep the reference's
+signatures and side effects (DataTypes.py:258-289, 589-602).  The design is table-first:
+
+* ``File.parse(..., segmenter=, filter_params=)`` runs threshold scan -> [Bessel filtfilt] -> split search ->
+  statistics in ONE device-resident pass and keeps what came back as ``wire.FileTables`` (event rows, segment rows,
+  in samples).  ``file.events`` is a lazy view on those tables: an ``Event`` / ``Segment`` object exists only once
+  somebody indexes it.
+* ``File.to_json`` / ``File.to_meta`` / the verbose lines of ``Experiment.parse`` work on the tables directly while
+  no object has been handed out (``wire.file_tree``); after that they walk the objects, like the reference.
+
+HMM-guided parsing, plotting, MySQL and .abf reading are out of scope.
 """
 import json
-from functools import lru_cache, reduce
+from functools import lru_cache
 
 import numpy as np
 
-from . import _lib
-from .core import MetaSegment, Segment, ignored, _jsonable
-from .parsers import RuleSet, SpeedyStatSplit, lambda_event_parser, parser, _as_float32_trace
+from . import _lib, wire
+from .core import MetaSegment, Segment
+from .parsers import SpeedyStatSplit, lambda_event_parser, parser, _device_trace
+
+_STAT_SPAN = wire.FIELDS["MetaSegment"]
 
 
 class MetaEvent(MetaSegment):
-    """Metadata of an event (DataTypes.py:49-80)."""
-
-    def __init__(self, **kwargs):
-        MetaSegment.__init__(self, **kwargs)
-
-    def delete(self):
-        with ignored(AttributeError):
-            del self.state_parser
-        for segment in self.segments:
-            segment.delete()
-        del self
-
-    def to_dict(self):
-        """DataTypes.py:196-201 (no 'filtered' key, unlike Event.to_dict)."""
-        keys = ['mean', 'std', 'min', 'max', 'start', 'end', 'duration',
-                'filter_order', 'filter_cutoff', 'n', 'state_parser', 'segments']
-        d = {i: _jsonable(getattr(self, i)) for i in keys if hasattr(self, i)}
-        d['name'] = self.__class__.__name__
-        return d
+    """An event reduced to metadata (DataTypes.py:49-80): its segments are MetaSegments, no samples anywhere."""
 
     def to_json(self, filename=None):
-        """DataTypes.py:203-216."""
-        d = self.to_dict()
-        with ignored(KeyError, AttributeError):
-            d['segments'] = [seg.to_dict() for seg in d['segments']]
-        with ignored(KeyError, AttributeError):
-            d['state_parser'] = d['state_parser'].to_dict()
-        _json = json.dumps(d, indent=4, separators=(',', ' : '))
-        if filename:
-            with open(filename, 'w') as out:
-                out.write(_json)
-        return _json
+        return wire.dumps(wire.expand_event(self, strict=False), filename)
 
     @classmethod
     def from_json(cls, _json):
-        """DataTypes.py:218-225."""
-        if _json.endswith(".json"):
-            with open(_json, 'r') as infile:
-                _json = ''.join(line for line in infile)
-        return cls(**json.loads(_json))
+        return cls(**json.loads(wire.source_text(_json)))
 
-    @classmethod
-    def from_segments(cls, segments):
-        return cls(segments=segments)
+    from_segments = classmethod(lambda cls, segments: cls(segments=segments))
+    n = property(lambda self: len(getattr(self, "segments", ())))
 
-    @property
-    def n(self):
-        try:
-            return len(self.segments)
-        except Exception:
-            return 0
+    def delete(self):
+        self.__dict__.pop("state_parser", None)
+        _each(self.segments, "delete")
+
+
+def _each(items, method):
+    """Call a no-argument method on every item."""
+    for item in items:
+        getattr(item, method)()
+
+
+_NEEDS_CURRENT = "Cannot filter a metaevent. Must have the current."
 
 
 def bessel_coefficients(order, cutoff, second):
@@ -104,107 +83,72 @@ class Event(Segment):
     """An event: a stretch of the file holding useful data (DataTypes.py:241-565)."""
 
     def __init__(self, current, segments=[], **kwargs):
-        if len(segments) > 0:
+        if len(segments):
+            # an event given as its segments is the concatenation of their samples (nothing, if they have none)
             try:
-                current = np.concatenate([seg.current for seg in segments])
+                current = np.concatenate([piece.current for piece in segments])
             except Exception:
                 current = []
-        Segment.__init__(self, current, filtered=False, segments=segments, **kwargs)
+        super(Event, self).__init__(current, filtered=False, segments=segments, **kwargs)
 
     def filter(self, order=1, cutoff=2000.):
-        """Zero-phase Bessel low-pass of ``self.current`` (DataTypes.py:258-274)."""
-        if type(self) != Event:
-            raise TypeError("Cannot filter a metaevent. Must have the current.")
+        """Zero-phase Bessel low-pass of ``self.current`` (DataTypes.py:258-274), on the device (csrc/filter.cuh)."""
+        if type(self) is not Event:
+            raise TypeError(_NEEDS_CURRENT)
         b, a, zi = bessel_coefficients(order, cutoff, self.second)
-        cur = np.ascontiguousarray(self.current, dtype=np.float64)
+        samples = np.ascontiguousarray(self.current, dtype=np.float64)
         padlen = 3 * len(b)
-        if cur.shape[0] <= padlen:
-            raise ValueError("The length of the input vector x must be greater than padlen, which is %d."
-                             % padlen)
+        if samples.shape[0] <= padlen:
+            raise ValueError("The length of the input vector x must be greater than padlen, which is %d." % padlen)
         ctx = _lib.default_context()
-        ctx.upload_events_f64([cur])
+        ctx.upload_events_f64([samples])
         ctx.filter_events(b, a, zi)
-        self.current = ctx.event_samples(cur.shape[0])
-        self.filtered = True
-        self.filter_order = order
-        self.filter_cutoff = cutoff
+        self.current = ctx.event_samples(samples.shape[0])
+        self.filtered, self.filter_order, self.filter_cutoff = True, order, cutoff
 
     def parse(self, parser=SpeedyStatSplit(prior_segments_per_second=10), hmm=None):
-        """Segment the event with a plug-in state parser (DataTypes.py:276-289,333)."""
-        if hmm:
+        """Segment the event with a plug-in state parser (DataTypes.py:276-289,333); returns the segment count."""
+        if hmm is not None and hmm:
             raise NotImplementedError("HMM-guided segmentation needs yahmm and is out of scope")
-        self.segments = parser.parse(self.current)
-        for segment in self.segments:
-            segment.event = self
-            segment.scale(float(self.file.second))
-        self.state_parser = parser
+        second = float(self.file.second)
+        pieces = parser.parse(self.current)
+        for piece in pieces:
+            piece.event = self
+            piece.scale(second)
+        self.segments, self.state_parser = pieces, parser
+        return len(pieces)
 
     def delete(self):
-        with ignored(AttributeError):
-            del self.current
-        with ignored(AttributeError):
-            del self.state_parser
-        for segment in self.segments:
-            segment.delete()
-        del self
+        for name in ("current", "state_parser"):
+            self.__dict__.pop(name, None)
+        _each(self.segments, "delete")
 
     def to_meta(self):
-        for prop in ['mean', 'std', 'duration', 'start', 'min', 'max', 'end', 'start']:
-            with ignored(AttributeError, KeyError):
-                self.__dict__[prop] = getattr(self, prop)
-        self.__dict__.pop('_stats', None)
-        with ignored(AttributeError):
-            del self.current
-        for segment in self.segments:
-            segment.to_meta()
-        self.__class__ = type("MetaEvent", (MetaEvent,), self.__dict__)
-
-    def to_dict(self):
-        """DataTypes.py:493-498."""
-        keys = ['mean', 'std', 'min', 'max', 'start', 'end', 'duration', 'filtered',
-                'filter_order', 'filter_cutoff', 'n', 'state_parser', 'segments']
-        d = {i: _jsonable(getattr(self, i)) for i in keys if hasattr(self, i)}
-        d['name'] = self.__class__.__name__
-        return d
+        self._freeze(_STAT_SPAN, MetaEvent)
+        _each(self.segments, "to_meta")
 
     def to_json(self, filename=None):
-        """DataTypes.py:500-513."""
-        d = self.to_dict()
-        with ignored(KeyError, AttributeError):
-            d['segments'] = [seg.to_dict() for seg in d['segments']]
-        with ignored(KeyError, AttributeError):
-            d['state_parser'] = d['state_parser'].to_dict()
-        _json = json.dumps(d, indent=4, separators=(',', ' : '))
-        if filename:
-            with open(filename, 'w') as out:
-                out.write(_json)
-        return _json
+        return wire.dumps(wire.expand_event(self, strict=False), filename)
 
     @classmethod
     def from_json(cls, _json):
-        """DataTypes.py:515-529: a JSON without 'current' gives a MetaEvent."""
-        if _json.endswith(".json"):
-            with open(_json, 'r') as infile:
-                _json = ''.join(line for line in infile)
-        d = json.loads(_json)
-        event = MetaSegment()
-        if 'current' not in d.keys():
-            event.__class__ = type("MetaEvent", (MetaEvent,), d)
-        else:
-            event = cls(d['current'], start=d['start'])
-        return event
+        """An Event if the JSON carries the samples, a MetaEvent otherwise (DataTypes.py:515-529)."""
+        d = json.loads(wire.source_text(_json))
+        if "current" in d:
+            return cls(d["current"], start=d["start"])
+        return MetaEvent(**d)
 
-    @property
-    def n(self):
-        return len(self.segments)
+    n = property(lambda self: len(self.segments))
 
 
 class _LazyList(object):
-    """List-like whose items are built on first access (object creation is the
-    dominant host cost at 10^5..10^6 segments)."""
+    """Sequence whose items are built on first access (object creation is the dominant host cost at 10^5..10^6
+    segments).  ``untouched`` says that nothing has been handed out yet."""
 
     def __init__(self, n, factory):
         self._n, self._factory, self._cache = int(n), factory, {}
+
+    untouched = property(lambda self: not self._cache)
 
     def __len__(self):
         return self._n
@@ -222,8 +166,13 @@ class _LazyList(object):
         return item
 
     def __iter__(self):
-        for i in range(self._n):
-            yield self[i]
+        return (self[i] for i in range(self._n))
+
+    def __add__(self, other):
+        return list(self) + list(other)
+
+    def __radd__(self, other):
+        return list(other) + list(self)
 
 
 class File(Segment):
@@ -234,22 +183,14 @@ class File(Segment):
     """
 
     def __init__(self, filename=None, current=None, timestep=None, **kwargs):
-        if current is not None and timestep is not None:
-            filename = ""
-        elif filename and current is None and timestep is None:
-            raise NotImplementedError("reading .abf files is out of scope; pass current= and timestep=")
-        else:
-            raise SyntaxError("Must provide current and timestep, or filename "
-                              "corresponding to a valid abf file.")
-        Segment.__init__(self, current=current, filename=filename, second=1000. / timestep,
-                         events=[], sample=None)
+        if current is None or timestep is None:
+            if filename and current is None and timestep is None:
+                raise NotImplementedError("reading .abf files is out of scope; pass current= and timestep=")
+            raise SyntaxError("Must provide current and timestep, or filename corresponding to a valid abf file.")
+        super(File, self).__init__(current=current, filename="", second=1000. / timestep, events=[], sample=None)
 
-    def __getitem__(self, index):
-        return self.events[index]
-
-    @property
-    def n(self):
-        return len(self.events)
+    __getitem__ = lambda self, index: self.events[index]     # noqa: E731
+    n = property(lambda self: len(self.events))
 
     def parse(self, parser=lambda_event_parser(threshold=90), segmenter=None, filter_params=None,
               context=None):
@@ -260,181 +201,169 @@ class File(Segment):
         split search, statistics -- and every event comes back with its
         ``segments`` already parsed, as after ``event.parse(parser=segmenter)``.
         """
+        self.__dict__.pop("_tables", None)
         if segmenter is None and filter_params is None and not isinstance(parser, lambda_event_parser):
-            # any duck-typed parser, exactly like the reference
-            self.events = [Event(current=seg.current, start=seg.start / self.second,
-                                 end=(seg.start + seg.duration) / self.second,
-                                 duration=seg.duration / self.second, second=self.second, file=self)
-                           for seg in parser.parse(self.current)]
+            # any duck-typed parser, exactly like the reference: seg.current / seg.start / seg.duration in samples
+            second = self.second
+            self.events = [Event(current=seg.current, start=seg.start / second,
+                                 end=(seg.start + seg.duration) / second, duration=seg.duration / second,
+                                 second=second, file=self) for seg in parser.parse(self.current)]
             self.event_parser = parser
             return
         if not isinstance(parser, lambda_event_parser):
             raise TypeError("the device-resident pipeline needs a pypore_b200 lambda_event_parser")
-        ctx = context or _lib.default_context()
-        host = np.asarray(self.current)
-        self._parse_resident(ctx, host, _as_float32_trace(host), parser, segmenter, filter_params)
+        self._parse_resident(context or _lib.default_context(), np.asarray(self.current), parser, segmenter,
+                             filter_params)
 
     # ------------------------------------------------------------------
-    def _parse_resident(self, ctx, host, x32, parser, segmenter, filter_params):
-        second = self.second
-        filt = None
-        if filter_params is not None:
-            order, cutoff = filter_params
-            filt = bessel_coefficients(order, cutoff, second)
-        rs = parser._device_rules()
-        tables = None
+    def _parse_resident(self, ctx, host, parser, segmenter, filter_params):
+        filt = bessel_coefficients(filter_params[0], filter_params[1], self.second) if filter_params is not None else None
+        rules = parser._device_rules()
+        seg_table = None
+        n_samples = host.shape[0]
         if segmenter is not None:
             mw, MW, W, gain = segmenter._params()
-        if rs is not None and segmenter is not None:
+        if n_samples == 0:
+            ev_start = ev_len = np.zeros(0, np.int64)
+        elif rules is not None and segmenter is not None:
             # one call from host memory: the copy is chunked and overlapped with the stages (pp_pipeline_host)
             counts = ctx.pipeline(parser.threshold, min_width=mw, max_width=MW, window_width=W, min_gain=gain,
-                                  filter_ba=filt, with_stats=True, host_trace=x32, **rs.device_args())
+                                  filter_ba=filt, with_stats=True, host_trace=_device_trace(host),
+                                  **rules.device_args())
             ev_start, ev_len = ctx.events(counts["events"])
-            tables = ctx.segments(counts["segments"])
-            r_start, _, r_min, r_max, _ = ctx.runs(counts["runs"])
-            idx = np.searchsorted(r_start, ev_start)
-            ev_min, ev_max = r_min[idx], r_max[idx]
+            seg_table = ctx.segments(counts["segments"])
         else:
-            ctx.upload_trace(x32)
-            ev_start, ev_len, ev_min, ev_max = parser._detect(ctx, host)
+            ctx.upload_trace(_device_trace(host))
+            ev_start, ev_len = parser._detect(ctx, host)[:2]
             if filt is not None and len(ev_start):
                 ctx.filter_events(*filt)
             if segmenter is not None and len(ev_start):
                 n_seg = ctx.statsplit(mw, MW, W, gain)
                 ctx.segment_stats()
-                tables = ctx.segments(n_seg)
-        filtered = None
-        if filt is not None and len(ev_start):
-            filtered = ctx.event_samples(int(ev_len.sum()))
-        self.event_table = dict(start=ev_start, length=ev_len, min=ev_min, max=ev_max)
-        self.segment_table = tables
-        ev_off = np.concatenate(([0], np.cumsum(ev_len)))
-        seg_bounds = None
-        if tables is not None:
-            seg_bounds = np.searchsorted(tables["event"], np.arange(len(ev_start) + 1))
+                seg_table = ctx.segments(n_seg)
+        n_ev = len(ev_start)
+        ev_stats = ctx.event_stats(n_ev) if n_ev else {k: np.zeros(0) for k in ("mean", "std", "min", "max")}
+        filtered = ctx.event_samples(int(ev_len.sum())) if filt is not None and n_ev else None
+        if segmenter is not None and seg_table is None:
+            seg_table = {"event": np.zeros(0, np.int32), "start": np.zeros(0, np.int64), "end": np.zeros(0, np.int64),
+                         **{k: np.zeros(0) for k in ("mean", "std", "min", "max")}}
+        self.event_table = dict(start=ev_start, length=ev_len, **ev_stats)
+        self.segment_table = seg_table
+        self.event_parser = parser
+        self._attach(wire.FileTables(self.second, self.event_table, seg_table, filter_params, segmenter),
+                     host=host, filtered=filtered)
 
-        def make_event(i):
-            s, n = int(ev_start[i]), int(ev_len[i])
-            if filtered is not None:
-                cur = filtered[ev_off[i]:ev_off[i + 1]]
-            else:
-                cur = np.array(host[s:s + n])
-            ev = Event(current=cur, start=s / second, end=(s + n) / second, duration=n / second,
-                       second=second, file=self)
-            if filtered is not None:
-                ev.filtered = True
-                ev.filter_order, ev.filter_cutoff = filter_params
-            if tables is not None:
-                lo, hi = int(seg_bounds[i]), int(seg_bounds[i + 1])
+    def _attach(self, tables, host=None, filtered=None):
+        """Make the file a view on `tables`: ``events`` builds Event / Segment objects (MetaEvent / MetaSegment for
+        tables.meta) on demand."""
+        self._tables = tables
+        second = tables.second
+        ev, sg = tables.events, tables.segments
+        n_ev = len(ev["start"])
+        ev_off = np.concatenate(([0], np.cumsum(ev["length"]))) if filtered is not None else None
+        bounds = np.searchsorted(sg["event"], np.arange(n_ev + 1)) if sg is not None else None
+        fp = tables.filter_params
 
-                def make_segment(k, cur=cur, ev=ev, lo=lo):
-                    k += lo
-                    a, b = int(tables["start"][k]), int(tables["end"][k])
-                    seg = Segment(current=cur[a:b], start=a, duration=(b - a), end=b)
-                    seg._set_stats(tables["mean"][k], tables["std"][k], tables["min"][k], tables["max"][k])
-                    seg.event = ev
+        def span(a, n):
+            return dict(start=a / second, end=(a + n) / second, duration=n / second)
+
+        def stats(table, k):
+            return table["mean"][k], table["std"][k], table["min"][k], table["max"][k]
+
+        def meta_event(i):
+            kw = dict(zip(("mean", "std", "min", "max"), stats(ev, i)))
+            kw.update(span(int(ev["start"][i]), int(ev["length"][i])), second=second, file=self,
+                      filtered=fp is not None, segments=[])
+            if fp is not None:
+                kw["filter_order"], kw["filter_cutoff"] = fp
+            if sg is not None:
+                kw["segments"] = [MetaSegment(**dict(zip(("mean", "std", "min", "max"), stats(sg, k))),
+                                              **span(int(sg["start"][k]), int(sg["end"][k]) - int(sg["start"][k])))
+                                  for k in range(int(bounds[i]), int(bounds[i + 1]))]
+                kw["state_parser"] = tables.state_parser
+            return MetaEvent(**kw)
+
+        def live_event(i):
+            a, n = int(ev["start"][i]), int(ev["length"][i])
+            samples = filtered[ev_off[i]:ev_off[i + 1]] if filtered is not None else np.array(host[a:a + n])
+            event = Event(current=samples, second=second, file=self, **span(a, n))
+            event._set_stats(*stats(ev, i))
+            if fp is not None:
+                event.filtered, (event.filter_order, event.filter_cutoff) = True, fp
+            if sg is not None:
+                lo = int(bounds[i])
+
+                def segment(j):
+                    k = lo + j
+                    s, e = int(sg["start"][k]), int(sg["end"][k])
+                    seg = Segment(current=samples[s:e], start=s, duration=e - s, end=e)._set_stats(*stats(sg, k))
+                    seg.event = event
                     seg.scale(float(second))
                     return seg
-                ev.segments = _LazyList(hi - lo, make_segment)
-                ev.state_parser = segmenter
-            return ev
+                event.segments = _LazyList(int(bounds[i + 1]) - lo, segment)
+                event.state_parser = tables.state_parser
+            return event
 
-        self.events = _LazyList(len(ev_start), make_event)
-        self.event_parser = parser
+        self.events = _LazyList(n_ev, meta_event if tables.meta else live_event)
+
+    def _tables_current(self):
+        """The tables still describe the file: no event object was handed out that the caller could have changed."""
+        return isinstance(self.events, _LazyList) and self.events.untouched and "_tables" in self.__dict__
+
+    def _segment_counts(self):
+        """Segments per event, from the tables when they are current (no object is built for it)."""
+        if self._tables_current() and self._tables.segments is not None:
+            return np.bincount(np.asarray(self._tables.segments["event"], np.int64),
+                               minlength=len(self.events)).tolist()
+        return [event.n for event in self.events]
 
     def to_meta(self):
         """Drop the ionic current of the file and of everything under it (DataTypes.py:683-693)."""
-        with ignored(AttributeError):
-            del self.current
-        events = list(self.events)  # lazily built events are materialised once, then reduced to metadata
-        for event in events:
-            event.to_meta()
-        self.events = events
+        self.__dict__.pop("current", None)
+        if self._tables_current():
+            self._tables.meta = True
+            self._attach(self._tables)
+            return
+        self.events = list(self.events)
+        _each(self.events, "to_meta")
 
     def to_dict(self):
-        """DataTypes.py:695-706."""
-        keys = ['filename', 'n', 'event_parser', 'mean', 'std', 'duration', 'start', 'end', 'events']
-        if not hasattr(self, 'end') and (hasattr(self, 'start') and hasattr(self, 'duration')):
-            setattr(self, 'end', self.start + self.duration)
-        d = {i: _jsonable(getattr(self, i)) for i in keys if hasattr(self, i)}
-        d['name'] = self.__class__.__name__
-        return d
+        """DataTypes.py:695-706 (a file with start and duration also gets its end)."""
+        if not hasattr(self, "end") and hasattr(self, "start") and hasattr(self, "duration"):
+            self.end = self.start + self.duration
+        return wire.record(self, "File")
 
     def to_json(self, filename=None):
         """The file, its events and their segments as the reference's JSON (DataTypes.py:708-738)."""
-        d = self.to_dict()
-        devents = []
-        for event in d['events']:
-            devent = event.to_dict()
-            try:
-                devent['segments'] = [state.to_dict() for state in devent['segments']]
-                devent['state_parser'] = devent['state_parser'].to_dict()
-            except Exception:
-                with ignored(KeyError, AttributeError):
-                    del devent['segments']
-                    del devent['state_parser']
-            devents.append(devent)
-        d['events'] = devents
-        d['event_parser'] = d['event_parser'].to_dict()
-        _json = json.dumps(d, indent=4, separators=(',', ' : '))
-        if filename:
-            with open(filename, 'w') as outfile:
-                outfile.write(_json)
-        return _json
+        return wire.dumps(wire.file_tree(self), filename)
 
     @classmethod
     def from_json(cls, _json):
-        """Rebuild a file and its events from to_json's output (DataTypes.py:740-796).  Without the .abf
-        file -- always the case here, reading .abf is out of scope -- the result holds MetaEvents /
-        MetaSegments, exactly the reference's own fallback."""
-        if _json.endswith(".json"):
-            with open(_json, 'r') as infile:
-                _json = ''.join(line for line in infile)
-        d = json.loads(_json)
-        if d['name'] != "File":
+        """Rebuild a file from to_json's output (DataTypes.py:740-796).  The reference re-reads the .abf file named
+        in the JSON and falls back to metadata objects when it cannot; reading .abf is out of scope here, so the
+        result always holds MetaEvents / MetaSegments."""
+        tree = json.loads(wire.source_text(_json))
+        if tree["name"] != "File":
             raise TypeError("JSON does not encode a file")
-        try:
-            file = File(filename=d['filename'] + ".abf")
-            meta = False
-        except Exception:
-            file = File(current=[], timestep=1)
-            meta = True
-        file.event_parser = parser.from_json(json.dumps(d['event_parser']))
-        file.events = []
-        for _json in d['events']:
-            s, e = int(_json['start'] * file.second), int(_json['end'] * file.second)
-            if meta:
-                event = MetaEvent(**_json)
-            else:
-                current = file.current[s:e]
-                event = Event(current=current, start=s / file.second, end=e / file.second,
-                              duration=(e - s) / file.second, second=file.second, file=file)
-            if _json['filtered']:
-                if not meta:
-                    event.filter(order=_json['filter_order'], cutoff=_json['filter_cutoff'])
-            if meta:
-                event.segments = [MetaSegment(**s_json) for s_json in _json['segments']]
-            else:
-                event.segments = [Segment(current=event.current[int(s_json['start'] * file.second):
-                                                                int(s_json['end'] * file.second)],
-                                          second=file.second, event=event, **s_json)
-                                  for s_json in _json['segments']]
-            event.state_parser = parser.from_json(json.dumps(_json['state_parser']))
-            event.filtered = _json['filtered']
-            file.events.append(event)
-        return file
+        f = cls(current=[], timestep=1)
+        f.event_parser = parser.from_json(json.dumps(tree["event_parser"]))
+        f.events = []
+        for row in tree["events"]:
+            event = MetaEvent(**row)
+            event.segments = [MetaSegment(**seg_row) for seg_row in row["segments"]]
+            event.state_parser = parser.from_json(json.dumps(row["state_parser"]))
+            event.filtered = row["filtered"]
+            f.events.append(event)
+        return f
 
     def delete(self):
-        with ignored(AttributeError):
-            del self.current
-        with ignored(AttributeError):
-            del self.event_parser
-        for event in self.events:
-            event.delete()
-        del self
+        for name in ("current", "event_parser", "_tables"):
+            self.__dict__.pop(name, None)
+        if isinstance(self.events, _LazyList):
+            self.events = []
+        _each(self.events, "delete")
 
-    def close(self):
-        self.delete()
+    close = delete
 
 
 class Experiment(object):
@@ -448,9 +377,15 @@ class Experiment(object):
     """
 
     def __init__(self, filenames, name=None):
-        self.filenames = filenames
-        self.name = name or "Experiment"
-        self.files = []
+        self.filenames, self.name, self.files = filenames, name or "Experiment", []
+
+    @staticmethod
+    def _report(file, with_segments):
+        print("Opening {}".format(file.filename))
+        print("\tDetected {} Events".format(file.n))
+        if with_segments:
+            for i, count in enumerate(file._segment_counts()):
+                print("\t\tEvent {} has {} segments".format(i + 1, count))
 
     def parse(self, event_detector=lambda_event_parser(threshold=90),
               segmenter=SpeedyStatSplit(prior_segments_per_second=10, cutoff_freq=2000.),
@@ -461,29 +396,28 @@ class Experiment(object):
         tables (kept as ``self.tables``)."""
         if batch is not None:
             return self._parse_batch(batch, event_detector, segmenter, filter_params, verbose, meta)
-        for file in (f if isinstance(f, File) else File(f) for f in self.filenames):
-            if verbose:
-                print("Opening {}".format(file.filename))
-            batched = (isinstance(event_detector, lambda_event_parser) and event_detector._device_rules() is not None
-                       and (segmenter is None or isinstance(segmenter, SpeedyStatSplit)))
-            if batched and (segmenter is not None or filter_params is not None):
-                file.parse(parser=event_detector, segmenter=segmenter, filter_params=filter_params)
+        on_device = (isinstance(event_detector, lambda_event_parser) and event_detector._device_rules() is not None
+                     and (segmenter is None or isinstance(segmenter, SpeedyStatSplit))
+                     and (segmenter is not None or filter_params is not None))
+        for f in self._opened():
+            if on_device:
+                f.parse(parser=event_detector, segmenter=segmenter, filter_params=filter_params)
             else:
-                # arbitrary Python rules or a foreign segmenter: the reference's own loop (DataTypes.py:972-982)
-                file.parse(parser=event_detector)
-                for event in file.events:
+                # arbitrary Python rules or a foreign segmenter: per event, like the reference (DataTypes.py:972-982)
+                f.parse(parser=event_detector)
+                for ev in f.events:
                     if filter_params is not None:
-                        event.filter(*filter_params)
+                        ev.filter(*filter_params)
                     if segmenter is not None:
-                        event.parse(parser=segmenter)
+                        ev.parse(parser=segmenter)
             if verbose:
-                print("\tDetected {} Events".format(file.n))
-                if segmenter is not None:
-                    for i, event in enumerate(file.events):
-                        print("\t\tEvent {} has {} segments".format(i + 1, event.n))
+                self._report(f, segmenter is not None)
             if meta:
-                file.to_meta()
-            self.files.append(file)
+                f.to_meta()
+            self.files += [f]
+
+    def _opened(self):
+        return (f if isinstance(f, File) else File(f) for f in self.filenames)
 
     def _parse_batch(self, batch, event_detector, segmenter, filter_params, verbose, meta):
         if not meta:
@@ -494,52 +428,36 @@ class Experiment(object):
                 and isinstance(segmenter, SpeedyStatSplit)):
             raise TypeError("batch= needs a lambda_event_parser with device-evaluable rules (parsers.RuleSet or the "
                             "defaults) and a SpeedyStatSplit; other plug-ins go through the sequential loop")
-        files = [f if isinstance(f, File) else File(f) for f in self.filenames]
-        tables = batch.parse([f.current for f in files], [1000. / f.second for f in files], event_detector,
-                             segmenter, filter_params)
-        self.tables = tables
-        for file in tables.files([f.filename for f in files], event_detector, segmenter, filter_params):
+        files = list(self._opened())
+        self.tables = batch.parse([f.current for f in files], [1000. / f.second for f in files], event_detector,
+                                  segmenter, filter_params)
+        for f in self.tables.files([f.filename for f in files], event_detector, segmenter, filter_params):
             if verbose:
-                print("Opening {}".format(file.filename))
-                print("\tDetected {} Events".format(file.n))
-                for i, event in enumerate(file.events):
-                    print("\t\tEvent {} has {} segments".format(i + 1, event.n))
-            self.files.append(file)
+                self._report(f, True)
+            self.files += [f]
 
     def delete(self):
-        with ignored(AttributeError):
-            del self.events
-        with ignored(AttributeError):
-            del self.segments
-        for file in self.files:
-            file.delete()
-        del self
+        _each(self.files, "delete")
+        self.files = []
 
-    @property
-    def n(self):
-        return len(self.files)
+    n = property(lambda self: len(self.files))
 
     @property
     def events(self):
         """All the events in all files."""
-        try:
-            return reduce(list.__add__, [list(file.events) for file in self.files])
-        except Exception:
-            return []
+        return [event for file in self.files for event in file.events]
 
     @property
     def segments(self):
         """All segments of all events."""
-        try:
-            return reduce(list.__add__, [list(event.segments) for event in self.events])
-        except Exception:
-            return []
+        return [segment for event in self.events for segment in event.segments]
 
 
 class Sample(object):
     """A container for events all suggested to be from the same substrate (DataTypes.py:1034-1040)."""
 
     def __init__(self, events=[], files=[], label=None):
-        self.events = events
-        self.files = files
-        self.label = label
+        self.events, self.files, self.label = events, files, label
+
+    def delete(self):
+        _each(self.files, "delete")

@@ -186,9 +186,10 @@ class BatchTables(object):
     def files(self, filenames=None, event_detector=None, segmenter=None, filter_params=None):
         """The batch as the reference leaves it after Experiment.parse(..., meta=True): one File per file
         with MetaEvents / MetaSegments, start / end / duration in seconds (DataTypes.py:595-600,
-        core.py:199-207), statistics from the device tables."""
-        from .core import MetaSegment
-        from .DataTypes import File, MetaEvent
+        core.py:199-207), statistics from the device tables.  Every File is a lazy view on its rows of the
+        tables (wire.FileTables): objects are built when somebody indexes them, to_json never builds any."""
+        from . import wire
+        from .DataTypes import File
         out = []
         ev, sg = self.events, self.segments
         for i in range(self.n_files):
@@ -197,25 +198,9 @@ class BatchTables(object):
             del f.current
             f.filename = filenames[i] if filenames is not None else ""
             (e0, e1), (s0, s1) = self.file_rows(i)
-            bounds = s0 + np.searchsorted(sg["event"][s0:s1], np.arange(e1 - e0 + 1))
-            events = []
-            for k in range(e0, e1):
-                s, n = int(ev["start"][k]), int(ev["length"][k])
-                segments = []
-                for r in range(int(bounds[k - e0]), int(bounds[k - e0 + 1])):
-                    a, b = int(sg["start"][r]), int(sg["end"][r])
-                    segments.append(MetaSegment(start=a / second, end=b / second, duration=(b - a) / second,
-                                                mean=sg["mean"][r], std=sg["std"][r], min=sg["min"][r],
-                                                max=sg["max"][r]))
-                kw = dict(start=s / second, end=(s + n) / second, duration=n / second, mean=ev["mean"][k],
-                          std=ev["std"][k], min=ev["min"][k], max=ev["max"][k], second=second, file=f,
-                          filtered=filter_params is not None, segments=segments)
-                if filter_params is not None:
-                    kw["filter_order"], kw["filter_cutoff"] = filter_params
-                if segmenter is not None:
-                    kw["state_parser"] = segmenter
-                events.append(MetaEvent(**kw))
-            f.events = events
+            rows_e = {k: ev[k][e0:e1] for k in ("start", "length") + STAT_KEYS}
+            rows_s = {k: sg[k][s0:s1] for k in ("event", "start", "end") + STAT_KEYS}
+            f._attach(wire.FileTables(second, rows_e, rows_s, filter_params, segmenter, meta=True))
             if event_detector is not None:
                 f.event_parser = event_detector
             out.append(f)

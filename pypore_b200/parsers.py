@@ -103,8 +103,14 @@ class RuleSet(list):
     def device_args(self):
         """Arguments for pp_select_events.  ``duration > v`` on integer sample counts
         equals ``duration > floor(v)``; ``duration < v`` equals ``duration < ceil(v)``."""
+        def whole(v, rounding):
+            # +-inf (and anything beyond int64) clamps to the int64 limits: the comparison's outcome is the same
+            v = float(v)
+            if v != v:
+                raise ValueError("a duration rule cannot be NaN")
+            return int(rounding(max(min(v, 9.2e18), -9.2e18)))
         return dict(rule_mask=self.mask,
-                    duration_gt=int(math.floor(self.duration_gt)), duration_lt=int(math.ceil(self.duration_lt)),
+                    duration_gt=whole(self.duration_gt, math.floor), duration_lt=whole(self.duration_lt, math.ceil),
                     min_gt=float(self.min_gt), max_lt=float(self.max_lt))
 
 
@@ -142,17 +148,19 @@ class lambda_event_parser(parser):
 
     def __init__(self, threshold=90, rules=None):
         self.threshold = threshold
-        self.rules = rules or [lambda event: event.duration > 100000,
+        self._builtin_rules = [lambda event: event.duration > 100000,
                                lambda event: event.min > -0.5,
                                lambda event: event.max < self.threshold]
-        self._default_rules = not rules
+        self.rules = rules or self._builtin_rules
 
     def _device_rules(self):
-        if getattr(self, "_default_rules", False):
+        """The rules as a device-evaluable RuleSet, or None (arbitrary callables: evaluated on the host).  The
+        reference's defaults qualify only while ``rules`` still IS the list built in __init__ -- assigning
+        ``parser.rules = [...]`` afterwards, which the reference supports, takes effect like any other list."""
+        rules = self.rules
+        if rules is self.__dict__.get("_builtin_rules"):
             return RuleSet(duration_gt=100000, min_gt=-0.5, max_lt=self.threshold)
-        if isinstance(self.rules, RuleSet):
-            return self.rules
-        return None
+        return rules if isinstance(rules, RuleSet) else None
 
     def _lambda_select(self, events):
         return [event for event in events if np.all([rule(event) for rule in self.rules])]
@@ -190,6 +198,11 @@ class lambda_event_parser(parser):
             seg = Segment(current=np.array(host[int(s):int(s) + int(n)]), copy=True, start=s, duration=int(n))
             out.append(seg)
         return out
+
+
+def _device_trace(x):
+    """The array handed to the device for a trace given as `x`."""
+    return _as_float32_trace(x)
 
 
 def _as_float32_trace(x):
