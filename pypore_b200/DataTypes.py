@@ -312,7 +312,9 @@ class File(Segment):
 
     def _segment_counts(self):
         """Segments per event, from the tables when they are current (no object is built for it)."""
-        if self._tables_current() and self._tables.segments is not None:
+        if self._tables_current():
+            if self._tables.segments is None:
+                return [0] * len(self.events)
             return np.bincount(np.asarray(self._tables.segments["event"], np.int64),
                                minlength=len(self.events)).tolist()
         return [event.n for event in self.events]

@@ -80,7 +80,7 @@ class _Stretch(object):
     def to_json(self, filename=None):
         return wire.dumps(self.to_dict(), filename)
 
-    __repr__ = to_json                      # the representation IS the JSON
+    __repr__ = lambda self: self.to_json()  # noqa: E731  (the representation IS the JSON, subclass overrides included)
     __len__ = lambda self: self.n           # noqa: E731
 
 

@@ -150,3 +150,107 @@ def test_file_json_round_trip_of_the_reference_format():
     ev = f.events[1]
     again = MetaEvent.from_json(ev.to_json())
     assert again.start == ev.start and again.n == ev.n and len(again.segments) == len(ev.segments)
+
+
+def _fake_tables(meta, with_segments=True, filtered=True):
+    """Three events (one without segments) as the device would hand them back, in samples."""
+    from pypore_b200 import wire
+    rng = np.random.RandomState(5)
+    ev = dict(start=np.array([100, 5000, 9000], np.int64), length=np.array([3000, 2000, 500], np.int64))
+    for k in ("mean", "std", "min", "max"):
+        ev[k] = rng.rand(3)
+    sg = None
+    if with_segments:
+        sg = dict(event=np.array([0, 0, 0, 1, 1], np.int32), start=np.array([0, 700, 1800, 0, 900], np.int64),
+                  end=np.array([700, 1800, 3000, 900, 2000], np.int64))
+        for k in ("mean", "std", "min", "max"):
+            sg[k] = rng.rand(5)
+    seg = parsers.SpeedyStatSplit(prior_segments_per_second=10, cutoff_freq=2000.) if with_segments else None
+    return wire.FileTables(1e5, ev, sg, (1, 2000.) if filtered else None, seg, meta=meta)
+
+
+@pytest.mark.parametrize("meta", [False, True])
+@pytest.mark.parametrize("with_segments", [False, True])
+@pytest.mark.parametrize("filtered", [False, True])
+def test_table_first_json_equals_the_object_walk(meta, with_segments, filtered):
+    """File.to_json straight from the tables (no Event / Segment object built) gives the same tree as walking the
+    objects the lazy view builds from the same tables -- for live files, metadata files, with and without segments."""
+    import json
+    from pypore_b200 import wire
+    from pypore_b200.DataTypes import File, MetaEvent, _LazyList
+    x = np.zeros(10000)
+    f = File(current=x, timestep=0.01)
+    f.event_parser = parsers.lambda_event_parser(threshold=110)
+    f._attach(_fake_tables(meta, with_segments, filtered), host=x,
+              filtered=np.zeros(5500) if filtered and not meta else None)
+    del f.current   # (the file-level mean / std would otherwise ask the device)
+    assert f._tables_current() and isinstance(f.events, _LazyList)
+    counts = f._segment_counts()
+    from_tables = json.loads(f.to_json())
+    assert f._tables_current()                      # still no object handed out
+    events = list(f.events)
+    for e in events:
+        list(e.segments)
+    assert not f._tables_current()
+    walked = json.loads(f.to_json())
+    assert from_tables == walked
+    assert counts == [e.n for e in events] == ([3, 2, 0] if with_segments else [0, 0, 0])
+    assert from_tables["events"][0]["name"] == ("MetaEvent" if meta else "Event")
+    assert ("segments" in from_tables["events"][0]) == with_segments
+    assert all(isinstance(e, MetaEvent) == meta for e in events)
+    if not meta:
+        # to_meta on an untouched table-backed file flips the tables, on a touched one it converts the objects
+        g = File(current=x, timestep=0.01)
+        g.event_parser = f.event_parser
+        g._attach(_fake_tables(False, with_segments, filtered), host=x, filtered=np.zeros(5500) if filtered else None)
+        g.to_meta()
+        f.to_meta()
+        a, b = json.loads(g.to_json()), json.loads(f.to_json())
+        assert a == b and not hasattr(g, "current")
+        assert all(isinstance(e, MetaEvent) for e in list(g.events) + list(f.events))
+
+
+def test_rules_assigned_after_construction_take_effect():
+    """`parser.rules = [...]` after construction (supported by the reference, whose lambdas are looked up
+    at call time) must not be shadowed by the device form of the default rules."""
+    p = parsers.lambda_event_parser(threshold=110)
+    assert p._device_rules().device_args()["duration_gt"] == 100000
+    p.threshold = 95
+    assert p._device_rules().max_lt == 95            # the default rule reads the threshold at call time
+    p.rules = [lambda e: e.duration > 10]
+    assert p._device_rules() is None                 # arbitrary callables: evaluated on the host
+    p.rules = parsers.RuleSet(duration_gt=10)
+    assert p._device_rules().device_args()["duration_gt"] == 10
+    q = parsers.parser.from_json(p.to_json())        # the private list of defaults stays out of the JSON
+    assert q.threshold == 95 and "_builtin_rules" not in p.to_dict()
+
+
+def test_infinite_duration_rules_clamp():
+    a = parsers.RuleSet(duration_gt=-np.inf, duration_lt=np.inf).device_args()
+    assert a["duration_gt"] < -9e18 and a["duration_lt"] > 9e18
+    assert -2**63 <= a["duration_gt"] and a["duration_lt"] < 2**63
+    assert parsers.RuleSet(duration_gt=10.5, duration_lt=10.5).device_args()["duration_gt"] == 10
+    with pytest.raises(ValueError):
+        parsers.RuleSet(duration_gt=float("nan")).device_args()
+
+
+def test_ignored_and_segment_semantics_without_a_device():
+    from pypore_b200.core import MetaSegment, Segment, ignored
+    with ignored(KeyError, AttributeError):
+        {}["x"]
+    with pytest.raises(ValueError):
+        with ignored(KeyError):
+            raise ValueError("not swallowed")
+    s = Segment(np.arange(5.), start=10, duration=5, mean=99.0)     # statistics cannot be overridden
+    assert "mean" not in s.__dict__ and s.n == 5 and len(s) == 5
+    s._set_stats(2.0, 1.4, 0.0, 4.0)
+    assert s.to_dict() == {"mean": 2.0, "std": 1.4, "min": 0.0, "max": 4.0, "start": 10, "duration": 5,
+                           "name": "Segment"}
+    s.scale(10.)                                                    # no `end`: stops after `start` (core.py:199-207)
+    assert s.start == 1.0 and s.duration == 5
+    s.to_meta()
+    assert type(s) is MetaSegment and not hasattr(s, "current") and s.mean == 2.0
+    m = MetaSegment(start=2, end=5)
+    assert m.duration == 3 and MetaSegment(end=5, duration=3).start == 2 and MetaSegment(start=2, duration=3).end == 5
+    back = MetaSegment.from_json(json=m.to_json())
+    assert back.start == "2" and back.name == "MetaSegment"         # the flat reader keeps strings, like the reference
