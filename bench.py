@@ -286,6 +286,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mw, MW, W, gain = statsplit_min_gain(**SPLIT)
     ctx = _lib.Context(local)
+    if args.split_kernel is not None:
+        ctx.set_split_kernel(args.split_kernel == "flow")
     # every kernel, copy-stream join and collective of a step is ordered on the context's stream:
     # the timing events are recorded there
     stream = torch.cuda.ExternalStream(ctx.stream_handle, device=torch.device("cuda", local))
@@ -464,6 +466,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events-per-gpu", type=int, default=EVENTS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split-kernel", default=None, choices=["flow", "level"],
+                    help="development: force k3_flow / k3_split (default: the library's default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -85,7 +85,11 @@ enum pp_option {
      * same tables.  Contexts that share a GPU (pypore_b200/batch.py: several files in flight, each with a few
      * hundred events) take a fraction of a wave each, so that their searches are resident side by side instead of
      * one after the other. */
-    PP_OPT_SPLIT_CTAS = 2
+    PP_OPT_SPLIT_CTAS = 2,
+    /* PP_OPT_SPLIT_KERNEL -- which kernel runs the split search: 0: k3_split, CTAs that resolve a task level by level
+     * between barriers; 1: k3_flow, every warp an independent worker on a CTA-shared stack of window pieces, no
+     * barriers.  Same tables bit for bit (the result of a window depends only on its interval and the prefix sums). */
+    PP_OPT_SPLIT_KERNEL = 3
 };
 int pp_set_option(pp_ctx *ctx, int option, int64_t value);
 /* Number of kernel launches this context has issued since creation. */

@@ -271,6 +271,11 @@ class Context(object):
         a GPU take a fraction of a wave each (batch.FileBatch)."""
         self.set_option(2, int(n))
 
+    def set_split_kernel(self, flow):
+        """Split search kernel: True = k3_flow (independent warps, no barriers), False = k3_split (level-synchronous
+        CTAs).  Same tables either way."""
+        self.set_option(3, 1 if flow else 0)
+
     @property
     def launch_count(self):
         return int(self._L.pp_launch_count(self._h))

@@ -6,6 +6,7 @@
 #include "threshold.cuh"
 #include "prefix.cuh"
 #include "split.cuh"
+#include "split_flow.cuh"
 #include "stats.cuh"
 #include "filter.cuh"
 
@@ -63,6 +64,7 @@ struct pp_ctx {
     int T_len = 0;
     int opt_screen = 1;
     int opt_split_ctas = 0;  // 0: one full wave (K3_CTAS_PER_SM per SM)
+    int opt_split_kernel = PP_SPLIT_KERNEL_DEFAULT;  // 0: k3_split (level-synchronous CTAs), 1: k3_flow (barrier-free warps)
     int64_t q_cap = 0;
     DevBuf seg_flat, seg_event, seg_start, seg_end, seg_mean, seg_std, seg_min, seg_max;
     int64_t cap_segs = 0;
@@ -477,9 +479,12 @@ int enqueue_search(pp_ctx *ctx, int mw, int MW, int W, double min_gain)
     }
     // the queue is served by however many CTAs there are; contexts that share the GPU (file batches) take a
     // fraction of a wave each so that their searches are resident side by side
-    const int wave = ctx->sm_count * K3_CTAS_PER_SM;
+    const int wave = ctx->sm_count * (ctx->opt_split_kernel ? K3F_CTAS_PER_SM : K3_CTAS_PER_SM);
     const int k3_grid = ctx->opt_split_ctas > 0 && ctx->opt_split_ctas < wave ? ctx->opt_split_ctas : wave;
-    k3_split<<<k3_grid, K3_THREADS, K3_SMEM_BYTES, ctx->stream>>>(G, P);
+    if (ctx->opt_split_kernel)
+        k3_flow<<<k3_grid, K3F_THREADS, K3F_SMEM_BYTES, ctx->stream>>>(G, P);
+    else
+        k3_split<<<k3_grid, K3_THREADS, K3_SMEM_BYTES, ctx->stream>>>(G, P);
     LAUNCHED(ctx);
     return PP_OK;
 }
@@ -629,6 +634,8 @@ int pp_create(int device, void *cuda_stream, pp_ctx **out)
     for (int i = 0; ok && i <= ST_COUNT; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k3_split, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)K3_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k3_flow, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)K3F_SMEM_BYTES) == cudaSuccess;
     if (!ok) { pp_destroy(ctx); return PP_ERR_CUDA; }
     memset(ctx->h_ctr, 0, sizeof(PPCounters));
     *out = ctx;
@@ -691,6 +698,7 @@ int pp_set_option(pp_ctx *ctx, int option, int64_t value)
     switch (option) {
     case PP_OPT_SCREEN: ctx->opt_screen = value ? 1 : 0; return PP_OK;
     case PP_OPT_SPINE: ctx->opt_spine = value ? 1 : 0; return PP_OK;
+    case PP_OPT_SPLIT_KERNEL: ctx->opt_split_kernel = value ? 1 : 0; return PP_OK;
     case PP_OPT_SPLIT_CTAS:
         if (value < 0 || value > (1 << 20)) return fail(ctx, PP_ERR_ARG, "bad CTA count %lld", (long long)value);
         ctx->opt_split_ctas = (int)value;
