@@ -148,6 +148,8 @@ class Context(object):
                 "pp_create(device=%d) failed (code %d): a CUDA device of compute capability 10.x "
                 "(B200) is required; there is no CPU fallback" % (device, r))
         self._h = h
+        if os.environ.get("PYPORE_B200_SPLIT_KERNEL"):   # development: flow | level
+            self._L.pp_set_option(h, 3, 1 if os.environ["PYPORE_B200_SPLIT_KERNEL"] == "flow" else 0)
         self.device = int(device)
         self._keep = []  # host arrays that must outlive async copies
 

@@ -347,6 +347,10 @@ __device__ __forceinline__ void k3_scr_update(K3Scr &a, bool ok, unsigned long l
 #ifndef K3_CFG_UNROLL
 #define K3_CFG_UNROLL 2
 #endif
+#ifndef K3_CFG_L1PF
+#define K3_CFG_L1PF 1   // measured on configs[1] (profiles/r02c_k3_prefetch_variants.txt): k3_split 1.054 -> 1.015 ms, 2 / 3 trips no better
+#endif
+__device__ __forceinline__ void k3_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #if K3_CFG_LDCS
 #define K3_LD_MID(p) __ldcs(p)
 #else
@@ -369,8 +373,23 @@ __device__ __forceinline__ void k3_screen_lane(const double2 *__restrict__ ccg, 
     if (i + stride <= i_last) {
         double2 mA = K3_LD_MID(pm), mB = K3_LD_MID(pm + stride);
         double rA1 = __ldg(p1), rA2 = __ldg(p2), rB1 = __ldg(p1 + stride), rB2 = __ldg(p2 - stride);
+#if K3_CFG_L1PF > 0
+        // the pair K3_CFG_L1PF trips ahead into L1 (no register held): the register prefetch below is issued half a
+        // trip ahead at best (the compiler sinks it under the 72-register cap) and a miss to HBM takes longer
+        const int pf = K3_CFG_L1PF * s2;
+        if (i + pf <= i_last) k3_prefetch_l1(pm + pf);
+        if (i + pf + stride <= i_last) k3_prefetch_l1(pm + pf + stride);
+        if (K3_CFG_L1PF > 1) {
+            if (i + s2 <= i_last) k3_prefetch_l1(pm + s2);
+            if (i + s2 + stride <= i_last) k3_prefetch_l1(pm + s2 + stride);
+        }
+#endif
         for (;;) {
             const bool more = i + s2 + stride <= i_last;
+#if K3_CFG_L1PF > 0
+            if (i + pf + s2 <= i_last) k3_prefetch_l1(pm + pf + s2);
+            if (i + pf + s2 + stride <= i_last) k3_prefetch_l1(pm + pf + s2 + stride);
+#endif
 #if !K3_CFG_PREFETCH
             if (true) {
                 unsigned long long keyA, keyB;

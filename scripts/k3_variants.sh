@@ -13,12 +13,14 @@ done
 wait
 for spec in "$@"; do
   name=${spec%%:*}
-  echo "== $spec" | tee -a $out
-  PYPORE_B200_LIB=$PWD/build/lib_$name.so timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
+  for kern in ${KERNELS:-flow}; do
+  echo "== $spec [$kern]" | tee -a $out
+  PYPORE_B200_LIB=$PWD/build/lib_$name.so timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --split-kernel $kern 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
         d = json.loads(l); p = d.get('parity') or {}
         print({k: round(v, 3) for k, v in d['stage_ms'].items()}, 'ms/step', round(d['ms_per_step'], 3), 'e2e', round(d['e2e']['value']), 'parity', p.get('events_bit_exact'), p.get('segments_bit_exact'))
 " | tee -a $out
+  done
 done

@@ -48,16 +48,17 @@ def check_split_f64(ctx, arrays, **kw):
     ctx.set_screening(True)
     tab = gpu_split_f64(ctx, arrays, **kw)
     assert all(np.array_equal(ref_tab[k], tab[k]) for k in ("event", "start", "end"))
-    # the level-synchronous kernel (k3_split) against the barrier-free one (k3_flow, the default), both modes
-    ctx.set_split_kernel(False)
+    # the barrier-free kernel (k3_flow) against the level-synchronous one (k3_split, the default), both modes
+    ctx.set_split_kernel(True)
     try:
-        lvl = gpu_split_f64(ctx, arrays, **kw)
+        flow = gpu_split_f64(ctx, arrays, **kw)
         ctx.set_screening(False)
-        lvl_exact = gpu_split_f64(ctx, arrays, **kw)
+        flow_exact = gpu_split_f64(ctx, arrays, **kw)
     finally:
         ctx.set_screening(True)
-        ctx.set_split_kernel(True)
-    assert all(np.array_equal(lvl[k], tab[k]) and np.array_equal(lvl_exact[k], tab[k]) for k in ("event", "start", "end"))
+        ctx.set_split_kernel(False)
+    assert all(np.array_equal(flow[k], tab[k]) and np.array_equal(flow_exact[k], tab[k])
+               for k in ("event", "start", "end"))
     if max(len(a) for a in arrays) > 10240:
         # long events: the 1024-thread spine kernel (default) against the work-queue CTAs walking the spine
         ctx.set_option(1, 0)
