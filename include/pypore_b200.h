@@ -104,6 +104,11 @@ int pp_stage_ms(pp_ctx *ctx, int stage, float *ms);
  * DataTypes.py:572-583).  `extra_capacity` samples are reserved after the trace
  * for pp_trace_append (multi-GPU halo). */
 int pp_trace_upload(pp_ctx *ctx, const float *host, int64_t n, int64_t extra_capacity);
+/* Same for a float64 trace -- what the reference's own loader produces (PyPore/read_abf.py:208-210: int16 ADC counts
+ * times a float64 scale factor).  The trace stays float64 on the device (8 B per sample): the threshold scan
+ * compares the doubles themselves, run extrema are the doubles' own, and the later stages read the events out of
+ * it like out of a float32 trace.  pp_trace_append / pp_trace_extend / the streamed host pipeline are float32-only. */
+int pp_trace_upload_f64(pp_ctx *ctx, const double *host, int64_t n);
 /* Use device memory the caller owns (no copy; must stay valid; capacity in samples). */
 int pp_trace_adopt(pp_ctx *ctx, const float *dev, int64_t n, int64_t capacity);
 /* Append `n` samples (device or host pointer) after the current trace end: the

@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib, wire
 from .core import MetaSegment, Segment
-from .parsers import SpeedyStatSplit, lambda_event_parser, parser, _device_trace
+from .parsers import SpeedyStatSplit, lambda_event_parser, parser, _run_pipeline, _upload_trace
 
 _STAT_SPAN = wire.FIELDS["MetaSegment"]
 
@@ -227,13 +227,12 @@ class File(Segment):
             ev_start = ev_len = np.zeros(0, np.int64)
         elif rules is not None and segmenter is not None:
             # one call from host memory: the copy is chunked and overlapped with the stages (pp_pipeline_host)
-            counts = ctx.pipeline(parser.threshold, min_width=mw, max_width=MW, window_width=W, min_gain=gain,
-                                  filter_ba=filt, with_stats=True, host_trace=_device_trace(host),
-                                  **rules.device_args())
+            counts = _run_pipeline(ctx, host, parser.threshold, min_width=mw, max_width=MW, window_width=W,
+                                   min_gain=gain, filter_ba=filt, with_stats=True, **rules.device_args())
             ev_start, ev_len = ctx.events(counts["events"])
             seg_table = ctx.segments(counts["segments"])
         else:
-            ctx.upload_trace(_device_trace(host))
+            _upload_trace(ctx, host)
             ev_start, ev_len = parser._detect(ctx, host)[:2]
             if filt is not None and len(ev_start):
                 ctx.filter_events(*filt)

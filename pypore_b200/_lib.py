@@ -63,6 +63,7 @@ SIGNATURES = {
     "pp_launch_count": (_i64, [_c.c_void_p]),
     "pp_stage_ms": (_c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(_c.c_float)]),
     "pp_trace_upload": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _i64]),
+    "pp_trace_upload_f64": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64]),
     "pp_trace_adopt": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _i64]),
     "pp_trace_append": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _c.c_int]),
     "pp_trace_truncate": (_c.c_int, [_c.c_void_p, _i64]),
@@ -221,6 +222,30 @@ class Context(object):
         self.sync()  # pageable host memory: do not return before the copy has consumed it
         self._keep = []
         return x32.shape[0]
+
+    def upload_trace_f64(self, x64):
+        """A float64 trace, kept as float64 on the device (pp_trace_upload_f64)."""
+        x64 = np.ascontiguousarray(x64, dtype=np.float64)
+        self._keep = [x64]
+        self._ck(self._L.pp_trace_upload_f64(self._h, x64.ctypes.data, x64.shape[0]))
+        self.sync()
+        self._keep = []
+        return x64.shape[0]
+
+    def upload_trace_any(self, x):
+        """float32 arrays go up as they are, float64 ones as float32 when that loses nothing (half the bytes,
+        same results: double(x32) == x), as float64 otherwise; integer arrays are exact in float64."""
+        x = np.asarray(x)
+        if x.dtype == np.float32:
+            return self.upload_trace(x)
+        if x.dtype.kind in "iub":
+            x = x.astype(np.float64)
+        if x.dtype != np.float64:
+            raise TypeError("trace must be float32, float64 or an integer type, got %s" % x.dtype)
+        x32 = x.astype(np.float32)
+        if np.array_equal(x32.astype(np.float64), x, equal_nan=True):
+            return self.upload_trace(x32)
+        return self.upload_trace_f64(x)
 
     def upload_trace_async(self, x32, extra_capacity=0):
         """For pinned host arrays; caller keeps `x32` alive until sync()."""

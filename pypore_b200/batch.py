@@ -28,7 +28,7 @@ import threading
 import numpy as np
 
 from . import _lib
-from .parsers import SpeedyStatSplit, lambda_event_parser, _as_float32_trace
+from .parsers import SpeedyStatSplit, lambda_event_parser, _device_trace, _run_pipeline
 
 STAT_KEYS = ("mean", "std", "min", "max")
 SPLIT_WAVE = 148 * 7   # persistent CTAs of one full k3_split wave on a B200 (csrc/split.cuh: 7 CTAs per SM)
@@ -52,9 +52,11 @@ def device_file_pass(ctx, current, second, event_detector, segmenter, filter_par
         raise TypeError("the batched pipeline needs a pypore_b200 SpeedyStatSplit")
     mw, MW, W, gain = segmenter._params()
     filt = bessel_coefficients(filter_params[0], filter_params[1], second) if filter_params is not None else None
-    x32 = _as_float32_trace(np.asarray(current))
-    c = ctx.pipeline(event_detector.threshold, min_width=mw, max_width=MW, window_width=W, min_gain=gain,
-                     filter_ba=filt, with_stats=True, host_trace=x32, **rs.device_args())
+    if len(current) == 0:   # an empty recording has no events; it must not abort the batch
+        return dict(ev_int=np.zeros((0, 2), np.int64), ev_flt=np.zeros((0, 4)), seg_int=np.zeros((0, 3), np.int64),
+                    seg_flt=np.zeros((0, 4)))
+    c = _run_pipeline(ctx, current, event_detector.threshold, min_width=mw, max_width=MW, window_width=W,
+                      min_gain=gain, filter_ba=filt, with_stats=True, **rs.device_args())
     ne, ns = c["events"], c["segments"]
     ev_start, ev_len = ctx.events(ne)
     est = ctx.event_stats(ne)
@@ -112,7 +114,10 @@ def device_group_pass(ctx, currents, second, event_detector, segmenter, filter_p
     rs = event_detector._device_rules()
     mw, MW, W, gain = segmenter._params()
     filt = bessel_coefficients(filter_params[0], filter_params[1], second) if filter_params is not None else None
-    xs = [_as_float32_trace(np.asarray(c)) for c in currents]
+    xs = [_device_trace(c) for c in currents]
+    if any(x.dtype != np.float32 for x in xs):
+        # a float64 trace that float32 cannot hold goes up as float64 and runs on its own (the shared trace is float32)
+        return [device_file_pass(ctx, c, second, event_detector, segmenter, filter_params) for c in currents]
     sep = getattr(ctx, "_batch_separator", None)
     if sep is None:
         sep = ctx._batch_separator = ctx.pinned_empty(1, np.float32)

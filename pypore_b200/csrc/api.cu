@@ -33,9 +33,10 @@ struct pp_ctx {
     char err[512] = {0};
     int64_t launches = 0;
 
-    // trace
+    // trace: float32 (trace) or float64 (trace64) samples, one of the two
     DevBuf trace_buf;
     const float *trace = nullptr;
+    const double *trace64 = nullptr;
     int64_t n = 0, trace_cap = 0;
     bool adopted = false;
 
@@ -44,10 +45,12 @@ struct pp_ctx {
     PPCounters *h_ctr = nullptr;  // pinned
 
     // K1
-    DevBuf tile_state, run_start, run_minkey, run_maxkey, run_len, run_min, run_max, run_below;
+    DevBuf k1_rec, k1_staged, k1_blk, run_start, run_minkey, run_maxkey, run_len, run_min, run_max, run_below;
     int64_t cap_runs = 0;
     int64_t n_runs = -1;
     int64_t scan_len = 0;
+    int64_t k1_tiles_done = 0;  // tiles scanned so far (the streamed pipeline scans chunk after chunk)
+    int k1_flip = 0;            // which n_edges slot the next k1_stitch reads
 
     // events
     DevBuf ev_start, ev_len, ev_off;
@@ -168,11 +171,22 @@ PPSource make_source(pp_ctx *ctx)
 {
     PPSource s;
     s.trace = ctx->trace;
+    s.trace64 = ctx->trace64;
     s.flat = (const double *)ctx->flat64.p;
     s.ev_start = (const int64_t *)ctx->ev_start.p;
     s.ev_off = (const int64_t *)ctx->ev_off.p;
     s.kind = ctx->src_kind;
     return s;
+}
+
+// float64 samples of the current events and the table that locates an event in them
+const double *f64_samples(pp_ctx *ctx)
+{
+    return ctx->src_kind == PP_SRC_TRACE64 ? ctx->trace64 : (const double *)ctx->flat64.p;
+}
+const int64_t *f64_bases(pp_ctx *ctx)
+{
+    return (const int64_t *)(ctx->src_kind == PP_SRC_TRACE64 ? ctx->ev_start.p : ctx->ev_off.p);
 }
 
 int fetch_counters(pp_ctx *ctx)
@@ -186,8 +200,8 @@ int ensure_run_buffers(pp_ctx *ctx, int64_t cap_runs)
 {
     if (cap_runs <= ctx->cap_runs) return PP_OK;
     CKR(ensure(ctx, ctx->run_start, sizeof(int64_t) * cap_runs));
-    CKR(ensure(ctx, ctx->run_minkey, sizeof(unsigned) * cap_runs));
-    CKR(ensure(ctx, ctx->run_maxkey, sizeof(unsigned) * cap_runs));
+    CKR(ensure(ctx, ctx->run_minkey, sizeof(unsigned long long) * cap_runs));
+    CKR(ensure(ctx, ctx->run_maxkey, sizeof(unsigned long long) * cap_runs));
     CKR(ensure(ctx, ctx->run_len, sizeof(int64_t) * cap_runs));
     CKR(ensure(ctx, ctx->run_min, sizeof(double) * cap_runs));
     CKR(ensure(ctx, ctx->run_max, sizeof(double) * cap_runs));
@@ -217,11 +231,15 @@ int begin_threshold(pp_ctx *ctx, int64_t scan_len)
     CKR(ensure_run_buffers(ctx, want));
     CKR(ensure_event_buffers(ctx, ctx->cap_runs));
     const int64_t ntiles = (scan_len + K1_TILE - 1) / K1_TILE;
-    CKR(ensure(ctx, ctx->tile_state, sizeof(unsigned long long) * ntiles));
+    const int64_t nrec = ntiles * K1_WARPS;
+    CKR(ensure(ctx, ctx->k1_rec, sizeof(K1Record) * nrec));
+    CKR(ensure(ctx, ctx->k1_staged, sizeof(K1Staged) * nrec * K1_STAGE));
+    CKR(ensure(ctx, ctx->k1_blk, sizeof(unsigned long long) * ((nrec + K1B_THREADS - 1) / K1B_THREADS + 1)));
     CK(cudaMemsetAsync(ctx->ctr, 0, sizeof(PPCounters), ctx->stream));
-    CK(cudaMemsetAsync(ctx->tile_state.p, 0, sizeof(unsigned long long) * ntiles, ctx->stream));
-    CK(cudaMemsetAsync(ctx->run_minkey.p, 0xff, sizeof(unsigned) * ctx->cap_runs, ctx->stream));
-    CK(cudaMemsetAsync(ctx->run_maxkey.p, 0, sizeof(unsigned) * ctx->cap_runs, ctx->stream));
+    CK(cudaMemsetAsync(ctx->run_minkey.p, 0xff, sizeof(unsigned long long) * ctx->cap_runs, ctx->stream));
+    CK(cudaMemsetAsync(ctx->run_maxkey.p, 0, sizeof(unsigned long long) * ctx->cap_runs, ctx->stream));
+    ctx->k1_tiles_done = 0;
+    ctx->k1_flip = 0;
     ctx->n_runs = -1;
     ctx->n_events = ctx->n_event_samples = ctx->n_segments = -1;
     ctx->stats_valid = false;
@@ -229,21 +247,51 @@ int begin_threshold(pp_ctx *ctx, int64_t scan_len)
     return PP_OK;
 }
 
+template <typename T>
+int launch_threshold_tiles(pp_ctx *ctx, const T *x, T thr, int64_t upto, int64_t tile_begin, int64_t ntiles)
+{
+    const size_t smem = sizeof(K1Smem<T>);
+    static bool configured = false;   // per instantiation; the attribute is per function, not per context
+    if (!configured) {
+        CK(cudaFuncSetAttribute(k1_scan_tiles<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int per_sm = (int)(200 * 1024 / smem) > 0 ? (int)(200 * 1024 / smem) : 1;
+    int64_t grid = (int64_t)ctx->sm_count * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    k1_scan_tiles<T><<<(unsigned)grid, K1_THREADS, smem, ctx->stream>>>(
+        x, upto, thr, tile_begin, ntiles, (K1Record *)ctx->k1_rec.p, (K1Staged *)ctx->k1_staged.p);
+    LAUNCHED(ctx);
+    const int64_t rec_begin = tile_begin * K1_WARPS, rec_end = (tile_begin + ntiles) * K1_WARPS;
+    const int64_t nblk = (rec_end - rec_begin + K1B_THREADS - 1) / K1B_THREADS;
+    CK(cudaMemsetAsync(ctx->k1_blk.p, 0, sizeof(unsigned long long) * nblk, ctx->stream));
+    k1_stitch<T><<<(unsigned)nblk, K1B_THREADS, 0, ctx->stream>>>(
+        x, upto, thr, rec_begin, rec_end, (const K1Record *)ctx->k1_rec.p, (const K1Staged *)ctx->k1_staged.p,
+        (unsigned long long *)ctx->k1_blk.p, ctx->ctr, ctx->k1_flip, (int64_t *)ctx->run_start.p,
+        (unsigned long long *)ctx->run_minkey.p, (unsigned long long *)ctx->run_maxkey.p, ctx->cap_runs);
+    LAUNCHED(ctx);
+    ctx->k1_flip ^= 1;
+    return PP_OK;
+}
+
 // Scan the next `ntiles` tiles (the tile counter continues across calls) of the trace prefix
 // [0, upto) and decode the run table found so far.
 int enqueue_threshold_tiles(pp_ctx *ctx, double threshold, int64_t upto, int64_t ntiles)
 {
-    // smallest float32 >= threshold: double(x) < thr  <=>  x < thr_up for every float32 x
-    float thr_f = (float)threshold;
-    if ((double)thr_f < threshold) thr_f = nextafterf(thr_f, INFINITY);
-    k1_threshold_scan<<<(unsigned)ntiles, K1_THREADS, 0, ctx->stream>>>(
-        ctx->trace, upto, thr_f, (unsigned long long *)ctx->tile_state.p, ctx->ctr,
-        (int64_t *)ctx->run_start.p, (unsigned *)ctx->run_minkey.p, (unsigned *)ctx->run_maxkey.p,
-        ctx->cap_runs);
-    LAUNCHED(ctx);
+    if (ntiles > 0) {
+        if (ctx->trace64) {
+            CKR(launch_threshold_tiles<double>(ctx, ctx->trace64, threshold, upto, ctx->k1_tiles_done, ntiles));
+        } else {
+            // smallest float32 >= threshold: double(x) < thr  <=>  x < thr_up for every float32 x
+            float thr_f = (float)threshold;
+            if ((double)thr_f < threshold) thr_f = nextafterf(thr_f, INFINITY);
+            CKR(launch_threshold_tiles<float>(ctx, ctx->trace, thr_f, upto, ctx->k1_tiles_done, ntiles));
+        }
+        ctx->k1_tiles_done += ntiles;
+    }
     k1_finalize_runs<<<ctx->sm_count, 256, 0, ctx->stream>>>(
-        upto, ctx->ctr, (const int64_t *)ctx->run_start.p, (const unsigned *)ctx->run_minkey.p,
-        (const unsigned *)ctx->run_maxkey.p, ctx->cap_runs, (int64_t *)ctx->run_len.p,
+        upto, ctx->ctr, (const int64_t *)ctx->run_start.p, (const unsigned long long *)ctx->run_minkey.p,
+        (const unsigned long long *)ctx->run_maxkey.p, ctx->cap_runs, (int64_t *)ctx->run_len.p,
         (double *)ctx->run_min.p, (double *)ctx->run_max.p, (unsigned char *)ctx->run_below.p);
     LAUNCHED(ctx);
     return PP_OK;
@@ -251,7 +299,7 @@ int enqueue_threshold_tiles(pp_ctx *ctx, double threshold, int64_t upto, int64_t
 
 int enqueue_threshold(pp_ctx *ctx, double threshold, int64_t scan_len)
 {
-    if (!ctx->trace || ctx->n <= 0) return fail(ctx, PP_ERR_STATE, "no trace resident");
+    if ((!ctx->trace && !ctx->trace64) || ctx->n <= 0) return fail(ctx, PP_ERR_STATE, "no trace resident");
     if (scan_len < 0 || scan_len > ctx->n) scan_len = ctx->n;
     CKR(begin_threshold(ctx, scan_len));
     return enqueue_threshold_tiles(ctx, threshold, scan_len, (scan_len + K1_TILE - 1) / K1_TILE);
@@ -261,7 +309,7 @@ int enqueue_select(pp_ctx *ctx, int rule_mask, int64_t duration_gt, int64_t dura
                    double min_gt, double max_lt, int skip_first, int skip_last, int incremental = 0,
                    const long long *dev_plan = nullptr)
 {
-    ctx->src_kind = 0;
+    ctx->src_kind = ctx->trace64 ? PP_SRC_TRACE64 : PP_SRC_TRACE32;
     ctx->flat_cap = ctx->n;
     k1_select_events<<<1, SEL_THREADS, 0, ctx->stream>>>(
         ctx->ctr, (const int64_t *)ctx->run_start.p, (const int64_t *)ctx->run_len.p,
@@ -323,7 +371,7 @@ int enqueue_filter(pp_ctx *ctx, const double *b, const double *a, const double *
         }
         LAUNCHED(ctx);
     }
-    ctx->src_kind = 1;  // from here on the events' current is the filtered float64 signal
+    ctx->src_kind = PP_SRC_FLAT64;  // from here on the events' current is the filtered float64 signal
     CKR(record_boundary(ctx, ST_FILTER + 1));
     ctx->stage_ran[ST_FILTER] = true;
     ctx->n_segments = -1;
@@ -396,24 +444,24 @@ int enqueue_prefix(pp_ctx *ctx, int prefix_mode)
                                                      (unsigned *)ctx->inexact.p);
         LAUNCHED(ctx);
         // short events: one pass, one warp per event
-        if (ctx->src_kind == 0)
+        if (ctx->src_kind == PP_SRC_TRACE32)
             k2_event_scan<float><<<ctx->sm_count * K2F_CFG_CTAS * 2, K2F_WARPS * 32, 0, ctx->stream>>>(
                 src, ctx->trace, (const int64_t *)ctx->ev_len.p, ctx->ctr, (unsigned *)ctx->inexact.p,
                 (double2 *)ctx->cc.p, prefix_mode != PP_PREFIX_PARALLEL);
         else
             k2_event_scan<double><<<ctx->sm_count * K2F_CFG_CTAS * 2, K2F_WARPS * 32, 0, ctx->stream>>>(
-                src, (const double *)ctx->flat64.p, (const int64_t *)ctx->ev_len.p, ctx->ctr,
+                src, f64_samples(ctx), (const int64_t *)ctx->ev_len.p, ctx->ctr,
                 (unsigned *)ctx->inexact.p, (double2 *)ctx->cc.p, prefix_mode != PP_PREFIX_PARALLEL);
         LAUNCHED(ctx);
         // long events: multi-CTA reduce / carries / scan over their tiles
         const int grid = ctx->sm_count * 8;
-        if (ctx->src_kind == 0)
+        if (ctx->src_kind == PP_SRC_TRACE32)
             k2_tile_reduce<float><<<grid, K2_THREADS, 0, ctx->stream>>>(
                 src, ctx->trace, (const int64_t *)ctx->ev_len.p, (const int64_t *)ctx->ev_tile_off.p, ctx->ctr,
                 (K2TileState *)ctx->k2_tiles.p, (K2EventBits *)ctx->k2_bits.p);
         else
             k2_tile_reduce<double><<<grid, K2_THREADS, 0, ctx->stream>>>(
-                src, (const double *)ctx->flat64.p, (const int64_t *)ctx->ev_len.p,
+                src, f64_samples(ctx), (const int64_t *)ctx->ev_len.p,
                 (const int64_t *)ctx->ev_tile_off.p, ctx->ctr, (K2TileState *)ctx->k2_tiles.p,
                 (K2EventBits *)ctx->k2_bits.p);
         LAUNCHED(ctx);
@@ -422,13 +470,13 @@ int enqueue_prefix(pp_ctx *ctx, int prefix_mode)
             (K2TileState *)ctx->k2_tiles.p, (const K2EventBits *)ctx->k2_bits.p, (unsigned *)ctx->inexact.p,
             prefix_mode != PP_PREFIX_PARALLEL);
         LAUNCHED(ctx);
-        if (ctx->src_kind == 0)
+        if (ctx->src_kind == PP_SRC_TRACE32)
             k2_tile_scan<float><<<grid, K2_THREADS, 0, ctx->stream>>>(
                 src, ctx->trace, (const int64_t *)ctx->ev_len.p, (const int64_t *)ctx->ev_tile_off.p, ctx->ctr,
                 (const K2TileState *)ctx->k2_tiles.p, (double2 *)ctx->cc.p);
         else
             k2_tile_scan<double><<<grid, K2_THREADS, 0, ctx->stream>>>(
-                src, (const double *)ctx->flat64.p, (const int64_t *)ctx->ev_len.p,
+                src, f64_samples(ctx), (const int64_t *)ctx->ev_len.p,
                 (const int64_t *)ctx->ev_tile_off.p, ctx->ctr, (const K2TileState *)ctx->k2_tiles.p,
                 (double2 *)ctx->cc.p);
         LAUNCHED(ctx);
@@ -546,7 +594,7 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
 
 int enqueue_stats(pp_ctx *ctx)
 {
-    if (ctx->src_kind == 0)
+    if (ctx->src_kind == PP_SRC_TRACE32)
         k4_segment_stats<float><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
             ctx->trace, (const int64_t *)ctx->ev_start.p, (const int64_t *)ctx->ev_off.p, ctx->ctr, 0,
             (const int64_t *)ctx->seg_flat.p, (const int *)ctx->seg_event.p, ctx->cap_segs,
@@ -554,7 +602,7 @@ int enqueue_stats(pp_ctx *ctx)
             (double *)ctx->seg_max.p);
     else
         k4_segment_stats<double><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
-            (const double *)ctx->flat64.p, (const int64_t *)ctx->ev_off.p, (const int64_t *)ctx->ev_off.p,
+            f64_samples(ctx), f64_bases(ctx), (const int64_t *)ctx->ev_off.p,
             ctx->ctr, 0, (const int64_t *)ctx->seg_flat.p, (const int *)ctx->seg_event.p, ctx->cap_segs,
             (double *)ctx->seg_mean.p, (double *)ctx->seg_std.p, (double *)ctx->seg_min.p,
             (double *)ctx->seg_max.p);
@@ -647,7 +695,7 @@ void pp_destroy(pp_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->trace_buf, &ctx->tile_state, &ctx->run_start, &ctx->run_minkey,
+    DevBuf *bufs[] = {&ctx->trace_buf, &ctx->k1_rec, &ctx->k1_staged, &ctx->k1_blk, &ctx->run_start, &ctx->run_minkey,
                       &ctx->run_maxkey, &ctx->run_len, &ctx->run_min, &ctx->run_max, &ctx->run_below,
                       &ctx->ev_start, &ctx->ev_len, &ctx->ev_off, &ctx->flat64, &ctx->cc, &ctx->bits,
                       &ctx->tasks, &ctx->ready, &ctx->block_count, &ctx->block_off, &ctx->inexact, &ctx->Ttab, &ctx->ev_tile_off, &ctx->k2_bits, &ctx->k2_tiles,
@@ -722,20 +770,30 @@ int pp_stage_ms(pp_ctx *ctx, int stage, float *ms)
 }
 
 // ---- trace ------------------------------------------------------------------
-int pp_trace_upload(pp_ctx *ctx, const float *host, int64_t n, int64_t extra_capacity)
+static int trace_upload_impl(pp_ctx *ctx, const void *host, int64_t n, int64_t extra_capacity, size_t elem)
 {
     if (!ctx || !host || n <= 0 || extra_capacity < 0) return fail(ctx, PP_ERR_ARG, "bad trace");
     CKR(set_device(ctx));
-    CKR(ensure(ctx, ctx->trace_buf, sizeof(float) * (size_t)(n + extra_capacity)));
-    CK(cudaMemcpyAsync(ctx->trace_buf.p, host, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice,
-                       ctx->stream));
-    ctx->trace = (const float *)ctx->trace_buf.p;
+    CKR(ensure(ctx, ctx->trace_buf, elem * (size_t)(n + extra_capacity)));
+    CK(cudaMemcpyAsync(ctx->trace_buf.p, host, elem * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->trace = elem == sizeof(float) ? (const float *)ctx->trace_buf.p : nullptr;
+    ctx->trace64 = elem == sizeof(double) ? (const double *)ctx->trace_buf.p : nullptr;
     ctx->n = n;
-    ctx->trace_cap = (int64_t)(ctx->trace_buf.cap / sizeof(float));
+    ctx->trace_cap = (int64_t)(ctx->trace_buf.cap / elem);
     ctx->adopted = false;
     ctx->n_runs = ctx->n_events = ctx->n_event_samples = ctx->n_segments = -1;
     ctx->prefix_valid = false;
     return PP_OK;
+}
+
+int pp_trace_upload(pp_ctx *ctx, const float *host, int64_t n, int64_t extra_capacity)
+{
+    return trace_upload_impl(ctx, host, n, extra_capacity, sizeof(float));
+}
+
+int pp_trace_upload_f64(pp_ctx *ctx, const double *host, int64_t n)
+{
+    return trace_upload_impl(ctx, host, n, 0, sizeof(double));
 }
 
 int pp_trace_adopt(pp_ctx *ctx, const float *dev, int64_t n, int64_t capacity)
@@ -743,6 +801,7 @@ int pp_trace_adopt(pp_ctx *ctx, const float *dev, int64_t n, int64_t capacity)
     if (!ctx || !dev || n <= 0 || capacity < n) return fail(ctx, PP_ERR_ARG, "bad trace");
     if (((uintptr_t)dev) & 15) return fail(ctx, PP_ERR_ARG, "device trace must be 16-byte aligned");
     ctx->trace = dev;
+    ctx->trace64 = nullptr;
     ctx->n = n;
     ctx->trace_cap = capacity;
     ctx->adopted = true;
@@ -754,7 +813,7 @@ int pp_trace_adopt(pp_ctx *ctx, const float *dev, int64_t n, int64_t capacity)
 int pp_trace_append(pp_ctx *ctx, const float *src, int64_t n, int src_is_device)
 {
     if (!ctx || !src || n < 0) return fail(ctx, PP_ERR_ARG, "bad append");
-    if (!ctx->trace) return fail(ctx, PP_ERR_STATE, "no trace resident");
+    if (!ctx->trace) return fail(ctx, PP_ERR_STATE, "no float32 trace resident");
     if (ctx->n + n > ctx->trace_cap) return fail(ctx, PP_ERR_CAPACITY, "trace capacity exceeded");
     CKR(set_device(ctx));
     CK(cudaMemcpyAsync((void *)(ctx->trace + ctx->n), src, sizeof(float) * (size_t)n,
@@ -773,7 +832,7 @@ int pp_trace_truncate(pp_ctx *ctx, int64_t n)
 int pp_trace_extend(pp_ctx *ctx, int64_t n)
 {
     if (!ctx || n < 0) return fail(ctx, PP_ERR_ARG, "bad extend");
-    if (!ctx->trace) return fail(ctx, PP_ERR_STATE, "no trace resident");
+    if (!ctx->trace) return fail(ctx, PP_ERR_STATE, "no float32 trace resident");
     if (ctx->n + n > ctx->trace_cap) return fail(ctx, PP_ERR_CAPACITY, "trace capacity exceeded");
     ctx->n += n;
     return PP_OK;
@@ -862,7 +921,7 @@ int pp_set_events(pp_ctx *ctx, const int64_t *start, const int64_t *length, int6
 {
     if (!ctx || n_events < 0 || (n_events > 0 && (!start || !length)))
         return fail(ctx, PP_ERR_ARG, "bad events");
-    if (!ctx->trace) return fail(ctx, PP_ERR_STATE, "no trace resident");
+    if (!ctx->trace && !ctx->trace64) return fail(ctx, PP_ERR_STATE, "no trace resident");
     CKR(set_device(ctx));
     for (int64_t i = 0; i < n_events; ++i)
         if (start[i] < 0 || length[i] <= 0 || start[i] + length[i] > ctx->n)
@@ -875,7 +934,7 @@ int pp_set_events(pp_ctx *ctx, const int64_t *start, const int64_t *length, int6
     k1_event_offsets<<<1, SEL_THREADS, 0, ctx->stream>>>(ctx->ctr, (const int64_t *)ctx->ev_len.p, n_events,
                                                          (int64_t *)ctx->ev_off.p);
     LAUNCHED(ctx);
-    ctx->src_kind = 0;
+    ctx->src_kind = ctx->trace64 ? PP_SRC_TRACE64 : PP_SRC_TRACE32;
     int64_t tot = 0;
     for (int64_t i = 0; i < n_events; ++i) tot += length[i];
     ctx->flat_cap = tot > 0 ? tot : 1;
@@ -951,7 +1010,7 @@ int pp_events_upload_f64(pp_ctx *ctx, const double *host, const int64_t *length,
     CK(cudaMemcpyAsync(ctx->ev_start.p, ctx->ev_off.p, 8 * (size_t)n_events, cudaMemcpyDeviceToDevice,
                        ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->src_kind = 1;
+    ctx->src_kind = PP_SRC_FLAT64;
     ctx->flat_cap = tot;
     ctx->n_events = n_events;
     ctx->n_event_samples = tot;
@@ -981,7 +1040,7 @@ int pp_event_samples_download(pp_ctx *ctx, int64_t cap, double *out)
     if (ctx->n_event_samples < 0) return fail(ctx, PP_ERR_STATE, "no event table");
     if (cap < ctx->n_event_samples) return fail(ctx, PP_ERR_CAPACITY, "sample buffer too small");
     CKR(set_device(ctx));
-    if (ctx->src_kind != 1) return fail(ctx, PP_ERR_STATE, "events are float32 views of the trace");
+    if (ctx->src_kind != PP_SRC_FLAT64) return fail(ctx, PP_ERR_STATE, "events are views of the trace");
     CK(cudaMemcpyAsync(out, ctx->flat64.p, 8 * (size_t)ctx->n_event_samples, cudaMemcpyDeviceToHost,
                        ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1113,14 +1172,14 @@ int pp_event_stats_download(pp_ctx *ctx, int64_t cap, double *mean, double *std,
     CKR(ensure(ctx, ctx->evs_std, 8 * e));
     CKR(ensure(ctx, ctx->evs_min, 8 * e));
     CKR(ensure(ctx, ctx->evs_max, 8 * e));
-    if (ctx->src_kind == 0)
+    if (ctx->src_kind == PP_SRC_TRACE32)
         k4_segment_stats<float><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
             ctx->trace, (const int64_t *)ctx->ev_start.p, (const int64_t *)ctx->ev_off.p, ctx->ctr, 1,
             (const int64_t *)ctx->ev_off.p, nullptr, (int64_t)e, (double *)ctx->evs_mean.p,
             (double *)ctx->evs_std.p, (double *)ctx->evs_min.p, (double *)ctx->evs_max.p);
     else
         k4_segment_stats<double><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
-            (const double *)ctx->flat64.p, (const int64_t *)ctx->ev_off.p, (const int64_t *)ctx->ev_off.p,
+            f64_samples(ctx), f64_bases(ctx), (const int64_t *)ctx->ev_off.p,
             ctx->ctr, 1, (const int64_t *)ctx->ev_off.p, nullptr, (int64_t)e, (double *)ctx->evs_mean.p,
             (double *)ctx->evs_std.p, (double *)ctx->evs_min.p, (double *)ctx->evs_max.p);
     LAUNCHED(ctx);
@@ -1399,10 +1458,11 @@ static int pipeline_host_impl(pp_ctx *ctx, const float *host, int64_t n, int64_t
     }
     CKR(ensure(ctx, ctx->trace_buf, sizeof(float) * (size_t)n));
     ctx->trace = (const float *)ctx->trace_buf.p;
+    ctx->trace64 = nullptr;
     ctx->n = n;
     ctx->trace_cap = (int64_t)(ctx->trace_buf.cap / sizeof(float));
     ctx->adopted = false;
-    ctx->src_kind = 0;
+    ctx->src_kind = PP_SRC_TRACE32;
     ctx->flat_cap = n;
     reset_stages(ctx);
     CKR(begin_threshold(ctx, n));

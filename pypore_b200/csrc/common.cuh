@@ -13,8 +13,7 @@
 
 // Device-side counters, one instance per context (zeroed per stage as needed).
 struct PPCounters {
-    unsigned long long ticket;        // K1 dynamic tile id
-    unsigned long long n_edges;       // K1 total threshold crossings
+    unsigned long long n_edges[2];    // K1 threshold crossings found so far (two slots: k1_stitch reads one, writes the other)
     unsigned long long n_runs;        // n_edges + 1 (0 for an empty trace)
     unsigned long long n_events;
     unsigned long long n_event_samples;
@@ -50,18 +49,22 @@ enum { PP_OVF_RUNS = 1, PP_OVF_QUEUE = 2, PP_OVF_SEGS = 4, PP_OVF_FILTER_SHORT =
 
 // Where an event's samples live.
 //   kind 0: float32 trace, sample j of event e = trace[ev_start[e] + j]
-//   kind 1: float64 packed array, sample j of event e = flat[ev_off[e] + j]
+//   kind 1: float64 packed array, sample j of event e = flat[ev_off[e] + j]   (uploaded events, filtered current)
+//   kind 2: float64 trace, sample j of event e = trace64[ev_start[e] + j]
 struct PPSource {
     const float *trace;
+    const double *trace64;
     const double *flat;
     const int64_t *ev_start;
     const int64_t *ev_off;
     int kind;
 };
+enum { PP_SRC_TRACE32 = 0, PP_SRC_FLAT64 = 1, PP_SRC_TRACE64 = 2 };
 
 __device__ __forceinline__ double pp_sample(const PPSource &s, int64_t ev, int64_t j)
 {
-    if (s.kind == 0) return (double)__ldg(s.trace + s.ev_start[ev] + j);
+    if (s.kind == PP_SRC_TRACE32) return (double)__ldg(s.trace + s.ev_start[ev] + j);
+    if (s.kind == PP_SRC_TRACE64) return __ldg(s.trace64 + s.ev_start[ev] + j);
     return __ldg(s.flat + s.ev_off[ev] + j);
 }
 

@@ -104,7 +104,8 @@ k2_prefix_sequential(PPSource src, const int64_t *__restrict__ ev_len, PPCounter
         }
         const int64_t len = ev_len[e];
         const int64_t off = src.ev_off[e];
-        if (src.kind == 0) k2s_event(src.trace + src.ev_start[e], len, cc + off, sv[warp], lane);
+        if (src.kind == PP_SRC_TRACE32) k2s_event(src.trace + src.ev_start[e], len, cc + off, sv[warp], lane);
+        else if (src.kind == PP_SRC_TRACE64) k2s_event(src.trace64 + src.ev_start[e], len, cc + off, sv[warp], lane);
         else k2s_event(src.flat + off, len, cc + off, sv[warp], lane);
     }
 }
@@ -269,7 +270,7 @@ k2_event_scan(PPSource src, const T *__restrict__ samples, const int64_t *__rest
         const int64_t len = ev_len[e];
         if (len > K2F_MAX_LEN) continue;
         const int64_t off = src.ev_off[e];
-        const T *in = samples + (src.kind == 0 ? src.ev_start[e] : off);
+        const T *in = samples + (src.kind != PP_SRC_FLAT64 ? src.ev_start[e] : off);
         double2 *out = cc + off;
         double carry_c = 0.0, carry_c2 = 0.0;
         K2FBits fb;
@@ -446,7 +447,7 @@ k2_tile_reduce(PPSource src, const T *__restrict__ samples /* trace (kind 0) or 
     const int64_t n_tiles = (int64_t)ctr->n_scan_tiles;
     for (int64_t tile = (int64_t)ctr->tile_begin + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const K2Tile t = k2_locate(src, ev_len, ev_tile_off, n_events, tile);
-        const T *in = samples + (src.kind == 0 ? src.ev_start[t.ev] : t.off) + t.base;
+        const T *in = samples + (src.kind != PP_SRC_FLAT64 ? src.ev_start[t.ev] : t.off) + t.base;
         T xv[K2_ITEMS];
 #pragma unroll
         for (int i = 0; i < K2_ITEMS; ++i) {
@@ -556,7 +557,7 @@ k2_tile_scan(PPSource src, const T *__restrict__ samples, const int64_t *__restr
 
     for (int64_t tile = (int64_t)ctr->tile_begin + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const K2Tile t = k2_locate(src, ev_len, ev_tile_off, n_events, tile);
-        const T *in = samples + (src.kind == 0 ? src.ev_start[t.ev] : t.off) + t.base;
+        const T *in = samples + (src.kind != PP_SRC_FLAT64 ? src.ev_start[t.ev] : t.off) + t.base;
         const double carry_c = tiles[tile].carry_c, carry_c2 = tiles[tile].carry_c2;
         __syncthreads();  // the previous tile's output staging has been drained
         // coalesced load -> padded shared memory (conflict-free blocked reads)

@@ -2,139 +2,354 @@
 //
 // Replaces PyPore/parsers.py:148-155 (mask / diff / where / split) and the
 // np.min / np.max second pass of _lambda_select (parsers.py:136-140 through
-// core.py:215-220).  One read of the float32 trace (4 B/sample): every tile of
-// 4096 samples builds a below-threshold bitmask with 128-bit loads, finds the
-// crossings with one XOR per 32 samples, gets its global run offset by a
-// decoupled look-back over the per-tile crossing counts, scatters the run
-// starts, and folds per-run min/max through shared-memory keys into the global
-// run table (one atomic pair per run per tile).
+// core.py:215-220).  One read of the trace (4 B/sample for float32 input, 8 B/sample for float64 input):
+//
+//   k1_scan_tiles   persistent CTAs stream 4096-sample tiles through a ring of shared-memory stages filled by
+//                   1-D TMA bulk copies (cp.async.bulk + mbarrier, three tiles in flight per CTA).  Each WARP owns a
+//                   512-sample span of the tile and works on its own: below-threshold bits, crossings, min / max
+//                   (NaN dominates like np.min / np.max).  A span without a crossing -- 11 out of 12 on the headline
+//                   workload -- costs 16 compares, a vote and two 64-bit warp minima, and writes one 24-byte record.
+//                   Spans with crossings also stage up to K1_STAGE of them (position, min / max of the piece that
+//                   starts there).  No inter-tile dependency, no global atomic, one CTA barrier per tile (the stage
+//                   hand-back).
+//   k1_stitch       one thread per span record: exclusive scan of the crossing counts (decoupled look-back over
+//                   1024-record blocks -- a chain of 15 for 60 M samples, off the streaming path) gives every span
+//                   its first run index; run starts are written and the min / max pieces folded into the run table.
+//                   A span with more than K1_STAGE crossings (noise riding on the threshold) is walked again here,
+//                   sample by sample.
+//   k1_finalize_runs decodes the run table (length, side, min / max as float64).
+//
+// The first round's kernel did all of this in one pass with the look-back inside the streaming kernel: 28 % of the
+// HBM peak, 11 barrier-stall cycles per issue (profiles/r01o_ncu_summary.csv).
 #pragma once
 #include "common.cuh"
 
 constexpr int K1_THREADS = 256;
-#ifndef K1_CFG_ROWS  // development knob
-#define K1_CFG_ROWS 4
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_SPAN = 512;                        // samples per warp and tile
+constexpr int K1_TILE = K1_WARPS * K1_SPAN;         // 4096 samples
+#ifndef K1_CFG_STAGES
+#define K1_CFG_STAGES 3
 #endif
-constexpr int K1_ROWS = K1_CFG_ROWS;  // <= 8 (one thread per mask word)
-constexpr int K1_TILE = K1_THREADS * 4 * K1_ROWS;  // 4096 samples
-constexpr int K1_WORDS = K1_TILE / 32;             // 128 mask words
-constexpr int K1_LOCAL_RUNS = 64;
+constexpr int K1_STAGES = K1_CFG_STAGES;            // tiles in flight per CTA
+constexpr int K1_STAGE = 8;                         // crossings staged per span; more: the span is walked again by k1_stitch
+constexpr int K1_LEAD = 4;                          // samples copied in front of a tile (16 / 32 bytes: keeps the bulk copy aligned)
 
+// Monotone double -> uint64 key (larger double <=> larger key; -0.0 < +0.0).
+__device__ __forceinline__ unsigned long long pp_dkey(double x)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ double pp_dkey_inv(unsigned long long k)
+{
+    const unsigned long long b = k ^ ((k >> 63) ? 0x8000000000000000ull : ~0ull);
+    return __longlong_as_double((long long)b);
+}
+// Min tracking: NaN -> 0 (dominates the min like np.min), empty = ~0.  Max tracking: NaN -> ~0, empty = 0.
+#define PP_MINKEY64_EMPTY (~0ull)
+#define PP_MAXKEY64_EMPTY 0ull
+
+struct K1Record {            // one per 512-sample span
+    unsigned count;          // crossings inside the span (a crossing at p: sample p is on the other side than p - 1)
+    unsigned first_below;    // side of the span's first sample
+    unsigned long long head_min, head_max;   // keys of the samples before the first crossing (empty keys if there are none)
+};
+
+struct K1Staged {            // crossing k < K1_STAGE of a span
+    unsigned long long mn, mx;               // keys of the samples from this crossing to the next one / the span's end
+    unsigned pos, pad;                       // position inside the span
+};
+
+__device__ __forceinline__ unsigned long long k1_warp_min_u64(unsigned long long k)
+{
+    const unsigned hi = (unsigned)(k >> 32);
+    const unsigned mh = __reduce_min_sync(PP_FULL, hi);
+    const unsigned lo = hi == mh ? (unsigned)k : 0xffffffffu;
+    const unsigned ml = __reduce_min_sync(PP_FULL, lo);
+    return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ unsigned long long k1_warp_max_u64(unsigned long long k)
+{
+    const unsigned hi = (unsigned)(k >> 32);
+    const unsigned mh = __reduce_max_sync(PP_FULL, hi);
+    const unsigned lo = hi == mh ? (unsigned)k : 0u;
+    const unsigned ml = __reduce_max_sync(PP_FULL, lo);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+// ---- mbarrier / bulk-copy plumbing (PTX; one CTA, no cluster) --------------------------------------
+__device__ __forceinline__ unsigned k1_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void k1_mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k1_smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void k1_mbar_expect(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k1_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void k1_mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "K1_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra K1_WAIT_LOOP;\n"
+        "}\n" ::"r"(k1_smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void k1_bulk_load(void *dst, const void *src, unsigned bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(k1_smem_addr(dst)), "l"(src), "r"(bytes), "r"(k1_smem_addr(bar)) : "memory");
+}
+
+template <typename T> __device__ __forceinline__ T k1_min(T a, T b);
+template <> __device__ __forceinline__ float k1_min<float>(float a, float b) { return fminf(a, b); }
+template <> __device__ __forceinline__ double k1_min<double>(double a, double b) { return fmin(a, b); }
+template <typename T> __device__ __forceinline__ T k1_max(T a, T b);
+template <> __device__ __forceinline__ float k1_max<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ double k1_max<double>(double a, double b) { return fmax(a, b); }
+
+// Shared memory of k1_scan_tiles: the stages (each K1_LEAD samples of the previous tile + the tile), their
+// barriers, and per-warp scratch keys for spans with crossings.
+template <typename T>
+struct K1Smem {
+    alignas(128) T stage[K1_STAGES][K1_LEAD + K1_TILE];
+    unsigned long long full[K1_STAGES];
+    unsigned long long smin[K1_WARPS][K1_STAGE + 1], smax[K1_WARPS][K1_STAGE + 1];
+};
+
+// Tiles [tile_begin, tile_begin + n_tiles) of the trace prefix x[0, n).  thr: `sample < thr` <=> below
+// (float32 input: the smallest float32 >= the threshold, so that the comparison equals the reference's
+// double(x) < threshold for every float32 x; float64 input: the threshold itself).
+template <typename T>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_scan_tiles(const T *__restrict__ x, int64_t n, T thr, int64_t tile_begin, int64_t n_tiles,
+              K1Record *__restrict__ rec, K1Staged *__restrict__ staged)
+{
+    extern __shared__ __align__(128) unsigned char k1_raw[];
+    K1Smem<T> &S = *reinterpret_cast<K1Smem<T> *>(k1_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr unsigned TILE_BYTES = (unsigned)((K1_LEAD + K1_TILE) * sizeof(T));
+
+    if (tid == 0) {
+        for (int s = 0; s < K1_STAGES; ++s) k1_mbar_init(&S.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // a tile is copied whole by the TMA unit when it lies inside [K1_LEAD, n); the first tile of the trace and a
+    // ragged last one are filled by the threads (fill value for samples past n: the last sample, which adds no
+    // crossing and no new extreme)
+    auto issue = [&](int64_t it) {   // thread 0: start the copy of this CTA's it-th tile into its stage
+        const int64_t tile = tile_begin + blockIdx.x + it * (int64_t)gridDim.x;
+        const int64_t base = tile * K1_TILE;
+        const int s = (int)(it % K1_STAGES);
+        if (base >= K1_LEAD && base + K1_TILE <= n) {
+            k1_mbar_expect(&S.full[s], TILE_BYTES);
+            k1_bulk_load(&S.stage[s][0], x + base - K1_LEAD, TILE_BYTES, &S.full[s]);
+        }
+    };
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid == 0)
+        for (int64_t it = 0; it < K1_STAGES && it < my_tiles; ++it) issue(it);
+
+    unsigned phases = 0u;   // bit s: parity of the next completion of stage s's barrier (only bulk copies complete one)
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        const int64_t tile = tile_begin + blockIdx.x + it * (int64_t)gridDim.x;
+        const int64_t base = tile * K1_TILE;
+        const int s = (int)(it % K1_STAGES);
+        T *buf = &S.stage[s][0];
+        if (base >= K1_LEAD && base + K1_TILE <= n) {
+            k1_mbar_wait(&S.full[s], (phases >> s) & 1u);
+            phases ^= 1u << s;
+        } else {
+            const T fill = __ldg(x + (n - 1));
+            for (int k = tid; k < K1_LEAD + K1_TILE; k += K1_THREADS) {
+                const int64_t g = base - K1_LEAD + k;
+                buf[k] = g < 0 ? __ldg(x) : (g < n ? __ldg(x + g) : fill);   // (before sample 0: sample 0 itself -- no crossing there)
+            }
+            __syncthreads();
+        }
+        // ---- this warp's span: 4 rows of 128 samples, lane l holds samples 4l .. 4l+3 of each row ----
+        const T *sp = buf + K1_LEAD + warp * K1_SPAN;
+        T v[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (sizeof(T) == 4) {
+                const float4 q = *reinterpret_cast<const float4 *>(sp + r * 128 + lane * 4);
+                v[r][0] = (T)q.x; v[r][1] = (T)q.y; v[r][2] = (T)q.z; v[r][3] = (T)q.w;
+            } else {
+                const double2 q0 = *reinterpret_cast<const double2 *>(sp + r * 128 + lane * 4);
+                const double2 q1 = *reinterpret_cast<const double2 *>(sp + r * 128 + lane * 4 + 2);
+                v[r][0] = (T)q0.x; v[r][1] = (T)q0.y; v[r][2] = (T)q1.x; v[r][3] = (T)q1.y;
+            }
+        }
+        const bool carry_below = sp[-1] < thr;   // side of the sample in front of the span
+        __syncthreads();                         // every warp has its samples in registers: the stage is free again
+        if (tid == 0 && it + K1_STAGES < my_tiles) issue(it + K1_STAGES);
+
+        unsigned nib[4];
+        bool any_below = false, any_above = false, nan = false;
+        T m = v[0][0], M = v[0][0];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            nib[r] = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool b = v[r][k] < thr;
+                nib[r] |= b ? (1u << k) : 0u;
+                any_below |= b;
+                any_above |= !b;
+                nan |= (v[r][k] != v[r][k]);
+                m = k1_min<T>(m, v[r][k]);
+                M = k1_max<T>(M, v[r][k]);
+            }
+        }
+        const bool w_below = __any_sync(PP_FULL, any_below), w_above = __any_sync(PP_FULL, any_above);
+        const bool w_nan = __any_sync(PP_FULL, nan);
+        const int64_t r_idx = tile * K1_WARPS + warp;
+        const bool first_below = __shfl_sync(PP_FULL, (int)(nib[0] & 1u), 0) != 0;
+        // the very first sample of the trace never starts a new run
+        const bool carry = (base == 0 && warp == 0) ? first_below : carry_below;
+        if (!(w_below && w_above) && carry == w_below) {
+            // ---- no crossing: the whole span continues the open run ----
+            unsigned long long kmin = k1_warp_min_u64(pp_dkey((double)m));
+            unsigned long long kmax = k1_warp_max_u64(pp_dkey((double)M));
+            if (w_nan) { kmin = 0ull; kmax = ~0ull; }
+            if (lane == 0) {
+                K1Record R;
+                R.count = 0u; R.first_below = first_below ? 1u : 0u; R.head_min = kmin; R.head_max = kmax;
+                rec[r_idx] = R;
+            }
+            continue;
+        }
+        // ---- crossings: words of 32 below-bits (lanes 8g .. 8g+7 hold word g of a row), crossing bits, counts ----
+        unsigned long long *smin = S.smin[warp], *smax = S.smax[warp];
+        if (lane <= K1_STAGE) { smin[lane] = PP_MINKEY64_EMPTY; smax[lane] = PP_MAXKEY64_EMPTY; }
+        __syncwarp();
+        unsigned e[4], off[4];
+        unsigned running = 0u;
+        unsigned prev_top = carry ? 1u : 0u;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            unsigned w = nib[r] << ((lane & 7) * 4);
+            w |= __shfl_xor_sync(PP_FULL, w, 1);
+            w |= __shfl_xor_sync(PP_FULL, w, 2);
+            w |= __shfl_xor_sync(PP_FULL, w, 4);
+            // top bit of the previous word: previous lane group, or the previous row's last word / the carry
+            const unsigned left = __shfl_sync(PP_FULL, w, (lane & 24) - 8 < 0 ? 0 : (lane & 24) - 8) >> 31;
+            const unsigned cin = (lane >> 3) == 0 ? prev_top : left;
+            e[r] = w ^ ((w << 1) | cin);
+            prev_top = __shfl_sync(PP_FULL, w, 31) >> 31;
+            const unsigned c = __popc(e[r]);
+            const unsigned c0 = __shfl_sync(PP_FULL, c, 0), c1 = __shfl_sync(PP_FULL, c, 8);
+            const unsigned c2 = __shfl_sync(PP_FULL, c, 16), c3 = __shfl_sync(PP_FULL, c, 24);
+            const int g = lane >> 3;
+            off[r] = running + (g > 0 ? c0 : 0u) + (g > 1 ? c1 : 0u) + (g > 2 ? c2 : 0u);
+            running += c0 + c1 + c2 + c3;
+        }
+        const unsigned count = running;
+        // ---- min / max per piece: local run id of every sample = crossings up to and including its own bit ----
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int b0 = (lane & 7) * 4;
+            unsigned rid = off[r] + __popc(e[r] & ((2u << b0) - 1u));
+            const unsigned inner = (e[r] >> (b0 + 1)) & 7u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k > 0) rid += (inner >> (k - 1)) & 1u;
+                if (rid <= (unsigned)K1_STAGE) {
+                    const T val = v[r][k];
+                    const bool isn = val != val;
+                    atomicMin(&smin[rid], isn ? 0ull : pp_dkey((double)val));
+                    atomicMax(&smax[rid], isn ? ~0ull : pp_dkey((double)val));
+                }
+            }
+        }
+        __syncwarp();
+        // ---- positions of the first K1_STAGE crossings ----
+        if ((lane & 7) == 0) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                unsigned bits = e[r], k = off[r];
+                while (bits && k < (unsigned)K1_STAGE) {
+                    const int bit = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    staged[r_idx * K1_STAGE + k].pos = (unsigned)(r * 128 + (lane >> 3) * 32 + bit);
+                    ++k;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < K1_STAGE && (unsigned)lane < count) {
+            staged[r_idx * K1_STAGE + lane].mn = smin[lane + 1];
+            staged[r_idx * K1_STAGE + lane].mx = smax[lane + 1];
+        }
+        if (lane == 0) {
+            K1Record R;
+            R.count = count; R.first_below = first_below ? 1u : 0u; R.head_min = smin[0]; R.head_max = smax[0];
+            rec[r_idx] = R;
+        }
+        __syncwarp();
+    }
+}
+
+// One thread per span record of [rec_begin, rec_end): first run index of every span by an exclusive scan of the
+// crossing counts (block scan + decoupled look-back over the blocks of THIS launch, seeded with the crossings
+// found by earlier launches: ctr->n_edges), then the run starts and the min / max pieces go into the run table.
+// `blk_state` holds one word per block of the launch, zeroed beforehand.
+constexpr int K1B_THREADS = 256;
 #define PP_TS_AGG (1ull << 62)
 #define PP_TS_INC (2ull << 62)
 #define PP_TS_MASK (3ull << 62)
 
-__device__ __forceinline__ void k1_local_update(unsigned rid, float m, float M, bool nan,
-                                                unsigned *lmin, unsigned *lmax)
+template <typename T>
+__global__ void __launch_bounds__(K1B_THREADS)
+k1_stitch(const T *__restrict__ x, int64_t n, T thr, int64_t rec_begin, int64_t rec_end,
+          const K1Record *__restrict__ rec, const K1Staged *__restrict__ staged,
+          unsigned long long *__restrict__ blk_state, PPCounters *ctr, int flip, int64_t *__restrict__ run_start,
+          unsigned long long *__restrict__ run_minkey, unsigned long long *__restrict__ run_maxkey, int64_t cap_runs)
 {
-    unsigned kmin = nan ? 0u : pp_fkey(m);
-    unsigned kmax = nan ? 0xffffffffu : pp_fkey(M);
-    // rid >= K1_LOCAL_RUNS is handled by the caller
-    atomicMin(&lmin[rid], kmin);
-    atomicMax(&lmax[rid], kmax);
-}
-
-#ifdef K1_CFG_MINBLOCKS  // development knob: 8 = all 2048 threads of an SM resident (32 registers per thread)
-__global__ void __launch_bounds__(K1_THREADS, K1_CFG_MINBLOCKS)
-#else
-__global__ void __launch_bounds__(K1_THREADS)
-#endif
-k1_threshold_scan(const float *__restrict__ x, int64_t n, float thr_f,
-                  unsigned long long *__restrict__ tile_state, PPCounters *ctr,
-                  int64_t *__restrict__ run_start, unsigned *__restrict__ run_minkey,
-                  unsigned *__restrict__ run_maxkey, int64_t cap_runs)
-{
-    __shared__ unsigned B[K1_WORDS];
-    __shared__ unsigned E[K1_WORDS];
-    __shared__ unsigned Eoff[K1_WORDS];
-    __shared__ unsigned warp_tot[K1_WORDS / 32];
-    __shared__ unsigned lmin[K1_LOCAL_RUNS], lmax[K1_LOCAL_RUNS];
-    __shared__ float red_min[K1_THREADS / 32], red_max[K1_THREADS / 32];
-    __shared__ int red_nan[K1_THREADS / 32];
-    __shared__ unsigned long long s_tile, s_prefix;
-    __shared__ unsigned s_total;
-
+    __shared__ unsigned long long wtot[K1B_THREADS / 32];
+    __shared__ unsigned long long s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(&ctr->ticket, 1ull);
-    if (tid < K1_LOCAL_RUNS) { lmin[tid] = PP_MINKEY_EMPTY; lmax[tid] = PP_MAXKEY_EMPTY; }
-    __syncthreads();
-    const unsigned long long tile = s_tile;
-    const int64_t base = (int64_t)tile * K1_TILE;
-    const bool full_tile = base + K1_TILE <= n;
-    const float fill = full_tile ? 0.f : __ldg(x + (n - 1));
-
-    float v[K1_ROWS][4];
+    const int64_t r = rec_begin + (int64_t)blockIdx.x * K1B_THREADS + tid;
+    const bool live = r < rec_end;
+    K1Record R;
+    R.count = 0u; R.first_below = 0u; R.head_min = PP_MINKEY64_EMPTY; R.head_max = PP_MAXKEY64_EMPTY;
+    if (live) R = rec[r];
+    // crossings of the launches before this one (0 for a fresh scan).  Read from one slot, written to the other
+    // (`flip` alternates per launch), so that a block starting late cannot pick up this launch's own total.
+    const unsigned long long seed = ctr->n_edges[flip & 1];
+    unsigned long long inc = R.count;
 #pragma unroll
-    for (int r = 0; r < K1_ROWS; ++r) {
-        const int64_t idx = base + r * (K1_THREADS * 4) + tid * 4;
-        if (idx + 3 < n) {
-            const float4 q = __ldg(reinterpret_cast<const float4 *>(x + idx));
-            v[r][0] = q.x; v[r][1] = q.y; v[r][2] = q.z; v[r][3] = q.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[r][k] = (idx + k < n) ? __ldg(x + idx + k) : fill;
-        }
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(PP_FULL, inc, d);
+        if (lane >= d) inc += t;
     }
-    // below-threshold bitmask of the tile
-#pragma unroll
-    for (int r = 0; r < K1_ROWS; ++r) {
-        unsigned nib = (v[r][0] < thr_f ? 1u : 0u) | (v[r][1] < thr_f ? 2u : 0u) |
-                       (v[r][2] < thr_f ? 4u : 0u) | (v[r][3] < thr_f ? 8u : 0u);
-        unsigned w = nib << ((lane & 7) * 4);
-        w |= __shfl_xor_sync(PP_FULL, w, 1);
-        w |= __shfl_xor_sync(PP_FULL, w, 2);
-        w |= __shfl_xor_sync(PP_FULL, w, 4);
-        if ((lane & 7) == 0) B[r * 32 + warp * 4 + (lane >> 3)] = w;
-    }
+    if (lane == 31) wtot[warp] = inc;
     __syncthreads();
-    // crossings: bit p set <=> sample base+p is on the other side than base+p-1
-    if (tid < K1_WORDS) {
-        const unsigned b = B[tid];
-        unsigned carry;
-        if (tid > 0) carry = B[tid - 1] >> 31;
-        else if (base == 0) carry = b & 1u;  // sample 0 never starts a new run
-        else carry = (__ldg(x + base - 1) < thr_f) ? 1u : 0u;
-        const unsigned e = b ^ ((b << 1) | carry);
-        E[tid] = e;
-        const unsigned cnt = __popc(e);
-        unsigned inc = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned t = __shfl_up_sync(PP_FULL, inc, d);
-            if (lane >= d) inc += t;
-        }
-        Eoff[tid] = inc - cnt;
-        if (lane == 31) warp_tot[warp] = inc;
+    unsigned long long add = 0, total = 0;
+    for (int w = 0; w < K1B_THREADS / 32; ++w) {
+        if (w < warp) add += wtot[w];
+        total += wtot[w];
     }
-    __syncthreads();
-    if (tid < K1_WORDS) {
-        unsigned add = 0;
-        for (int w = 0; w < warp; ++w) add += warp_tot[w];
-        Eoff[tid] += add;
-        if (tid == K1_WORDS - 1) s_total = Eoff[tid] + __popc(E[tid]);
-    }
-    __syncthreads();
-    const unsigned total = s_total;
-
-    // decoupled look-back over per-tile crossing counts
     if (warp == 0) {
+        // decoupled look-back over the blocks of this launch
         unsigned long long prefix = 0;
-        if (tile == 0) {
-            if (lane == 0) {
-                atomicExch(&tile_state[0], PP_TS_INC | (unsigned long long)total);
-                ctr->first_below = B[0] & 1u;
-                if (cap_runs > 0) run_start[0] = 0;
-            }
+        if (blockIdx.x == 0) {
+            if (lane == 0) atomicExch(&blk_state[0], PP_TS_INC | total);
         } else {
-            if (lane == 0) atomicExch(&tile_state[tile], PP_TS_AGG | (unsigned long long)total);
-            long long j = (long long)tile - 1;
+            if (lane == 0) atomicExch(&blk_state[blockIdx.x], PP_TS_AGG | total);
+            long long j = (long long)blockIdx.x - 1;
             for (;;) {
                 const long long idx = j - lane;
-                unsigned long long s = idx >= 0 ? pp_ld_volatile_u64(tile_state + idx) : PP_TS_INC;
-                while (__any_sync(PP_FULL, (s & PP_TS_MASK) == 0ull))
-                    s = idx >= 0 ? pp_ld_volatile_u64(tile_state + idx) : PP_TS_INC;
-                const unsigned inc_mask = __ballot_sync(PP_FULL, (s & PP_TS_MASK) == PP_TS_INC);
-                unsigned long long val = s & ~PP_TS_MASK;
+                unsigned long long st = idx >= 0 ? pp_ld_volatile_u64(blk_state + idx) : PP_TS_INC;
+                while (__any_sync(PP_FULL, (st & PP_TS_MASK) == 0ull))
+                    st = idx >= 0 ? pp_ld_volatile_u64(blk_state + idx) : PP_TS_INC;
+                const unsigned inc_mask = __ballot_sync(PP_FULL, (st & PP_TS_MASK) == PP_TS_INC);
+                unsigned long long val = st & ~PP_TS_MASK;
                 if (inc_mask) {
                     const int first = __ffs(inc_mask) - 1;
                     if (lane > first) val = 0;
@@ -145,119 +360,84 @@ k1_threshold_scan(const float *__restrict__ x, int64_t n, float thr_f,
                 if (inc_mask) break;
                 j -= 32;
             }
-            if (lane == 0) atomicExch(&tile_state[tile], PP_TS_INC | (prefix + total));
+            if (lane == 0) atomicExch(&blk_state[blockIdx.x], PP_TS_INC | (prefix + total));
         }
-        if (lane == 0) {
-            s_prefix = prefix;
-            if (base + K1_TILE >= n) {  // last tile
-                ctr->n_edges = prefix + total;
-                ctr->n_runs = prefix + total + 1;
-            }
-        }
+        if (lane == 0) s_base = seed + prefix;
     }
-
-    // per-thread min/max (independent of the look-back)
-    if (total == 0) {
-        float m = v[0][0], M = v[0][0];
-        bool nan = false;
-#pragma unroll
-        for (int r = 0; r < K1_ROWS; ++r)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                m = fminf(m, v[r][k]); M = fmaxf(M, v[r][k]);
-                nan |= (v[r][k] != v[r][k]);
-            }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            m = fminf(m, __shfl_xor_sync(PP_FULL, m, d));
-            M = fmaxf(M, __shfl_xor_sync(PP_FULL, M, d));
+    __syncthreads();
+    if (!live) return;
+    const unsigned long long first_run = s_base + add + inc - R.count;   // the run this span's first samples belong to
+    if (r == 0) {
+        ctr->first_below = R.first_below;
+        if (cap_runs > 0) run_start[0] = 0;
+    }
+    if (r == rec_end - 1) {
+        ctr->n_edges[(flip & 1) ^ 1] = first_run + R.count;   // the next launch (a later chunk) continues from here
+        if (rec_end * K1_SPAN >= n) ctr->n_runs = first_run + R.count + 1;   // the trace's last span
+    }
+    const int64_t span0 = r * K1_SPAN;
+    if (R.count <= (unsigned)K1_STAGE) {
+        if ((int64_t)first_run < cap_runs && R.head_min != PP_MINKEY64_EMPTY) {
+            atomicMin(&run_minkey[first_run], R.head_min);
+            atomicMax(&run_maxkey[first_run], R.head_max);
         }
-        const bool wnan = __any_sync(PP_FULL, nan);
-        if (lane == 0) { red_min[warp] = m; red_max[warp] = M; red_nan[warp] = wnan; }
-        __syncthreads();
-        if (tid == 0) {
-            bool anynan = false;
-            for (int w = 0; w < K1_THREADS / 32; ++w) {
-                m = fminf(m, red_min[w]); M = fmaxf(M, red_max[w]); anynan |= (red_nan[w] != 0);
-            }
-            const unsigned long long g = s_prefix;
-            if ((int64_t)g < cap_runs) {
-                atomicMin(&run_minkey[g], anynan ? 0u : pp_fkey(m));
-                atomicMax(&run_maxkey[g], anynan ? 0xffffffffu : pp_fkey(M));
+        for (unsigned k = 0; k < R.count; ++k) {
+            const K1Staged c = staged[r * K1_STAGE + k];
+            const unsigned long long rid = first_run + k + 1;
+            if ((int64_t)rid < cap_runs) {
+                run_start[rid] = span0 + c.pos;
+                atomicMin(&run_minkey[rid], c.mn);
+                atomicMax(&run_maxkey[rid], c.mx);
             }
         }
         return;
     }
+    // ---- more crossings than were staged (noise riding on the threshold): walk the span again ----
+    unsigned long long rid = first_run;
+    bool below = span0 > 0 ? (__ldg(x + span0 - 1) < thr) : (__ldg(x) < thr);
+    unsigned long long kmin = PP_MINKEY64_EMPTY, kmax = PP_MAXKEY64_EMPTY;
+    const int64_t end = span0 + K1_SPAN < n ? span0 + K1_SPAN : n;
+    for (int64_t p = span0; p < end; ++p) {
+        const T val = __ldg(x + p);
+        const bool b = val < thr;
+        if (b != below) {
+            if ((int64_t)rid < cap_runs && kmin != PP_MINKEY64_EMPTY) {
+                atomicMin(&run_minkey[rid], kmin);
+                atomicMax(&run_maxkey[rid], kmax);
+            }
+            ++rid;
+            if ((int64_t)rid < cap_runs) run_start[rid] = p;
+            kmin = PP_MINKEY64_EMPTY; kmax = PP_MAXKEY64_EMPTY;
+            below = b;
+        }
+        const bool isn = val != val;
+        const unsigned long long k = pp_dkey((double)val);
+        const unsigned long long lo = isn ? 0ull : k, hi = isn ? ~0ull : k;
+        kmin = lo < kmin ? lo : kmin;
+        kmax = hi > kmax ? hi : kmax;
+    }
+    if ((int64_t)rid < cap_runs && kmin != PP_MINKEY64_EMPTY) {
+        atomicMin(&run_minkey[rid], kmin);
+        atomicMax(&run_maxkey[rid], kmax);
+    }
+}
 
-    __syncthreads();  // s_prefix visible
-    const unsigned long long prefix = s_prefix;
-    // scatter run starts: crossing k (0-based, global) starts run k+1
-    if (tid < K1_WORDS) {
-        unsigned e = E[tid];
-        unsigned long long k = prefix + Eoff[tid];
-        while (e) {
-            const int bit = __ffs(e) - 1;
-            e &= e - 1;
-            const unsigned long long rid = ++k;
-            if ((int64_t)rid < cap_runs) run_start[rid] = base + tid * 32 + bit;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < K1_ROWS; ++r) {
-        const int j = r * 32 + warp * 4 + (lane >> 3);
-        const int b0 = (lane & 7) * 4;
-        const unsigned e = E[j];
-        const unsigned rid0 = Eoff[j] + __popc(e & ((2u << b0) - 1u));
-        const unsigned inner = (e >> (b0 + 1)) & 7u;
-        const unsigned rid_first = __shfl_sync(PP_FULL, rid0, 0);
-        const bool uniform = __all_sync(PP_FULL, inner == 0u && rid0 == rid_first);
-        if (uniform) {
-            float m = fminf(fminf(v[r][0], v[r][1]), fminf(v[r][2], v[r][3]));
-            float M = fmaxf(fmaxf(v[r][0], v[r][1]), fmaxf(v[r][2], v[r][3]));
-            bool nan = (v[r][0] != v[r][0]) | (v[r][1] != v[r][1]) | (v[r][2] != v[r][2]) |
-                       (v[r][3] != v[r][3]);
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                m = fminf(m, __shfl_xor_sync(PP_FULL, m, d));
-                M = fmaxf(M, __shfl_xor_sync(PP_FULL, M, d));
-            }
-            nan = __any_sync(PP_FULL, nan);
-            if (lane == 0) {
-                if (rid0 < K1_LOCAL_RUNS) k1_local_update(rid0, m, M, nan, lmin, lmax);
-                else if ((int64_t)(prefix + rid0) < cap_runs) {
-                    atomicMin(&run_minkey[prefix + rid0], nan ? 0u : pp_fkey(m));
-                    atomicMax(&run_maxkey[prefix + rid0], nan ? 0xffffffffu : pp_fkey(M));
-                }
-            }
-        } else {
-            unsigned rid = rid0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (k > 0) rid += (inner >> (k - 1)) & 1u;
-                const float val = v[r][k];
-                const bool nan = val != val;
-                if (rid < K1_LOCAL_RUNS) k1_local_update(rid, val, val, nan, lmin, lmax);
-                else if ((int64_t)(prefix + rid) < cap_runs) {
-                    atomicMin(&run_minkey[prefix + rid], nan ? 0u : pp_fkey(val));
-                    atomicMax(&run_maxkey[prefix + rid], nan ? 0xffffffffu : pp_fkey(val));
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (tid < K1_LOCAL_RUNS && (unsigned)tid <= total) {
-        const unsigned long long g = prefix + tid;
-        if ((int64_t)g < cap_runs && lmin[tid] != PP_MINKEY_EMPTY) {
-            atomicMin(&run_minkey[g], lmin[tid]);
-            atomicMax(&run_maxkey[g], lmax[tid]);
-        }
-    }
+__device__ __forceinline__ double pp_decode_min64(unsigned long long k)
+{
+    if (k == 0ull || k == PP_MINKEY64_EMPTY) return __longlong_as_double(0x7ff8000000000000LL);
+    return pp_dkey_inv(k);
+}
+__device__ __forceinline__ double pp_decode_max64(unsigned long long k)
+{
+    if (k == ~0ull || k == PP_MAXKEY64_EMPTY) return __longlong_as_double(0x7ff8000000000000LL);
+    return pp_dkey_inv(k);
 }
 
 // Decode the run table: length, side, min/max as float64 (what the rules see).
 __global__ void __launch_bounds__(256)
 k1_finalize_runs(int64_t n, const PPCounters *ctr, const int64_t *__restrict__ run_start,
-                 const unsigned *__restrict__ run_minkey, const unsigned *__restrict__ run_maxkey,
+                 const unsigned long long *__restrict__ run_minkey,
+                 const unsigned long long *__restrict__ run_maxkey,
                  int64_t cap_runs, int64_t *__restrict__ run_len, double *__restrict__ run_min,
                  double *__restrict__ run_max, unsigned char *__restrict__ run_below)
 {
@@ -269,8 +449,8 @@ k1_finalize_runs(int64_t n, const PPCounters *ctr, const int64_t *__restrict__ r
         const int64_t s = run_start[r];
         const int64_t e = (r + 1 < (int64_t)ctr->n_runs && r + 1 < cap_runs) ? run_start[r + 1] : n;
         run_len[r] = e - s;
-        run_min[r] = pp_decode_min(run_minkey[r]);
-        run_max[r] = pp_decode_max(run_maxkey[r]);
+        run_min[r] = pp_decode_min64(run_minkey[r]);
+        run_max[r] = pp_decode_max64(run_maxkey[r]);
         run_below[r] = (unsigned char)((first_below ^ (unsigned)(r & 1)) & 1u);
     }
 }

@@ -189,9 +189,10 @@ class lambda_event_parser(parser):
         """One Segment per surviving run: ``current`` (a copy), ``start`` (np.int64
         sample index) and ``duration`` (samples) -- no ``end``, like the reference."""
         host = np.asarray(current)
-        x32 = _as_float32_trace(host)
+        if host.shape[0] == 0:
+            return []
         ctx = _lib.default_context()
-        ctx.upload_trace(x32)
+        _upload_trace(ctx, host)
         start, length, mn, mx = self._detect(ctx, host)
         out = []
         for s, n in zip(start, length):
@@ -201,24 +202,41 @@ class lambda_event_parser(parser):
 
 
 def _device_trace(x):
-    """The array handed to the device for a trace given as `x`."""
-    return _as_float32_trace(x)
-
-
-def _as_float32_trace(x):
-    """The device trace is float32.  float64 input is accepted when every sample is
-    float32-representable (then double(x32) == x and all comparisons agree)."""
+    """The array handed to the device for a trace given as `x`: float32 input as it is; float64 input as
+    float32 when that loses nothing (half the bytes, identical results: double(x32) == x), as float64
+    otherwise -- the reference's own loader yields int16 counts times a float64 scale (read_abf.py:208-210),
+    which in general is not float32-representable; integer input is exact in float64."""
     x = np.asarray(x)
     if x.dtype == np.float32:
         return np.ascontiguousarray(x)
-    if x.dtype == np.float64:
-        x32 = x.astype(np.float32)
-        if not np.array_equal(x32.astype(np.float64), x, equal_nan=True):
-            raise NotImplementedError(
-                "float64 traces that are not float32-representable are not supported by the "
-                "float32 device trace; pass float32 samples")
+    if x.dtype.kind in "iub":
+        x = x.astype(np.float64)
+    if x.dtype != np.float64:
+        raise TypeError("trace must be float32, float64 or an integer type, got %s" % x.dtype)
+    x32 = x.astype(np.float32)
+    if np.array_equal(x32.astype(np.float64), x, equal_nan=True):
         return x32
-    raise TypeError("trace must be float32 or float64, got %s" % x.dtype)
+    return np.ascontiguousarray(x)
+
+
+def _upload_trace(ctx, x):
+    """`x` (any accepted dtype) resident on `ctx`; returns the array that went up."""
+    dev = _device_trace(x)
+    if dev.dtype == np.float32:
+        ctx.upload_trace(dev)
+    else:
+        ctx.upload_trace_f64(dev)
+    return dev
+
+
+def _run_pipeline(ctx, x, threshold, **kw):
+    """pp_pipeline for a host trace of any accepted dtype: float32 traces stream through the chunked host call,
+    float64 ones are uploaded whole (8 B per sample) and run resident."""
+    dev = _device_trace(x)
+    if dev.dtype == np.float32:
+        return ctx.pipeline(threshold, host_trace=dev, **kw)
+    ctx.upload_trace_f64(dev)
+    return ctx.pipeline(threshold, **kw)
 
 
 # --------------------------------------------------------------------------

@@ -276,3 +276,51 @@ def test_filter_derivative_segmenter_matches_reference():
     assert p.to_dict()["name"] == "FilterDerivativeSegmenter"
     with pytest.raises(ValueError):
         FilterDerivativeSegmenter().parse(np.zeros(5))                         # not longer than filtfilt's padlen
+
+
+def test_float64_file_and_empty_trace_and_reassigned_rules():
+    """The public API on the reference's native input: a float64 trace float32 cannot hold (int16 x scale,
+    read_abf.py:208-210) through File.parse / lambda_event_parser.parse / Event.parse; an empty trace gives no
+    events instead of an error; rules assigned after construction are the ones applied."""
+    x32 = synth.make_trace(6, seed=13, tier="A")
+    x = np.round(x32.astype(np.float64) / 0.0305).astype(np.int16) * 0.0305
+    assert not np.array_equal(x.astype(np.float32).astype(np.float64), x)
+    ws, wl = oracle.events(x, 110, [lambda e: e.duration > 1000, lambda e: e.min > -0.5, lambda e: e.max < 110])
+    seg = SpeedyStatSplit(min_width=100, window_width=10000, prior_segments_per_second=10)
+    f = File(current=x, timestep=0.01)
+    f.parse(parser=lambda_event_parser(threshold=110, rules=RuleSet(duration_gt=1000, min_gt=-0.5, max_lt=110)),
+            segmenter=seg)
+    assert np.array_equal(f.event_table["start"], ws) and np.array_equal(f.event_table["length"], wl)
+    oe, ost, oen, _ = oracle.statsplit_events(x, ws, wl, prior_segments_per_second=10)
+    t = f.segment_table
+    assert np.array_equal(t["event"], oe) and np.array_equal(t["start"], ost) and np.array_equal(t["end"], oen)
+    # the reference's own call sequence, event by event, on the same doubles
+    g = File(current=x, timestep=0.01)
+    g.parse(parser=lambda_event_parser(threshold=110, rules=RULES_1000))
+    assert [int(round(e.start * g.second)) for e in g.events] == list(ws)
+    n0 = g.events[0].parse(parser=seg)
+    assert n0 == g.events[0].n == int((oe == 0).sum())           # Event.parse returns the segment count
+    assert np.array_equal(g.events[0].current, x[ws[0]:ws[0] + wl[0]])
+    # integer counts are accepted like the reference accepts them
+    h = File(current=np.round(x32.astype(np.float64)).astype(np.int16), timestep=0.01)
+    h.parse(parser=lambda_event_parser(threshold=110, rules=RULES_1000))
+    assert h.n == len(oracle.events(np.round(x32.astype(np.float64)), 110, RULES_1000)[0])
+    # empty trace
+    e = File(current=np.zeros(0, np.float32), timestep=0.01)
+    e.parse(parser=lambda_event_parser(threshold=110, rules=RuleSet(duration_gt=1000)), segmenter=seg)
+    assert e.n == 0 and len(e.segment_table["start"]) == 0 and json_ok(e)
+    assert lambda_event_parser(threshold=110).parse(np.zeros(0)) == []
+    # rules reassigned after construction
+    p = lambda_event_parser(threshold=110)
+    assert len(p.parse(x)) == 0                                   # the defaults want duration > 100000
+    p.rules = [lambda ev: ev.duration > 1000, lambda ev: ev.max < 110]
+    assert len(p.parse(x)) == len(oracle.events(x, 110, p.rules)[0]) > 0
+    k = File(current=x, timestep=0.01)
+    k.parse(parser=p, segmenter=seg)                              # host-evaluated rules through the resident path
+    assert k.n == len(p.parse(x))
+
+
+def json_ok(f):
+    import json
+    d = json.loads(f.to_json())
+    return d["n"] == 0 and d["events"] == []

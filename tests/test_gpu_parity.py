@@ -125,6 +125,67 @@ def test_threshold_edge_cases(ctx):
     check_runs(ctx, x, 110.0)
 
 
+def test_threshold_float64_trace(ctx):
+    """A float64 trace that float32 cannot hold (int16 counts x a float64 scale, like read_abf.py:208-210) stays
+    float64 on the device: runs, extrema, events and the whole pipeline equal the oracle's on the doubles."""
+    rng = np.random.RandomState(3)
+    x32 = synth.make_trace(12, seed=9, tier="A")
+    counts = np.round(x32.astype(np.float64) / 0.0305).astype(np.int16)
+    x = counts * 0.0305 + 0.0123                               # read_abf: counts * scale + offset, float64
+    assert not np.array_equal(x.astype(np.float32).astype(np.float64), x)
+    x[1000:1003] = [np.nan, np.inf, -np.inf]
+    thr = 110.0000001                                          # not float32-representable either
+    ctx.upload_trace_f64(x)
+    got = ctx.runs(ctx.threshold_scan(thr))
+    want = oracle.threshold_runs(x, thr)
+    for g, w, name in zip(got, want, ("start", "length", "min", "max", "below")):
+        assert np.array_equal(g, w, equal_nan=True), name
+    x[1000:1003] = x[999]
+    ws, wl = oracle.events(x, thr, RULES_1000)
+    ctx.upload_trace_f64(x)
+    c = ctx.pipeline(thr, rule_mask=7, duration_gt=1000, duration_lt=0, min_gt=-0.5, max_lt=110.0,
+                     min_width=100, max_width=1000000, window_width=10000,
+                     min_gain=oracle.min_gain(prior_segments_per_second=10))
+    es, el = ctx.events(c["events"])
+    assert np.array_equal(es, ws) and np.array_equal(el, wl) and len(ws) == 12
+    oe, ost, oen, _ = oracle.statsplit_events(x, ws, wl, prior_segments_per_second=10)
+    t = ctx.segments(c["segments"])
+    assert np.array_equal(t["event"], oe) and np.array_equal(t["start"], ost) and np.array_equal(t["end"], oen)
+    for e in (0, 5, 11):
+        sel = oe == e
+        m, s, mn, mx = oracle.segment_stats(x[ws[e]:ws[e] + wl[e]], ost[sel], oen[sel])
+        assert rel_err(t["mean"][sel], m) < STAT_RTOL and rel_err(t["std"][sel], s) < STAT_RTOL
+        assert np.array_equal(t["min"][sel], mn) and np.array_equal(t["max"][sel], mx)
+    # ragged float64 lengths around the tile / span edges
+    for n in (1, 5, 511, 512, 513, 4095, 4096, 4097, 8191, 12289):
+        y = (np.round(rng.normal(100, 20, n) / 0.0305) * 0.0305)
+        ctx.upload_trace_f64(y)
+        got = ctx.runs(ctx.threshold_scan(105.0))
+        want = oracle.threshold_runs(y, 105.0)
+        for g, w, name in zip(got, want, ("start", "length", "min", "max", "below")):
+            assert np.array_equal(g, w, equal_nan=True), (n, name)
+
+
+def test_threshold_dense_crossings_and_span_edges(ctx):
+    """More crossings per 512-sample span than k1_scan_tiles stages (the span is walked again by k1_stitch),
+    crossings exactly on span / tile boundaries, and NaN inside pieces."""
+    rng = np.random.RandomState(11)
+    x = rng.normal(100.0, 5.0, 3 * 4096 + 77).astype(np.float32)       # every other sample crosses 100
+    check_runs(ctx, x, 100.0)
+    y = np.full(5 * 4096, 120.0, np.float32)
+    for p in (512, 1024, 4096, 4096 + 511, 8192, 3 * 4096 - 1, 4 * 4096):     # steps exactly at the edges
+        y[p:p + 300] = 50.0
+    y[515] = np.nan
+    y[9000] = np.nan
+    check_runs(ctx, y, 110.0)
+    z = np.full(4096 * 2, 50.0, np.float32)                             # 9 and 10 crossings in one span, 8 in another
+    for k in range(9):
+        z[10 + 20 * k] = 120.0 if k % 2 == 0 else 50.0
+    z[600:4000:400] = 120.0
+    z[4096 + 5:4096 + 5 + 16 * 4:16] = 120.0
+    check_runs(ctx, z, 110.0)
+
+
 def test_threshold_subzero_rule(ctx):
     x = synth.make_trace(40, seed=5, tier="A")
     s, l = oracle.events(x.astype(np.float64), 110, RULES_1000)

@@ -106,13 +106,21 @@ def test_bessel_coefficients_match_scipy_fixture(name):
     assert np.allclose(zi, g["zi"], rtol=1e-10)
 
 
-def test_float64_trace_must_be_float32_representable():
+def test_device_trace_dtype_choice():
+    """float64 traces go up as float32 only when that is lossless; what float32 cannot hold (the reference's own
+    int16 x float64-scale data, read_abf.py:208-210) stays float64; integers are exact."""
     x = np.array([1.0, 2.5, 120.03125])
-    assert parsers._as_float32_trace(x).dtype == np.float32
-    with pytest.raises(NotImplementedError):
-        parsers._as_float32_trace(np.array([0.1]))
+    assert parsers._device_trace(x).dtype == np.float32
+    assert parsers._device_trace(x.astype(np.float32)).dtype == np.float32
+    y = parsers._device_trace(np.array([0.1, 120.0]))
+    assert y.dtype == np.float64 and y[0] == 0.1
+    counts = np.array([1, -2, 3000], np.int16)
+    assert parsers._device_trace(counts).dtype == np.float32                       # small integers fit float32
+    assert parsers._device_trace(counts * 0.030517578125).dtype == np.float32      # power-of-two scale: still exact
+    assert parsers._device_trace(counts * 0.0305).dtype == np.float64              # a typical ADC scale is not
+    assert parsers._device_trace(np.array([2**40 + 1], np.int64)).dtype == np.float64
     with pytest.raises(TypeError):
-        parsers._as_float32_trace(np.array([1, 2, 3]))
+        parsers._device_trace(np.array(["a"]))
 
 
 def test_file_json_round_trip_of_the_reference_format():
