@@ -226,7 +226,9 @@ int ensure_event_buffers(pp_ctx *ctx, int64_t cap_events)
 int begin_threshold(pp_ctx *ctx, int64_t scan_len)
 {
     ctx->scan_len = scan_len;
-    int64_t want = scan_len / 64 + 4096;
+    // one run per 256 samples to begin with (the headline traces have one per 6000); a noisier trace overflows once,
+    // the table is regrown to what the scan counted and the call repeats (the capacity stays with the context)
+    int64_t want = scan_len / 256 + 4096;
     if (want < ctx->cap_runs) want = ctx->cap_runs;
     CKR(ensure_run_buffers(ctx, want));
     CKR(ensure_event_buffers(ctx, ctx->cap_runs));
@@ -251,15 +253,16 @@ template <typename T>
 int launch_threshold_tiles(pp_ctx *ctx, const T *x, T thr, int64_t upto, int64_t tile_begin, int64_t ntiles)
 {
     const size_t smem = sizeof(K1Smem<T>);
-    static bool configured = false;   // per instantiation; the attribute is per function, not per context
-    if (!configured) {
+    static int per_sm = 0;   // per instantiation: resident CTAs per SM (the kernel is persistent: one wave exactly)
+    if (per_sm == 0) {
         CK(cudaFuncSetAttribute(k1_scan_tiles<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1_scan_tiles<T>, K1_CTA_THREADS, smem));
+        per_sm = nb > 0 ? nb : 1;
     }
-    const int per_sm = (int)(200 * 1024 / smem) > 0 ? (int)(200 * 1024 / smem) : 1;
     int64_t grid = (int64_t)ctx->sm_count * per_sm;
     if (grid > ntiles) grid = ntiles;
-    k1_scan_tiles<T><<<(unsigned)grid, K1_THREADS, smem, ctx->stream>>>(
+    k1_scan_tiles<T><<<(unsigned)grid, K1_CTA_THREADS, smem, ctx->stream>>>(
         x, upto, thr, tile_begin, ntiles, (K1Record *)ctx->k1_rec.p, (K1Staged *)ctx->k1_staged.p);
     LAUNCHED(ctx);
     const int64_t rec_begin = tile_begin * K1_WARPS, rec_end = (tile_begin + ntiles) * K1_WARPS;

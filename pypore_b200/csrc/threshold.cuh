@@ -29,11 +29,10 @@ constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_SPAN = 512;                        // samples per warp and tile
 constexpr int K1_TILE = K1_WARPS * K1_SPAN;         // 4096 samples
 #ifndef K1_CFG_STAGES
-#define K1_CFG_STAGES 3
+#define K1_CFG_STAGES 4
 #endif
 constexpr int K1_STAGES = K1_CFG_STAGES;            // tiles in flight per CTA
 constexpr int K1_STAGE = 8;                         // crossings staged per span; more: the span is walked again by k1_stitch
-constexpr int K1_LEAD = 4;                          // samples copied in front of a tile (16 / 32 bytes: keeps the bulk copy aligned)
 
 // Monotone double -> uint64 key (larger double <=> larger key; -0.0 < +0.0).
 __device__ __forceinline__ unsigned long long pp_dkey(double x)
@@ -111,68 +110,92 @@ template <typename T> __device__ __forceinline__ T k1_max(T a, T b);
 template <> __device__ __forceinline__ float k1_max<float>(float a, float b) { return fmaxf(a, b); }
 template <> __device__ __forceinline__ double k1_max<double>(double a, double b) { return fmax(a, b); }
 
-// Shared memory of k1_scan_tiles: the stages (each K1_LEAD samples of the previous tile + the tile), their
-// barriers, and per-warp scratch keys for spans with crossings.
+__device__ __forceinline__ void k1_mbar_arrive(void *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(k1_smem_addr(bar)) : "memory");
+}
+
+// m = min ignoring NaN, M = max PROPAGATING NaN: `m < thr` says "a sample is below", `!(M < thr)` says "a sample is
+// above" (NaN compares false, i.e. counts as above, like the reference's mask), and M != M says "there is a NaN" --
+// the no-crossing path needs nothing else, in particular no per-sample compare.
+__device__ __forceinline__ float k1_max_nan(float a, float b)
+{
+    float d;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ double k1_max_nan(double a, double b) { return (a != a || b != b) ? a + b : fmax(a, b); }
+
+// Shared memory of k1_scan_tiles: the stages (one tile each, source and destination of the bulk copy 128-byte
+// aligned -- a copy that started 16 bytes before the tile to bring the previous sample along ran at a third of
+// the rate), their full / empty barriers, and per-warp scratch keys for spans with crossings.
 template <typename T>
 struct K1Smem {
-    alignas(128) T stage[K1_STAGES][K1_LEAD + K1_TILE];
-    unsigned long long full[K1_STAGES];
+    alignas(128) T stage[K1_STAGES][K1_TILE];
+    unsigned long long full[K1_STAGES], empty[K1_STAGES];
     unsigned long long smin[K1_WARPS][K1_STAGE + 1], smax[K1_WARPS][K1_STAGE + 1];
 };
+
+constexpr int K1_CTA_THREADS = K1_THREADS + 32;   // eight consumer warps + the producer warp
 
 // Tiles [tile_begin, tile_begin + n_tiles) of the trace prefix x[0, n).  thr: `sample < thr` <=> below
 // (float32 input: the smallest float32 >= the threshold, so that the comparison equals the reference's
 // double(x) < threshold for every float32 x; float64 input: the threshold itself).
 template <typename T>
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_CTA_THREADS)
 k1_scan_tiles(const T *__restrict__ x, int64_t n, T thr, int64_t tile_begin, int64_t n_tiles,
               K1Record *__restrict__ rec, K1Staged *__restrict__ staged)
 {
     extern __shared__ __align__(128) unsigned char k1_raw[];
     K1Smem<T> &S = *reinterpret_cast<K1Smem<T> *>(k1_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr unsigned TILE_BYTES = (unsigned)((K1_LEAD + K1_TILE) * sizeof(T));
+    constexpr unsigned TILE_BYTES = (unsigned)(K1_TILE * sizeof(T));
 
     if (tid == 0) {
-        for (int s = 0; s < K1_STAGES; ++s) k1_mbar_init(&S.full[s], 1);
+        for (int s = 0; s < K1_STAGES; ++s) { k1_mbar_init(&S.full[s], 1); k1_mbar_init(&S.empty[s], K1_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // a tile is copied whole by the TMA unit when it lies inside [K1_LEAD, n); the first tile of the trace and a
-    // ragged last one are filled by the threads (fill value for samples past n: the last sample, which adds no
-    // crossing and no new extreme)
-    auto issue = [&](int64_t it) {   // thread 0: start the copy of this CTA's it-th tile into its stage
-        const int64_t tile = tile_begin + blockIdx.x + it * (int64_t)gridDim.x;
-        const int64_t base = tile * K1_TILE;
-        const int s = (int)(it % K1_STAGES);
-        if (base >= K1_LEAD && base + K1_TILE <= n) {
-            k1_mbar_expect(&S.full[s], TILE_BYTES);
-            k1_bulk_load(&S.stage[s][0], x + base - K1_LEAD, TILE_BYTES, &S.full[s]);
-        }
-    };
     const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    if (tid == 0)
-        for (int64_t it = 0; it < K1_STAGES && it < my_tiles; ++it) issue(it);
 
-    unsigned phases = 0u;   // bit s: parity of the next completion of stage s's barrier (only bulk copies complete one)
+    if (warp == K1_WARPS) {
+        // ---- producer warp: keeps K1_STAGES tiles in flight.  A whole tile is one 1-D TMA bulk copy; a ragged last
+        //      one is filled by the warp's lanes (past n: the last sample, which adds no crossing and no new extreme) ----
+        for (int64_t it = 0; it < my_tiles; ++it) {
+            const int64_t base = (tile_begin + blockIdx.x + it * (int64_t)gridDim.x) * K1_TILE;
+            const int s = (int)(it % K1_STAGES);
+            if (it >= K1_STAGES) k1_mbar_wait(&S.empty[s], (unsigned)((it / K1_STAGES - 1) & 1));
+            if (base + K1_TILE <= n) {
+                if (lane == 0) {
+                    k1_mbar_expect(&S.full[s], TILE_BYTES);
+                    k1_bulk_load(&S.stage[s][0], x + base, TILE_BYTES, &S.full[s]);
+                }
+            } else {
+                const T fill = __ldg(x + (n - 1));
+                T *buf = &S.stage[s][0];
+                for (int k = lane; k < K1_TILE; k += 32) {
+                    const int64_t g = base + k;
+                    buf[k] = g < n ? __ldg(x + g) : fill;
+                }
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) k1_mbar_arrive(&S.full[s]);
+            }
+        }
+        return;
+    }
+
     for (int64_t it = 0; it < my_tiles; ++it) {
         const int64_t tile = tile_begin + blockIdx.x + it * (int64_t)gridDim.x;
         const int64_t base = tile * K1_TILE;
         const int s = (int)(it % K1_STAGES);
-        T *buf = &S.stage[s][0];
-        if (base >= K1_LEAD && base + K1_TILE <= n) {
-            k1_mbar_wait(&S.full[s], (phases >> s) & 1u);
-            phases ^= 1u << s;
-        } else {
-            const T fill = __ldg(x + (n - 1));
-            for (int k = tid; k < K1_LEAD + K1_TILE; k += K1_THREADS) {
-                const int64_t g = base - K1_LEAD + k;
-                buf[k] = g < 0 ? __ldg(x) : (g < n ? __ldg(x + g) : fill);   // (before sample 0: sample 0 itself -- no crossing there)
-            }
-            __syncthreads();
-        }
+        // the sample in front of the tile comes straight from global memory (warp 0 alone needs it; the load is
+        // in flight while the warp waits for the tile)
+        T before = (T)0;
+        if (warp == 0 && base > 0) before = __ldg(x + base - 1);
+        k1_mbar_wait(&S.full[s], (unsigned)((it / K1_STAGES) & 1));
         // ---- this warp's span: 4 rows of 128 samples, lane l holds samples 4l .. 4l+3 of each row ----
-        const T *sp = buf + K1_LEAD + warp * K1_SPAN;
+        const T *sp = &S.stage[s][0] + warp * K1_SPAN;
         T v[4][4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -185,31 +208,22 @@ k1_scan_tiles(const T *__restrict__ x, int64_t n, T thr, int64_t tile_begin, int
                 v[r][0] = (T)q0.x; v[r][1] = (T)q0.y; v[r][2] = (T)q1.x; v[r][3] = (T)q1.y;
             }
         }
-        const bool carry_below = sp[-1] < thr;   // side of the sample in front of the span
-        __syncthreads();                         // every warp has its samples in registers: the stage is free again
-        if (tid == 0 && it + K1_STAGES < my_tiles) issue(it + K1_STAGES);
+        const bool carry_below = (warp == 0 ? before : sp[-1]) < thr;   // side of the sample in front of the span
+        __syncwarp();
+        if (lane == 0) k1_mbar_arrive(&S.empty[s]);   // this warp has its samples in registers
 
-        unsigned nib[4];
-        bool any_below = false, any_above = false, nan = false;
         T m = v[0][0], M = v[0][0];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            nib[r] = 0u;
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const bool b = v[r][k] < thr;
-                nib[r] |= b ? (1u << k) : 0u;
-                any_below |= b;
-                any_above |= !b;
-                nan |= (v[r][k] != v[r][k]);
                 m = k1_min<T>(m, v[r][k]);
-                M = k1_max<T>(M, v[r][k]);
+                M = k1_max_nan(M, v[r][k]);
             }
-        }
-        const bool w_below = __any_sync(PP_FULL, any_below), w_above = __any_sync(PP_FULL, any_above);
-        const bool w_nan = __any_sync(PP_FULL, nan);
+        const bool w_below = __any_sync(PP_FULL, m < thr), w_above = __any_sync(PP_FULL, !(M < thr));
+        const bool w_nan = __any_sync(PP_FULL, M != M);
         const int64_t r_idx = tile * K1_WARPS + warp;
-        const bool first_below = __shfl_sync(PP_FULL, (int)(nib[0] & 1u), 0) != 0;
+        const bool first_below = __shfl_sync(PP_FULL, (int)(v[0][0] < thr), 0) != 0;
         // the very first sample of the trace never starts a new run
         const bool carry = (base == 0 && warp == 0) ? first_below : carry_below;
         if (!(w_below && w_above) && carry == w_below) {
@@ -226,14 +240,14 @@ k1_scan_tiles(const T *__restrict__ x, int64_t n, T thr, int64_t tile_begin, int
         }
         // ---- crossings: words of 32 below-bits (lanes 8g .. 8g+7 hold word g of a row), crossing bits, counts ----
         unsigned long long *smin = S.smin[warp], *smax = S.smax[warp];
-        if (lane <= K1_STAGE) { smin[lane] = PP_MINKEY64_EMPTY; smax[lane] = PP_MAXKEY64_EMPTY; }
-        __syncwarp();
         unsigned e[4], off[4];
         unsigned running = 0u;
         unsigned prev_top = carry ? 1u : 0u;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            unsigned w = nib[r] << ((lane & 7) * 4);
+            const unsigned nib = (v[r][0] < thr ? 1u : 0u) | (v[r][1] < thr ? 2u : 0u) | (v[r][2] < thr ? 4u : 0u) |
+                                 (v[r][3] < thr ? 8u : 0u);
+            unsigned w = nib << ((lane & 7) * 4);
             w |= __shfl_xor_sync(PP_FULL, w, 1);
             w |= __shfl_xor_sync(PP_FULL, w, 2);
             w |= __shfl_xor_sync(PP_FULL, w, 4);
@@ -250,22 +264,40 @@ k1_scan_tiles(const T *__restrict__ x, int64_t n, T thr, int64_t tile_begin, int
             running += c0 + c1 + c2 + c3;
         }
         const unsigned count = running;
-        // ---- min / max per piece: local run id of every sample = crossings up to and including its own bit ----
+        // ---- min / max per piece: local run id of every sample = crossings up to and including its own bit.
+        //      One warp reduction per piece (a handful per span) -- 64-bit shared-memory atomics per sample would
+        //      serialise 512 compare-and-swap loops on two addresses (measured: the whole kernel at 2.0 TB/s) ----
+        unsigned rid[4][4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int b0 = (lane & 7) * 4;
-            unsigned rid = off[r] + __popc(e[r] & ((2u << b0) - 1u));
+            unsigned q = off[r] + __popc(e[r] & ((2u << b0) - 1u));
             const unsigned inner = (e[r] >> (b0 + 1)) & 7u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (k > 0) rid += (inner >> (k - 1)) & 1u;
-                if (rid <= (unsigned)K1_STAGE) {
-                    const T val = v[r][k];
-                    const bool isn = val != val;
-                    atomicMin(&smin[rid], isn ? 0ull : pp_dkey((double)val));
-                    atomicMax(&smax[rid], isn ? ~0ull : pp_dkey((double)val));
-                }
+                if (k > 0) q += (inner >> (k - 1)) & 1u;
+                rid[r][k] = q;
             }
+        }
+        const unsigned q_last = count < (unsigned)K1_STAGE ? count : (unsigned)K1_STAGE;
+        for (unsigned q = 0; q <= q_last; ++q) {
+            T pm = v[0][0], pM = v[0][0];
+            bool have = false, pnan = false;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool mine = rid[r][k] == q;
+                    const T val = v[r][k];
+                    pm = mine ? (have ? k1_min<T>(pm, val) : val) : pm;
+                    pM = mine ? (have ? k1_max<T>(pM, val) : val) : pM;
+                    pnan |= mine && (val != val);
+                    have |= mine;
+                }
+            unsigned long long kmin = k1_warp_min_u64(have ? pp_dkey((double)pm) : PP_MINKEY64_EMPTY);
+            unsigned long long kmax = k1_warp_max_u64(have ? pp_dkey((double)pM) : PP_MAXKEY64_EMPTY);
+            if (__any_sync(PP_FULL, pnan)) { kmin = 0ull; kmax = ~0ull; }
+            if (lane == 0) { smin[q] = kmin; smax[q] = kmax; }
         }
         __syncwarp();
         // ---- positions of the first K1_STAGE crossings ----
