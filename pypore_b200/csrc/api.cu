@@ -131,7 +131,7 @@ int fail(pp_ctx *c, int code, const char *fmt, ...)
 int ensure(pp_ctx *ctx, DevBuf &b, size_t bytes)
 {
     if (bytes <= b.cap && b.p) return PP_OK;
-    if (bytes < 256) bytes = 256;
+    bytes = (bytes + 255) & ~(size_t)255;   // whole 256-byte units: vector loads may touch the rest of a row's last 16 bytes
     CK(cudaStreamSynchronize(ctx->stream));
     if (b.p) CK(cudaFree(b.p));
     b.p = nullptr;

@@ -3,18 +3,22 @@
 //
 // A group of G lanes (8 for short rows, 32 for long ones) owns one row (segment or event).
 // std is computed from deviations, never from prefix-sum differences:
-//   * rows of at most K4_ONE_PASS samples: ONE pass with the shift K = mean of the row's
-//     first min(G, len) samples:  d = x - K,  mean = K + sum(d)/n,
-//     var = sum(d*d)/n - (sum(d)/n)^2.  The cancellation in the last line is bounded by
-//     1 + (K - mean)^2 / var <= ~K4_ONE_PASS / G even when the first samples are all
-//     outliers, which keeps the relative error of std below 1e-10;
+//   * rows of at most K4_ONE_PASS samples: ONE pass with the shift K = the row's first sample:
+//     d = x - K,  mean = K + sum(d)/n,  var = sum(d*d)/n - (sum(d)/n)^2.  The cancellation in the
+//     last line is bounded by 1 + (K - mean)^2 / var <= 1 + n (K is one of the samples, so
+//     (K - mean)^2 <= n var), i.e. a relative error of var below ~4 (1 + n) 2^-53 < 3e-11 for
+//     n <= 65536: std stays within 1e-9 even when the first sample is the worst outlier of the row;
+//   * samples travel as 16-byte vectors (float4 / double2) from the row's 16-byte-aligned start, the
+//     elements in front of and behind the row are masked: a row of ~130 float32 samples is 5 trips of an
+//     8-lane group instead of 17 (the first cut issued 32 thread instructions per sample, most of them
+//     per-row set-up and scalar loads: 31 % of the HBM peak);
 //   * longer rows: two passes (mean first, then deviations from it), like np.std.
 // min / max run on the samples' own type; a NaN anywhere makes both NaN like np.min / np.max.
 #pragma once
 #include "common.cuh"
 
-constexpr int K4_ONE_PASS = 4096;
-constexpr int K4_U = 4;  // independent loads per lane and trip
+constexpr int K4_ONE_PASS = 65536;
+constexpr int K4_U = 4;  // independent 16-byte loads per lane and trip (8 lanes x 4 x float4 = 128 samples: most rows are one trip)
 
 template <int G>
 __device__ __forceinline__ double k4_group_sum(double v)
@@ -56,6 +60,18 @@ __device__ __forceinline__ float k4_max(float a, float b) { return fmaxf(a, b); 
 __device__ __forceinline__ double k4_min(double a, double b) { return fmin(a, b); }
 __device__ __forceinline__ double k4_max(double a, double b) { return fmax(a, b); }
 
+template <typename T> struct K4Vec;
+template <> struct K4Vec<float> {
+    static constexpr int N = 4;
+    typedef float4 V;
+    static __device__ __forceinline__ void get(const V &q, float *o) { o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; }
+};
+template <> struct K4Vec<double> {
+    static constexpr int N = 2;
+    typedef double2 V;
+    static __device__ __forceinline__ void get(const V &q, double *o) { o[0] = q.x; o[1] = q.y; }
+};
+
 // Rows k = group, group + ngroups, ...; every lane of a warp runs the same number of rows
 // so that the full-mask shuffles stay convergent (inactive groups work on an empty row).
 template <typename T, int G>
@@ -65,6 +81,8 @@ __device__ __forceinline__ void k4_rows(const T *__restrict__ samples, const int
                                         double *__restrict__ o_mean, double *__restrict__ o_std,
                                         double *__restrict__ o_min, double *__restrict__ o_max)
 {
+    typedef K4Vec<T> VT;
+    constexpr int N = VT::N;
     const int gl = threadIdx.x & (G - 1);
     const int64_t group0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
     const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
@@ -82,43 +100,61 @@ __device__ __forceinline__ void k4_rows(const T *__restrict__ samples, const int
             len = f1 - f0;
             p = samples + ev_base[ev] + (f0 - ev_off[ev]);
         }
-        const int n0 = (int)(len < G ? len : G);
-        // the lane's first K4_U samples are requested together (a row of ~130 samples is 4 trips of 8 lanes x 4
-        // loads instead of 16 dependent round trips); the very first one also serves the shift K
-        T xq[K4_U];
-#pragma unroll
-        for (int u = 0; u < K4_U; ++u) xq[u] = (gl + u * G) < len ? p[gl + u * G] : (T)0;
-        double K = k4_group_sum<G>(gl < n0 ? (double)xq[0] : 0.0) / (double)(n0 > 0 ? n0 : 1);
-        if (!(fabs(K) <= 1.7e308)) K = 0.0;  // inf / NaN among the first samples: plain sums below
         double s1 = 0.0, s2 = 0.0;
         T mn = inf, mx = -inf;
         int nan = 0;
         double mean, var;
         if (__all_sync(PP_FULL, len <= K4_ONE_PASS)) {
-            for (int64_t j = gl; j < len; j += K4_U * G) {
-                T xn[K4_U];
+            // 16-byte vectors from the aligned start: `mis` elements of the first vector lie in front of the row
+            const int mis = (int)((reinterpret_cast<uintptr_t>(p) & 15) / sizeof(T));
+            const typename VT::V *pv = reinterpret_cast<const typename VT::V *>(p - mis);
+            const int64_t last = mis + len;                  // elements [mis, last) of the vector stream are the row
+            const int64_t nvec = (last + N - 1) / N;
+            double K = len > 0 ? (double)__ldg(p) : 0.0;     // the shift: the row's first sample
+            if (!(fabs(K) <= 1.7e308)) K = 0.0;              // inf / NaN: plain sums
+            for (int64_t v0 = gl; v0 < nvec; v0 += K4_U * G) {
+                typename VT::V q[K4_U];
 #pragma unroll
-                for (int u = 0; u < K4_U; ++u) xn[u] = (j + (K4_U + u) * G) < len ? p[j + (K4_U + u) * G] : (T)0;
+                for (int u = 0; u < K4_U; ++u)
+                    if (v0 + u * G < nvec) q[u] = __ldg(pv + v0 + u * G);
 #pragma unroll
                 for (int u = 0; u < K4_U; ++u) {
-                    if (j + u * G < len) {
-                        const T x = xq[u];
-                        const double d = (double)x - K;
-                        s1 += d;
-                        s2 = fma(d, d, s2);
-                        mn = k4_min(mn, x);
-                        mx = k4_max(mx, x);
-                        nan |= (x != x);
+                    const int64_t e0 = (v0 + u * G) * N;
+                    if (v0 + u * G >= nvec) continue;
+                    T x[N];
+                    VT::get(q[u], x);
+                    if (e0 >= mis && e0 + N <= last) {
+#pragma unroll
+                        for (int c = 0; c < N; ++c) {
+                            const double d = (double)x[c] - K;
+                            s1 += d;
+                            s2 = fma(d, d, s2);
+                            mn = k4_min(mn, x[c]);
+                            mx = k4_max(mx, x[c]);
+                            nan |= (x[c] != x[c]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < N; ++c) {
+                            if (e0 + c >= mis && e0 + c < last) {
+                                const double d = (double)x[c] - K;
+                                s1 += d;
+                                s2 = fma(d, d, s2);
+                                mn = k4_min(mn, x[c]);
+                                mx = k4_max(mx, x[c]);
+                                nan |= (x[c] != x[c]);
+                            }
+                        }
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < K4_U; ++u) xq[u] = xn[u];
             }
             s1 = k4_group_sum<G>(s1);
             s2 = k4_group_sum<G>(s2);
-            const double m1 = s1 / (double)len;
+            const double rl = 1.0 / (double)(len > 0 ? len : 1);
+            const double m1 = s1 * rl;
             mean = K + m1;
-            var = s2 / (double)len - m1 * m1;
+            var = s2 * rl - m1 * m1;
+            if (len == 0) { mean = __longlong_as_double(0x7ff8000000000000LL); var = mean; }
         } else {
             for (int64_t j = gl; j < len; j += G) {
                 const T x = p[j];

@@ -509,6 +509,8 @@ k1_select_events(PPCounters *ctr, const int64_t *__restrict__ run_start,
     __shared__ long long wlen[SEL_THREADS / 32];
     __shared__ unsigned long long s_cnt_carry;
     __shared__ long long s_len_carry;
+    __shared__ unsigned s_cnt_total;
+    __shared__ long long s_len_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int64_t n_runs = (int64_t)ctr->n_runs;
     if (n_runs > cap_runs) n_runs = cap_runs;
@@ -524,20 +526,31 @@ k1_select_events(PPCounters *ctr, const int64_t *__restrict__ run_start,
         s_len_carry = incremental ? (long long)ctr->n_event_samples : 0;
     }
     __syncthreads();
+    // one run per thread and trip, coalesced; the next trip's rows are requested before this trip's scan, so that a
+    // trip costs its two barriers and not a round trip to memory (a single SM serves this kernel: eight strided rows
+    // per thread had its load unit queue 25 k line requests, 25 us for 10^4 runs)
+    auto fetch = [&](int64_t r, long long &len, double &mn, double &mx, long long &st) {
+        const bool in = r < n_runs;
+        len = in ? run_len[r] : 0;
+        st = in ? run_start[r] : 0;
+        mn = in && (rule_mask & PP_RULE_MIN_GT) ? run_min[r] : 0.0;
+        mx = in && (rule_mask & PP_RULE_MAX_LT) ? run_max[r] : 0.0;
+    };
+    long long len_n, st_n;
+    double mn_n, mx_n;
+    fetch(r_begin + tid, len_n, mn_n, mx_n, st_n);
     for (int64_t c0 = r_begin; c0 < n_runs; c0 += SEL_THREADS) {
         const int64_t r = c0 + tid;
-        bool keep = false;
-        long long len = 0;
-        if (r < n_runs) {
-            len = run_len[r];
-            keep = true;
-            if (rule_mask & PP_RULE_DURATION_GT) keep = keep && (len > duration_gt);
-            if (rule_mask & PP_RULE_DURATION_LT) keep = keep && (len < duration_lt);
-            if (rule_mask & PP_RULE_MIN_GT) keep = keep && (run_min[r] > min_gt);
-            if (rule_mask & PP_RULE_MAX_LT) keep = keep && (run_max[r] < max_lt);
-            if (skip_first && r == 0) keep = false;
-            if (skip_last && r == n_runs - 1) keep = false;
-        }
+        const long long len = len_n, st = st_n;
+        const double mn = mn_n, mx = mx_n;
+        fetch(r + SEL_THREADS, len_n, mn_n, mx_n, st_n);
+        bool keep = r < n_runs;
+        if (rule_mask & PP_RULE_DURATION_GT) keep = keep && (len > duration_gt);
+        if (rule_mask & PP_RULE_DURATION_LT) keep = keep && (len < duration_lt);
+        if (rule_mask & PP_RULE_MIN_GT) keep = keep && (mn > min_gt);
+        if (rule_mask & PP_RULE_MAX_LT) keep = keep && (mx < max_lt);
+        if (skip_first && r == 0) keep = false;
+        if (skip_last && r == n_runs - 1) keep = false;
         unsigned c = keep ? 1u : 0u;
         long long l = keep ? len : 0;
         unsigned ci = c;
@@ -550,20 +563,31 @@ k1_select_events(PPCounters *ctr, const int64_t *__restrict__ run_start,
         }
         if (lane == 31) { wcnt[warp] = ci; wlen[warp] = li; }
         __syncthreads();
-        unsigned cb = 0;
-        long long lb = 0;
-        for (int w = 0; w < warp; ++w) { cb += wcnt[w]; lb += wlen[w]; }
-        const unsigned long long idx = s_cnt_carry + cb + (ci - c);
-        const long long off = s_len_carry + lb + (li - l);
+        if (warp == 0) {   // exclusive scan of the 32 warp totals by one warp (a loop per thread cost 100 instructions a trip)
+            unsigned wc = wcnt[lane], wci = wc;
+            long long wl = wlen[lane], wli = wl;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned tc = __shfl_up_sync(PP_FULL, wci, d);
+                long long tl = __shfl_up_sync(PP_FULL, wli, d);
+                if (lane >= d) { wci += tc; wli += tl; }
+            }
+            wcnt[lane] = wci - wc;
+            wlen[lane] = wli - wl;
+            if (lane == 31) { s_cnt_total = wci; s_len_total = wli; }
+        }
+        __syncthreads();
+        const unsigned long long idx = s_cnt_carry + wcnt[warp] + (ci - c);
+        const long long off = s_len_carry + wlen[warp] + (li - l);
         if (keep && (int64_t)idx < cap_events) {
-            ev_start[idx] = run_start[r];
+            ev_start[idx] = st;
             ev_len[idx] = len;
             ev_off[idx] = off;
         }
         __syncthreads();
-        if (tid == SEL_THREADS - 1) {
-            s_cnt_carry = idx + c;
-            s_len_carry = off + l;
+        if (tid == 0) {
+            s_cnt_carry += s_cnt_total;
+            s_len_carry += s_len_total;
         }
         __syncthreads();
     }
