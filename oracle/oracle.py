@@ -197,6 +197,22 @@ def statsplit(event, min_width=100, max_width=1000000, window_width=10000, gain=
     return bp[:k].astype(np.int64)
 
 
+def margin_audit(event, min_width=100, max_width=1000000, window_width=10000, gain=None, **gain_kwargs):
+    """Smallest decision margins of FastStatSplit.parse on one event:
+    (best - runner-up over the scans that split, min_gain - best over those that did not, number of scans)."""
+    x = _f64(event)
+    if gain is None:
+        gain = min_gain(min_width, max_width, window_width, **gain_kwargs)
+    out = np.zeros(3)
+    f = lib().orc_statsplit_audit
+    f.restype = ctypes.c_int
+    f.argtypes = [_f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, _f64p]
+    if f(_p(x, _f64p), x.shape[0], int(min_width), int(max_width), int(window_width), float(gain),
+         _p(out, _f64p)) != 0:
+        raise RuntimeError("oracle audit overflow")
+    return float(out[0]), float(out[1]), int(out[2])
+
+
 def _window_gains(c, c2, start, end, first, last):
     out = np.empty(max(last - first + 1, 0))
     if out.shape[0]:

@@ -105,6 +105,9 @@ typedef struct {
     double *gain_out; /* optional: winning gain per emitted breakpoint (NaN for forced) */
     double *margin_out; /* optional: best - second best gain of the winning scan */
     double last_gain, last_margin;
+    /* margin audit: the smallest distance of any decision from flipping */
+    double min_split_margin;   /* over scans that split: best gain - max(second best gain, min_gain) */
+    double min_nosplit_margin; /* over scans that did not: min_gain - best gain */
 } split_ctx;
 
 /* _best_split_stepwise: PyPore/cparsers.pyx:157-178 */
@@ -114,7 +117,7 @@ static int best_split_stepwise(split_ctx *S, int start, int end)
     if (end - start <= 2 * mw) return -1;
     const double *c = S->c, *c2 = S->c2;
     double var_summed = (end - start) * log(var_c(start, end, c, c2));
-    double min_gain = S->min_gain, second = -INFINITY;
+    double min_gain = S->min_gain, second = -INFINITY, top = -INFINITY;
     int x = -1;
     S->nscan++;
     for (int i = start + mw; i < end + 1 - mw; ++i) {
@@ -129,9 +132,15 @@ static int best_split_stepwise(split_ctx *S, int start, int end)
         } else if (gain > second) {
             second = gain;
         }
+        if (gain > top) top = gain;
     }
     S->last_gain = min_gain;
     S->last_margin = min_gain - second;
+    if (x >= 0) {
+        if (S->last_margin < S->min_split_margin) S->min_split_margin = S->last_margin;
+    } else if (S->min_gain - top < S->min_nosplit_margin) {
+        S->min_nosplit_margin = S->min_gain - top;
+    }
     return x;
 }
 
@@ -213,10 +222,38 @@ int orc_statsplit(const double *x, int n, int min_width, int max_width,
     S.min_gain = min_gain;
     S.bp = bp; S.cap = cap;
     S.gain_out = gain_out; S.margin_out = margin_out;
+    S.min_split_margin = INFINITY; S.min_nosplit_margin = INFINITY;
     recursive_split(&S, 0, n);
     free(c); free(c2);
     if (stats_out) { stats_out[0] = S.ncand; stats_out[1] = S.nscan; }
     return S.overflow ? -1 : S.nbp;
+}
+
+/* Margin audit of one event: out[0] = smallest (best gain - runner-up) over the scans that
+ * split, the runner-up being the second best candidate or min_gain itself, whichever is closer; out[1] = smallest
+ * (min_gain - best gain) over the scans that did not split; out[2] = window scans.  +inf where there was none.
+ * A decision can only differ between two correct implementations of the reference's arithmetic if its margin is
+ * below their rounding differences (libm log: a few ulp, i.e. ~1e-10 on a gain). */
+int orc_statsplit_audit(const double *x, int n, int min_width, int max_width, int window_width, double min_gain,
+                        double *out)
+{
+    split_ctx S;
+    const int cap = n / (min_width > 0 ? min_width : 1) * 2 + 16;
+    double *c = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    double *c2 = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    int *bp = (int *)malloc(sizeof(int) * (size_t)cap);
+    if (!c || !c2 || !bp) { free(c); free(c2); free(bp); return -1; }
+    orc_cumsum(x, n, c, c2);
+    memset(&S, 0, sizeof S);
+    S.c = c; S.c2 = c2;
+    S.min_width = min_width; S.max_width = max_width; S.window_width = window_width;
+    S.min_gain = min_gain;
+    S.bp = bp; S.cap = cap;
+    S.min_split_margin = INFINITY; S.min_nosplit_margin = INFINITY;
+    recursive_split(&S, 0, n);
+    out[0] = S.min_split_margin; out[1] = S.min_nosplit_margin; out[2] = (double)S.nscan;
+    free(c); free(c2); free(bp);
+    return S.overflow ? -1 : 0;
 }
 
 /* Same on many events of one trace; events are independent

@@ -14,6 +14,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <nvtx3/nvToolsExt.h>   // header-only (no link dependency); ranges cost nothing without a profiler attached
+
 namespace {
 
 struct DevBuf {
@@ -22,6 +24,13 @@ struct DevBuf {
 };
 
 enum { ST_THRESHOLD = 0, ST_SELECT, ST_FILTER, ST_PREFIX, ST_SPLIT, ST_COMPACT, ST_STATS, ST_COUNT };
+
+// NVTX range over the host-side enqueue of a stage (tracing); shows up in Nsight Systems next to
+// the kernels it launched
+struct StageRange {
+    explicit StageRange(const char *name) { nvtxRangePushA(name); }
+    ~StageRange() { nvtxRangePop(); }
+};
 
 }  // namespace
 
@@ -281,6 +290,7 @@ int launch_threshold_tiles(pp_ctx *ctx, const T *x, T thr, int64_t upto, int64_t
 // [0, upto) and decode the run table found so far.
 int enqueue_threshold_tiles(pp_ctx *ctx, double threshold, int64_t upto, int64_t ntiles)
 {
+    StageRange nvtx_range("pypore:threshold");
     if (ntiles > 0) {
         if (ctx->trace64) {
             CKR(launch_threshold_tiles<double>(ctx, ctx->trace64, threshold, upto, ctx->k1_tiles_done, ntiles));
@@ -312,6 +322,7 @@ int enqueue_select(pp_ctx *ctx, int rule_mask, int64_t duration_gt, int64_t dura
                    double min_gt, double max_lt, int skip_first, int skip_last, int incremental = 0,
                    const long long *dev_plan = nullptr)
 {
+    StageRange nvtx_range("pypore:select");
     ctx->src_kind = ctx->trace64 ? PP_SRC_TRACE64 : PP_SRC_TRACE32;
     ctx->flat_cap = ctx->n;
     k1_select_events<<<1, SEL_THREADS, 0, ctx->stream>>>(
@@ -346,6 +357,7 @@ void launch_filter_pass(pp_ctx *ctx, const PPSource &src, int backward)
 
 int enqueue_filter(pp_ctx *ctx, const double *b, const double *a, const double *zi, int nc)
 {
+    StageRange nvtx_range("pypore:filter");
     if (nc < 2 || nc > FILT_MAX_COEF) return fail(ctx, PP_ERR_ARG, "filter order must be 1..%d", FILT_NZ);
     if (a[0] != 1.0) return fail(ctx, PP_ERR_ARG, "filter coefficients must be normalised (a[0] == 1)");
     const int64_t ncap = ctx->flat_cap;
@@ -391,9 +403,11 @@ int prepare_split(pp_ctx *ctx, int mw, int MW, int W)
                     mw, MW, W);
     const int64_t ncap = ctx->flat_cap;
     if (ncap <= 0) return fail(ctx, PP_ERR_STATE, "no events selected");
+    // a forced max_width split min(s + MW, e - mw) may leave ONE piece shorter than min_width next to one that is at
+    // least min_width long (mw = MW = 100: 150 samples -> 50 + 100), so segments average at least min_width / 2
     const int64_t div = mw > 0 ? mw : 1;
-    const int64_t cap_segs = ncap / div + ctx->cap_events + 16;
-    const int64_t q_cap = ctx->cap_events + ncap / div + 1024;
+    const int64_t cap_segs = 2 * (ncap / div) + ctx->cap_events + 16;
+    const int64_t q_cap = ctx->cap_events + 2 * (ncap / div) + 1024;
     const int64_t n_words = (ncap + 31) / 32 + 1;
     const int64_t n_blocks = (n_words + CP_BLOCK_WORDS - 1) / CP_BLOCK_WORDS;
     CKR(ensure(ctx, ctx->cc, sizeof(double2) * ncap));
@@ -430,6 +444,7 @@ int prepare_split(pp_ctx *ctx, int mw, int MW, int W)
 // K2 over the events [ev_begin, n_events) (device-side range)
 int enqueue_prefix(pp_ctx *ctx, int prefix_mode)
 {
+    StageRange nvtx_range("pypore:prefix");
     const int64_t ncap = ctx->flat_cap;
     PPSource src = make_source(ctx);
     if (prefix_mode == PP_PREFIX_SEQUENTIAL) {
@@ -496,6 +511,7 @@ int enqueue_prefix(pp_ctx *ctx, int prefix_mode)
 // K3 over the events [ev_begin, n_events)
 int enqueue_search(pp_ctx *ctx, int mw, int MW, int W, double min_gain)
 {
+    StageRange nvtx_range("pypore:split");
     const int64_t q_cap = ctx->q_cap;
     CK(cudaMemsetAsync(ctx->ready.p, 0, sizeof(int) * q_cap, ctx->stream));
     K3Global G;
@@ -544,6 +560,7 @@ int enqueue_search(pp_ctx *ctx, int mw, int MW, int W, double min_gain)
 // per chunk)
 int enqueue_compact(pp_ctx *ctx)
 {
+    StageRange nvtx_range("pypore:compact");
     const int64_t n_blocks = ctx->n_blocks;
     k3c_count<<<(unsigned)n_blocks, CP_THREADS, 0, ctx->stream>>>((const unsigned *)ctx->bits.p, ctx->ctr,
                                                                  (unsigned *)ctx->block_count.p);
@@ -567,6 +584,7 @@ int enqueue_compact(pp_ctx *ctx)
 // rows / events finalised since the last call -> page-locked host tables, then the range advances
 int enqueue_export(pp_ctx *ctx, const PPHostTables &H, int with_stats)
 {
+    StageRange nvtx_range("pypore:export");
     k_export_tables<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(
         ctx->ctr, H, (const int64_t *)ctx->ev_start.p, (const int64_t *)ctx->ev_len.p, (const int *)ctx->seg_event.p,
         (const int64_t *)ctx->seg_start.p, (const int64_t *)ctx->seg_end.p, (const double *)ctx->seg_mean.p,
@@ -597,6 +615,7 @@ int enqueue_split(pp_ctx *ctx, int mw, int MW, int W, double min_gain, int prefi
 
 int enqueue_stats(pp_ctx *ctx)
 {
+    StageRange nvtx_range("pypore:stats");
     if (ctx->src_kind == PP_SRC_TRACE32)
         k4_segment_stats<float><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
             ctx->trace, (const int64_t *)ctx->ev_start.p, (const int64_t *)ctx->ev_off.p, ctx->ctr, 0,
@@ -1101,14 +1120,15 @@ int pp_window_gains(pp_ctx *ctx, int64_t ev, int n_windows, const int32_t *ps, c
     }
     if (total > cap) { free(off); return fail(ctx, PP_ERR_CAPACITY, "gain buffer too small"); }
     DevBuf d_ps, d_pe, d_off, d_out;
-    int rc = ensure(ctx, d_ps, 4 * (size_t)n_windows);
-    if (rc == PP_OK) rc = ensure(ctx, d_pe, 4 * (size_t)n_windows);
-    if (rc == PP_OK) rc = ensure(ctx, d_off, 8 * (size_t)n_windows);
-    if (rc == PP_OK) rc = ensure(ctx, d_out, 8 * (size_t)(total > 0 ? total : 1));
-    if (rc == PP_OK) {
-        cudaMemcpyAsync(d_ps.p, ps, 4 * (size_t)n_windows, cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemcpyAsync(d_pe.p, pe, 4 * (size_t)n_windows, cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemcpyAsync(d_off.p, off, 8 * (size_t)n_windows, cudaMemcpyHostToDevice, ctx->stream);
+    // every CUDA call checked; the scratch buffers are released on every path
+    auto run = [&]() -> int {
+        CKR(ensure(ctx, d_ps, 4 * (size_t)n_windows));
+        CKR(ensure(ctx, d_pe, 4 * (size_t)n_windows));
+        CKR(ensure(ctx, d_off, 8 * (size_t)n_windows));
+        CKR(ensure(ctx, d_out, 8 * (size_t)(total > 0 ? total : 1)));
+        CK(cudaMemcpyAsync(d_ps.p, ps, 4 * (size_t)n_windows, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_pe.p, pe, 4 * (size_t)n_windows, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_off.p, off, 8 * (size_t)n_windows, cudaMemcpyHostToDevice, ctx->stream));
         K3Global G;
         memset(&G, 0, sizeof G);
         G.cc = (const double2 *)ctx->cc.p;
@@ -1117,13 +1137,13 @@ int pp_window_gains(pp_ctx *ctx, int64_t ev, int n_windows, const int32_t *ps, c
         k3_window_gains<<<grid, 256, 0, ctx->stream>>>(G, (int)ev, n_windows, (const int *)d_ps.p,
                                                        (const int *)d_pe.p, min_width, (const int64_t *)d_off.p,
                                                        (double *)d_out.p);
-        ctx->launches++;
+        LAUNCHED(ctx);
         if (total > 0)
-            cudaMemcpyAsync(out, d_out.p, 8 * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (e == cudaSuccess) e = cudaGetLastError();
-        if (e != cudaSuccess) rc = fail(ctx, PP_ERR_CUDA, "pp_window_gains: %s", cudaGetErrorString(e));
-    }
+            CK(cudaMemcpyAsync(out, d_out.p, 8 * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return PP_OK;
+    };
+    const int rc = run();
     release(d_ps); release(d_pe); release(d_off); release(d_out);
     free(off);
     return rc;
