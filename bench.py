@@ -237,8 +237,8 @@ def parity_sharded(tables, world):
 
         def sha(a):
             return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
-        ev = np.asarray(tables["events"], np.int64)
-        rows = np.asarray(tables["seg_int"], np.int64)
+        ev = np.stack([np.asarray(tables["ev_start"], np.int64), np.asarray(tables["ev_len"], np.int64)], axis=1)
+        rows = np.stack([np.asarray(tables[k], np.int64) for k in ("seg_event", "seg_start", "seg_end")], axis=1)
         return {"fixture": "tests/golden/sharded_full.npz (CPU oracle on the uncut trace, full size)",
                 "events": int(len(ev)), "events_expected": int(g[k + "events"]),
                 "segments": int(len(rows)), "segments_expected": int(g[k + "segments"]),
@@ -314,6 +314,10 @@ def run_ours(args):
         return shard.step(THRESHOLD, rules, mw, MW, W, gain)
 
     last_download = {}
+    # Multi-GPU end to end: the upload of step i+1 (the context's copy stream, into a second device buffer) runs
+    # under step i's kernels and collectives, and the copy-out of step i's tables (a side stream, the other PCIe
+    # direction) under both.  Every step's H2D and D2H are inside the timed region.
+    e2e = {"remaining": 0, "loaded": False}
 
     def step_e2e():
         if shard is None:
@@ -324,11 +328,27 @@ def run_ours(args):
                              with_stats=True, host_trace=xp, export=True, **rules)
             assert len(r["segment_table"]["mean"]) == r["segments"]
             return r
-        shard.load(xp)
+        if not e2e["loaded"]:
+            shard.load(xp)                     # first step of a run: nothing was prefetched for it
+        e2e["remaining"] -= 1
+        e2e["loaded"] = e2e["remaining"] > 0
+        if e2e["loaded"]:
+            shard.prefetch(xp)                 # the next step's trace starts its way up before this step runs
         r = shard.step(THRESHOLD, rules, mw, MW, W, gain)
         if rank == 0:
-            last_download["tables"] = shard.download()  # every GPU holds the whole result; the caller reads it once
+            # every GPU holds the whole result; the caller reads it once.  The copy-out is enqueued on a side stream
+            # and collected before the next one is started; finish_e2e() collects the last one.
+            if last_download.get("pending") is not None:
+                last_download["tables"] = last_download["pending"].wait()
+            last_download["pending"] = shard.download_async()
+        if e2e["loaded"]:
+            shard.swap()
         return r
+
+    def finish_e2e():
+        if shard is not None and last_download.get("pending") is not None:
+            last_download["tables"] = last_download["pending"].wait()
+            last_download["pending"] = None
 
     def barrier():
         if world > 1:
@@ -340,12 +360,16 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         r = None
+        e2e["remaining"], e2e["loaded"] = steps, False
         for _ in range(steps):
             r = fn()
         if shard is not None:
-            shard.wait()   # the last step's asynchronous table all-gather belongs to the timed region
+            shard.wait()   # the last step's asynchronous table all-gather belongs to the timed region, and so does
+            shard.join()   # the copy-out of its tables on the side stream: the closing event waits for both
         e1.record(stream)
         barrier()
+        if fn is step_e2e:
+            finish_e2e()
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -377,8 +401,10 @@ def run_ours(args):
     split_ms = float(np.mean(split_ms))
     clocks = sampler.stop()
 
+    e2e["remaining"] = 2
     for _ in range(2):
         step_e2e()
+    finish_e2e()
     ms_e2e, res_e2e = timed(step_e2e, args.steps)
 
     totals = torch.tensor([n_local, res["events"], res["segments"], res["event_samples"]], device="cuda",

@@ -109,6 +109,12 @@ int pp_trace_upload(pp_ctx *ctx, const float *host, int64_t n, int64_t extra_cap
  * compares the doubles themselves, run extrema are the doubles' own, and the later stages read the events out of
  * it like out of a float32 trace.  pp_trace_append / pp_trace_extend / the streamed host pipeline are float32-only. */
 int pp_trace_upload_f64(pp_ctx *ctx, const double *host, int64_t n);
+/* Back-to-back traces: pp_trace_prefetch starts the copy of the NEXT float32 trace (ideally from page-locked memory)
+ * into a second device buffer on the context's copy stream and returns at once -- it runs under whatever the
+ * context's stream is doing with the current trace; pp_trace_swap makes the prefetched trace the resident one (the
+ * context's stream waits for the copy, the host does not). */
+int pp_trace_prefetch(pp_ctx *ctx, const float *host, int64_t n, int64_t extra_capacity);
+int pp_trace_swap(pp_ctx *ctx);
 /* Use device memory the caller owns (no copy; must stay valid; capacity in samples). */
 int pp_trace_adopt(pp_ctx *ctx, const float *dev, int64_t n, int64_t capacity);
 /* Append `n` samples (device or host pointer) after the current trace end: the
@@ -277,6 +283,22 @@ int pp_shard_plan(pp_ctx *ctx, const double *dev_infos, int rank, int world, con
                   int64_t halo_avail, int64_t *dev_plan);
 int pp_shard_finish_planned(pp_ctx *ctx, const pp_pipeline_params *p, const int64_t *dev_plan, int64_t *dev_record);
 int pp_shard_commit(pp_ctx *ctx, const int64_t rec[8]);
+/* pp_unpack_tables: the all-gathered packed tables (world rows of words_per_rank words -- an even number --, row r
+ *   = rank r's pp_pack_tables output) as the caller's tables in one pass, one contiguous array per column:
+ *   events {global start, length}, segments {global event id, start, end (int64), mean, std, min, max (float64)};
+ *   E / S = the sums over the all-gathered result records (device memory).  out_is_host = 1: the arrays are
+ *   page-locked host memory (pp_host_alloc) and are written by the kernel directly -- the call returns when the
+ *   rows are there; 0: device memory.  PP_ERR_CAPACITY if cap_events / cap_segments rows do not suffice.
+ *   cuda_stream != NULL: the kernel is only enqueued on that stream (the caller synchronises with it; the copy-out
+ *   of one step's tables then overlaps the upload of the next step's trace -- opposite PCIe directions). */
+typedef struct pp_unpacked_tables {
+    int64_t cap_events, cap_segments;
+    int64_t *ev_start, *ev_len;
+    int64_t *seg_event, *seg_start, *seg_end;
+    double *mean, *std, *min, *max;
+} pp_unpacked_tables;
+int pp_unpack_tables(pp_ctx *ctx, const int64_t *dev_gathered, int world, int64_t words_per_rank,
+                     const int64_t *dev_records, const pp_unpacked_tables *out, int out_is_host, void *cuda_stream);
 int pp_pack_tables(pp_ctx *ctx, const int64_t *dev_records, int rank, int64_t sample_offset, int64_t *dev_out,
                    int64_t cap_words);
 

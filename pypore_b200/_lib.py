@@ -51,6 +51,13 @@ class HostTables(_c.Structure):
     ]
 
 
+class UnpackedTables(_c.Structure):
+    """pp_unpacked_tables: one array per column of the gathered multi-GPU result."""
+    _fields_ = [("cap_events", _i64), ("cap_segments", _i64), ("ev_start", _c.c_void_p), ("ev_len", _c.c_void_p),
+                ("seg_event", _c.c_void_p), ("seg_start", _c.c_void_p), ("seg_end", _c.c_void_p),
+                ("mean", _c.c_void_p), ("std", _c.c_void_p), ("min", _c.c_void_p), ("max", _c.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/pypore_b200.h declares
 SIGNATURES = {
     "pp_version": (_c.c_int, []),
@@ -64,6 +71,8 @@ SIGNATURES = {
     "pp_stage_ms": (_c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(_c.c_float)]),
     "pp_trace_upload": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _i64]),
     "pp_trace_upload_f64": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64]),
+    "pp_trace_prefetch": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _i64]),
+    "pp_trace_swap": (_c.c_int, [_c.c_void_p]),
     "pp_trace_adopt": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _i64]),
     "pp_trace_append": (_c.c_int, [_c.c_void_p, _c.c_void_p, _i64, _c.c_int]),
     "pp_trace_truncate": (_c.c_int, [_c.c_void_p, _i64]),
@@ -102,6 +111,8 @@ SIGNATURES = {
     "pp_shard_finish_planned": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _c.c_void_p, _c.c_void_p]),
     "pp_trace_extend": (_c.c_int, [_c.c_void_p, _i64]),
     "pp_pack_tables": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _i64, _c.c_void_p, _i64]),
+    "pp_unpack_tables": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _i64, _c.c_void_p, _c.POINTER(UnpackedTables),
+                                    _c.c_int, _c.c_void_p]),
     "pp_pipeline_host": (_c.c_int, [_c.c_void_p, _f32p, _i64, _i64, _c.POINTER(PipelineParams), _i64p]),
     "pp_pipeline_host_tables": (_c.c_int, [_c.c_void_p, _f32p, _i64, _i64, _c.POINTER(PipelineParams),
                                            _c.POINTER(HostTables), _i64p]),
@@ -159,6 +170,9 @@ class Context(object):
             if getattr(self, "_arena", None):
                 self._L.pp_host_free(self._h, self._arena[0])
                 self._arena = None
+            for p, _cap in getattr(self, "_table_arenas", {}).values():
+                self._L.pp_host_free(self._h, p)
+            self._table_arenas = {}
             for p in getattr(self, "_pinned_keep", []):   # pinned_empty() arrays die with the context
                 self._L.pp_host_free(self._h, p)
             self._pinned_keep = []
@@ -252,6 +266,18 @@ class Context(object):
         assert x32.dtype == np.float32 and x32.flags.c_contiguous
         self._keep = [x32]
         self._ck(self._L.pp_trace_upload(self._h, x32.ctypes.data, x32.shape[0], int(extra_capacity)))
+
+    def prefetch_trace(self, x32, extra_capacity=0):
+        """Start the upload of the NEXT trace (pinned float32 array; the caller keeps it alive until swap_trace()
+        has been followed by a sync) while the resident one is being processed."""
+        assert x32.dtype == np.float32 and x32.flags.c_contiguous
+        self._keep_next = x32
+        self._ck(self._L.pp_trace_prefetch(self._h, x32.ctypes.data, x32.shape[0], int(extra_capacity)))
+
+    def swap_trace(self):
+        """The prefetched trace becomes the resident one (stream-level wait for its copy)."""
+        self._ck(self._L.pp_trace_swap(self._h))
+        self._keep = [getattr(self, "_keep_next", None)]
 
     def adopt_trace(self, dev_ptr, n, capacity=None):
         self._ck(self._L.pp_trace_adopt(self._h, _c.c_void_p(int(dev_ptr)), int(n), int(capacity or n)))
@@ -565,6 +591,42 @@ class Context(object):
     def pack_tables(self, dev_records_ptr, rank, sample_offset, dev_out_ptr, cap_words):
         self._ck(self._L.pp_pack_tables(self._h, _c.c_void_p(int(dev_records_ptr)), int(rank), int(sample_offset),
                                         _c.c_void_p(int(dev_out_ptr)), int(cap_words)))
+
+
+    def unpack_tables(self, dev_gathered_ptr, world, words_per_rank, dev_records_ptr, n_events, n_segments,
+                      stream=None, slot=0):
+        """The all-gathered packed tables as host tables, one array per column (views of one of the context's two
+        pinned table arenas, valid until that arena's next use): ev_start, ev_len, seg_event, seg_start, seg_end
+        [int64], mean, std, min, max [float64].  With `stream` (a cudaStream_t as an integer) the kernel is only
+        enqueued there and the caller synchronises before it reads."""
+        cols_e, cols_i, cols_f = ("ev_start", "ev_len"), ("seg_event", "seg_start", "seg_end"), ("mean", "std", "min", "max")
+        spec = ([(k, n_events, np.int64) for k in cols_e] + [(k, n_segments, np.int64) for k in cols_i] +
+                [(k, n_segments, np.float64) for k in cols_f])
+        total = sum(((n * 8 + 63) // 64) * 64 for _, n, _ in spec) + 64
+        arenas = self.__dict__.setdefault("_table_arenas", {})
+        arena = arenas.get(slot)
+        if arena is None or arena[1] < total:
+            if arena is not None:
+                self.sync()
+                self._L.pp_host_free(self._h, arena[0])
+            p = _c.c_void_p()
+            cap = int(total * 1.25)
+            self._ck(self._L.pp_host_alloc(self._h, cap, _c.byref(p)))
+            arenas[slot] = arena = (p.value, cap)
+            self._pinned_keep = getattr(self, "_pinned_keep", [])
+        v, off = {}, 0
+        for name, n, dt in spec:
+            buf = (_c.c_char * max(n * 8, 1)).from_address(arena[0] + off)
+            v[name] = np.frombuffer(buf, dtype=dt, count=n)
+            off += ((n * 8 + 63) // 64) * 64
+        t = UnpackedTables()
+        t.cap_events, t.cap_segments = int(n_events), int(n_segments)
+        for k in cols_e + cols_i + cols_f:
+            setattr(t, k, v[k].ctypes.data)
+        self._ck(self._L.pp_unpack_tables(self._h, _c.c_void_p(int(dev_gathered_ptr)), int(world),
+                                          int(words_per_rank), _c.c_void_p(int(dev_records_ptr)), _c.byref(t), 1,
+                                          _c.c_void_p(int(stream)) if stream else None))
+        return v
 
 
 _default = {}

@@ -44,6 +44,8 @@ struct pp_ctx {
 
     // trace: float32 (trace) or float64 (trace64) samples, one of the two
     DevBuf trace_buf;
+    DevBuf trace_next;          // pp_trace_prefetch: the NEXT float32 trace, on its way up while this one is processed
+    int64_t next_n = -1;
     const float *trace = nullptr;
     const double *trace64 = nullptr;
     int64_t n = 0, trace_cap = 0;
@@ -72,6 +74,7 @@ struct pp_ctx {
     // K2/K3
     DevBuf cc, bits, tasks, ready, block_count, block_off, inexact, Ttab, ev_tile_off, k2_bits, k2_tiles;
     DevBuf hk;  // K3_CFG_HALFKEY development variant: half-keys, 2 x 8 B per flat sample
+    DevBuf unpack_flag;
     int opt_spine = 1;
     int T_len = 0;
     int opt_screen = 1;
@@ -717,13 +720,13 @@ void pp_destroy(pp_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->trace_buf, &ctx->k1_rec, &ctx->k1_staged, &ctx->k1_blk, &ctx->run_start, &ctx->run_minkey,
+    DevBuf *bufs[] = {&ctx->trace_buf, &ctx->trace_next, &ctx->k1_rec, &ctx->k1_staged, &ctx->k1_blk, &ctx->run_start, &ctx->run_minkey,
                       &ctx->run_maxkey, &ctx->run_len, &ctx->run_min, &ctx->run_max, &ctx->run_below,
                       &ctx->ev_start, &ctx->ev_len, &ctx->ev_off, &ctx->flat64, &ctx->cc, &ctx->bits,
                       &ctx->tasks, &ctx->ready, &ctx->block_count, &ctx->block_off, &ctx->inexact, &ctx->Ttab, &ctx->ev_tile_off, &ctx->k2_bits, &ctx->k2_tiles,
                       &ctx->seg_flat, &ctx->seg_event, &ctx->seg_start, &ctx->seg_end, &ctx->seg_mean,
                       &ctx->seg_std, &ctx->seg_min, &ctx->seg_max, &ctx->evs_mean, &ctx->evs_std,
-                      &ctx->evs_min, &ctx->evs_max, &ctx->filt_tmp, &ctx->filt_carry, &ctx->filt_coef, &ctx->hk};
+                      &ctx->evs_min, &ctx->evs_max, &ctx->filt_tmp, &ctx->filt_carry, &ctx->filt_coef, &ctx->hk, &ctx->unpack_flag};
     for (DevBuf *b : bufs) release(*b);
     if (ctx->ctr) cudaFree(ctx->ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
@@ -816,6 +819,52 @@ int pp_trace_upload(pp_ctx *ctx, const float *host, int64_t n, int64_t extra_cap
 int pp_trace_upload_f64(pp_ctx *ctx, const double *host, int64_t n)
 {
     return trace_upload_impl(ctx, host, n, 0, sizeof(double));
+}
+
+// ---- double-buffered upload (back-to-back traces: the copy of trace i+1 runs under the kernels of trace i) ----
+static int ensure_copy_stream(pp_ctx *ctx)
+{
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->compute_ev, cudaEventDisableTiming));
+    }
+    return PP_OK;
+}
+
+int pp_trace_prefetch(pp_ctx *ctx, const float *host, int64_t n, int64_t extra_capacity)
+{
+    if (!ctx || !host || n <= 0 || extra_capacity < 0) return fail(ctx, PP_ERR_ARG, "bad trace");
+    CKR(set_device(ctx));
+    CKR(ensure_copy_stream(ctx));
+    CKR(ensure(ctx, ctx->trace_next, sizeof(float) * (size_t)(n + extra_capacity)));
+    // the buffer was the resident trace two traces ago: whatever still reads it was enqueued before this point
+    CK(cudaEventRecord(ctx->compute_ev, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_ev, 0));
+    CK(cudaMemcpyAsync(ctx->trace_next.p, host, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->copy_ev, ctx->copy_stream));
+    ctx->next_n = n;
+    return PP_OK;
+}
+
+int pp_trace_swap(pp_ctx *ctx)
+{
+    if (!ctx) return PP_ERR_ARG;
+    if (ctx->next_n <= 0) return fail(ctx, PP_ERR_STATE, "no prefetched trace");
+    CKR(set_device(ctx));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev, 0));   // stream-level: the host goes on
+    DevBuf t = ctx->trace_buf;
+    ctx->trace_buf = ctx->trace_next;
+    ctx->trace_next = t;
+    ctx->trace = (const float *)ctx->trace_buf.p;
+    ctx->trace64 = nullptr;
+    ctx->n = ctx->next_n;
+    ctx->next_n = -1;
+    ctx->trace_cap = (int64_t)(ctx->trace_buf.cap / sizeof(float));
+    ctx->adopted = false;
+    ctx->n_runs = ctx->n_events = ctx->n_event_samples = ctx->n_segments = -1;
+    ctx->prefix_valid = false;
+    return PP_OK;
 }
 
 int pp_trace_adopt(pp_ctx *ctx, const float *dev, int64_t n, int64_t capacity)
@@ -1427,6 +1476,43 @@ int pp_pack_tables(pp_ctx *ctx, const int64_t *dev_records, int rank, int64_t sa
     return PP_OK;
 }
 
+int pp_unpack_tables(pp_ctx *ctx, const int64_t *dev_gathered, int world, int64_t words_per_rank,
+                     const int64_t *dev_records, const pp_unpacked_tables *out, int out_is_host, void *cuda_stream)
+{
+    if (!ctx || !dev_gathered || !dev_records || !out || world < 1 || world > PP_MAX_WORLD || words_per_rank < 0 ||
+        (words_per_rank & 1) || !out->ev_start || !out->ev_len || !out->seg_event || !out->seg_start ||
+        !out->seg_end || !out->mean || !out->std || !out->min || !out->max)
+        return fail(ctx, PP_ERR_ARG, "bad unpack arguments");
+    CKR(set_device(ctx));
+    PPUnpacked O;
+    O.cap_events = out->cap_events;
+    O.cap_segments = out->cap_segments;
+    void *src[9] = {out->ev_start, out->ev_len, out->seg_event, out->seg_start, out->seg_end,
+                    out->mean, out->std, out->min, out->max};
+    void *dst[9];
+    for (int i = 0; i < 9; ++i) {
+        dst[i] = src[i];
+        // device-visible aliases of page-locked buffers (pp_host_alloc); fails for pageable memory
+        if (out_is_host) CK(cudaHostGetDevicePointer(&dst[i], src[i], 0));
+    }
+    O.ev_start = (long long *)dst[0]; O.ev_len = (long long *)dst[1];
+    O.seg_event = (long long *)dst[2]; O.seg_start = (long long *)dst[3]; O.seg_end = (long long *)dst[4];
+    O.mean = (double *)dst[5]; O.sd = (double *)dst[6]; O.mn = (double *)dst[7]; O.mx = (double *)dst[8];
+    CKR(ensure(ctx, ctx->unpack_flag, 256));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CK(cudaMemsetAsync(ctx->unpack_flag.p, 0, sizeof(unsigned), st));
+    k_unpack_tables<<<ctx->sm_count * 4, 256, 0, st>>>(
+        (const long long *)dev_gathered, world, words_per_rank, (const long long *)dev_records, O,
+        (unsigned *)ctx->unpack_flag.p);
+    LAUNCHED(ctx);
+    if (cuda_stream) return PP_OK;   // the caller synchronises with its stream (and sized the tables from the counts)
+    unsigned flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->unpack_flag.p, sizeof flag, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));   // the rows are in the caller's memory when this returns
+    if (flag & 1u) return fail(ctx, PP_ERR_CAPACITY, "unpack tables too small");
+    return PP_OK;
+}
+
 // Same pipeline fed from host memory: the trace is copied in chunks on a second stream and every
 // stage up to the split search runs on the events completed so far while the next chunk is in flight.
 // With host tables (pp_pipeline_host_tables) compaction, statistics and the copy-out of the finished rows also
@@ -1474,11 +1560,7 @@ static int pipeline_host_impl(pp_ctx *ctx, const float *host, int64_t n, int64_t
         }
         return PP_OK;
     }
-    if (!ctx->copy_stream) {
-        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ctx->compute_ev, cudaEventDisableTiming));
-    }
+    CKR(ensure_copy_stream(ctx));
     CKR(ensure(ctx, ctx->trace_buf, sizeof(float) * (size_t)n));
     ctx->trace = (const float *)ctx->trace_buf.p;
     ctx->trace64 = nullptr;

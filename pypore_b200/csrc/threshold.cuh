@@ -800,3 +800,78 @@ k_pack_tables(const long long *__restrict__ rec_all, int rank, int64_t cap_words
         seg[2 * k + 1] = make_longlong2(__double_as_longlong(sd[k]), (long long)(lo | hi));
     }
 }
+
+// Multi-GPU: the all-gathered packed tables (row r of `g`, `m` words long, = rank r's k_pack_tables output) unpacked
+// into the caller's tables in ONE pass, one contiguous array per column -- events {global start, length}, segments
+// {global event id, start, end, mean, std, min, max} -- written straight into page-locked host memory
+// (device-visible aliases) or into device memory; consecutive threads write consecutive 8-byte elements, so every
+// store is a full line on its way over PCIe (rows of 24 + 32 bytes written per thread ran at 7 GB/s).  `end` is
+// the next row's start inside the same event, else the event's length.  Counts come from the all-gathered result
+// records on the device (rec_all[8 r + 1] events, rec_all[8 r + 3] segments of rank r).  The first version did
+// this with a dozen eager torch operations over 2.4 M rows followed by pageable copies: 60 of the 77 ms of an
+// 8-GPU end-to-end step.
+constexpr int PP_MAX_WORLD = 64;
+
+struct PPUnpacked {
+    int64_t cap_events, cap_segments;
+    long long *ev_start, *ev_len;
+    long long *seg_event, *seg_start, *seg_end;
+    double *mean, *sd, *mn, *mx;
+};
+
+__global__ void __launch_bounds__(256)
+k_unpack_tables(const long long *__restrict__ g, int world, int64_t m, const long long *__restrict__ rec_all,
+                PPUnpacked O, unsigned *__restrict__ status)
+{
+    __shared__ long long e_base[PP_MAX_WORLD + 1], s_base[PP_MAX_WORLD + 1];
+    if (threadIdx.x == 0) {
+        long long e = 0, sg = 0;
+        for (int r = 0; r < world; ++r) {
+            e_base[r] = e; s_base[r] = sg;
+            e += rec_all[8 * r + 1];
+            sg += rec_all[8 * r + 3];
+        }
+        e_base[world] = e; s_base[world] = sg;
+    }
+    __syncthreads();
+    const long long E = e_base[world], S = s_base[world];
+    if (E > O.cap_events || S > O.cap_segments) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, 1u);
+        return;
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t k = t0; k < E; k += stride) {
+        int r = 0;
+        while (k >= e_base[r + 1]) ++r;
+        const long long *row = g + (int64_t)r * m + 2 * (k - e_base[r]);
+        O.ev_start[k] = row[0];
+        O.ev_len[k] = row[1];
+    }
+    for (int64_t k = t0; k < S; k += stride) {
+        int r = 0;
+        while (k >= s_base[r + 1]) ++r;
+        const long long n_ev = e_base[r + 1] - e_base[r], n_sg = s_base[r + 1] - s_base[r];
+        const long long j = k - s_base[r];
+        const long long *gr = g + (int64_t)r * m;
+        const longlong2 *seg = reinterpret_cast<const longlong2 *>(gr + 2 * n_ev);
+        const longlong2 a = seg[2 * j], b = seg[2 * j + 1];
+        const long long event = a.x & 0xffffffffLL, start = (long long)((unsigned long long)a.x >> 32);
+        long long end;
+        bool same = false;
+        long long nxt = 0;
+        if (j + 1 < n_sg) {
+            nxt = seg[2 * (j + 1)].x;
+            same = (nxt & 0xffffffffLL) == event;
+        }
+        if (same) end = (long long)((unsigned long long)nxt >> 32);
+        else end = gr[2 * (event - e_base[r]) + 1];   // the event's length (events of rank r carry ids e_base[r] ..)
+        O.seg_event[k] = event;
+        O.seg_start[k] = start;
+        O.seg_end[k] = end;
+        O.mean[k] = __longlong_as_double(a.y);
+        O.sd[k] = __longlong_as_double(b.x);
+        O.mn[k] = (double)__uint_as_float((unsigned)((unsigned long long)b.y & 0xffffffffull));
+        O.mx[k] = (double)__uint_as_float((unsigned)((unsigned long long)b.y >> 32));
+    }
+}

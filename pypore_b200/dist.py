@@ -260,27 +260,53 @@ class ShardedPipeline(object):
         self.n_owned = 0
         self.offsets = None
         self.gathered = self.counts = self._tables = None
-        self.rec = self.res = self.pack = self.plan = self.infos_dev = None
+        self.rec = self.res = self.pack = self.plan = self.infos_dev = self.allr_dev = None
         self.pad_words = 0
         self.lens = None
         self._halo = 0       # speculative halo samples resident after the chunk
         self._table_work = None   # outstanding asynchronous table all-gather
+        self._side = None         # side stream of download_async
+        self._n_agreed = self._n_next = -1
         # the tiny control collectives (chunk lengths, boundary records, result records) get their own communicator:
         # they sit on every step's critical path and must not queue behind the previous step's table all-gather
         self.ctl_group = dist.new_group() if world > 1 and dist.is_initialized() else group
         self.fallbacks = 0   # steps that had to be repeated with the host-made plan
 
-    def load(self, host_chunk):
-        """Upload this rank's chunk; ranks exchange their chunk lengths once (sample offsets of the global
-        trace and the size of the speculative halo each neighbour sends)."""
+    def _agree_lengths(self, n_local):
+        """The chunk lengths are exchanged when they change, not once per load: every rank takes the same branch
+        (`same` is agreed on by a tiny all-reduce)."""
         import torch
-        self.n_local = int(host_chunk.shape[0])
         with torch.cuda.stream(self.stream):
-            mine = torch.tensor([self.n_local], dtype=torch.int64, device=self.device)
-            lens = torch.empty(self.world, dtype=torch.int64, device=self.device)
-            self.dist.all_gather_into_tensor(lens, mine, group=self.ctl_group)
-            self.lens = lens.cpu().numpy()
-        self.ctx.upload_trace_async(host_chunk, extra_capacity=self.HALO_CAPACITY)   # after the read-back: not waited on
+            same = torch.tensor([1 if (self.lens is not None and n_local == self._n_agreed) else 0],
+                                dtype=torch.int64, device=self.device)
+            self.dist.all_reduce(same, op=self.dist.ReduceOp.MIN, group=self.ctl_group)
+            if int(same.item()) == 0:
+                mine = torch.tensor([n_local], dtype=torch.int64, device=self.device)
+                lens = torch.empty(self.world, dtype=torch.int64, device=self.device)
+                self.dist.all_gather_into_tensor(lens, mine, group=self.ctl_group)
+                self.lens = lens.cpu().numpy()
+        self._n_agreed = n_local
+
+    def load(self, host_chunk):
+        """Upload this rank's chunk; ranks exchange their chunk lengths when they change (sample offsets of the
+        global trace and the size of the speculative halo each neighbour sends)."""
+        n_local = int(host_chunk.shape[0])
+        self._agree_lengths(n_local)
+        self.ctx.upload_trace_async(host_chunk, extra_capacity=self.HALO_CAPACITY)
+        self.n_local = n_local
+        self._exchange_speculative_halo()
+
+    def prefetch(self, host_chunk):
+        """Back-to-back traces: start the upload of the NEXT chunk (same length on every call in a row) on the
+        context's copy stream; it runs under the step on the resident chunk.  swap() makes it the resident one."""
+        n_local = int(host_chunk.shape[0])
+        self._agree_lengths(n_local)
+        self.ctx.prefetch_trace(host_chunk, extra_capacity=self.HALO_CAPACITY)
+        self._n_next = n_local
+
+    def swap(self):
+        self.ctx.swap_trace()
+        self.n_local = self._n_next
         self._exchange_speculative_halo()
 
     def _exchange_speculative_halo(self):
@@ -364,6 +390,7 @@ class ShardedPipeline(object):
             ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
                             self.pad_words)
             g, work = gather_packed_raw(self.pack, self.pad_words, dist, self.group, async_op=True)
+        self.allr_dev = allr_dev
         allr = allr_dev.cpu().numpy().reshape(self.world, 8)             # host sync (nothing waits on it)
         if redo_mask and (allr[:, 4] & redo_mask).any():
             if work is not None:
@@ -376,13 +403,13 @@ class ShardedPipeline(object):
         if g is None or need_words > self.pad_words:
             if work is not None:
                 work.wait()
-            self.pad_words = int(need_words * 1.125) + 64
+            self.pad_words = (int(need_words * 1.125) + 65) & ~1   # even: rows of the gathered buffer stay 16-byte aligned
             self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
             ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
                             self.pad_words)
             g, work = gather_packed_raw(self.pack, self.pad_words, dist, self.group, async_op=True)
         else:
-            self.pad_words = max(int(need_words * 1.125) + 64, 1)
+            self.pad_words = max((int(need_words * 1.125) + 65) & ~1, 2)
         self._table_work = work
         self.gathered, self.counts, self._tables = g, counts, None
         ne, n_seg = counts[self.rank]
@@ -429,6 +456,11 @@ class ShardedPipeline(object):
         """The context's stream waits for everything the last step left in flight (the table all-gather)."""
         self._wait_tables()
 
+    def join(self):
+        """The context's stream waits for the side stream of download_async (stream-level, the host goes on)."""
+        if self._side is not None:
+            self.stream.wait_stream(self._side)
+
     def _wait_tables(self):
         """Make the context's stream wait for the outstanding table all-gather (stream-level, the host goes on)."""
         if self._table_work is not None:
@@ -448,7 +480,68 @@ class ShardedPipeline(object):
         return self._tables
 
     def download(self):
-        """Device-to-host read of the gathered tables (what a caller of the public API receives)."""
+        """The gathered tables in host memory (what a caller of the public API receives), one array per column:
+        ev_start, ev_len (global samples), seg_event (global event id), seg_start, seg_end, mean, std, min, max.
+        ONE kernel unpacks the all-gathered rows straight into page-locked host tables (pp_unpack_tables); the
+        arrays are views of the context's pinned arena, valid until its next pinned use.  Without a library context
+        (the CPU tests) the tensor path answers."""
         import torch
-        with torch.cuda.stream(self.stream):
-            return {k: v.cpu().numpy() for k, v in self.tables.items()}
+        if self.gathered is None:
+            return None
+        if not hasattr(self.ctx, "unpack_tables") or self.gathered.device.type != "cuda":
+            with torch.cuda.stream(self.stream):
+                return columns({k: v.cpu().numpy() for k, v in self.tables.items()})
+        self._wait_tables()
+        n_ev = sum(c[0] for c in self.counts)
+        n_seg = sum(c[1] for c in self.counts)
+        return self.ctx.unpack_tables(self.gathered.data_ptr(), self.world, self.gathered.shape[1],
+                                      self.allr_dev.data_ptr(), n_ev, n_seg)
+
+    def download_async(self):
+        """download() that only ENQUEUES the copy-out, on a side stream: returns a handle whose wait() gives the
+        column arrays.  The next step's load() -- the other PCIe direction -- overlaps it.  Two pinned table arenas
+        alternate, so the arrays of one handle stay valid until the handle after the next is created."""
+        import torch
+        if self.gathered is None:
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._slot = 0
+        side = self._side
+        with torch.cuda.stream(side):
+            if self._table_work is not None:
+                self._table_work.wait()        # the side stream waits for the table all-gather ...
+        side.wait_stream(self.stream)          # ... and for everything the step enqueued on the context's stream
+        n_ev = sum(c[0] for c in self.counts)
+        n_seg = sum(c[1] for c in self.counts)
+        self._slot ^= 1
+        cols = self.ctx.unpack_tables(self.gathered.data_ptr(), self.world, self.gathered.shape[1],
+                                      self.allr_dev.data_ptr(), n_ev, n_seg, stream=side.cuda_stream, slot=self._slot)
+        done = torch.cuda.Event()
+        done.record(side)
+        keep = (self.gathered, self.allr_dev)   # the kernel reads them: they must outlive it
+
+        class Handle(object):
+            def wait(h):
+                done.synchronize()
+                h.keep = None
+                return cols
+        h = Handle()
+        h.keep = keep
+        return h
+
+
+def columns(t):
+    """dict(events [E,2], seg_int [S,3], seg_flt [S,4]) -> one array per column (the layout of download())."""
+    out = dict(ev_start=t["events"][:, 0], ev_len=t["events"][:, 1], seg_event=t["seg_int"][:, 0],
+               seg_start=t["seg_int"][:, 1], seg_end=t["seg_int"][:, 2])
+    for j, k in enumerate(("mean", "std", "min", "max")):
+        out[k] = t["seg_flt"][:, j]
+    return out
+
+
+def rows(c):
+    """The inverse of `columns`: stacked row tables from the column arrays of download()."""
+    return dict(events=np.stack([c["ev_start"], c["ev_len"]], axis=1),
+                seg_int=np.stack([c["seg_event"], c["seg_start"], c["seg_end"]], axis=1),
+                seg_flt=np.stack([c["mean"], c["std"], c["min"], c["max"]], axis=1))

@@ -30,14 +30,17 @@ def main():
         mw, MW, W, gain = statsplit_min_gain(**kw)
         for _ in range(2):  # twice: buffers, counters and the asynchronous table gather are reused across steps
             shard.step(110.0, rules, mw, MW, W, gain)
-        tabs = shard.download()
+        tabs = ppdist.rows(shard.download())   # (stacked copies: the column views live in a pinned arena that is reused)
         assert shard.fallbacks == 0
+        # the one-kernel unpack into page-locked host tables against the tensor path on the gathered buffer
+        eager = {k: v.cpu().numpy() for k, v in shard.tables.items()}
+        assert all(np.array_equal(tabs[k], eager[k], equal_nan=True) for k in tabs), "pp_unpack_tables differs"
         # the host-planned step (the fallback of the device-planned one) must give the same tables
         shard.step(110.0, rules, mw, MW, W, gain, host_planned=True)
-        alt = shard.download()
+        alt = ppdist.rows(shard.download())
         assert all(np.array_equal(tabs[k], alt[k], equal_nan=True) for k in tabs), "host-planned step differs"
         shard.step(110.0, rules, mw, MW, W, gain)   # and back: the speculative halo is still in place
-        alt = shard.download()
+        alt = ppdist.rows(shard.download())
         assert all(np.array_equal(tabs[k], alt[k], equal_nan=True) for k in tabs), "device-planned step after it differs"
         glob = ppdist.synthetic_global(world, epr, seed0=70).astype(np.float64)
         pyrules = [lambda e: e.duration > 1000, lambda e: e.min > -0.5, lambda e: e.max < 110]
