@@ -465,11 +465,25 @@ def run_trace(args):
     n_local = len(x)
     xp = torch.from_numpy(x).pin_memory().numpy()
 
+    inflight = {"ticket": None, "last": None}
+
     def step_resident():
         if shard is None:
             return ctx.pipeline(THRESHOLD, min_width=mw, max_width=MW, window_width=W, min_gain=gain,
                                 with_stats=True, **DEV_RULES)
-        return shard.step(THRESHOLD, DEV_RULES, mw, MW, W, gain)
+        # step i+1 is enqueued before the result records of step i are read: the device never waits for the host;
+        # drain_resident() reads the last step's records inside the timed region
+        t = shard.step_async(THRESHOLD, DEV_RULES, mw, MW, W, gain)
+        if inflight["ticket"] is not None:
+            inflight["last"] = shard.finish(inflight["ticket"])
+        inflight["ticket"] = t
+        return inflight["last"]
+
+    def drain_resident():
+        if shard is not None and inflight["ticket"] is not None:
+            inflight["last"] = shard.finish(inflight["ticket"])
+            inflight["ticket"] = None
+        return inflight["last"]
 
     last_download = {}
     # Multi-GPU end to end: the upload of step i+1 (the context's copy stream, into a second device buffer) runs
@@ -513,6 +527,7 @@ def run_trace(args):
 
     def closing():
         if shard is not None:
+            drain_resident()   # (resident loop) the last step's records are read inside the timed region
             shard.wait()   # the last step's asynchronous table all-gather belongs to the timed region, and so does
             shard.join()   # the copy-out of its tables on the side stream: the closing event waits for both
 
@@ -522,10 +537,12 @@ def run_trace(args):
         shard.load(xp)
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    drain_resident()
     sampler = ClockSampler(local)
     launches0 = ctx.launch_count
     sampler.start()
     ms, res = timer.run(step_resident, args.steps, closing=closing)
+    res = drain_resident() if shard is not None else res
     launches = ctx.launch_count - launches0
     stage = ctx.stage_ms() if shard is None else dict(shard.stage_ms)
     counters = ctx.split_counters()
@@ -535,6 +552,7 @@ def run_trace(args):
     k = 0
     while k < min(args.steps, 5) or (world == 1 and len(sampler.samples) < 8 and k < 200):  # ranks stay in step
         step_resident()
+        drain_resident()
         split_ms.append(ctx.stage_ms()["split"] if shard is None else shard.stage_ms["split"])
         k += 1
     split_ms = float(np.mean(split_ms))

@@ -283,6 +283,18 @@ int pp_shard_plan(pp_ctx *ctx, const double *dev_infos, int rank, int world, con
                   int64_t halo_avail, int64_t *dev_plan);
 int pp_shard_finish_planned(pp_ctx *ctx, const pp_pipeline_params *p, const int64_t *dev_plan, int64_t *dev_record);
 int pp_shard_commit(pp_ctx *ctx, const int64_t rec[8]);
+/* pp_ctl_create / pp_ctl_open / pp_ctl_exchange: the control records of a sharded step (12-double boundary record,
+ *   8-word result record) without a collective.  pp_ctl_create allocates this rank's record buffer and returns its
+ *   CUDA IPC handle (64 bytes; and / or the device pointer, for contexts of ONE process); after the caller has
+ *   all-gathered the handles ONCE, pp_ctl_open maps every peer's buffer.  pp_ctl_exchange(src, n_words <= 16, dst)
+ *   then enqueues one tiny kernel on the context's stream: it stores this rank's record into every peer's buffer
+ *   over NVLink, raises a flag, waits for all ranks' flags in its own buffer and writes the world x n_words gathered
+ *   records to dst (device memory) -- what an all-gather of the records would have produced, without NCCL's launch
+ *   latency on the step's critical path.  Every rank must call it the same number of times (a sequence number
+ *   pairs the calls); a record that does not arrive within seconds raises flag 64 in the result record. */
+int pp_ctl_create(pp_ctx *ctx, int rank, int world, void *ipc_handle_out, void **local_ptr_out);
+int pp_ctl_open(pp_ctx *ctx, const void *ipc_handles, void *const *local_ptrs);
+int pp_ctl_exchange(pp_ctx *ctx, const void *dev_src, int n_words, void *dev_dst);
 /* pp_unpack_tables: the all-gathered packed tables (world rows of words_per_rank words -- an even number --, row r
  *   = rank r's pp_pack_tables output) as the caller's tables in one pass, one contiguous array per column:
  *   events {global start, length}, segments {global event id, start, end (int64), mean, std, min, max (float64)};

@@ -111,6 +111,9 @@ SIGNATURES = {
     "pp_shard_finish_planned": (_c.c_int, [_c.c_void_p, _c.POINTER(PipelineParams), _c.c_void_p, _c.c_void_p]),
     "pp_trace_extend": (_c.c_int, [_c.c_void_p, _i64]),
     "pp_pack_tables": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _i64, _c.c_void_p, _i64]),
+    "pp_ctl_create": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.POINTER(_c.c_void_p)]),
+    "pp_ctl_open": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p)]),
+    "pp_ctl_exchange": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "pp_unpack_tables": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _i64, _c.c_void_p, _c.POINTER(UnpackedTables),
                                     _c.c_int, _c.c_void_p]),
     "pp_pipeline_host": (_c.c_int, [_c.c_void_p, _f32p, _i64, _i64, _c.POINTER(PipelineParams), _i64p]),
@@ -592,6 +595,28 @@ class Context(object):
         self._ck(self._L.pp_pack_tables(self._h, _c.c_void_p(int(dev_records_ptr)), int(rank), int(sample_offset),
                                         _c.c_void_p(int(dev_out_ptr)), int(cap_words)))
 
+
+    # -- control records over peer memory (pp_ctl_*) -----------------------------------------------------------
+    def ctl_create(self, rank, world):
+        """Allocate this rank's record buffer; returns (64-byte CUDA IPC handle, device pointer)."""
+        h = (_c.c_char * 64)()
+        p = _c.c_void_p()
+        self._ck(self._L.pp_ctl_create(self._h, int(rank), int(world), _c.cast(h, _c.c_void_p), _c.byref(p)))
+        return bytes(h), int(p.value)
+
+    def ctl_open(self, handles=None, local_ptrs=None):
+        """Map every rank's record buffer: `handles` = the world x 64 bytes of IPC handles (other processes), or
+        `local_ptrs` = the device pointers themselves (contexts of this process)."""
+        if local_ptrs is not None:
+            arr = (_c.c_void_p * len(local_ptrs))(*[_c.c_void_p(int(p)) for p in local_ptrs])
+            self._ck(self._L.pp_ctl_open(self._h, None, arr))
+        else:
+            buf = _c.create_string_buffer(bytes(handles), len(handles))
+            self._ck(self._L.pp_ctl_open(self._h, _c.cast(buf, _c.c_void_p), None))
+
+    def ctl_exchange(self, dev_src_ptr, n_words, dev_dst_ptr):
+        self._ck(self._L.pp_ctl_exchange(self._h, _c.c_void_p(int(dev_src_ptr)), int(n_words),
+                                         _c.c_void_p(int(dev_dst_ptr))))
 
     def unpack_tables(self, dev_gathered_ptr, world, words_per_rank, dev_records_ptr, n_events, n_segments,
                       stream=None, slot=0):

@@ -75,6 +75,12 @@ struct pp_ctx {
     DevBuf cc, bits, tasks, ready, block_count, block_off, inexact, Ttab, ev_tile_off, k2_bits, k2_tiles;
     DevBuf hk;  // K3_CFG_HALFKEY development variant: half-keys, 2 x 8 B per flat sample
     DevBuf unpack_flag;
+    // multi-GPU control exchange over peer memory (pp_ctl_*)
+    DevBuf ctl_buf, ctl_peers_dev;
+    void *ctl_peers[64] = {nullptr};
+    bool ctl_ipc[64] = {false};
+    int ctl_rank = -1, ctl_world = 0;
+    unsigned long long ctl_seq = 0;
     int opt_spine = 1;
     int T_len = 0;
     int opt_screen = 1;
@@ -720,13 +726,15 @@ void pp_destroy(pp_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int q = 0; q < 64; ++q)
+        if (ctx->ctl_ipc[q] && ctx->ctl_peers[q]) cudaIpcCloseMemHandle(ctx->ctl_peers[q]);
     DevBuf *bufs[] = {&ctx->trace_buf, &ctx->trace_next, &ctx->k1_rec, &ctx->k1_staged, &ctx->k1_blk, &ctx->run_start, &ctx->run_minkey,
                       &ctx->run_maxkey, &ctx->run_len, &ctx->run_min, &ctx->run_max, &ctx->run_below,
                       &ctx->ev_start, &ctx->ev_len, &ctx->ev_off, &ctx->flat64, &ctx->cc, &ctx->bits,
                       &ctx->tasks, &ctx->ready, &ctx->block_count, &ctx->block_off, &ctx->inexact, &ctx->Ttab, &ctx->ev_tile_off, &ctx->k2_bits, &ctx->k2_tiles,
                       &ctx->seg_flat, &ctx->seg_event, &ctx->seg_start, &ctx->seg_end, &ctx->seg_mean,
                       &ctx->seg_std, &ctx->seg_min, &ctx->seg_max, &ctx->evs_mean, &ctx->evs_std,
-                      &ctx->evs_min, &ctx->evs_max, &ctx->filt_tmp, &ctx->filt_carry, &ctx->filt_coef, &ctx->hk, &ctx->unpack_flag};
+                      &ctx->evs_min, &ctx->evs_max, &ctx->filt_tmp, &ctx->filt_carry, &ctx->filt_coef, &ctx->hk, &ctx->unpack_flag, &ctx->ctl_buf, &ctx->ctl_peers_dev};
     for (DevBuf *b : bufs) release(*b);
     if (ctx->ctr) cudaFree(ctx->ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
@@ -1456,6 +1464,7 @@ int pp_shard_commit(pp_ctx *ctx, const int64_t rec[8])
     ctx->split_counters[1] = rec[6];
     ctx->split_counters[4] = rec[7];
     const unsigned o = (unsigned)rec[4];
+    if (o & PP_OVF_CTL) return fail(ctx, PP_ERR_STATE, "a peer's control record did not arrive (pp_ctl_exchange timed out)");
     if (rec[0] > ctx->cap_runs) return fail(ctx, PP_ERR_CAPACITY, "run table overflow");
     if (o & PP_OVF_QUEUE) return fail(ctx, PP_ERR_CAPACITY, "split work queue overflow");
     if (o & PP_OVF_SEGS) return fail(ctx, PP_ERR_CAPACITY, "segment table overflow");
@@ -1472,6 +1481,62 @@ int pp_pack_tables(pp_ctx *ctx, const int64_t *dev_records, int rank, int64_t sa
         (const int64_t *)ctx->ev_len.p, (const int *)ctx->seg_event.p, (const int64_t *)ctx->seg_start.p,
         (const int64_t *)ctx->seg_end.p, (const double *)ctx->seg_mean.p, (const double *)ctx->seg_std.p,
         (const double *)ctx->seg_min.p, (const double *)ctx->seg_max.p, (long long *)dev_out);
+    LAUNCHED(ctx);
+    return PP_OK;
+}
+
+// ---- control exchange over peer memory -------------------------------------------------------------------------
+int pp_ctl_create(pp_ctx *ctx, int rank, int world, void *ipc_handle_out, void **local_ptr_out)
+{
+    if (!ctx || rank < 0 || world < 1 || world > PP_MAX_WORLD || rank >= world)
+        return fail(ctx, PP_ERR_ARG, "bad control-exchange arguments");
+    CKR(set_device(ctx));
+    const size_t bytes = sizeof(unsigned long long) * 2 * (size_t)world * PP_CTL_SLOT;
+    CKR(ensure(ctx, ctx->ctl_buf, bytes));
+    CK(cudaMemsetAsync(ctx->ctl_buf.p, 0, ctx->ctl_buf.cap, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->ctl_rank = rank;
+    ctx->ctl_world = world;
+    ctx->ctl_seq = 0;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ctx->ctl_buf.p));
+        memcpy(ipc_handle_out, &h, sizeof h);
+    }
+    if (local_ptr_out) *local_ptr_out = ctx->ctl_buf.p;
+    return PP_OK;
+}
+
+int pp_ctl_open(pp_ctx *ctx, const void *ipc_handles, void *const *local_ptrs)
+{
+    if (!ctx || ctx->ctl_world < 1 || (!ipc_handles && !local_ptrs))
+        return fail(ctx, PP_ERR_ARG, "pp_ctl_create first; handles or pointers of every rank");
+    CKR(set_device(ctx));
+    for (int q = 0; q < ctx->ctl_world; ++q) {
+        if (q == ctx->ctl_rank) { ctx->ctl_peers[q] = ctx->ctl_buf.p; continue; }
+        if (local_ptrs) { ctx->ctl_peers[q] = local_ptrs[q]; continue; }   // same process: the pointer itself
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)ipc_handles + (size_t)q * sizeof h, sizeof h);
+        CK(cudaIpcOpenMemHandle(&ctx->ctl_peers[q], h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ctl_ipc[q] = true;
+    }
+    CKR(ensure(ctx, ctx->ctl_peers_dev, sizeof(void *) * PP_MAX_WORLD));
+    CK(cudaMemcpyAsync(ctx->ctl_peers_dev.p, ctx->ctl_peers, sizeof(void *) * (size_t)ctx->ctl_world,
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PP_OK;
+}
+
+int pp_ctl_exchange(pp_ctx *ctx, const void *dev_src, int n_words, void *dev_dst)
+{
+    if (!ctx || !dev_src || !dev_dst || n_words < 1 || n_words > PP_CTL_PAYLOAD)
+        return fail(ctx, PP_ERR_ARG, "bad control record");
+    if (!ctx->ctl_peers_dev.p) return fail(ctx, PP_ERR_STATE, "pp_ctl_open has not run");
+    CKR(set_device(ctx));
+    const unsigned long long seq = ++ctx->ctl_seq;
+    k_ctl_exchange<<<1, 64, 0, ctx->stream>>>((unsigned long long *const *)ctx->ctl_peers_dev.p, ctx->ctl_rank,
+                                              ctx->ctl_world, seq, (const unsigned long long *)dev_src, n_words,
+                                              (unsigned long long *)dev_dst, ctx->ctr);
     LAUNCHED(ctx);
     return PP_OK;
 }

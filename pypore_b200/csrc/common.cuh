@@ -45,7 +45,8 @@ struct PPCounters {
 
 enum { PP_OVF_RUNS = 1, PP_OVF_QUEUE = 2, PP_OVF_SEGS = 4, PP_OVF_FILTER_SHORT = 8,
        PP_OVF_HALO = 16 /* multi-GPU: the speculative halo did not cover a straddling event */,
-       PP_OVF_EXPORT = 32 /* host tables of pp_pipeline_host_tables too small */ };
+       PP_OVF_EXPORT = 32 /* host tables of pp_pipeline_host_tables too small */,
+       PP_OVF_CTL = 64 /* multi-GPU: a peer's record did not arrive (pp_ctl_exchange timed out) */ };
 
 // Where an event's samples live.
 //   kind 0: float32 trace, sample j of event e = trace[ev_start[e] + j]

@@ -247,6 +247,7 @@ class ShardedPipeline(object):
 
     HALO_CAPACITY = 1 << 20
     HALO_SPECULATIVE = 1 << 16   # samples every rank ships to its left neighbour up front (256 KB over NVLink)
+    RECORD_RING = 4              # steps that may be in flight between step_async() and finish()
 
     def __init__(self, ctx, rank, world, group=None):
         import torch
@@ -266,11 +267,50 @@ class ShardedPipeline(object):
         self._halo = 0       # speculative halo samples resident after the chunk
         self._table_work = None   # outstanding asynchronous table all-gather
         self._side = None         # side stream of download_async
+        self._rec_ring, self._rec_next = None, 0   # page-locked slots for the result records of steps in flight
         self._n_agreed = self._n_next = -1
         # the tiny control collectives (chunk lengths, boundary records, result records) get their own communicator:
         # they sit on every step's critical path and must not queue behind the previous step's table all-gather
         self.ctl_group = dist.new_group() if world > 1 and dist.is_initialized() else group
         self.fallbacks = 0   # steps that had to be repeated with the host-made plan
+        self.peer_ctl = self._open_peer_ctl()
+
+    def _open_peer_ctl(self):
+        """Map every rank's control-record buffer (CUDA IPC over NVLink), once.  Returns True when EVERY rank
+        succeeded -- the step then exchanges its boundary / result records with pp_ctl_exchange (plain peer stores +
+        flags, one tiny launch) instead of NCCL all-gathers; otherwise all ranks keep the collectives."""
+        import os
+        import torch
+        dist = self.dist
+        if (self.world <= 1 or not dist.is_initialized() or not hasattr(self.ctx, "ctl_create")
+                or os.environ.get("PYPORE_B200_NO_PEER_CTL")):
+            return False
+        ok = 1
+        handle = b"\0" * 64
+        try:
+            handle, _ = self.ctx.ctl_create(self.rank, self.world)
+        except Exception:
+            ok = 0
+        with torch.cuda.stream(self.stream):
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+            allh = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, mine, group=self.ctl_group)
+            handles = bytes(allh.cpu().numpy().tobytes())
+            if ok:
+                try:
+                    self.ctx.ctl_open(handles=handles)
+                except Exception:
+                    ok = 0
+            agreed = torch.tensor([ok], dtype=torch.int64, device=self.device)
+            dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=self.ctl_group)
+            return bool(int(agreed.item()))
+
+    def _exchange_records(self, src, n_words, dst):
+        """Every rank's `src` record (n_words 8-byte words) in `dst` on every rank."""
+        if self.peer_ctl:
+            self.ctx.ctl_exchange(src.data_ptr(), n_words, dst.data_ptr())
+        else:
+            self.dist.all_gather_into_tensor(dst, src, group=self.ctl_group)
 
     def _agree_lengths(self, n_local):
         """The chunk lengths are exchanged when they change, not once per load: every rank takes the same branch
@@ -363,7 +403,7 @@ class ShardedPipeline(object):
             self.infos_dev = torch.empty(self.world * INFO_LEN, dtype=torch.float64, device=dev)
         ctx.truncate_trace(self.n_local)
         ctx.shard_scan(threshold, self.n_local, self.rec.data_ptr())
-        dist.all_gather_into_tensor(self.infos_dev, self.rec, group=self.ctl_group)
+        self._exchange_records(self.rec, INFO_LEN, self.infos_dev)
         halo = self._halo
         ctx.extend_trace(halo)
         ctx.shard_plan(self.infos_dev.data_ptr(), self.rank, self.world, threshold, rules, halo, self.plan.data_ptr())
@@ -371,11 +411,16 @@ class ShardedPipeline(object):
         return self._gather_results(redo_mask=_REDO_MASK)
 
     def _gather_results(self, redo_mask=0):
-        """All-gather of the result records and of the packed tables; the only host synchronisation."""
+        """Exchange of the result records and all-gather of the packed tables, then the only host synchronisation."""
+        return self._finish_results(self._enqueue_results(), redo_mask)
+
+    def _enqueue_results(self):
+        """Device side of the step's end: result records to every rank, tables packed and their all-gather started,
+        the records on their way to page-locked host memory.  No host synchronisation; returns a ticket."""
         import torch
         ctx, dist, dev = self.ctx, self.dist, self.device
         allr_dev = torch.empty(self.world * 8, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allr_dev, self.res, group=self.ctl_group)
+        self._exchange_records(self.res, 8, allr_dev)
         # Speculative sizing: pack and all-gather with the padding of the previous step (+12.5 %) before the host
         # knows this step's counts -- the pack kernel takes them from allr_dev on the device -- so the GPU is not
         # idle during the host round trip.  Every rank reads the same records and takes the same decision.
@@ -384,36 +429,95 @@ class ShardedPipeline(object):
         # kernel wait for it.
         self._wait_tables()                      # the previous step's gather still reads self.pack
         g = work = None
-        if self.pad_words:
-            if self.pack is None or self.pack.shape[0] < self.pad_words:
-                self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
-            ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
-                            self.pad_words)
-            g, work = gather_packed_raw(self.pack, self.pad_words, dist, self.group, async_op=True)
+        pad = self.pad_words
+        if pad:
+            if self.pack is None or self.pack.shape[0] < pad:
+                self.pack = torch.empty(pad, dtype=torch.int64, device=dev)
+            ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(), pad)
+            g, work = gather_packed_raw(self.pack, pad, dist, self.group, async_op=True)
+            self._table_work = work
+        # page-locked room for the records: a small ring owned by the context (at most RECORD_RING tickets may be
+        # outstanding), not torch's pinned allocator -- that one records events when a block is released, which
+        # at interpreter exit is after the CUDA context is gone
+        if self._rec_ring is None:
+            self._rec_ring = [torch.from_numpy(ctx.pinned_empty(self.world * 8, np.int64))
+                              for _ in range(self.RECORD_RING)]
+        allr_host = self._rec_ring[self._rec_next % self.RECORD_RING]
+        self._rec_next += 1
+        allr_host.copy_(allr_dev, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        return dict(allr_dev=allr_dev, allr_host=allr_host, done=done, g=g, work=work, pad=pad, n_local=self.n_local)
+
+    def _finish_results(self, t, redo_mask=0):
+        """Host side: read the records (waits for the step that produced them, not for anything enqueued after it),
+        commit the counts, redo the table all-gather if the speculative padding was too small."""
+        import torch
+        ctx, dist, dev = self.ctx, self.dist, self.device
+        t["done"].synchronize()
+        allr_dev, g, work = t["allr_dev"], t["g"], t["work"]
+        allr = t["allr_host"].numpy().reshape(self.world, 8).copy()
         self.allr_dev = allr_dev
-        allr = allr_dev.cpu().numpy().reshape(self.world, 8)             # host sync (nothing waits on it)
         if redo_mask and (allr[:, 4] & redo_mask).any():
             if work is not None:
                 work.wait()
             return None
         ctx.shard_commit(allr[self.rank])
-        self.n_owned = self.n_local
+        self.n_owned = t["n_local"]
         counts = [(int(r[1]), int(r[3])) for r in allr]
         need_words = max(max(2 * e + SEG_WORDS * s for e, s in counts), 1)
-        if g is None or need_words > self.pad_words:
-            if work is not None:
-                work.wait()
-            self.pad_words = (int(need_words * 1.125) + 65) & ~1   # even: rows of the gathered buffer stay 16-byte aligned
-            self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
-            ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
-                            self.pad_words)
-            g, work = gather_packed_raw(self.pack, self.pad_words, dist, self.group, async_op=True)
+        if g is None or need_words > t["pad"]:
+            with torch.cuda.stream(self.stream):
+                if work is not None:
+                    work.wait()
+                self._wait_tables()
+                self.pad_words = (int(need_words * 1.125) + 65) & ~1   # even: rows of the gathered buffer stay 16-byte aligned
+                self.pack = torch.empty(self.pad_words, dtype=torch.int64, device=dev)
+                ctx.pack_tables(allr_dev.data_ptr(), self.rank, int(self.offsets[self.rank]), self.pack.data_ptr(),
+                                self.pad_words)
+                g, work = gather_packed_raw(self.pack, self.pad_words, dist, self.group, async_op=True)
+                self._table_work = work
         else:
             self.pad_words = max((int(need_words * 1.125) + 65) & ~1, 2)
-        self._table_work = work
         self.gathered, self.counts, self._tables = g, counts, None
         ne, n_seg = counts[self.rank]
         return dict(runs=int(allr[self.rank, 0]), events=ne, event_samples=int(allr[self.rank, 2]), segments=n_seg)
+
+    def step_async(self, threshold, rules, mw, MW, W, gain):
+        """The device-planned step WITHOUT its closing host synchronisation: everything is enqueued and a ticket comes
+        back; `finish(ticket)` reads the result records.  A caller that runs steps on the same resident trace back to
+        back enqueues step i+1 before it finishes step i, so the device never waits for the host (the records of
+        step i are read while step i+1 runs).  A step whose records ask for the host-planned redo is repeated inside
+        finish() -- on the trace that is resident THEN, so do not swap traces between step_async and finish."""
+        import torch
+        with torch.cuda.stream(self.stream):
+            ctx = self.ctx
+            dev = self.device
+            if self.rec is None:
+                self.rec = torch.zeros(INFO_LEN, dtype=torch.float64, device=dev)
+                self.res = torch.zeros(8, dtype=torch.int64, device=dev)
+            if self.plan is None:
+                self.plan = torch.zeros(8, dtype=torch.int64, device=dev)
+                self.infos_dev = torch.empty(self.world * INFO_LEN, dtype=torch.float64, device=dev)
+            ctx.truncate_trace(self.n_local)
+            ctx.shard_scan(threshold, self.n_local, self.rec.data_ptr())
+            self._exchange_records(self.rec, INFO_LEN, self.infos_dev)
+            ctx.extend_trace(self._halo)
+            ctx.shard_plan(self.infos_dev.data_ptr(), self.rank, self.world, threshold, rules, self._halo,
+                           self.plan.data_ptr())
+            ctx.shard_finish_planned(threshold, rules, mw, MW, W, gain, self.plan.data_ptr(), self.res.data_ptr())
+            t = self._enqueue_results()
+        t["args"] = (threshold, rules, mw, MW, W, gain)
+        return t
+
+    def finish(self, ticket):
+        import torch
+        with torch.cuda.stream(self.stream):
+            r = self._finish_results(ticket, redo_mask=_REDO_MASK)
+            if r is None:
+                self.fallbacks += 1
+                r = self._step_host_planned(*ticket["args"])
+        return r
 
     def _step_host_planned(self, threshold, rules, mw, MW, W, gain):
         """Two more host synchronisations: after the all-gather of the boundary records the plan is made on
@@ -427,7 +531,7 @@ class ShardedPipeline(object):
             ctx.truncate_trace(self.n_local)
             ctx.shard_scan(threshold, self.n_local, self.rec.data_ptr())
             out = torch.empty(self.world * INFO_LEN, dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(out, self.rec, group=self.ctl_group)
+            self._exchange_records(self.rec, INFO_LEN, out)
             infos = out.cpu().numpy().reshape(self.world, INFO_LEN)      # host sync 1
             if not infos[:, I_PAD].any():
                 break

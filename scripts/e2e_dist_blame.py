@@ -34,7 +34,7 @@ def wrap(obj, name, label, stream):
         return r
     setattr(obj, name, g)
 
-for n in ("truncate_trace", "shard_scan", "extend_trace", "shard_plan", "shard_finish_planned", "pack_tables", "shard_commit"):
+for n in ("truncate_trace", "shard_scan", "extend_trace", "shard_plan", "shard_finish_planned", "pack_tables", "shard_commit", "ctl_exchange"):
     wrap(cur.ctx, n, "ctx." + n, cur.stream)
 real_ag = dist.all_gather_into_tensor
 def ag(*a, **k):
@@ -53,7 +53,8 @@ for n in dir(dist):
 cur.dist.all_gather_into_tensor = ag
 dist.barrier(); torch.cuda.synchronize()
 T0[0] = time.perf_counter()
-nxt.ctx.upload_trace_async(xp, extra_capacity=nxt.HALO_CAPACITY)
+if not os.environ.get("NOUPLOAD"):
+    nxt.ctx.upload_trace_async(xp, extra_capacity=nxt.HALO_CAPACITY)
 log.append(("other context: upload enqueued", (time.perf_counter() - T0[0]) * 1e3))
 cur.step(110.0, rules, mw, MW, W, gain)
 log.append(("step returned", (time.perf_counter() - T0[0]) * 1e3))

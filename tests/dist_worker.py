@@ -42,6 +42,13 @@ def main():
         shard.step(110.0, rules, mw, MW, W, gain)   # and back: the speculative halo is still in place
         alt = ppdist.rows(shard.download())
         assert all(np.array_equal(tabs[k], alt[k], equal_nan=True) for k in tabs), "device-planned step after it differs"
+        # steps without their closing host synchronisation: the second is enqueued before the first is finished
+        t1 = shard.step_async(110.0, rules, mw, MW, W, gain)
+        t2 = shard.step_async(110.0, rules, mw, MW, W, gain)
+        r1, r2 = shard.finish(t1), shard.finish(t2)
+        assert r1 == r2 and shard.fallbacks == 0
+        alt = ppdist.rows(shard.download())
+        assert all(np.array_equal(tabs[k], alt[k], equal_nan=True) for k in tabs), "step_async differs"
         glob = ppdist.synthetic_global(world, epr, seed0=70).astype(np.float64)
         pyrules = [lambda e: e.duration > 1000, lambda e: e.min > -0.5, lambda e: e.max < 110]
         ws, wl = oracle.events(glob, 110, pyrules)

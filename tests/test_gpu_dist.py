@@ -164,3 +164,34 @@ def test_device_planned_step_on_one_gpu(world, halo_spec):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_peer_control_exchange_on_one_gpu():
+    """pp_ctl_exchange (peer stores + flags instead of an all-gather of the control records): three contexts of one
+    process map each other's record buffers by pointer and exchange records of both kinds over many rounds, every
+    context on its own stream; what each receives must be the stacked records of that round."""
+    import numpy as np
+    import torch
+    from pypore_b200 import _lib
+    world = 3
+    ctxs = [_lib.Context(0) for _ in range(world)]
+    try:
+        ptrs = [c.ctl_create(r, world)[1] for r, c in enumerate(ctxs)]
+        for c in ctxs:
+            c.ctl_open(local_ptrs=ptrs)
+        rng = np.random.RandomState(2)
+        for rnd in range(40):
+            n_words = 12 if rnd % 2 == 0 else 8
+            recs = rng.randint(-2**62, 2**62, size=(world, n_words)).astype(np.int64)
+            src = [torch.from_numpy(recs[r]).cuda() for r in range(world)]
+            dst = [torch.zeros(world * n_words, dtype=torch.int64, device="cuda") for _ in range(world)]
+            torch.cuda.synchronize()
+            for r, c in enumerate(ctxs):                      # all three enqueued before anybody waits
+                c.ctl_exchange(src[r].data_ptr(), n_words, dst[r].data_ptr())
+            for c in ctxs:
+                c.sync()
+            for r in range(world):
+                assert np.array_equal(dst[r].cpu().numpy().reshape(world, n_words), recs), (rnd, r)
+    finally:
+        for c in ctxs:
+            c.close()
