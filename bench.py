@@ -414,8 +414,17 @@ def init_dist(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus != world and world == 1 and args.gpus > 1:
         raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    if world > 1:
+        # a job smaller than the node takes GPUs from both halves of the board (both sockets' upload bandwidth)
+        from pypore_b200.dist import device_for_rank
+        local = device_for_rank(local, torch.cuda.device_count())
     torch.cuda.set_device(local)
     if world > 1:
+        # one process per GPU: stay on the cores (and host memory) next to this GPU's PCIe root
+        from pypore_b200.dist import bind_near_gpu
+        bound = bind_near_gpu(local)
+        if os.environ.get("PYPORE_B200_BENCH_VERBOSE"):
+            print("rank %d bound to %d cores" % (rank, bound), file=sys.stderr)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return torch, dist, world, rank, local
 
@@ -450,7 +459,7 @@ def run_trace(args):
     # ---- synthetic input ---------------------------------------------------------------
     epg = args.events_per_gpu or cfg["events"]
     full = epg == cfg["events"]
-    shard = None
+    shard = whole = None
     if world == 1:
         x = synth.make_trace(epg, seed=cfg["seed"], tier="A")
     else:
@@ -460,7 +469,6 @@ def run_trace(args):
         else:   # one fixed trace, cut into `world` contiguous chunks wherever the cut falls
             whole = synth.make_trace(epg, seed=cfg["seed"], tier="A")
             x = np.ascontiguousarray(whole[len(whole) * rank // world:len(whole) * (rank + 1) // world])
-            del whole
         shard = ppdist.ShardedPipeline(ctx, rank, world)
     n_local = len(x)
     xp = torch.from_numpy(x).pin_memory().numpy()
@@ -489,7 +497,7 @@ def run_trace(args):
     # Multi-GPU end to end: the upload of step i+1 (the context's copy stream, into a second device buffer) runs
     # under step i's kernels and collectives, and the copy-out of step i's tables (a side stream, the other PCIe
     # direction) under both.  Every step's H2D and D2H are inside the timed region.
-    e2e = {"remaining": 0, "loaded": False}
+    e2e = {"remaining": 0, "loaded": False, "x": xp, "queued": 0}
 
     def step_e2e():
         if shard is None:
@@ -497,17 +505,19 @@ def run_trace(args):
             # the event / segment rows a chunk has finalised are written into page-locked host tables while the
             # next chunk is still on its way, so the call returns with the whole result in host memory
             r = ctx.pipeline(THRESHOLD, min_width=mw, max_width=MW, window_width=W, min_gain=gain,
-                             with_stats=True, host_trace=xp, export=True, **DEV_RULES)
+                             with_stats=True, host_trace=e2e["x"], export=True, **DEV_RULES)
             assert len(r["segment_table"]["mean"]) == r["segments"]
             return r
         if not e2e["loaded"]:
-            shard.load(xp)                     # first step of a run: nothing was prefetched for it
+            shard.load(e2e["x"])               # first step of a run: nothing was prefetched for it
+            e2e["queued"] = 0
         e2e["remaining"] -= 1
         e2e["loaded"] = e2e["remaining"] > 0
-        if e2e["loaded"]:
-            shard.prefetch(xp)                 # the next step's trace starts its way up before this step runs
+        while e2e["queued"] < min(2, e2e["remaining"]):
+            shard.prefetch(e2e["x"])           # the traces of the next two steps are on their way (or queued behind
+            e2e["queued"] += 1                 # the running copy) before this step runs
         r = shard.step(THRESHOLD, DEV_RULES, mw, MW, W, gain)
-        if rank == 0:
+        if rank == 0 and not os.environ.get("PYPORE_B200_BENCH_NO_DOWNLOAD"):   # (development switch: invalid e2e)
             # every GPU holds the whole result; the caller reads it once.  The copy-out is enqueued on a side stream
             # and collected before the next one is started; finish_e2e() collects the last one.
             if last_download.get("pending") is not None:
@@ -515,6 +525,7 @@ def run_trace(args):
             last_download["pending"] = shard.download_async()
         if e2e["loaded"]:
             shard.swap()
+            e2e["queued"] -= 1
         return r
 
     def finish_e2e():
@@ -558,12 +569,82 @@ def run_trace(args):
     split_ms = float(np.mean(split_ms))
     clocks = sampler.stop()
 
+    # End to end, the chunks need not be equal: the GPUs of a node do not get equal shares of the host's upload
+    # bandwidth when all of them copy at once (on the 8 x B200 box GPUs 0-3 get 23 GB/s each, GPUs 4-7 36 GB/s).
+    # The rates are measured, the SAME global trace is cut in proportion to them, and every upload ends at the same
+    # time.  Results are global tables, so the parity fixture is the same.
+    e2e_cut = None
+    chunk_cache = {}
+
+    def all_ranks(value):
+        mine = torch.tensor([value], dtype=torch.float64, device="cuda")
+        out = torch.empty(world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(out, mine)
+        return out.cpu().numpy()
+
+    def cut_by(rates):
+        """This rank's chunk of the global trace when the shares follow `rates` (same array on every rank)."""
+        lens = np.asarray(shard.lens0, np.int64)
+        offs = np.concatenate(([0], np.cumsum(lens)))
+        cuts = ppdist.proportional_cuts(int(offs[-1]), rates)
+        a, b = int(cuts[rank]), int(cuts[rank + 1])
+        if cfg["scaling"] == "weak":
+            parts = []
+            for q in range(world):
+                lo, hi = max(a, int(offs[q])), min(b, int(offs[q + 1]))
+                if lo < hi:
+                    if q != rank and q not in chunk_cache:
+                        chunk_cache[q] = ppdist.synthetic_chunk(q, world, epg, seed0=cfg["seed"])
+                    cq = x if q == rank else chunk_cache[q]
+                    parts.append(cq[lo - int(offs[q]):hi - int(offs[q])])
+            xe = np.concatenate(parts)
+        else:
+            xe = whole[a:b]
+        e2e["x"] = torch.from_numpy(np.ascontiguousarray(xe)).pin_memory().numpy()
+        return [int(v) for v in np.diff(cuts)]
+
+    if shard is not None and not args.even_cut:
+        shard.lens0 = np.array(shard.lens)       # the even cut's chunk lengths: where the global trace's pieces lie
+        rates = ppdist.measure_upload_rates(ctx, xp, dist, torch.device("cuda", local), world)
+        if args.upload_rates:
+            rates = np.array([float(v) for v in args.upload_rates.split(",")])[:world] * 1e9
+        e2e_cut = {"upload_GBps_all_ranks_at_once": [round(4e-9 * r, 1) for r in rates], "cut": "even"}
+        if rates.max() > 1.1 * rates.min():          # (same rates on every rank: same decision)
+            per_rank = cut_by(rates)
+            # second pass under the real step (result download, collectives and kernels running beside the uploads):
+            # every rank's copy time of a warm end-to-end step gives the rates the final cut follows
+            for _ in range(2):
+                arm_e2e(3)
+                for _ in range(3):
+                    step_e2e()
+                finish_e2e()
+                rates = all_ranks(len(e2e["x"]) / max(ctx.prefetch_ms(), 1e-3) * 1e3)
+                if args.upload_rates:
+                    break
+                per_rank = cut_by(rates)
+            e2e_cut["cut"] = "proportional to the measured rates"
+            e2e_cut["upload_GBps_in_the_step"] = [round(4e-9 * r, 1) for r in rates]
+            e2e_cut["samples_per_rank"] = per_rank
+    chunk_cache.clear()
+    whole = None
+
     arm_e2e(2)
     for _ in range(2):
         step_e2e()
     finish_e2e()
     ms_e2e, res_e2e = timer.run(step_e2e, args.steps, before=arm_e2e, closing=closing)
     finish_e2e()
+
+    upload_ms = [round(float(v), 3) for v in all_ranks(ctx.prefetch_ms())] if shard is not None else None
+
+    # the floor under the end-to-end number on this box: every rank's upload alone (all ranks at once, nothing else
+    # in flight), same page-locked buffer, same copy call
+    def step_upload():
+        ctx.upload_trace_async(e2e["x"], extra_capacity=0 if shard is None else shard.HALO_CAPACITY)
+    ms_h2d, _ = timer.run(step_upload, min(args.steps, 5))
+    ms_h2d /= min(args.steps, 5)
+    if shard is not None:
+        shard.load(e2e["x"])
 
     totals = torch.tensor([n_local, res["events"], res["segments"], res["event_samples"]], device="cuda",
                           dtype=torch.float64)
@@ -584,6 +665,14 @@ def run_trace(args):
         b_alg = 4.0 * n_total + 20.0 * evs_total + 16.0 * counters["candidates"] * world + 4.0 * evs_total + 56.0 * seg_total
         line = base_line(args, cfg, world, n_total / sec / 1e6, ms, n_total / sec_e2e / 1e6, 4 * n_total,
                          56 * seg_total + 16 * ev_total + 160 * world, launches, clocks)
+        line["e2e"]["ms_per_step"] = ms_e2e / args.steps
+        line["e2e"]["h2d_only_ms_per_step"] = ms_h2d
+        line["e2e"]["h2d_only_note"] = ("the uploads of all %d ranks alone, at once: %.1f GB/s of host-to-device copy "
+                                        "on this box; the end-to-end step cannot be shorter" %
+                                        (world, 4.0 * n_total / ms_h2d / 1e6))
+        if e2e_cut is not None:
+            e2e_cut["upload_ms_per_rank_last_step"] = upload_ms
+            line["e2e"]["chunks"] = e2e_cut
         line["roofline"] = split_roofline(counters["candidates"], split_ms, "k3_split", "issue", K3_NOTE,
                                           world == 1 and args.config == "c2" and full)
         # 617 M warp instructions per 240.4 M candidates (ncu, profiles/) scale with the candidate count
@@ -607,7 +696,7 @@ def run_trace(args):
                 seg_rows = np.stack([np.asarray(t["event"]).astype(np.int64), np.asarray(t["start"], np.int64),
                                      np.asarray(t["end"], np.int64)], axis=1)
             else:
-                t = last_download.get("tables")
+                t = last_download.get("tables") or shard.download()
                 ev_rows = np.stack([np.asarray(t["ev_start"], np.int64), np.asarray(t["ev_len"], np.int64)], axis=1)
                 seg_rows = np.stack([np.asarray(t[k], np.int64) for k in ("seg_event", "seg_start", "seg_end")], axis=1)
             if args.config == "c2":
@@ -849,6 +938,9 @@ def main():
     ap.add_argument("--long-events", type=int, default=None, help="development: fewer c4 events")
     ap.add_argument("--files", type=int, default=None, help="development: fewer c5 files")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--upload-rates", default=None, help="development: relative upload rates per rank, e.g. 1,1.5")
+    ap.add_argument("--even-cut", action="store_true",
+                    help="N > 1, end to end: equal chunks per GPU instead of chunks proportional to the measured upload rates")
     ap.add_argument("--split-kernel", default=None, choices=["flow", "level"],
                     help="development: force k3_flow / k3_split (default: the library's default)")
     args = ap.parse_args()

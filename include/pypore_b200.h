@@ -110,11 +110,17 @@ int pp_trace_upload(pp_ctx *ctx, const float *host, int64_t n, int64_t extra_cap
  * it like out of a float32 trace.  pp_trace_append / pp_trace_extend / the streamed host pipeline are float32-only. */
 int pp_trace_upload_f64(pp_ctx *ctx, const double *host, int64_t n);
 /* Back-to-back traces: pp_trace_prefetch starts the copy of the NEXT float32 trace (ideally from page-locked memory)
- * into a second device buffer on the context's copy stream and returns at once -- it runs under whatever the
- * context's stream is doing with the current trace; pp_trace_swap makes the prefetched trace the resident one (the
- * context's stream waits for the copy, the host does not). */
+ * into another device buffer on the context's copy stream and returns at once -- it runs under whatever the
+ * context's stream is doing with the current trace; pp_trace_swap makes the oldest prefetched trace the resident one
+ * (the context's stream waits for its copy, the host does not).  Up to TWO traces may be waiting for their swap
+ * (PP_ERR_STATE beyond that): with two, the copy stream always has the next copy queued behind the running one and
+ * the upload link never idles between steps.  Three trace buffers live at most. */
 int pp_trace_prefetch(pp_ctx *ctx, const float *host, int64_t n, int64_t extra_capacity);
 int pp_trace_swap(pp_ctx *ctx);
+/* Duration in milliseconds of the copy that brought up the trace pp_trace_swap made resident last (waits for it).  A caller that
+ * shards one trace over the GPUs of a node uses it to cut the trace in proportion to what each GPU's upload path
+ * delivers when all of them copy at once. */
+int pp_trace_prefetch_ms(pp_ctx *ctx, float *ms);
 /* Use device memory the caller owns (no copy; must stay valid; capacity in samples). */
 int pp_trace_adopt(pp_ctx *ctx, const float *dev, int64_t n, int64_t capacity);
 /* Append `n` samples (device or host pointer) after the current trace end: the

@@ -98,6 +98,7 @@ SIGNATURES = {
     "pp_debug_screen": (_c.c_int, [_c.c_void_p, _i64, _c.c_int, _c.c_int, _c.c_int, _f64p, _f64p, _u8p, _f64p]),
     "pp_debug_lg2_error": (_c.c_int, [_c.c_void_p, _f64p]),
     "pp_stream": (_c.c_void_p, [_c.c_void_p]),
+    "pp_trace_prefetch_ms": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_float)]),
     "pp_host_alloc": (_c.c_int, [_c.c_void_p, _i64, _c.POINTER(_c.c_void_p)]),
     "pp_host_free": (None, [_c.c_void_p, _c.c_void_p]),
     "pp_prefix": (_c.c_int, [_c.c_void_p, _c.c_int]),
@@ -270,11 +271,17 @@ class Context(object):
         self._keep = [x32]
         self._ck(self._L.pp_trace_upload(self._h, x32.ctypes.data, x32.shape[0], int(extra_capacity)))
 
+    def prefetch_ms(self):
+        """Duration of the copy that brought up the trace swap_trace() made resident last (waits for it)."""
+        ms = _c.c_float()
+        self._ck(self._L.pp_trace_prefetch_ms(self._h, _c.byref(ms)))
+        return float(ms.value)
+
     def prefetch_trace(self, x32, extra_capacity=0):
         """Start the upload of the NEXT trace (pinned float32 array; the caller keeps it alive until swap_trace()
         has been followed by a sync) while the resident one is being processed."""
         assert x32.dtype == np.float32 and x32.flags.c_contiguous
-        self._keep_next = x32
+        self._keep_next = (getattr(self, "_keep_next", None) or [])[-2:] + [x32]
         self._ck(self._L.pp_trace_prefetch(self._h, x32.ctypes.data, x32.shape[0], int(extra_capacity)))
 
     def swap_trace(self):
@@ -619,11 +626,13 @@ class Context(object):
                                          _c.c_void_p(int(dev_dst_ptr))))
 
     def unpack_tables(self, dev_gathered_ptr, world, words_per_rank, dev_records_ptr, n_events, n_segments,
-                      stream=None, slot=0):
+                      stream=None, slot=0, staging_ptr=None):
         """The all-gathered packed tables as host tables, one array per column (views of one of the context's two
         pinned table arenas, valid until that arena's next use): ev_start, ev_len, seg_event, seg_start, seg_end
         [int64], mean, std, min, max [float64].  With `stream` (a cudaStream_t as an integer) the kernel is only
-        enqueued there and the caller synchronises before it reads."""
+        enqueued there and the caller synchronises before it reads.  With `staging_ptr` (device memory of
+        unpacked_bytes() bytes) the kernel writes the same layout THERE and (views, whole arena as bytes) comes
+        back: the caller moves it with one device-to-host copy."""
         cols_e, cols_i, cols_f = ("ev_start", "ev_len"), ("seg_event", "seg_start", "seg_end"), ("mean", "std", "min", "max")
         spec = ([(k, n_events, np.int64) for k in cols_e] + [(k, n_segments, np.int64) for k in cols_i] +
                 [(k, n_segments, np.float64) for k in cols_f])
@@ -647,11 +656,21 @@ class Context(object):
         t = UnpackedTables()
         t.cap_events, t.cap_segments = int(n_events), int(n_segments)
         for k in cols_e + cols_i + cols_f:
-            setattr(t, k, v[k].ctypes.data)
+            # staged: same layout in a device arena; the caller copies arena to arena (one DMA transfer)
+            setattr(t, k, v[k].ctypes.data if staging_ptr is None else int(staging_ptr) + (v[k].ctypes.data - arena[0]))
         self._ck(self._L.pp_unpack_tables(self._h, _c.c_void_p(int(dev_gathered_ptr)), int(world),
-                                          int(words_per_rank), _c.c_void_p(int(dev_records_ptr)), _c.byref(t), 1,
+                                          int(words_per_rank), _c.c_void_p(int(dev_records_ptr)), _c.byref(t),
+                                          1 if staging_ptr is None else 0,
                                           _c.c_void_p(int(stream)) if stream else None))
+        if staging_ptr is not None:
+            whole = np.frombuffer((_c.c_char * total).from_address(arena[0]), dtype=np.uint8, count=total)
+            return v, whole
         return v
+
+    @staticmethod
+    def unpacked_bytes(n_events, n_segments):
+        """Size of the arena unpack_tables lays the columns out in."""
+        return (2 * (((n_events * 8 + 63) // 64) * 64) + 7 * (((n_segments * 8 + 63) // 64) * 64)) + 64
 
 
 _default = {}

@@ -44,8 +44,15 @@ struct pp_ctx {
 
     // trace: float32 (trace) or float64 (trace64) samples, one of the two
     DevBuf trace_buf;
-    DevBuf trace_next;          // pp_trace_prefetch: the NEXT float32 trace, on its way up while this one is processed
-    int64_t next_n = -1;
+    // pp_trace_prefetch: up to two float32 traces on their way up while the resident one is processed (oldest first);
+    // trace_spare is the buffer the last swap retired
+    struct Pending {
+        DevBuf buf;
+        int64_t n = -1;
+        cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
+    } pend[2];
+    int n_pend = 0;
+    DevBuf trace_spare;
     const float *trace = nullptr;
     const double *trace64 = nullptr;
     int64_t n = 0, trace_cap = 0;
@@ -103,6 +110,7 @@ struct pp_ctx {
     // streamed pipeline (pp_pipeline_host): copies run on their own stream
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ev = nullptr, compute_ev = nullptr;
+    cudaEvent_t pf_t0 = nullptr, pf_t1 = nullptr;   // timing of the last pp_trace_prefetch copy
     int64_t n_words = 0, n_blocks = 0;
 
     cudaEvent_t ev[ST_COUNT + 1] = {0};
@@ -728,7 +736,7 @@ void pp_destroy(pp_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int q = 0; q < 64; ++q)
         if (ctx->ctl_ipc[q] && ctx->ctl_peers[q]) cudaIpcCloseMemHandle(ctx->ctl_peers[q]);
-    DevBuf *bufs[] = {&ctx->trace_buf, &ctx->trace_next, &ctx->k1_rec, &ctx->k1_staged, &ctx->k1_blk, &ctx->run_start, &ctx->run_minkey,
+    DevBuf *bufs[] = {&ctx->trace_buf, &ctx->pend[0].buf, &ctx->pend[1].buf, &ctx->trace_spare, &ctx->k1_rec, &ctx->k1_staged, &ctx->k1_blk, &ctx->run_start, &ctx->run_minkey,
                       &ctx->run_maxkey, &ctx->run_len, &ctx->run_min, &ctx->run_max, &ctx->run_below,
                       &ctx->ev_start, &ctx->ev_len, &ctx->ev_off, &ctx->flat64, &ctx->cc, &ctx->bits,
                       &ctx->tasks, &ctx->ready, &ctx->block_count, &ctx->block_off, &ctx->inexact, &ctx->Ttab, &ctx->ev_tile_off, &ctx->k2_bits, &ctx->k2_tiles,
@@ -742,6 +750,13 @@ void pp_destroy(pp_ctx *ctx)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->copy_ev) cudaEventDestroy(ctx->copy_ev);
     if (ctx->compute_ev) cudaEventDestroy(ctx->compute_ev);
+    if (ctx->pf_t0) cudaEventDestroy(ctx->pf_t0);
+    if (ctx->pf_t1) cudaEventDestroy(ctx->pf_t1);
+    for (auto &q : ctx->pend) {
+        if (q.done) cudaEventDestroy(q.done);
+        if (q.t0) cudaEventDestroy(q.t0);
+        if (q.t1) cudaEventDestroy(q.t1);
+    }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -843,31 +858,69 @@ static int ensure_copy_stream(pp_ctx *ctx)
 int pp_trace_prefetch(pp_ctx *ctx, const float *host, int64_t n, int64_t extra_capacity)
 {
     if (!ctx || !host || n <= 0 || extra_capacity < 0) return fail(ctx, PP_ERR_ARG, "bad trace");
+    if (ctx->n_pend >= 2) return fail(ctx, PP_ERR_STATE, "two prefetched traces are already waiting for pp_trace_swap");
     CKR(set_device(ctx));
     CKR(ensure_copy_stream(ctx));
-    CKR(ensure(ctx, ctx->trace_next, sizeof(float) * (size_t)(n + extra_capacity)));
-    // the buffer was the resident trace two traces ago: whatever still reads it was enqueued before this point
+    pp_ctx::Pending &q = ctx->pend[ctx->n_pend];
+    if (!q.done) {
+        CK(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
+        CK(cudaEventCreate(&q.t0));
+        CK(cudaEventCreate(&q.t1));
+    }
+    if (!q.buf.p && ctx->trace_spare.p) {     // the buffer the last swap retired
+        q.buf = ctx->trace_spare;
+        ctx->trace_spare = DevBuf();
+    }
+    CKR(ensure(ctx, q.buf, sizeof(float) * (size_t)(n + extra_capacity)));
+    // the buffer was the resident trace some swaps ago: whatever still reads it was enqueued before this point
     CK(cudaEventRecord(ctx->compute_ev, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_ev, 0));
-    CK(cudaMemcpyAsync(ctx->trace_next.p, host, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->copy_stream));
-    CK(cudaEventRecord(ctx->copy_ev, ctx->copy_stream));
-    ctx->next_n = n;
+    CK(cudaEventRecord(q.t0, ctx->copy_stream));
+    CK(cudaMemcpyAsync(q.buf.p, host, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(q.t1, ctx->copy_stream));
+    CK(cudaEventRecord(q.done, ctx->copy_stream));
+    q.n = n;
+    ++ctx->n_pend;
+    return PP_OK;
+}
+
+int pp_trace_prefetch_ms(pp_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return PP_ERR_ARG;
+    if (!ctx->pf_t1) return fail(ctx, PP_ERR_STATE, "no prefetched trace has been swapped in so far");
+    CKR(set_device(ctx));
+    CK(cudaEventSynchronize(ctx->pf_t1));
+    CK(cudaEventElapsedTime(ms, ctx->pf_t0, ctx->pf_t1));
     return PP_OK;
 }
 
 int pp_trace_swap(pp_ctx *ctx)
 {
     if (!ctx) return PP_ERR_ARG;
-    if (ctx->next_n <= 0) return fail(ctx, PP_ERR_STATE, "no prefetched trace");
+    if (ctx->n_pend <= 0) return fail(ctx, PP_ERR_STATE, "no prefetched trace");
     CKR(set_device(ctx));
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev, 0));   // stream-level: the host goes on
-    DevBuf t = ctx->trace_buf;
-    ctx->trace_buf = ctx->trace_next;
-    ctx->trace_next = t;
+    pp_ctx::Pending &q = ctx->pend[0];
+    CK(cudaStreamWaitEvent(ctx->stream, q.done, 0));   // stream-level: the host goes on
+    // the retired resident buffer becomes the spare one (an older spare is dropped: at most three buffers live)
+    if (ctx->trace_spare.p) release(ctx->trace_spare);
+    ctx->trace_spare = ctx->trace_buf;
+    ctx->trace_buf = q.buf;
+    q.buf = DevBuf();
+    // the timing events of the trace swapped in are what pp_trace_prefetch_ms reads
+    cudaEvent_t a = ctx->pf_t0, b = ctx->pf_t1;
+    ctx->pf_t0 = q.t0; ctx->pf_t1 = q.t1;
+    q.t0 = a; q.t1 = b;
+    if (!q.t0) { CK(cudaEventCreate(&q.t0)); CK(cudaEventCreate(&q.t1)); }
     ctx->trace = (const float *)ctx->trace_buf.p;
     ctx->trace64 = nullptr;
-    ctx->n = ctx->next_n;
-    ctx->next_n = -1;
+    ctx->n = q.n;
+    q.n = -1;
+    if (ctx->n_pend == 2) {       // the younger one moves up
+        pp_ctx::Pending t = ctx->pend[0];
+        ctx->pend[0] = ctx->pend[1];
+        ctx->pend[1] = t;
+    }
+    --ctx->n_pend;
     ctx->trace_cap = (int64_t)(ctx->trace_buf.cap / sizeof(float));
     ctx->adopted = false;
     ctx->n_runs = ctx->n_events = ctx->n_event_samples = ctx->n_segments = -1;

@@ -247,6 +247,7 @@ class ShardedPipeline(object):
 
     HALO_CAPACITY = 1 << 20
     HALO_SPECULATIVE = 1 << 16   # samples every rank ships to its left neighbour up front (256 KB over NVLink)
+    STAGED_DOWNLOAD = not __import__("os").environ.get("PYPORE_B200_DIRECT_DOWNLOAD")   # see download_async
     RECORD_RING = 4              # steps that may be in flight between step_async() and finish()
 
     def __init__(self, ctx, rank, world, group=None):
@@ -267,8 +268,10 @@ class ShardedPipeline(object):
         self._halo = 0       # speculative halo samples resident after the chunk
         self._table_work = None   # outstanding asynchronous table all-gather
         self._side = None         # side stream of download_async
+        self._stage = None        # device arena of download_async
         self._rec_ring, self._rec_next = None, 0   # page-locked slots for the result records of steps in flight
-        self._n_agreed = self._n_next = -1
+        self._n_agreed = -1
+        self._next_lens = []      # chunk lengths of the prefetched traces, oldest first
         # the tiny control collectives (chunk lengths, boundary records, result records) get their own communicator:
         # they sit on every step's critical path and must not queue behind the previous step's table all-gather
         self.ctl_group = dist.new_group() if world > 1 and dist.is_initialized() else group
@@ -338,15 +341,17 @@ class ShardedPipeline(object):
 
     def prefetch(self, host_chunk):
         """Back-to-back traces: start the upload of the NEXT chunk (same length on every call in a row) on the
-        context's copy stream; it runs under the step on the resident chunk.  swap() makes it the resident one."""
+        context's copy stream; it runs under the step on the resident chunk.  swap() makes the oldest prefetched
+        chunk the resident one.  Two chunks may be waiting: with the one after next already queued behind the running
+        copy, the upload link does not idle while the ranks meet for the halo exchange between two steps."""
         n_local = int(host_chunk.shape[0])
         self._agree_lengths(n_local)
         self.ctx.prefetch_trace(host_chunk, extra_capacity=self.HALO_CAPACITY)
-        self._n_next = n_local
+        self._next_lens.append(n_local)
 
     def swap(self):
         self.ctx.swap_trace()
-        self.n_local = self._n_next
+        self.n_local = self._next_lens.pop(0)
         self._exchange_speculative_halo()
 
     def _exchange_speculative_halo(self):
@@ -619,8 +624,22 @@ class ShardedPipeline(object):
         n_ev = sum(c[0] for c in self.counts)
         n_seg = sum(c[1] for c in self.counts)
         self._slot ^= 1
-        cols = self.ctx.unpack_tables(self.gathered.data_ptr(), self.world, self.gathered.shape[1],
-                                      self.allr_dev.data_ptr(), n_ev, n_seg, stream=side.cuda_stream, slot=self._slot)
+        if self.STAGED_DOWNLOAD:
+            # unpack in device memory, then ONE copy-engine transfer: large posted writes on the upstream PCIe lanes
+            # disturb the concurrent upload of the next trace (whose read requests share those lanes) less than the
+            # 32-byte stores of a kernel writing host memory directly
+            nbytes = self.ctx.unpacked_bytes(n_ev, n_seg)
+            if self._stage is None or self._stage.shape[0] < nbytes:
+                self._stage = torch.empty(int(nbytes * 1.25), dtype=torch.uint8, device=self.device)
+            cols, whole = self.ctx.unpack_tables(self.gathered.data_ptr(), self.world, self.gathered.shape[1],
+                                                 self.allr_dev.data_ptr(), n_ev, n_seg, stream=side.cuda_stream,
+                                                 slot=self._slot, staging_ptr=self._stage.data_ptr())
+            with torch.cuda.stream(side):
+                torch.from_numpy(whole).copy_(self._stage[:nbytes], non_blocking=True)
+        else:
+            cols = self.ctx.unpack_tables(self.gathered.data_ptr(), self.world, self.gathered.shape[1],
+                                          self.allr_dev.data_ptr(), n_ev, n_seg, stream=side.cuda_stream,
+                                          slot=self._slot)
         done = torch.cuda.Event()
         done.record(side)
         keep = (self.gathered, self.allr_dev)   # the kernel reads them: they must outlive it
@@ -633,6 +652,82 @@ class ShardedPipeline(object):
         h = Handle()
         h.keep = keep
         return h
+
+
+def bind_near_gpu(device_index):
+    """Pin this process to the CPU cores of the NUMA node the GPU hangs off (one process per GPU: the page-locked
+    trace buffers are then first-touched on the memory next to the GPU's PCIe root, so eight uploads do not cross
+    the socket link).  Call before allocating host buffers.  Returns the number of cores bound to, 0 when the
+    topology cannot be read (then nothing changes)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = device_index
+        if visible:
+            entry = visible.split(",")[device_index].strip()
+            if entry.isdigit():
+                index = int(entry)
+            else:
+                index = None
+                handle = pynvml.nvmlDeviceGetHandleByUUID(entry.encode() if hasattr(entry, "encode") else entry)
+        if index is not None:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cores = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cores &= os.sched_getaffinity(0)
+        if not cores:
+            return 0
+        os.sched_setaffinity(0, cores)
+        return len(cores)
+    except Exception:
+        return 0
+
+
+def device_for_rank(local_rank, n_devices):
+    """Which GPU of the node a local rank uses when the node has more GPUs than ranks.  On an HGX board the
+    first half of the GPUs hangs off one CPU socket and the second half off the other; NVLink is all-to-all,
+    so ranks are dealt to the two halves in turn (0, n/2, 1, n/2+1, ...) and a 2- or 4-rank job gets both
+    sockets' PCIe and memory bandwidth for its uploads.  (Measured on the 8 x B200 box: four concurrent
+    uploads through GPUs 0-3 share 115 GB/s; GPUs 0,4,1,5 get their full 55 GB/s each.)"""
+    if n_devices < 2 or n_devices % 2:
+        return local_rank % max(n_devices, 1)
+    half = n_devices // 2
+    r = local_rank % n_devices
+    return (r // 2) + half * (r % 2)
+
+
+def measure_upload_rates(ctx, pinned, dist, device, world, window_ms=100.0, piece=16 << 20):
+    """Samples per second every rank's host-to-device path delivers while ALL ranks upload at once (they share
+    root ports and host memory channels unevenly).  Every rank copies pieces of `pinned` for the same wall-clock
+    window.  The resident trace is overwritten: load again afterwards.  Returns one rate per rank."""
+    import time
+    import torch
+    piece = int(min(piece, pinned.shape[0]))
+    part = pinned[:piece]
+    dist.barrier()
+    ctx.sync()
+    t0 = time.perf_counter()
+    copied = 0
+    while (time.perf_counter() - t0) * 1e3 < window_ms:
+        ctx.upload_trace_async(part)
+        ctx.sync()
+        copied += piece
+    mine = torch.tensor([copied / (time.perf_counter() - t0)], dtype=torch.float64, device=device)
+    rates = torch.empty(world, dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(rates, mine)
+    return rates.cpu().numpy()
+
+
+def proportional_cuts(total, rates):
+    """Boundaries (world + 1 sample offsets) that give every rank a share of `total` samples proportional to
+    its rate: all uploads then end together."""
+    share = np.cumsum(np.asarray(rates, np.float64)) / float(np.sum(rates))
+    cuts = np.concatenate(([0], np.round(total * share).astype(np.int64)))
+    cuts[-1] = total
+    return cuts
 
 
 def columns(t):

@@ -243,3 +243,17 @@ def test_plan_boundaries_property_random_cuts():
                     assert (r, cnt) in plans[q]["send"] and cnt <= bounds[q + 1] - bounds[q]
         assert sorted(got) == want, "case %d world %d" % (case, world)
     assert n_straddle > 50 and n_multi > 5      # the generator does produce the interesting cases
+
+
+def test_device_dealing_and_proportional_cuts():
+    """Ranks of a job smaller than the node alternate between the two halves of the board; chunk boundaries follow
+    the measured upload rates."""
+    from pypore_b200.dist import device_for_rank, proportional_cuts
+    assert [device_for_rank(r, 8) for r in range(8)] == [0, 4, 1, 5, 2, 6, 3, 7]
+    assert [device_for_rank(r, 8) for r in range(2)] == [0, 4]
+    assert device_for_rank(0, 1) == 0 and [device_for_rank(r, 3) for r in range(3)] == [0, 1, 2]
+    assert sorted(device_for_rank(r, 4) for r in range(4)) == [0, 1, 2, 3]
+    cuts = proportional_cuts(1000, [23.0, 23.0, 35.0, 35.0])
+    assert cuts[0] == 0 and cuts[-1] == 1000 and (np.diff(cuts) > 0).all()
+    assert abs(int(np.diff(cuts)[0]) - 198) <= 1 and abs(int(np.diff(cuts)[3]) - 302) <= 1
+    assert list(proportional_cuts(12, [1, 1, 1])) == [0, 4, 8, 12]

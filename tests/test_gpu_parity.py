@@ -624,3 +624,36 @@ def test_pinned_downloads_and_pinned_trace(ctx):
     assert set(a) == set(b) and all(np.array_equal(a[k], b[k]) for k in a)
     c = ctx.segments(r["segments"], stats=False, pinned=True)
     assert set(c) == {"event", "start", "end"} and np.array_equal(c["end"], a["end"])
+
+
+def test_prefetched_traces_queue_two_deep(ctx):
+    """pp_trace_prefetch / pp_trace_swap: two traces may be on their way while the resident one is processed; they
+    become resident oldest first, each gives exactly the tables of a plain upload, a third prefetch is refused."""
+    import torch
+    from pypore_b200 import _lib
+    gain = oracle.min_gain()
+    traces = [synth.make_trace(n, seed=s, tier="A") for n, s in ((12, 41), (20, 42), (7, 43), (15, 44))]
+    want = []
+    for x in traces:
+        ctx.upload_trace(x)
+        r = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, gain)
+        want.append((r, ctx.events(r["events"]), ctx.segments(r["segments"])))
+    pinned = [torch.from_numpy(x).pin_memory().numpy() for x in traces]
+    ctx.upload_trace(pinned[0])
+    ctx.prefetch_trace(pinned[1])
+    ctx.prefetch_trace(pinned[2], extra_capacity=1000)
+    with pytest.raises(_lib.PyPoreCudaError):
+        ctx.prefetch_trace(pinned[3])
+    for k in range(4):
+        r = ctx.pipeline(110.0, 7, 1000, 0, -0.5, 110.0, 100, 1000000, 10000, gain)
+        ev, tab = ctx.events(r["events"]), ctx.segments(r["segments"])
+        assert r == want[k][0], k
+        assert np.array_equal(ev[0], want[k][1][0]) and np.array_equal(ev[1], want[k][1][1])
+        assert all(np.array_equal(tab[c], want[k][2][c], equal_nan=True) for c in tab)
+        if k == 1:
+            ctx.prefetch_trace(pinned[3])       # the queue refills while it drains
+        if k < 3:
+            ctx.swap_trace()
+            assert ctx.prefetch_ms() > 0.0
+    with pytest.raises(_lib.PyPoreCudaError):
+        ctx.swap_trace()                        # nothing left
