@@ -611,19 +611,7 @@ def run_trace(args):
         e2e_cut = {"upload_GBps_all_ranks_at_once": [round(4e-9 * r, 1) for r in rates], "cut": "even"}
         if rates.max() > 1.1 * rates.min():          # (same rates on every rank: same decision)
             per_rank = cut_by(rates)
-            # second pass under the real step (result download, collectives and kernels running beside the uploads):
-            # every rank's copy time of a warm end-to-end step gives the rates the final cut follows
-            for _ in range(2):
-                arm_e2e(3)
-                for _ in range(3):
-                    step_e2e()
-                finish_e2e()
-                rates = all_ranks(len(e2e["x"]) / max(ctx.prefetch_ms(), 1e-3) * 1e3)
-                if args.upload_rates:
-                    break
-                per_rank = cut_by(rates)
             e2e_cut["cut"] = "proportional to the measured rates"
-            e2e_cut["upload_GBps_in_the_step"] = [round(4e-9 * r, 1) for r in rates]
             e2e_cut["samples_per_rank"] = per_rank
     chunk_cache.clear()
     whole = None
