@@ -329,7 +329,7 @@ def parity_rows(ev_rows, seg_rows, fixture, key, what):
         return {"error": "%s: %s" % (type(exc).__name__, exc)}
 
 
-def ncu_traffic(kernel="k3_split"):
+def ncu_traffic(kernel="k3_split", metrics=("dram__bytes_read.sum", "dram__bytes_write.sum")):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the newest committed `ncu --set full`
     capture of the default command (profiles/*_ncu_summary.csv), plus whether that capture is of THIS state of the
     kernels: its file name must start with the tag in profiles/CURRENT (the tag the kernels were last profiled under;
@@ -347,8 +347,8 @@ def ncu_traffic(kernel="k3_split"):
             col = next(i for i, n in enumerate(rows[0]) if n.startswith(kernel))
             tot = 0.0
             for r in rows:
-                if r and r[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                    tot += float(r[col]) * unit[r[1]]
+                if r and r[0] in metrics:
+                    tot += float(r[col]) * unit.get(r[1], 1.0)
             if tot > 0:
                 base = os.path.basename(path)
                 return tot, base, bool(current and base.startswith(current))
@@ -402,8 +402,8 @@ def split_roofline(counters_cand, split_ms, kernel, bound, note, use_traffic):
 
 K3_NOTE = ("algorithmic bytes = one 16 B {c,c2} pair per candidate evaluation (SURVEY 8d).  The bound is NOT HBM: the "
            "prefix sums are re-read from L2 once per recursion level (DRAM traffic is a third of the algorithmic bytes) "
-           "and the kernel is bound by instruction issue and dependent latency -- 617 M warp instructions, ~0.6 "
-           "instructions per cycle and scheduler (issue_frac) -- see DESIGN.md 4")
+           "and the kernel is bound by instruction issue and dependent latency -- ~0.6 warp instructions per cycle and "
+           "scheduler (issue_frac; instruction count from the ncu capture named beside it) -- see DESIGN.md 4")
 
 
 def init_dist(args):
@@ -663,8 +663,14 @@ def run_trace(args):
             line["e2e"]["chunks"] = e2e_cut
         line["roofline"] = split_roofline(counters["candidates"], split_ms, "k3_split", "issue", K3_NOTE,
                                           world == 1 and args.config == "c2" and full)
-        # 617 M warp instructions per 240.4 M candidates (ncu, profiles/) scale with the candidate count
-        line["roofline"]["issue_frac"] = (617e6 / 240.4e6 * counters["candidates"]) / (148 * 4 * 1.965e9 * split_ms / 1e3)
+        # warp instructions of the profiled launch (smsp__inst_executed.sum of the newest committed capture, taken on
+        # configs[1]: 240.4 M candidates) scale with the candidate count; 148 SMs x 4 schedulers x 1 issue per cycle
+        inst, inst_src, inst_fresh = ncu_traffic("k3_split", ("smsp__inst_executed.sum",))
+        inst = inst or 617e6
+        line["roofline"]["issue_frac"] = (inst / 240.4e6 * counters["candidates"]) / (148 * 4 * 1.965e9 * split_ms / 1e3)
+        line["roofline"]["warp_instructions_per_launch_c2"] = inst
+        line["roofline"]["warp_instructions_source"] = inst_src
+        line["roofline"]["warp_instructions_stale"] = not inst_fresh
         line["pipeline_roofline"] = {
             "b_floor_bytes": b_floor, "achieved": b_floor / sec / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
             "frac": b_floor / sec / 1e9 / world / peak, "b_alg_bytes": b_alg,
