@@ -160,7 +160,7 @@ k1_scan_tiles(const T *__restrict__ x, int64_t n, T thr, int64_t tile_begin, int
 
     if (warp == K1_WARPS) {
         // ---- producer warp: keeps K1_STAGES tiles in flight.  A whole tile is one 1-D TMA bulk copy; a ragged last
-        //      one is filled by the warp's lanes (past n: the last sample, which adds no crossing and no new extreme) ----
+        //      one is not staged at all (the consumer warps read their spans of it straight from global memory) ----
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t base = (tile_begin + blockIdx.x + it * (int64_t)gridDim.x) * K1_TILE;
             const int s = (int)(it % K1_STAGES);
@@ -170,16 +170,8 @@ k1_scan_tiles(const T *__restrict__ x, int64_t n, T thr, int64_t tile_begin, int
                     k1_mbar_expect(&S.full[s], TILE_BYTES);
                     k1_bulk_load(&S.stage[s][0], x + base, TILE_BYTES, &S.full[s]);
                 }
-            } else {
-                const T fill = __ldg(x + (n - 1));
-                T *buf = &S.stage[s][0];
-                for (int k = lane; k < K1_TILE; k += 32) {
-                    const int64_t g = base + k;
-                    buf[k] = g < n ? __ldg(x + g) : fill;
-                }
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) k1_mbar_arrive(&S.full[s]);
+            } else if (lane == 0) {
+                k1_mbar_arrive(&S.full[s]);      // ragged last tile: nothing staged, the phase still completes
             }
         }
         return;
@@ -195,7 +187,18 @@ k1_scan_tiles(const T *__restrict__ x, int64_t n, T thr, int64_t tile_begin, int
         if (warp == 0 && base > 0) before = __ldg(x + base - 1);
         k1_mbar_wait(&S.full[s], (unsigned)((it / K1_STAGES) & 1));
         // ---- this warp's span: 4 rows of 128 samples, lane l holds samples 4l .. 4l+3 of each row ----
-        const T *sp = &S.stage[s][0] + warp * K1_SPAN;
+        T *sp = &S.stage[s][0] + warp * K1_SPAN;
+        const bool ragged = base + K1_TILE > n;
+        T ahead = (T)0;                                     // ragged tile: the sample in front of this warp's span
+        if (ragged) {
+            // last tile of the trace: nothing was staged; every warp brings its own span in (past n the last sample
+            // repeats, which adds no crossing and no new extreme) and reads back only what it wrote itself
+            const int64_t g0 = base + warp * K1_SPAN;
+            const T fill = __ldg(x + (n - 1));
+            for (int k = lane; k < K1_SPAN; k += 32) sp[k] = g0 + k < n ? __ldg(x + g0 + k) : fill;
+            if (warp > 0) ahead = g0 - 1 < n ? __ldg(x + g0 - 1) : fill;
+            __syncwarp();
+        }
         T v[4][4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -208,7 +211,8 @@ k1_scan_tiles(const T *__restrict__ x, int64_t n, T thr, int64_t tile_begin, int
                 v[r][0] = (T)q0.x; v[r][1] = (T)q0.y; v[r][2] = (T)q1.x; v[r][3] = (T)q1.y;
             }
         }
-        const bool carry_below = (warp == 0 ? before : sp[-1]) < thr;   // side of the sample in front of the span
+        // side of the sample in front of the span
+        const bool carry_below = (warp == 0 ? before : (ragged ? ahead : sp[-1])) < thr;
         __syncwarp();
         if (lane == 0) k1_mbar_arrive(&S.empty[s]);   // this warp has its samples in registers
 

@@ -47,8 +47,13 @@ def test_file_batch_matches_oracle_and_single_file_path():
                     assert np.array_equal(got.events["start"][e0:e1], et["start"])
                     assert np.array_equal(got.events["length"][e0:e1], et["length"])
                     if e1 > e0:
-                        for k in ("event", "start", "end", "mean", "std", "min", "max"):
+                        for k in ("event", "start", "end", "min", "max"):
                             assert np.array_equal(got.segments[k][s0:s1], st[k]), k
+                        # the statistics kernel reads 16-byte vectors from the row's aligned start, so the order of
+                        # its fp64 sums follows the row's position in the pass: same samples at another offset
+                        # agree to rounding, not to the bit (the bar against the reference is 1e-9)
+                        for k in ("mean", "std"):
+                            assert np.allclose(got.segments[k][s0:s1], st[k], rtol=1e-12, atol=0), k
                 # without the filter (float32 events, the parallel prefix path) and with default gains
                 from pypore_b200.parsers import SpeedyStatSplit
                 import oracle
