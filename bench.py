@@ -517,12 +517,16 @@ def run_trace(args):
             shard.prefetch(e2e["x"])           # the traces of the next two steps are on their way (or queued behind
             e2e["queued"] += 1                 # the running copy) before this step runs
         r = shard.step(THRESHOLD, DEV_RULES, mw, MW, W, gain)
-        if rank == 0 and not os.environ.get("PYPORE_B200_BENCH_NO_DOWNLOAD"):   # (development switch: invalid e2e)
-            # every GPU holds the whole result; the caller reads it once.  The copy-out is enqueued on a side stream
-            # and collected before the next one is started; finish_e2e() collects the last one.
-            if last_download.get("pending") is not None:
-                last_download["tables"] = last_download["pending"].wait()
-            last_download["pending"] = shard.download_async()
+        if not os.environ.get("PYPORE_B200_BENCH_NO_DOWNLOAD"):   # (development switch: invalid e2e)
+            # every GPU holds the whole result; it reaches host memory once, the way the trace went up: every rank's
+            # process reads the rows of its own chunk over its own link (PYPORE_B200_BENCH_RANK0_DOWNLOAD: rank 0 pulls
+            # the whole table instead).  The copy-out is enqueued on a side stream and collected before the next one
+            # is started; finish_e2e() collects the last one.
+            own = not os.environ.get("PYPORE_B200_BENCH_RANK0_DOWNLOAD")
+            if own or rank == 0:
+                if last_download.get("pending") is not None:
+                    last_download["tables"] = last_download["pending"].wait()
+                last_download["pending"] = shard.download_async(own_rows=own)
         if e2e["loaded"]:
             shard.swap()
             e2e["queued"] -= 1
@@ -690,7 +694,7 @@ def run_trace(args):
                 seg_rows = np.stack([np.asarray(t["event"]).astype(np.int64), np.asarray(t["start"], np.int64),
                                      np.asarray(t["end"], np.int64)], axis=1)
             else:
-                t = last_download.get("tables") or shard.download()
+                t = shard.download()          # (outside the timed regions) the whole table, for the hash
                 ev_rows = np.stack([np.asarray(t["ev_start"], np.int64), np.asarray(t["ev_len"], np.int64)], axis=1)
                 seg_rows = np.stack([np.asarray(t[k], np.int64) for k in ("seg_event", "seg_start", "seg_end")], axis=1)
             if args.config == "c2":

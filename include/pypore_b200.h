@@ -317,6 +317,13 @@ typedef struct pp_unpacked_tables {
 } pp_unpacked_tables;
 int pp_unpack_tables(pp_ctx *ctx, const int64_t *dev_gathered, int world, int64_t words_per_rank,
                      const int64_t *dev_records, const pp_unpacked_tables *out, int out_is_host, void *cuda_stream);
+/* The same for the rows of the ranks [rank_lo, rank_hi) only, written from index 0 of the tables (event ids and
+ * event starts stay global).  With one process per GPU every rank copies out the rows of its own chunk
+ * (rank_lo = rank, rank_hi = rank + 1): the result reaches host memory over all the GPUs' links at once, the way
+ * the trace went up. */
+int pp_unpack_tables_range(pp_ctx *ctx, const int64_t *dev_gathered, int world, int64_t words_per_rank,
+                           const int64_t *dev_records, int rank_lo, int rank_hi, const pp_unpacked_tables *out,
+                           int out_is_host, void *cuda_stream);
 int pp_pack_tables(pp_ctx *ctx, const int64_t *dev_records, int rank, int64_t sample_offset, int64_t *dev_out,
                    int64_t cap_words);
 

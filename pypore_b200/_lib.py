@@ -117,6 +117,8 @@ SIGNATURES = {
     "pp_ctl_exchange": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "pp_unpack_tables": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _i64, _c.c_void_p, _c.POINTER(UnpackedTables),
                                     _c.c_int, _c.c_void_p]),
+    "pp_unpack_tables_range": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _i64, _c.c_void_p, _c.c_int, _c.c_int,
+                                          _c.POINTER(UnpackedTables), _c.c_int, _c.c_void_p]),
     "pp_pipeline_host": (_c.c_int, [_c.c_void_p, _f32p, _i64, _i64, _c.POINTER(PipelineParams), _i64p]),
     "pp_pipeline_host_tables": (_c.c_int, [_c.c_void_p, _f32p, _i64, _i64, _c.POINTER(PipelineParams),
                                            _c.POINTER(HostTables), _i64p]),
@@ -626,13 +628,14 @@ class Context(object):
                                          _c.c_void_p(int(dev_dst_ptr))))
 
     def unpack_tables(self, dev_gathered_ptr, world, words_per_rank, dev_records_ptr, n_events, n_segments,
-                      stream=None, slot=0, staging_ptr=None):
+                      stream=None, slot=0, staging_ptr=None, ranks=None):
         """The all-gathered packed tables as host tables, one array per column (views of one of the context's two
         pinned table arenas, valid until that arena's next use): ev_start, ev_len, seg_event, seg_start, seg_end
         [int64], mean, std, min, max [float64].  With `stream` (a cudaStream_t as an integer) the kernel is only
         enqueued there and the caller synchronises before it reads.  With `staging_ptr` (device memory of
         unpacked_bytes() bytes) the kernel writes the same layout THERE and (views, whole arena as bytes) comes
-        back: the caller moves it with one device-to-host copy."""
+        back: the caller moves it with one device-to-host copy.  `ranks` = (lo, hi): only the rows of those ranks,
+        from index 0 (n_events / n_segments are then the counts of that range)."""
         cols_e, cols_i, cols_f = ("ev_start", "ev_len"), ("seg_event", "seg_start", "seg_end"), ("mean", "std", "min", "max")
         spec = ([(k, n_events, np.int64) for k in cols_e] + [(k, n_segments, np.int64) for k in cols_i] +
                 [(k, n_segments, np.float64) for k in cols_f])
@@ -658,10 +661,11 @@ class Context(object):
         for k in cols_e + cols_i + cols_f:
             # staged: same layout in a device arena; the caller copies arena to arena (one DMA transfer)
             setattr(t, k, v[k].ctypes.data if staging_ptr is None else int(staging_ptr) + (v[k].ctypes.data - arena[0]))
-        self._ck(self._L.pp_unpack_tables(self._h, _c.c_void_p(int(dev_gathered_ptr)), int(world),
-                                          int(words_per_rank), _c.c_void_p(int(dev_records_ptr)), _c.byref(t),
-                                          1 if staging_ptr is None else 0,
-                                          _c.c_void_p(int(stream)) if stream else None))
+        lo, hi = ranks if ranks is not None else (0, int(world))
+        self._ck(self._L.pp_unpack_tables_range(self._h, _c.c_void_p(int(dev_gathered_ptr)), int(world),
+                                                int(words_per_rank), _c.c_void_p(int(dev_records_ptr)), int(lo), int(hi),
+                                                _c.byref(t), 1 if staging_ptr is None else 0,
+                                                _c.c_void_p(int(stream)) if stream else None))
         if staging_ptr is not None:
             whole = np.frombuffer((_c.c_char * total).from_address(arena[0]), dtype=np.uint8, count=total)
             return v, whole

@@ -1597,7 +1597,16 @@ int pp_ctl_exchange(pp_ctx *ctx, const void *dev_src, int n_words, void *dev_dst
 int pp_unpack_tables(pp_ctx *ctx, const int64_t *dev_gathered, int world, int64_t words_per_rank,
                      const int64_t *dev_records, const pp_unpacked_tables *out, int out_is_host, void *cuda_stream)
 {
+    return pp_unpack_tables_range(ctx, dev_gathered, world, words_per_rank, dev_records, 0, world, out, out_is_host,
+                                  cuda_stream);
+}
+
+int pp_unpack_tables_range(pp_ctx *ctx, const int64_t *dev_gathered, int world, int64_t words_per_rank,
+                           const int64_t *dev_records, int rank_lo, int rank_hi, const pp_unpacked_tables *out,
+                           int out_is_host, void *cuda_stream)
+{
     if (!ctx || !dev_gathered || !dev_records || !out || world < 1 || world > PP_MAX_WORLD || words_per_rank < 0 ||
+        rank_lo < 0 || rank_hi > world || rank_lo >= rank_hi ||
         (words_per_rank & 1) || !out->ev_start || !out->ev_len || !out->seg_event || !out->seg_start ||
         !out->seg_end || !out->mean || !out->std || !out->min || !out->max)
         return fail(ctx, PP_ERR_ARG, "bad unpack arguments");
@@ -1620,7 +1629,7 @@ int pp_unpack_tables(pp_ctx *ctx, const int64_t *dev_gathered, int world, int64_
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     CK(cudaMemsetAsync(ctx->unpack_flag.p, 0, sizeof(unsigned), st));
     k_unpack_tables<<<ctx->sm_count * 4, 256, 0, st>>>(
-        (const long long *)dev_gathered, world, words_per_rank, (const long long *)dev_records, O,
+        (const long long *)dev_gathered, world, words_per_rank, (const long long *)dev_records, rank_lo, rank_hi, O,
         (unsigned *)ctx->unpack_flag.p);
     LAUNCHED(ctx);
     if (cuda_stream) return PP_OK;   // the caller synchronises with its stream (and sized the tables from the counts)

@@ -825,7 +825,7 @@ struct PPUnpacked {
 
 __global__ void __launch_bounds__(256)
 k_unpack_tables(const long long *__restrict__ g, int world, int64_t m, const long long *__restrict__ rec_all,
-                PPUnpacked O, unsigned *__restrict__ status)
+                int rank_lo, int rank_hi, PPUnpacked O, unsigned *__restrict__ status)
 {
     __shared__ long long e_base[PP_MAX_WORLD + 1], s_base[PP_MAX_WORLD + 1];
     if (threadIdx.x == 0) {
@@ -838,22 +838,27 @@ k_unpack_tables(const long long *__restrict__ g, int world, int64_t m, const lon
         e_base[world] = e; s_base[world] = sg;
     }
     __syncthreads();
-    const long long E = e_base[world], S = s_base[world];
-    if (E > O.cap_events || S > O.cap_segments) {
+    // rows of the ranks [rank_lo, rank_hi) only, written from index 0 (event ids and starts stay global)
+    const long long E0 = e_base[rank_lo], S0 = s_base[rank_lo];
+    const long long E = e_base[rank_hi], S = s_base[rank_hi];
+    if (E - E0 > O.cap_events || S - S0 > O.cap_segments) {
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, 1u);
         return;
     }
+    O.ev_start -= E0; O.ev_len -= E0;
+    O.seg_event -= S0; O.seg_start -= S0; O.seg_end -= S0;
+    O.mean -= S0; O.sd -= S0; O.mn -= S0; O.mx -= S0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    for (int64_t k = t0; k < E; k += stride) {
-        int r = 0;
+    for (int64_t k = E0 + t0; k < E; k += stride) {
+        int r = rank_lo;
         while (k >= e_base[r + 1]) ++r;
         const long long *row = g + (int64_t)r * m + 2 * (k - e_base[r]);
         O.ev_start[k] = row[0];
         O.ev_len[k] = row[1];
     }
-    for (int64_t k = t0; k < S; k += stride) {
-        int r = 0;
+    for (int64_t k = S0 + t0; k < S; k += stride) {
+        int r = rank_lo;
         while (k >= s_base[r + 1]) ++r;
         const long long n_ev = e_base[r + 1] - e_base[r], n_sg = s_base[r + 1] - s_base[r];
         const long long j = k - s_base[r];

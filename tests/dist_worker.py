@@ -42,6 +42,13 @@ def main():
         shard.step(110.0, rules, mw, MW, W, gain)   # and back: the speculative halo is still in place
         alt = ppdist.rows(shard.download())
         assert all(np.array_equal(tabs[k], alt[k], equal_nan=True) for k in tabs), "device-planned step after it differs"
+        # every rank's own rows (what each process copies out end to end) are its slice of the whole table
+        own = ppdist.rows(shard.download_async(own_rows=True).wait())
+        e0 = sum(c[0] for c in shard.counts[:rank]); s0 = sum(c[1] for c in shard.counts[:rank])
+        ne, ns = shard.counts[rank]
+        for k in tabs:
+            lo, n = (e0, ne) if k == "events" else (s0, ns)
+            assert np.array_equal(own[k], tabs[k][lo:lo + n], equal_nan=True), "own rows differ: " + k
         # steps without their closing host synchronisation: the second is enqueued before the first is finished
         t1 = shard.step_async(110.0, rules, mw, MW, W, gain)
         t2 = shard.step_async(110.0, rules, mw, MW, W, gain)
