@@ -88,7 +88,7 @@ class Event(Segment):
             try:
                 current = np.concatenate([piece.current for piece in segments])
             except Exception:
-                current = []
+                current = ()
         super(Event, self).__init__(current, filtered=False, segments=segments, **kwargs)
 
     def filter(self, order=1, cutoff=2000.):
@@ -204,11 +204,10 @@ class File(Segment):
         self.__dict__.pop("_tables", None)
         if segmenter is None and filter_params is None and not isinstance(parser, lambda_event_parser):
             # any duck-typed parser, exactly like the reference: seg.current / seg.start / seg.duration in samples
-            second = self.second
-            self.events = [Event(current=seg.current, start=seg.start / second,
-                                 end=(seg.start + seg.duration) / second, duration=seg.duration / second,
-                                 second=second, file=self) for seg in parser.parse(self.current)]
-            self.event_parser = parser
+            rate, self.event_parser = self.second, parser
+            self.events = [Event(current=seg.current, start=seg.start / rate,
+                                 end=(seg.start + seg.duration) / rate, duration=seg.duration / rate,
+                                 second=rate, file=self) for seg in parser.parse(self.current)]
             return
         if not isinstance(parser, lambda_event_parser):
             raise TypeError("the device-resident pipeline needs a pypore_b200 lambda_event_parser")
@@ -439,7 +438,7 @@ class Experiment(object):
 
     def delete(self):
         _each(self.files, "delete")
-        self.files = []
+        self.files = list()
 
     n = property(lambda self: len(self.files))
 
