@@ -743,20 +743,24 @@ def run_long(args):
     xp = torch.from_numpy(x).pin_memory().numpy()
     tables = {}
 
-    def gather(seg):
-        """Every rank's segment rows (global event id, start, end | mean, std, min, max) on every rank."""
+    state = {"pack": None}
+
+    def exchange(r):
+        """Every rank's event and segment rows on every GPU, without leaving the device: the result records are
+        all-gathered (8 words per rank), pp_pack_tables writes this rank's rows (event ids offset by the event counts of
+        the ranks before it), one all-gather moves the packed rows.  Returns (gathered [world, pad], records)."""
         from pypore_b200 import dist as ppdist
-        ev_ids = torch.tensor(mine if mine else [0], dtype=torch.int64, device="cuda")
-        ints = torch.stack([ev_ids[torch.from_numpy(seg["event"].astype(np.int64)).cuda()],
-                            torch.from_numpy(np.array(seg["start"])).cuda(),
-                            torch.from_numpy(np.array(seg["end"])).cuda()], dim=1)
-        flts = torch.stack([torch.from_numpy(np.array(seg[k])).cuda() for k in ("mean", "std", "min", "max")], dim=1)
-        cnt = torch.tensor([ints.shape[0]], dtype=torch.int64, device="cuda")
-        allc = torch.empty(world, dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(allc, cnt)
-        gi, gf = ppdist.gather_tables(ints, flts, [int(c) for c in allc.tolist()], dist)
-        order = torch.argsort(gi[:, 0] * (1 << 32) + gi[:, 1])
-        return gi[order].cpu().numpy(), gf[order].cpu().numpy()
+        rec = torch.tensor([0, r["events"], r["event_samples"], r["segments"], 0, 0, 0, 0], dtype=torch.int64,
+                           device="cuda")
+        allr = torch.empty(world * 8, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(allr, rec)
+        counts = allr.view(world, 8)[:, [1, 3]].cpu().numpy()
+        pad = (int(max(2 * e + ppdist.SEG_WORDS * sg for e, sg in counts)) + 65) & ~1
+        if state["pack"] is None or state["pack"].shape[0] < pad:
+            state["pack"] = torch.empty(pad, dtype=torch.int64, device="cuda")
+        ctx.pack_tables(allr.data_ptr(), rank, 0, state["pack"].data_ptr(), pad)
+        g = ppdist.gather_packed_raw(state["pack"], pad, dist)
+        return g, allr, counts
 
     def step(host):
         if host:
@@ -768,15 +772,30 @@ def run_long(args):
         else:
             r = ctx.pipeline(THRESHOLD, min_width=mw, max_width=MW, window_width=W, min_gain=gain, with_stats=True,
                              **DEV_RULES)
-        if host or world > 1:
+        if world > 1:
+            with torch.cuda.stream(stream):
+                g, allr, counts = exchange(r)
+                tables["gathered"] = (g, allr, counts)
+                if host:
+                    # end to end: every rank's process reads the rows of its own events into page-locked memory
+                    tables["own"] = ctx.unpack_tables(g.data_ptr(), world, g.shape[1], allr.data_ptr(),
+                                                      int(counts[rank][0]), int(counts[rank][1]), ranks=(rank, rank + 1))
+        elif host:
             seg = ctx.segments(r["segments"], pinned=True)
             tables["ev"] = ctx.events(r["events"])
-            if world > 1:
-                with torch.cuda.stream(stream):
-                    tables["seg_int"], tables["seg_flt"] = gather(seg)
-            else:
-                tables["seg_int"] = np.stack([seg["event"].astype(np.int64), seg["start"], seg["end"]], axis=1)
+            tables["seg_int"] = np.stack([seg["event"].astype(np.int64), seg["start"], seg["end"]], axis=1)
         return r
+
+    def merged_segment_rows():
+        """(outside the timed regions, rank 0) the whole gathered table with the events' round-robin ids, sorted."""
+        g, allr, counts = tables["gathered"]
+        cols = ctx.unpack_tables(g.data_ptr(), world, g.shape[1], allr.data_ptr(), int(counts[:, 0].sum()),
+                                 int(counts[:, 1].sum()))
+        e_base = np.concatenate(([0], np.cumsum(counts[:, 0])))
+        owner = np.searchsorted(e_base, cols["seg_event"], side="right") - 1        # rank that produced the row
+        event = owner + world * (cols["seg_event"] - e_base[owner])                 # dealt round-robin
+        rows = np.stack([event, cols["seg_start"], cols["seg_end"]], axis=1).astype(np.int64)
+        return rows[np.lexsort((rows[:, 1], rows[:, 0]))]
 
     ctx.upload_trace(xp)
     for _ in range(max(min(args.warmup, 3), 1)):
@@ -809,6 +828,8 @@ def run_long(args):
         line["counts"] = {"samples": n_total, "events": ev_total, "segments": seg_total, "candidates": cand_total}
         if n_events == cfg["events"]:
             ev_rows = np.stack(tables["ev"], axis=1) if world == 1 else None
+            if world > 1:
+                tables["seg_int"] = merged_segment_rows()
             line["parity"] = parity_rows(ev_rows, tables["seg_int"], "bench_configs.npz", "c4_",
                                          "CPU oracle, all 20 events" + ("" if world == 1 else "; segment rows only: event "
                                                                         "starts are rank-local when events are dealt out"))
