@@ -701,12 +701,14 @@ def run_trace(args):
                 line["parity"] = (parity_rows(ev_rows, seg_rows, "c2_full.npz", "", "real reference, full size")
                                   if world == 1 else
                                   parity_rows(ev_rows, seg_rows, "sharded_full.npz", "w%d_" % world,
-                                              "CPU oracle on the uncut trace, full size"))
+                                              "CPU oracle on the uncut trace, full size; hashes equal the real reference's, "
+                                              "tests/golden/reference_full_check.json"))
             elif args.config == "c1" and world == 1:
                 line["parity"] = parity_rows(ev_rows, seg_rows, "bench_configs.npz", "c1_", "real reference, full size")
             elif args.config == "c3":
                 line["parity"] = parity_rows(ev_rows, seg_rows, "bench_configs.npz", "c3_",
-                                             "CPU oracle on the uncut 360 M-sample trace")
+                                             "CPU oracle on the uncut 360 M-sample trace; hashes equal the real reference's, "
+                                             "tests/golden/reference_full_check.json")
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_line(cfg)
         print(json.dumps(line), flush=True)
@@ -831,7 +833,8 @@ def run_long(args):
             if world > 1:
                 tables["seg_int"] = merged_segment_rows()
             line["parity"] = parity_rows(ev_rows, tables["seg_int"], "bench_configs.npz", "c4_",
-                                         "CPU oracle, all 20 events" + ("" if world == 1 else "; segment rows only: event "
+                                         "CPU oracle, all 20 events; hashes equal the real reference's, tests/golden/"
+                                         "reference_full_check.json" + ("" if world == 1 else "; segment rows only: event "
                                                                         "starts are rank-local when events are dealt out"))
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_line(cfg)

@@ -4,8 +4,8 @@ counts and SHA-256 of the global event rows (start, length) and segment rows (gl
 
     python tests/golden/make_sharded_full.py        # ~70 s, ~12 GB of RAM at world 8
 
-The oracle is used here (not the reference itself, which needs minutes per 60 M samples); it hashes to the real
-reference's tables on the single-GPU workload (tests/golden/c2_full.npz, tests/test_oracle_golden.py)."""
+The oracle makes the fixture; tests/golden/make_reference_full_check.py then runs the REAL reference on the same traces
+and records that its table hashes equal these (tests/golden/reference_full_check.json)."""
 import hashlib
 import os
 import sys

@@ -6,12 +6,13 @@
 Nothing here needs a GPU.
 """
 import hashlib
+import os
 
 import numpy as np
 import pytest
 
 import oracle
-from conftest import RULES_1000, load_golden
+from conftest import GOLDEN, RULES_1000, load_golden
 from pypore_b200 import synth
 
 
@@ -221,3 +222,22 @@ def test_oracle_reproduces_the_full_size_bench_workload_fixture():
         oe, ost, oen, nc = oracle.statsplit_events(x, ws, wl, min_width=100, window_width=10000, threads=8, **kw)
         assert len(oe) == int(g[name + "_segments"]) and nc == cand
         assert sha(np.stack([oe, ost, oen], axis=1).astype(np.int64)) == str(g[name + "_sha"])
+
+
+def test_full_size_fixtures_equal_the_real_references_tables():
+    """The full-size fixtures the oracle made (configs[2], configs[3] at 20 events, the 2 / 4 / 8-GPU traces) were
+    re-derived with the REAL reference (tests/golden/make_reference_full_check.py, build container, minutes of CPU):
+    its table hashes are committed next to the fixtures and must equal them -- the GPU runs that hash to these fixtures
+    therefore hash to the reference's own output."""
+    import json
+    path = os.path.join(GOLDEN, "reference_full_check.json")
+    chk = json.load(open(path))
+    fix_b = np.load(os.path.join(GOLDEN, "bench_configs.npz"), allow_pickle=False)
+    fix_s = np.load(os.path.join(GOLDEN, "sharded_full.npz"), allow_pickle=False)
+    for name, fix, key in (("c3", fix_b, "c3_"), ("c4", fix_b, "c4_"), ("w2", fix_s, "w2_"), ("w4", fix_s, "w4_"),
+                           ("w8", fix_s, "w8_")):
+        r = chk[name]
+        assert r["matches_fixture"] is True, name
+        assert r["events_sha"] == str(fix[key + "events_sha"]) and r["segments_sha"] == str(fix[key + "segments_sha"]), name
+        assert r["events"] == int(fix[key + "events"]) and r["segments"] == int(fix[key + "segments"]), name
+        assert r["samples"] == int(fix[key + "samples"]), name
