@@ -934,7 +934,8 @@ def run_batch(args):
         ev_rows = np.stack([tb.events[k][:e8] for k in ("file", "start", "length")], axis=1)
         seg_rows = np.stack([tb.segments[k][:s8] for k in ("file", "event", "start", "end")], axis=1)
         par = parity_rows(ev_rows, seg_rows, "c5_files.npz", "psps10_", "CPU oracle: scipy-equivalent filtfilt + split, the "
-                          "eight distinct files of the batch")
+                          "eight distinct files of the batch; hashes equal the real reference's, tests/golden/"
+                          "reference_full_check.json")
         per_file = np.bincount(tb.segments["file"], minlength=n_files)
         par["every_file_like_its_template"] = bool(all(per_file[i] == per_file[i % 8] for i in range(n_files)))
         line["parity"] = par

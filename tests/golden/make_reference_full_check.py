@@ -1,8 +1,9 @@
 """tests/golden/reference_full_check.json: the REAL reference on every full-size bench workload whose fixture was
 made by the CPU oracle -- BASELINE configs[2] (one 360 M-sample trace), configs[3] (20 events of 10 M samples,
-max_width = 1e6) and the multi-GPU workloads of bench.py --gpus 2 / 4 / 8 (120 M / 240 M / 480 M samples).
+max_width = 1e6), the multi-GPU workloads of bench.py --gpus 2 / 4 / 8 (120 M / 240 M / 480 M samples) and the eight
+distinct files of configs[4] (Event.filter = scipy's filtfilt, then the split on the filtered current).
 
-    python tests/golden/make_reference_full_check.py        # build container only; ~10 min on 8 cores, ~25 GB of RAM
+    python tests/golden/make_reference_full_check.py        # build container only; ~3 min on 8 cores, ~25 GB of RAM
 
 The reference's own code does the work (loaded like tests/golden/make_golden.py does: File.parse with its
 lambda_event_parser on the whole float64 trace, then its SpeedyStatSplit -- the compiled cparsers.pyx -- per event; the
@@ -58,6 +59,36 @@ def through_reference(dt, parsers, x64, kw, grain):
                 events_sha=sha(ev), segments_sha=sha(rows), seconds=round(time.time() - t0, 1))
 
 
+def c5_through_reference(dt, parsers):
+    """BASELINE configs[4]'s eight distinct 250 kHz files: File.parse, then per event the reference's own
+    Event.filter(1, 2000) -- scipy's bessel + filtfilt -- and SpeedyStatSplit on the filtered current; both gains."""
+    fs = 2.5e5
+    settings = {"psps10": dict(min_width=100, window_width=10000, sampling_freq=fs, cutoff_freq=2000.,
+                               prior_segments_per_second=10),
+                "default": dict(min_width=100, window_width=10000)}
+    t0 = time.time()
+    ev_rows, seg_rows = [], {k: [] for k in settings}
+    samples = 0
+    for i in range(8):
+        x64 = synth.make_trace(208, seed=900 + i, tier="A").astype(np.float64)
+        samples += len(x64)
+        f = dt.File(current=x64, timestep=1000. / fs)
+        f.parse(parser=parsers.lambda_event_parser(threshold=110, rules=RULES))
+        for k, event in enumerate(f.events):
+            ev_rows.append((i, int(round(event.start * f.second)), len(event.current)))
+            event.filter(order=1, cutoff=2000.)
+            for name, kw in settings.items():
+                for seg in parsers.SpeedyStatSplit(**kw).parse(event.current):
+                    seg_rows[name].append((i, k, seg.start, seg.end))
+    ev = np.array(ev_rows, np.int64).reshape(-1, 3)
+    out = {}
+    for name in settings:
+        rows = np.array(seg_rows[name], np.int64).reshape(-1, 4)
+        out[name] = dict(samples=int(samples), events=int(len(ev)), segments=int(len(rows)), events_sha=sha(ev),
+                         segments_sha=sha(rows), seconds=round(time.time() - t0, 1))
+    return out
+
+
 def main():
     import make_golden
     dt, parsers, _ = make_golden.load_reference()
@@ -87,6 +118,16 @@ def main():
                                     r["events"] == int(fix[key + "events"]) and r["segments"] == int(fix[key + "segments"]))
         out[name] = r
         print(name, {k: v for k, v in r.items() if not k.endswith("sha")}, flush=True)
+        json.dump(out, open(path, "w"), indent=1, sort_keys=True)
+    if not only or "c5" in only:
+        fix = np.load(os.path.join(HERE, "c5_files.npz"), allow_pickle=False)
+        for name, r in c5_through_reference(dt, parsers).items():
+            r["fixture_events_sha"] = str(fix[name + "_events_sha"])
+            r["fixture_segments_sha"] = str(fix[name + "_segments_sha"])
+            r["matches_fixture"] = bool(r["events_sha"] == r["fixture_events_sha"] and
+                                        r["segments_sha"] == r["fixture_segments_sha"])
+            out["c5_" + name] = r
+            print("c5", name, {k: v for k, v in r.items() if not k.endswith("sha")}, flush=True)
         json.dump(out, open(path, "w"), indent=1, sort_keys=True)
     assert all(v["matches_fixture"] for v in out.values()), "the reference disagrees with a fixture"
 

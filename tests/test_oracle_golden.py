@@ -241,3 +241,9 @@ def test_full_size_fixtures_equal_the_real_references_tables():
         assert r["events_sha"] == str(fix[key + "events_sha"]) and r["segments_sha"] == str(fix[key + "segments_sha"]), name
         assert r["events"] == int(fix[key + "events"]) and r["segments"] == int(fix[key + "segments"]), name
         assert r["samples"] == int(fix[key + "samples"]), name
+    fix_5 = np.load(os.path.join(GOLDEN, "c5_files.npz"), allow_pickle=False)
+    for name in ("psps10", "default"):          # configs[4]: the reference's Event.filter is scipy's filtfilt
+        r = chk["c5_" + name]
+        assert r["matches_fixture"] is True and r["segments"] == int(fix_5[name + "_segments"]), name
+        assert r["events_sha"] == str(fix_5[name + "_events_sha"]), name
+        assert r["segments_sha"] == str(fix_5[name + "_segments_sha"]), name
