@@ -593,15 +593,11 @@ def run_trace(args):
         cuts = ppdist.proportional_cuts(int(offs[-1]), rates)
         a, b = int(cuts[rank]), int(cuts[rank + 1])
         if cfg["scaling"] == "weak":
-            parts = []
-            for q in range(world):
-                lo, hi = max(a, int(offs[q])), min(b, int(offs[q + 1]))
-                if lo < hi:
-                    if q != rank and q not in chunk_cache:
-                        chunk_cache[q] = ppdist.synthetic_chunk(q, world, epg, seed0=cfg["seed"])
-                    cq = x if q == rank else chunk_cache[q]
-                    parts.append(cq[lo - int(offs[q]):hi - int(offs[q])])
-            xe = np.concatenate(parts)
+            def other(q):
+                if q not in chunk_cache:
+                    chunk_cache[q] = ppdist.synthetic_chunk(q, world, epg, seed0=cfg["seed"])
+                return chunk_cache[q]
+            xe = ppdist.recut_chunk(rank, cuts, lens, x, other)
         else:
             xe = whole[a:b]
         e2e["x"] = torch.from_numpy(np.ascontiguousarray(xe)).pin_memory().numpy()

@@ -737,6 +737,21 @@ def proportional_cuts(total, rates):
     return cuts
 
 
+def recut_chunk(rank, cuts, lens, own_chunk, other_chunk):
+    """This rank's share [cuts[rank], cuts[rank + 1]) of the global trace whose even cut has the chunk lengths `lens`
+    (this rank holds `own_chunk`; `other_chunk(q)` produces rank q's chunk of the even cut, for the pieces of the
+    new share that lie in a neighbour's old chunk)."""
+    offs = np.concatenate(([0], np.cumsum(np.asarray(lens, np.int64))))
+    a, b = int(cuts[rank]), int(cuts[rank + 1])
+    parts = []
+    for q in range(len(lens)):
+        lo, hi = max(a, int(offs[q])), min(b, int(offs[q + 1]))
+        if lo < hi:
+            src = own_chunk if q == rank else other_chunk(q)
+            parts.append(src[lo - int(offs[q]):hi - int(offs[q])])
+    return np.concatenate(parts) if parts else np.zeros(0, own_chunk.dtype)
+
+
 def columns(t):
     """dict(events [E,2], seg_int [S,3], seg_flt [S,4]) -> one array per column (the layout of download())."""
     out = dict(ev_start=t["events"][:, 0], ev_len=t["events"][:, 1], seg_event=t["seg_int"][:, 0],

@@ -257,3 +257,17 @@ def test_device_dealing_and_proportional_cuts():
     assert cuts[0] == 0 and cuts[-1] == 1000 and (np.diff(cuts) > 0).all()
     assert abs(int(np.diff(cuts)[0]) - 198) <= 1 and abs(int(np.diff(cuts)[3]) - 302) <= 1
     assert list(proportional_cuts(12, [1, 1, 1])) == [0, 4, 8, 12]
+
+
+def test_recut_chunks_partition_the_same_global_trace():
+    """The chunks of a cut that follows upload rates are a partition of the very trace the even cut partitions."""
+    world, epr = 3, 4
+    chunks = [ppdist.synthetic_chunk(r, world, epr, seed0=5) for r in range(world)]
+    whole = np.concatenate(chunks)
+    assert np.array_equal(whole, ppdist.synthetic_global(world, epr, seed0=5))
+    lens = [len(c) for c in chunks]
+    for rates in ([1.0, 1.0, 1.0], [20.6, 36.0, 20.6], [1.0, 5.0, 0.2], [3.0, 0.01, 3.0]):
+        cuts = ppdist.proportional_cuts(len(whole), rates)
+        parts = [ppdist.recut_chunk(r, cuts, lens, chunks[r], lambda q: chunks[q]) for r in range(world)]
+        assert [len(p) for p in parts] == list(np.diff(cuts))
+        assert np.array_equal(np.concatenate(parts), whole)
