@@ -275,9 +275,14 @@ class File(Segment):
             if fp is not None:
                 kw["filter_order"], kw["filter_cutoff"] = fp
             if sg is not None:
-                kw["segments"] = [MetaSegment(**dict(zip(("mean", "std", "min", "max"), stats(sg, k))),
-                                              **span(int(sg["start"][k]), int(sg["end"][k]) - int(sg["start"][k])))
-                                  for k in range(int(bounds[i]), int(bounds[i + 1]))]
+                lo = int(bounds[i])
+
+                def meta_segment(j):
+                    k = lo + j
+                    a = int(sg["start"][k])
+                    return MetaSegment(**dict(zip(("mean", "std", "min", "max"), stats(sg, k))),
+                                       **span(a, int(sg["end"][k]) - a))
+                kw["segments"] = _LazyList(int(bounds[i + 1]) - lo, meta_segment)
                 kw["state_parser"] = tables.state_parser
             return MetaEvent(**kw)
 
