@@ -81,9 +81,104 @@ def expand_event(ev, strict):
     return d
 
 
+_SCALAR_WORDS = {"nan": "NaN", "inf": "Infinity", "-inf": "-Infinity"}
+_MARK = "\ue000%d\ue000"                               # stands for a list while the skeleton is encoded
+_MARK_RE = re.compile(r'"\\ue000(\d+)\\ue000"')      # ... and how it looks in the encoder's (ASCII) output
+_STEP = " " * LAYOUT["indent"]
+
+
+class _NotFlat(Exception):
+    pass
+
+
+def _scalar_text(v, strings):
+    t = type(v)
+    if t is float:
+        s = float.__repr__(v)
+        return _SCALAR_WORDS.get(s, s)
+    if t is int:
+        return int.__repr__(v)
+    if t is str:
+        s = strings.get(v)
+        if s is None:
+            s = strings[v] = json.dumps(v)
+        return s
+    if v is True:
+        return "true"
+    if v is False:
+        return "false"
+    if v is None:
+        return "null"
+    raise _NotFlat()
+
+
+def _column_text(col, strings):
+    """JSON text of every value of one column (a tuple of scalars), whole-column calls where the types allow."""
+    kinds = set(map(type, col))
+    if kinds == {float}:
+        out = list(map(float.__repr__, col))
+        if "nan" in out or "inf" in out or "-inf" in out:
+            out = [_SCALAR_WORDS.get(s, s) for s in out]
+        return out
+    if kinds == {int}:
+        return list(map(int.__repr__, col))
+    if kinds == {str}:
+        for v in set(col):
+            if v not in strings:
+                strings[v] = json.dumps(v)
+        return [strings[v] for v in col]
+    return [_scalar_text(v, strings) for v in col]
+
+
+def _flat_rows_text(rows, level, strings):
+    """A non-empty list of dicts of scalars, all with the same keys, at indent level `level`: the text json.dumps
+    would produce for it, made column by column and with one template per list instead of the pure-Python
+    pretty-printer (which is what `indent=` costs: the C encoder only writes compact JSON)."""
+    keys = tuple(rows[0])
+    values = []
+    for d in rows:
+        if type(d) is not dict or tuple(d) != keys:
+            raise _NotFlat()
+        values.append(tuple(d.values()))
+    inner, item = _STEP * (level + 2), _STEP * (level + 1)
+    row_template = "{\n" + ",\n".join(inner + json.dumps(k).replace("%", "%%") + " : %s" for k in keys) + "\n" + item + "}"
+    columns = [_column_text(c, strings) for c in zip(*values)]
+    return "[\n" + item + (",\n" + item).join(map(row_template.__mod__, zip(*columns))) + "\n" + _STEP * level + "]"
+
+
+def _skeleton(node, level, texts, strings):
+    """Copy of `node` with every list of flat dicts replaced by a marker; their texts go to `texts`."""
+    if type(node) is dict:
+        return {k: _skeleton(v, level + 1, texts, strings) for k, v in node.items()}
+    if type(node) is list and node:
+        if type(node[0]) is dict and node[0]:
+            try:
+                text = _flat_rows_text(node, level, strings)
+            except _NotFlat:
+                pass
+            else:
+                texts.append(text)
+                return _MARK % (len(texts) - 1)
+        return [_skeleton(v, level + 1, texts, strings) for v in node]
+    return node
+
+
+def pretty(tree):
+    """json.dumps(tree, **LAYOUT), byte for byte, but the long homogeneous lists (segment rows: 10^5..10^6 dicts of
+    eight numbers) are written from a template.  Anything unusual falls back to json.dumps itself."""
+    try:
+        texts = []
+        skeleton = _skeleton(tree, 0, texts, {})
+        if not texts:
+            return json.dumps(tree, **LAYOUT)
+        return _MARK_RE.sub(lambda m: texts[int(m.group(1))], json.dumps(skeleton, **LAYOUT))
+    except (_NotFlat, TypeError, ValueError, RecursionError):
+        return json.dumps(tree, **LAYOUT)
+
+
 def dumps(tree, filename=None):
     """Text of a tree in the reference's layout; also written to `filename` when given."""
-    text = json.dumps(tree, **LAYOUT)
+    text = pretty(tree)
     if filename:
         with open(filename, "w") as fh:
             fh.write(text)

@@ -262,3 +262,22 @@ def test_ignored_and_segment_semantics_without_a_device():
     assert m.duration == 3 and MetaSegment(end=5, duration=3).start == 2 and MetaSegment(start=2, duration=3).end == 5
     back = MetaSegment.from_json(json=m.to_json())
     assert back.start == "2" and back.name == "MetaSegment"         # the flat reader keeps strings, like the reference
+
+
+def test_fast_pretty_printer_is_json_dumps_byte_for_byte():
+    """wire.pretty writes long lists of flat dicts from a template; the text must be exactly what the reference's
+    json.dumps(indent=4, separators=(',', ' : ')) layout gives, including NaN / Infinity, escapes, empty containers,
+    lists that are not homogeneous (those fall back) and '%' in keys."""
+    import json
+    from pypore_b200 import wire
+    trees = [
+        {"a": [{"x": 1.5, "y": float("nan"), "n": "Segment"}, {"x": -float("inf"), "y": 2, "n": "Segé\"q"}],
+         "b": [], "c": [{}], "d": [{"k": [1]}], "e": [[{"z": 1}]], "f": {"g": [{"h": True, "i": None, "j": False}]}},
+        [{"a": 1}, {"a": 2}], {"a": [{"x": 1}, {"y": 2}]}, {"a": [{"x": 1}, 3]}, {"a": [{"%s": 1.0, "100%": 2}]},
+        {"a": [{"x": 1.0}, {"x": 2}]}, {"a": [{"x": True}, {"x": 2}]}, {"a": [{"x": np.float64(1.5)}, {"x": 2.0}]},
+        {"events": [{"mean": 1.0, "segments": [{"mean": 0.1, "name": "Segment"}] * 3,
+                     "state_parser": {"name": "p", "w": 1}}] * 2},
+        {"a": [{"x": float(i) / 7, "s": "v%d" % (i % 3), "i": i} for i in range(200)]}, 5, "text", [], {},
+    ]
+    for tree in trees:
+        assert wire.pretty(tree) == json.dumps(tree, **wire.LAYOUT)
